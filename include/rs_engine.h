@@ -1,0 +1,129 @@
+/*
+ * rs_engine.h -- C ABI of the B200-native FastConformer-RNNT engine.
+ *
+ * The reference (reazon-research/ReazonSpeech) has no native layer: its hot path is one
+ * opaque Python call into NeMo,
+ *     model.transcribe([waveform], batch_size=1, return_hypotheses=True, verbose=...)
+ *                                              pkg/nemo-asr/src/transcribe.py:48-53
+ * whose result is consumed as hyp.y_sequence / hyp.timestamp (pkg/nemo-asr/src/decode.py:40,44).
+ * This header is the boundary a binding for that call site would target (INTEGRATION.md shows
+ * the ctypes stub).  Each entry point names the NeMo stage it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns RS_OK (0) or a negative rs_status; rs_last_error() gives the text.
+ *   - "dev" pointers are CUDA device pointers on the engine's device, caller-allocated unless
+ *     stated; "host" pointers are host memory (pinned for best throughput).
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation
+ *     except where stated (rs_transcribe_batch synchronises before returning).
+ *   - an engine is bound to one device and is not re-entrant; distinct engines are independent.
+ *   - batched activations are padded row-major [B, T_max, ...] with a per-utterance length
+ *     vector; rows at or beyond an utterance's length never influence valid rows.
+ */
+#ifndef RS_ENGINE_H_
+#define RS_ENGINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rs_status {
+  RS_OK = 0,
+  RS_ERR_INVALID_ARG = -1,
+  RS_ERR_CUDA = -2,
+  RS_ERR_MISSING_WEIGHT = -3,
+  RS_ERR_WORKSPACE = -4,
+  RS_ERR_UNSUPPORTED = -5
+} rs_status;
+
+/* Mirrors the fields of the .nemo model_config.yaml the path consumes. */
+typedef struct rs_model_config {
+  int32_t sample_rate, n_window_size, n_window_stride, n_fft, n_mels;
+  float preemph, log_zero_guard, norm_eps;
+  int32_t n_layers, d_model, n_heads, d_ff, conv_kernel, sub_channels;
+  int32_t att_left, att_right, global_tokens;
+  float xscale, ln_eps;
+  int32_t vocab_size;   /* blank id == vocab_size; classes == vocab_size + 1 */
+  int32_t pred_hidden, joint_hidden, max_symbols;
+} rs_model_config;
+
+/* One packed weight tensor, resident on the device (packing: reazonspeech_b200/engine.py). */
+typedef enum rs_dtype { RS_F32 = 0, RS_BF16 = 1, RS_I32 = 2 } rs_dtype;
+typedef struct rs_tensor {
+  const char* name;
+  const void* dev_ptr;
+  int32_t dtype;     /* rs_dtype */
+  int64_t numel;
+} rs_tensor;
+
+typedef struct rs_engine rs_engine;
+
+/* Epilogues of the tcgen05 GEMM  out = epi(A[M,K] * W[N,K]^T)  (SURVEY.md App. A.3). */
+typedef enum rs_epilogue {
+  RS_EPI_BIAS_BF16 = 0,       /* out_bf16[M,N]   = acc + bias                                  */
+  RS_EPI_BIAS_RELU_BF16 = 1,  /* out_bf16[M,N]   = relu(acc + bias)                            */
+  RS_EPI_BIAS_SWISH_BF16 = 2, /* out_bf16[M,N]   = swish(acc + bias)                           */
+  RS_EPI_BIAS_GLU_BF16 = 3,   /* out_bf16[M,N/2] = a * sigmoid(g); W rows interleaved 16/16    */
+  RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias)   */
+  RS_EPI_BIAS_F32 = 5         /* out_f32[M,N]    = alpha * (acc + bias)                        */
+} rs_epilogue;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+/* Replaces EncDecRNNTBPEModel.from_pretrained (transcribe.py:26-28) below the Python loader. */
+int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n_weights,
+                     int device, rs_engine** out);
+void rs_engine_destroy(rs_engine* e);
+/* Text of the last failure on `e` (or of the last failed rs_engine_create when e == NULL). */
+const char* rs_last_error(const rs_engine* e);
+
+/* Scratch the engine needs for a batch of B utterances of at most L_max samples. */
+int rs_workspace_bytes(const rs_engine* e, int B, int L_max, size_t* bytes);
+int rs_set_workspace(rs_engine* e, void* dev_ptr, size_t bytes);
+
+/* ---- shape arithmetic (FilterbankFeatures.get_seq_len, ConvSubsampling.calc_length) ----- */
+int rs_mel_frames(const rs_engine* e, int n_samples);
+int rs_enc_frames(const rs_engine* e, int n_samples);
+
+/* ---- stages (each is also a parity-test seam) --------------------------------------------- */
+/* N1 AudioToMelSpectrogramPreprocessor: wav f32[B,L_max] + len -> mel f32[B,F_max,n_mels]
+ * (time-major, per-feature normalised, rows >= mel_len zero) + mel_len i32[B]. */
+int rs_logmel(rs_engine* e, const float* wav_dev, const int32_t* len_dev, int B, int L_max,
+              float* mel_dev, int32_t* mel_len_dev, void* stream);
+/* N2-N7 ConformerEncoder: mel -> enc f32[B,T_max,d_model] + enc_len i32[B].
+ * n_layers < 0 runs the configured depth (smaller values are for stage tests). */
+int rs_encode(rs_engine* e, const float* mel_dev, const int32_t* mel_len_dev, int B, int F_max,
+              float* enc_dev, int32_t* enc_len_dev, int n_layers, void* stream);
+/* N8-N9 RNNTDecoder + RNNTJoint + greedy loop: enc -> tokens/frames i32[B,U_max], n_tok i32[B].
+ * n_tok[b] is the true emission count (may exceed U_max; only U_max entries are stored). */
+int rs_rnnt_greedy(rs_engine* e, const float* enc_dev, const int32_t* enc_len_dev, int B,
+                   int T_max, int32_t* tokens_dev, int32_t* frames_dev, int32_t* n_tok_dev,
+                   int U_max, void* stream);
+/* Device-resident whole path (what bench.py's `value` times). */
+int rs_transcribe_device(rs_engine* e, const float* wav_dev, const int32_t* len_dev, int B,
+                         int L_max, int32_t* tokens_dev, int32_t* frames_dev, int32_t* n_tok_dev,
+                         int U_max, void* stream);
+/* The model.transcribe seam with HOST buffers: H2D + whole path + D2H; synchronises. */
+int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_host, int B,
+                        int L_max, int32_t* tokens_host, int32_t* frames_host,
+                        int32_t* n_tok_host, int U_max, void* stream);
+
+/* ---- kernel-level seams (parity tests and roofline measurement) --------------------------- */
+int rs_gemm_bf16(rs_engine* e, const void* a_bf16, const void* w_bf16, const float* bias,
+                 const float* resid, void* out, int M, int N, int K, int epilogue, float alpha,
+                 void* stream);
+int rs_layernorm(rs_engine* e, const float* x, const float* gamma, const float* beta,
+                 float* out_f32 /*nullable*/, void* out_bf16 /*nullable*/, int rows, int d,
+                 void* stream);
+/* Counters: kernels launched by this engine since creation (bench.py's gpu_launches). */
+int64_t rs_launch_count(const rs_engine* e);
+/* Per-stage device time of the last rs_transcribe_* call when timing was enabled. */
+int rs_enable_stage_timing(rs_engine* e, int on);
+int rs_stage_times_ms(const rs_engine* e, float* ms /*[8]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_ENGINE_H_ */

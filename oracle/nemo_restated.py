@@ -1,0 +1,254 @@
+"""CPU oracle: a plain-PyTorch fp32 restatement of the NeMo inference path that
+``reazonspeech.nemo.asr.transcribe`` reaches through ``model.transcribe(...)``
+(reference call site: pkg/nemo-asr/src/transcribe.py:48-53).
+
+THIS IS TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
+package ``reazonspeech_b200`` never does.
+
+PARITY UNPINNED.  The arithmetic of this path lives in the third-party dependency
+``nemo_toolkit[asr] >= 2.6.1`` (pkg/nemo-asr/pyproject.toml:13), which is absent from
+/root/reference, cannot be imported in the build container, and for which the reference
+ships no tests, golden vectors or fixtures.  What follows restates
+NeMo's published algorithm module by module from the upstream sources named in each
+docstring; it has not been diffed against a NeMo run.  Every place where upstream
+behaviour is recalled rather than verified is marked (R).
+
+Semantics are batch=1, exactly as the reference calls NeMo (transcribe.py:48-50): every
+function takes ONE utterance with no padding.  ``emulate`` switches on bf16 rounding of
+activations at the points where the sm_100a engine stores bf16 (used only to tighten the
+token-identity test; the reference semantics are ``emulate=False``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+from reazonspeech_b200.config import ModelConfig, conv_out_len, xscale
+from reazonspeech_b200.weights import hann_window, mel_filterbank, rel_pos_table
+
+StateDict = Dict[str, torch.Tensor]
+
+
+def _q(x: torch.Tensor, emulate: bool) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32) if emulate else x
+
+
+# --------------------------------------------------------------------------------------
+# N1  AudioToMelSpectrogramPreprocessor / FilterbankFeatures.forward
+#     (nemo/collections/asr/parts/preprocessing/features.py)
+# --------------------------------------------------------------------------------------
+def log_mel(wave: torch.Tensor, cfg: ModelConfig, independent_fb: bool = False) -> torch.Tensor:
+    """float32[L] -> float32[n_mels, F], F = L // hop + 1 (all frames valid at batch=1).
+
+    preemph -> torch.stft(center=True, zero pad (R: "constant"; identical to "reflect" on
+    transcribe() inputs, whose 0.5 s edges are silence -- audio.py:80-82)) -> |X| -> **2 ->
+    mel -> log(x + 2^-24) -> per-feature (mean, unbiased std + 1e-5) normalisation."""
+    x = wave.to(torch.float32)
+    if cfg.preemph:
+        x = torch.cat((x[:1], x[1:] - cfg.preemph * x[:-1]))
+    spec = torch.stft(x, n_fft=cfg.n_fft, hop_length=cfg.n_window_stride, win_length=cfg.n_window_size,
+                      window=hann_window(cfg), center=True, pad_mode="constant", return_complex=True)
+    mag = torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1))
+    power = mag.pow(2.0)
+    if independent_fb:      # cross-check of weights.mel_filterbank against torchaudio's construction
+        import torchaudio
+        fb = torchaudio.functional.melscale_fbanks(cfg.n_freq, 0.0, cfg.sample_rate / 2, cfg.n_mels,
+                                                   cfg.sample_rate, norm="slaney", mel_scale="slaney").T
+    else:
+        fb = mel_filterbank(cfg)
+    mel = torch.matmul(fb, power)
+    mel = torch.log(mel + cfg.log_zero_guard)
+    assert mel.shape[1] == cfg.mel_frames(wave.numel())
+    mean = mel.mean(dim=1, keepdim=True)
+    std = mel.std(dim=1, keepdim=True) + cfg.norm_eps          # unbiased (N-1)
+    return (mel - mean) / std
+
+
+# --------------------------------------------------------------------------------------
+# N2  ConvSubsampling (dw_striding, x8)   (parts/submodules/subsampling.py)
+# --------------------------------------------------------------------------------------
+def subsample(mel: torch.Tensor, sd: StateDict, cfg: ModelConfig, emulate: bool = False) -> torch.Tensor:
+    """float32[n_mels, F] -> float32[T, d_model] (before xscale)."""
+    p = "encoder.pre_encode."
+    x = mel.T.unsqueeze(0).unsqueeze(0)                                           # [1,1,F,80]
+    x = F.relu(F.conv2d(x, sd[p + "conv.0.weight"], sd[p + "conv.0.bias"], stride=2, padding=1))
+    for dw, pw in ((2, 3), (5, 6)):
+        c = x.shape[1]
+        x = F.conv2d(x, sd[p + f"conv.{dw}.weight"], sd[p + f"conv.{dw}.bias"], stride=2, padding=1, groups=c)
+        x = _q(x, emulate)
+        x = F.relu(F.conv2d(x, sd[p + f"conv.{pw}.weight"], sd[p + f"conv.{pw}.bias"]))
+        x = _q(x, emulate)
+    b, c, t, f = x.shape
+    x = x.transpose(1, 2).reshape(b, t, c * f)                                    # index c*f_out + f
+    x = F.linear(x, sd[p + "out.weight"], sd[p + "out.bias"])
+    return x[0]
+
+
+# --------------------------------------------------------------------------------------
+# N5  RelPositionMultiHeadAttentionLongformer  (parts/submodules/multi_head_attention.py) (R)
+# --------------------------------------------------------------------------------------
+def local_attention_core(q, k, v, p, u, vb, cfg: ModelConfig, emulate: bool = False) -> torch.Tensor:
+    """q,k,v: [H,T,dk]; p: [H,n_rel,dk] (linear_pos of the table); u,vb: [H,dk] -> [H,T,dk].
+
+    Dense restatement of the sliding-chunk computation:
+      local score(i, j) = ((q_i+u).k_j + (q_i+v).p[w_left-(i-j)]) / sqrt(dk),  -w_left <= j-i <= w_right
+      keys outside [0,T) or outside the band are excluded (upstream fills them with -inf / -1e4);
+      with global_tokens=G: an extra column per global key g with score (q_i/sqrt(dk)).k_g
+      (no positional term; the same key ALSO stays in the local band (R)); softmax over the
+      concatenation; output = P_glob.v_g + P_local.v.  Rows of the global tokens themselves
+      are overwritten with full attention softmax_j((q_g/sqrt(dk)).k_j).v_j over all T keys."""
+    H, T, dk = q.shape
+    wl, wr, G = cfg.att_left, cfg.att_right, cfg.global_tokens
+    scale = 1.0 / math.sqrt(dk)
+    qu = _q(q + u[:, None, :], emulate)
+    qv = _q(q + vb[:, None, :], emulate)
+    ac = torch.matmul(qu, k.transpose(1, 2))                                      # [H,T,T]
+    bd_rel = torch.matmul(qv, p.transpose(1, 2))                                  # [H,T,n_rel]
+    i = torch.arange(T)[:, None]
+    j = torch.arange(T)[None, :]
+    rel = j - i
+    band = (rel >= -wl) & (rel <= wr)
+    idx = (rel + wl).clamp(0, cfg.n_rel - 1)
+    bd = torch.gather(bd_rel, 2, idx.unsqueeze(0).expand(H, T, T))
+    s_local = ((ac + bd) * scale).masked_fill(~band.unsqueeze(0), float("-inf"))
+    if G > 0:
+        s_glob = torch.matmul(q * scale, k[:, :G].transpose(1, 2))                # [H,T,G]
+        probs = torch.softmax(torch.cat((s_glob, s_local), dim=-1), dim=-1)
+        probs = _q(probs, emulate)
+        out = torch.matmul(probs[..., :G], v[:, :G]) + torch.matmul(probs[..., G:], v)
+        sg = torch.matmul(q[:, :G] * scale, k.transpose(1, 2))                    # [H,G,T]
+        out[:, :G] = torch.matmul(_q(torch.softmax(sg, dim=-1), emulate), v)
+    else:
+        out = torch.matmul(_q(torch.softmax(s_local, dim=-1), emulate), v)
+    return out
+
+
+def self_attention(x: torch.Tensor, sd: StateDict, pfx: str, cfg: ModelConfig, emulate: bool = False) -> torch.Tensor:
+    """x: [T,d] (already layer-normed) -> [T,d]."""
+    T, d = x.shape
+    H, dk = cfg.n_heads, cfg.d_head
+    a = pfx + "self_attn."
+    def heads(t):
+        return t.view(T, H, dk).transpose(0, 1)
+    q = _q(F.linear(x, sd[a + "linear_q.weight"], sd[a + "linear_q.bias"]), emulate)
+    k = _q(F.linear(x, sd[a + "linear_k.weight"], sd[a + "linear_k.bias"]), emulate)
+    v = _q(F.linear(x, sd[a + "linear_v.weight"], sd[a + "linear_v.bias"]), emulate)
+    pos = F.linear(rel_pos_table(cfg), sd[a + "linear_pos.weight"])               # [n_rel,d], no bias
+    p = _q(pos, emulate).view(cfg.n_rel, H, dk).transpose(0, 1)
+    o = local_attention_core(heads(q), heads(k), heads(v), p, sd[a + "pos_bias_u"], sd[a + "pos_bias_v"], cfg, emulate)
+    o = _q(o.transpose(0, 1).reshape(T, d), emulate)
+    return F.linear(o, sd[a + "linear_out.weight"], sd[a + "linear_out.bias"])
+
+
+# --------------------------------------------------------------------------------------
+# N4 / N6 / N7  ConformerLayer  (parts/submodules/conformer_modules.py)
+# --------------------------------------------------------------------------------------
+def feed_forward(x, sd, pfx, emulate=False):
+    h = F.silu(F.linear(x, sd[pfx + "linear1.weight"], sd[pfx + "linear1.bias"]))
+    return F.linear(_q(h, emulate), sd[pfx + "linear2.weight"], sd[pfx + "linear2.bias"])
+
+
+def conv_module(x, sd, pfx, cfg: ModelConfig, emulate=False):
+    """pointwise_conv1 -> GLU(channels) -> depthwise k (zero pad) -> BatchNorm1d(eval) -> Swish -> pointwise_conv2."""
+    c = pfx + "conv."
+    y = F.linear(x, sd[c + "pointwise_conv1.weight"][:, :, 0], sd[c + "pointwise_conv1.bias"])
+    y = _q(F.glu(y, dim=-1), emulate)                                             # first half * sigmoid(second half)
+    y = y.T.unsqueeze(0)                                                          # [1,d,T]
+    pad = (cfg.conv_kernel - 1) // 2
+    y = F.conv1d(y, sd[c + "depthwise_conv.weight"], sd[c + "depthwise_conv.bias"], padding=pad, groups=y.shape[1])
+    y = F.batch_norm(y, sd[c + "batch_norm.running_mean"], sd[c + "batch_norm.running_var"],
+                     sd[c + "batch_norm.weight"], sd[c + "batch_norm.bias"], training=False, eps=cfg.bn_eps)
+    y = _q(F.silu(y)[0].T, emulate)
+    return F.linear(y, sd[c + "pointwise_conv2.weight"][:, :, 0], sd[c + "pointwise_conv2.bias"])
+
+
+def conformer_layer(x, sd, i: int, cfg: ModelConfig, emulate=False):
+    p = f"encoder.layers.{i}."
+    d = (cfg.d_model,)
+    def ln(t, name):
+        return F.layer_norm(t, d, sd[p + name + ".weight"], sd[p + name + ".bias"], cfg.ln_eps)
+    x = x + 0.5 * feed_forward(_q(ln(x, "norm_feed_forward1"), emulate), sd, p + "feed_forward1.", emulate)
+    x = x + self_attention(_q(ln(x, "norm_self_att"), emulate), sd, p, cfg, emulate)
+    x = x + conv_module(_q(ln(x, "norm_conv"), emulate), sd, p, cfg, emulate)
+    x = x + 0.5 * feed_forward(_q(ln(x, "norm_feed_forward2"), emulate), sd, p + "feed_forward2.", emulate)
+    return ln(x, "norm_out")
+
+
+def encoder(mel: torch.Tensor, sd: StateDict, cfg: ModelConfig, emulate: bool = False,
+            n_layers: Optional[int] = None) -> torch.Tensor:
+    """ConformerEncoder.forward_internal at batch=1: float32[n_mels,F] -> float32[T,d_model]."""
+    x = subsample(mel, sd, cfg, emulate) * xscale(cfg)
+    for i in range(cfg.n_layers if n_layers is None else n_layers):
+        x = conformer_layer(x, sd, i, cfg, emulate)
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# N8 / N9  RNNTDecoder.predict, RNNTJoint.joint, GreedyRNNTInfer._greedy_decode
+#          (modules/rnnt.py, parts/submodules/rnnt_greedy_decoding.py)
+# --------------------------------------------------------------------------------------
+@dataclass
+class GreedyResult:
+    tokens: List[int] = field(default_factory=list)
+    frames: List[int] = field(default_factory=list)       # encoder frame index of each emission
+    margins: List[float] = field(default_factory=list)    # top1 - top2 logit of EVERY joint evaluation
+    decisions: List[int] = field(default_factory=list)    # argmax of every joint evaluation (incl. blanks)
+
+
+def joint_enc_proj(enc: torch.Tensor, sd: StateDict) -> torch.Tensor:
+    return F.linear(enc, sd["joint.enc.weight"], sd["joint.enc.bias"])
+
+
+def lstm_step(x, h, c, sd):
+    l = "decoder.prediction.dec_rnn.lstm."
+    gates = (F.linear(x, sd[l + "weight_ih_l0"], sd[l + "bias_ih_l0"]) +
+             F.linear(h, sd[l + "weight_hh_l0"], sd[l + "bias_hh_l0"]))
+    i, f, g, o = gates.chunk(4)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    h2 = torch.sigmoid(o) * torch.tanh(c2)
+    return h2, c2
+
+
+def rnnt_greedy(enc: torch.Tensor, sd: StateDict, cfg: ModelConfig, emulate: bool = False) -> GreedyResult:
+    """enc: float32[T,d_model] -> greedy hypothesis (tokens, frame of each token).
+
+    For every frame t: up to max_symbols times { g = pred(last_token, state);
+    logits = W_out relu(W_enc f_t + W_pred g + b); k = argmax; blank -> next frame;
+    else emit k at t and commit the LSTM state }.  The start token is blank, whose
+    embedding row is the zero vector (blank_as_pad)."""
+    hp = cfg.pred_hidden
+    res = GreedyResult()
+    ep = joint_enc_proj(_q(enc, emulate), sd)
+    emb = sd["decoder.prediction.embed.weight"]
+    h = torch.zeros(hp); c = torch.zeros(hp)
+    h_new, c_new = lstm_step(torch.zeros(hp), h, c, sd)                            # SOS step
+    pp = F.linear(h_new, sd["joint.pred.weight"], sd["joint.pred.bias"])
+    W, b = sd["joint.joint_net.2.weight"], sd["joint.joint_net.2.bias"]
+    for t in range(enc.shape[0]):
+        for _ in range(cfg.max_symbols):
+            logits = F.linear(torch.relu(ep[t] + pp), W, b)
+            top2 = torch.topk(logits, 2)
+            k = int(top2.indices[0])
+            res.margins.append(float(top2.values[0] - top2.values[1]))
+            res.decisions.append(k)
+            if k == cfg.blank:
+                break
+            res.tokens.append(k); res.frames.append(t)
+            h, c = h_new, c_new
+            h_new, c_new = lstm_step(emb[k], h, c, sd)
+            pp = F.linear(h_new, sd["joint.pred.weight"], sd["joint.pred.bias"])
+    return res
+
+
+# --------------------------------------------------------------------------------------
+# Whole path at the model.transcribe seam
+# --------------------------------------------------------------------------------------
+def transcribe_tokens(wave: torch.Tensor, sd: StateDict, cfg: ModelConfig, emulate: bool = False) -> GreedyResult:
+    """The reference path from the padded waveform tensor (transcribe.py:46) to greedy tokens."""
+    with torch.no_grad():
+        return rnnt_greedy(encoder(log_mel(wave, cfg), sd, cfg, emulate), sd, cfg, emulate)

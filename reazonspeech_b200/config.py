@@ -1,0 +1,150 @@
+"""Model configuration for the FastConformer-RNNT path.
+
+Mirrors the fields of the ``model_config.yaml`` inside the ``.nemo`` archive that
+``reazonspeech.nemo.asr.load_model`` fetches (reference call site:
+pkg/nemo-asr/src/transcribe.py:26-28).  Field names follow NeMo's yaml so a real
+config can be mapped one-to-one (see ``ModelConfig.from_nemo_yaml``).  Defaults are
+the values SURVEY.md App. A.1 expects for ``reazon-research/reazonspeech-nemo-v2``
+(all tagged (R) there: NeMo and the checkpoint are not available offline).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class ModelConfig:
+    # --- preprocessor (AudioToMelSpectrogramPreprocessor) ---
+    sample_rate: int = 16000
+    n_window_size: int = 400          # window_size 0.025 s
+    n_window_stride: int = 160        # window_stride 0.01 s
+    n_fft: int = 512
+    n_mels: int = 80
+    preemph: float = 0.97
+    log_zero_guard: float = 2.0 ** -24
+    norm_eps: float = 1e-5            # CONSTANT added to per-feature std
+    # --- encoder (ConformerEncoder, dw_striding x8) ---
+    n_layers: int = 24
+    d_model: int = 1024
+    n_heads: int = 8
+    ff_expansion: int = 4
+    conv_kernel: int = 9
+    sub_channels: int = 256
+    sub_factor: int = 8
+    att_left: int = 128               # att_context_size[0]
+    att_right: int = 128              # att_context_size[1]
+    global_tokens: int = 1
+    xscaling: bool = True
+    ln_eps: float = 1e-5
+    bn_eps: float = 1e-5
+    # --- decoder / joint ---
+    vocab_size: int = 3000            # blank index == vocab_size
+    pred_hidden: int = 640
+    joint_hidden: int = 640
+    max_symbols: int = 10
+
+    # ---- derived ----
+    @property
+    def d_head(self) -> int:
+        return self.d_model // self.n_heads
+
+    @property
+    def d_ff(self) -> int:
+        return self.d_model * self.ff_expansion
+
+    @property
+    def n_freq(self) -> int:
+        return self.n_fft // 2 + 1
+
+    @property
+    def blank(self) -> int:
+        return self.vocab_size
+
+    @property
+    def n_classes(self) -> int:
+        return self.vocab_size + 1
+
+    @property
+    def sub_freq(self) -> int:
+        """Frequency bins left after the three stride-2 convs (80 -> 40 -> 20 -> 10)."""
+        f = self.n_mels
+        for _ in range(3):
+            f = conv_out_len(f)
+        return f
+
+    @property
+    def sub_out_dim(self) -> int:
+        return self.sub_channels * self.sub_freq
+
+    @property
+    def n_rel(self) -> int:
+        """Number of relative positions held by the local-attention table (2w+1)."""
+        return self.att_left + self.att_right + 1
+
+    def mel_frames(self, n_samples: int) -> int:
+        """FilterbankFeatures.get_seq_len with center=True: L // hop + 1."""
+        return n_samples // self.n_window_stride + 1
+
+    def enc_frames(self, n_samples: int) -> int:
+        t = self.mel_frames(n_samples)
+        for _ in range(3):
+            t = conv_out_len(t)
+        return t
+
+    def replace(self, **kw) -> "ModelConfig":
+        return dataclasses.replace(self, **kw)
+
+    @staticmethod
+    def tiny() -> "ModelConfig":
+        """Small shape-compatible config for CPU-side tests (same code paths, tiny dims).
+
+        d_model/d_ff/heads keep the alignment constraints of the kernels
+        (d_head == 128, every GEMM K and N a multiple of 128 / 64)."""
+        return ModelConfig(n_layers=2, d_model=256, n_heads=2, sub_channels=64,
+                           att_left=16, att_right=16, vocab_size=127,
+                           pred_hidden=128, joint_hidden=128)
+
+    @staticmethod
+    def from_nemo_yaml(cfg: dict) -> "ModelConfig":
+        """Map a parsed ``model_config.yaml`` (dict) onto ModelConfig."""
+        pre, enc = cfg["preprocessor"], cfg["encoder"]
+        dec, joint = cfg["decoder"], cfg["joint"]
+        sr = int(pre.get("sample_rate", 16000))
+        ctx = enc.get("att_context_size", [128, 128]) or [128, 128]
+        if enc.get("self_attention_model", "rel_pos_local_attn") != "rel_pos_local_attn":
+            raise ValueError("engine implements self_attention_model=rel_pos_local_attn only")
+        if enc.get("subsampling", "dw_striding") != "dw_striding":
+            raise ValueError("engine implements subsampling=dw_striding only")
+        return ModelConfig(
+            sample_rate=sr,
+            n_window_size=int(round(float(pre.get("window_size", 0.025)) * sr)),
+            n_window_stride=int(round(float(pre.get("window_stride", 0.01)) * sr)),
+            n_fft=int(pre.get("n_fft", 512)),
+            n_mels=int(pre.get("features", 80)),
+            preemph=float(pre.get("preemph", 0.97) or 0.0),
+            n_layers=int(enc["n_layers"]),
+            d_model=int(enc["d_model"]),
+            n_heads=int(enc.get("n_heads", 8)),
+            ff_expansion=int(enc.get("ff_expansion_factor", 4)),
+            conv_kernel=int(enc.get("conv_kernel_size", 9)),
+            sub_channels=int(enc.get("subsampling_conv_channels", 256)),
+            sub_factor=int(enc.get("subsampling_factor", 8)),
+            att_left=int(ctx[0]), att_right=int(ctx[1]),
+            global_tokens=int(enc.get("global_tokens", 1)),
+            xscaling=bool(enc.get("xscaling", True)),
+            vocab_size=int(dec.get("vocab_size", joint.get("num_classes", 3000))),
+            pred_hidden=int(dec["prednet"]["pred_hidden"]),
+            joint_hidden=int(joint["jointnet"]["joint_hidden"]),
+            max_symbols=int(cfg.get("decoding", {}).get("greedy", {}).get("max_symbols", 10) or 10),
+        )
+
+
+def conv_out_len(n: int) -> int:
+    """ConvSubsampling.calc_length for k=3, s=2, p=1: floor((n + 2 - 3) / 2) + 1."""
+    return (n - 1) // 2 + 1
+
+
+def xscale(cfg: ModelConfig) -> float:
+    return math.sqrt(cfg.d_model) if cfg.xscaling else 1.0

@@ -1,0 +1,357 @@
+// Relative-position local attention with a global token (N5): the core of NeMo's
+// RelPositionMultiHeadAttentionLongformer (parts/submodules/multi_head_attention.py), reached
+// through model.transcribe (pkg/nemo-asr/src/transcribe.py:48-53).  Semantics restated in
+// oracle/nemo_restated.py::local_attention_core.
+//
+// One CTA = 64 query rows of one (utterance, head); 4 warps x 16 rows, flash-style online
+// softmax in fp32, bf16 mma.sync m16n8k16 for QK^T, Q P^T and PV.  The positional term
+// (q+v).p[rel] is computed once per query tile for all 2w+1 relative offsets into shared memory
+// and added to each key tile through the skewed index rel = j - i + w_left (no rel-shift pass,
+// no [T,T] score tensor in HBM).  Only key tiles intersecting [i-w_left, i+w_right] are
+// visited, so cost is linear in T (long-form audio).  The global token enters as the initial
+// state of the online softmax; its own row (full attention) is a separate small kernel.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rs {
+
+constexpr int DK = 128;
+constexpr int QT = 64;            // query rows per CTA
+constexpr int KT = 64;            // keys per tile
+constexpr int LDS = DK + 8;       // padded smem row (bf16 elements): conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnDev {
+  const __nv_bfloat16* qkv; const __nv_bfloat16* pos; const float* bias_u; const float* bias_v;
+  __nv_bfloat16* out; const int32_t* enc_len;
+  int T_max, H, w_left, w_right, n_global, n_rel, n_rel_pad;
+};
+
+// Copy 64 rows x 128 bf16 (row stride `ld` elements, rows >= valid read as zero) into padded smem.
+__device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, size_t ld, int valid_rows) {
+  for (int id = threadIdx.x; id < 64 * 16; id += blockDim.x) {
+    const int r = id >> 4, c = (id & 15) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < valid_rows) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + c);
+    *reinterpret_cast<uint4*>(s + r * LDS + c) = v;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1)
+local_attention_kernel(const AttnDev p) {
+  extern __shared__ __align__(16) uint8_t at_smem[];
+  __nv_bfloat16* sQU = reinterpret_cast<__nv_bfloat16*>(at_smem);
+  __nv_bfloat16* sQV = sQU + QT * LDS;
+  __nv_bfloat16* sK = sQV + QT * LDS;
+  __nv_bfloat16* sV = sK + KT * LDS;
+  float* sBD = reinterpret_cast<float*>(sV + KT * LDS);
+  const int bdld = p.n_rel_pad + 1;
+  float* sG = sBD + QT * bdld;                      // [QT] global-key score (already scaled)
+
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int len = p.enc_len[b];
+  const int d = p.H * DK;
+  const size_t ld = static_cast<size_t>(3) * d;
+  const __nv_bfloat16* qbase = p.qkv + (static_cast<size_t>(b) * p.T_max) * ld + h * DK;
+  const __nv_bfloat16* kbase = qbase + d;
+  const __nv_bfloat16* vbase = qbase + 2 * d;
+  __nv_bfloat16* obase = p.out + (static_cast<size_t>(b) * p.T_max) * d + h * DK;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float scale = rsqrtf(static_cast<float>(DK));
+
+  if (q0 >= len) {                                   // fully padded tile: defined zeros
+    for (int id = threadIdx.x; id < QT * 16; id += blockDim.x) {
+      const int r = id >> 4, c = (id & 15) * 8;
+      if (q0 + r < p.T_max) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(q0 + r) * d + c) = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+
+  // ---- phase 0: Q tile -> (q+u), (q+v) in bf16; global-key scores
+  for (int id = threadIdx.x; id < QT * 16; id += blockDim.x) {
+    const int r = id >> 4, c = (id & 15) * 8;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (q0 + r < p.T_max) raw = *reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * ld + c);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t qu[4], qv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 q2 = unpack_bf16x2(w[i]);
+      const float2 u2 = *reinterpret_cast<const float2*>(p.bias_u + h * DK + c + 2 * i);
+      const float2 v2 = *reinterpret_cast<const float2*>(p.bias_v + h * DK + c + 2 * i);
+      qu[i] = pack_bf16x2(q2.x + u2.x, q2.y + u2.y);
+      qv[i] = pack_bf16x2(q2.x + v2.x, q2.y + v2.y);
+    }
+    *reinterpret_cast<uint4*>(sQU + r * LDS + c) = make_uint4(qu[0], qu[1], qu[2], qu[3]);
+    *reinterpret_cast<uint4*>(sQV + r * LDS + c) = make_uint4(qv[0], qv[1], qv[2], qv[3]);
+  }
+  if (p.n_global > 0) {
+    const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;     // 2 threads per row, 64 dims each
+    float acc = 0.f;
+    if (q0 + r < p.T_max) {
+      const uint4* qr = reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * ld + hf * 64);
+      const uint4* k0 = reinterpret_cast<const uint4*>(kbase + hf * 64);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 a = qr[i], bb = __ldg(k0 + i);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
+          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (hf == 0) sG[r] = acc * scale;
+  }
+  __syncthreads();
+
+  const int r0 = warp * 16;
+  const uint32_t sQU_a = smem_u32(sQU), sQV_a = smem_u32(sQV), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+  // per-lane ldmatrix offsets (bytes)
+  const uint32_t a_off = ((r0 + (lane & 15)) * LDS + (lane >> 4) * 8) * 2;             // A: rows r0.., k-halves
+  const uint32_t b_off = ((((lane >> 4) & 1) * 8 + (lane & 7)) * LDS + ((lane >> 3) & 1) * 8) * 2;   // B (K-major rows)
+  const uint32_t v_off = ((((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + ((lane >> 4) & 1) * 8) * 2;   // B via .trans (V)
+
+  // ---- phase 1: BD[i][c] = (q_i + v) . p[c] for all relative offsets c, fp32 in smem
+  const __nv_bfloat16* pbase = p.pos + static_cast<size_t>(h) * p.n_rel * DK;
+  for (int pc = 0; pc < p.n_rel_pad / KT; ++pc) {
+    __syncthreads();
+    load_tile(sK, pbase + static_cast<size_t>(pc) * KT * DK, DK, min(KT, p.n_rel - pc * KT));
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(sQV_a + a_off + ks * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK_a + b_off + (np * 16 * LDS) * 2 + ks * 32, b0, b1, b2, b3);
+        mma_bf16(acc[2 * np], a, b0, b1);
+        mma_bf16(acc[2 * np + 1], a, b2, b3);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int c = pc * KT + nt * 8 + 2 * t;
+      sBD[(r0 + g) * bdld + c] = acc[nt][0];
+      sBD[(r0 + g) * bdld + c + 1] = acc[nt][1];
+      sBD[(r0 + g + 8) * bdld + c] = acc[nt][2];
+      sBD[(r0 + g + 8) * bdld + c + 1] = acc[nt][3];
+    }
+  }
+
+  // ---- phase 2: online softmax over the key tiles that intersect the band
+  float o[16][4];
+  float m_run[2], l_run[2];
+  const int i_lo = q0 + r0 + g, i_hi = i_lo + 8;             // the two query rows this thread owns
+  if (p.n_global > 0) {
+    m_run[0] = sG[r0 + g]; m_run[1] = sG[r0 + g + 8];
+    l_run[0] = l_run[1] = 1.f;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float2 v0 = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(vbase + nt * 8 + 2 * t)));
+      o[nt][0] = v0.x; o[nt][1] = v0.y; o[nt][2] = v0.x; o[nt][3] = v0.y;
+    }
+  } else {
+    m_run[0] = m_run[1] = -INFINITY;
+    l_run[0] = l_run[1] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+  }
+  const int j_first = max(0, q0 - p.w_left);
+  const int j_last = min(len - 1, q0 + QT - 1 + p.w_right);
+  for (int kt = j_first / KT; kt <= j_last / KT; ++kt) {
+    const int j0 = kt * KT;
+    __syncthreads();
+    load_tile(sK, kbase + static_cast<size_t>(j0) * ld, ld, min(KT, p.T_max - j0));
+    load_tile(sV, vbase + static_cast<size_t>(j0) * ld, ld, min(KT, p.T_max - j0));
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      uint32_t a[4];
+      ldsm_x4(sQU_a + a_off + ks * 32, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(sK_a + b_off + (np * 16 * LDS) * 2 + ks * 32, b0, b1, b2, b3);
+        mma_bf16(s[2 * np], a, b0, b1);
+        mma_bf16(s[2 * np + 1], a, b2, b3);
+      }
+    }
+    // positional term, band / padding mask, scale
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + nt * 8 + 2 * t + (e & 1);
+        const int i = (e < 2) ? i_lo : i_hi;
+        const int rel = j - i;
+        const bool ok = (j < len) && (rel >= -p.w_left) && (rel <= p.w_right);
+        float v = -INFINITY;
+        if (ok) v = (s[nt][e] + sBD[(i - q0) * bdld + rel + p.w_left]) * scale;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      mx[hrow] = fmaxf(mx[hrow], __shfl_xor_sync(0xffffffffu, mx[hrow], 1));
+      mx[hrow] = fmaxf(mx[hrow], __shfl_xor_sync(0xffffffffu, mx[hrow], 2));
+    }
+    float corr[2], msafe[2];
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const float m_new = fmaxf(m_run[hrow], mx[hrow]);
+      msafe[hrow] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[hrow] = __expf(m_run[hrow] - msafe[hrow]);           // exp(-inf) == 0 when nothing seen yet
+      m_run[hrow] = m_new;
+      l_run[hrow] *= corr[hrow];
+    }
+    float rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = __expf(s[nt][e] - msafe[e >> 1]);
+        s[nt][e] = pv;
+        rs[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      rs[hrow] += __shfl_xor_sync(0xffffffffu, rs[hrow], 1);
+      rs[hrow] += __shfl_xor_sync(0xffffffffu, rs[hrow], 2);
+      l_run[hrow] += rs[hrow];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) { o[nt][0] *= corr[0]; o[nt][1] *= corr[0]; o[nt][2] *= corr[1]; o[nt][3] *= corr[1]; }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < KT / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+      a[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+      a[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      a[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 8; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(sV_a + v_off + (kk * 16 * LDS) * 2 + np * 32, b0, b1, b2, b3);
+        mma_bf16(o[2 * np], a, b0, b1);
+        mma_bf16(o[2 * np + 1], a, b2, b3);
+      }
+    }
+  }
+  // ---- write back
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int i = hrow == 0 ? i_lo : i_hi;
+    if (i >= p.T_max) continue;
+    const bool valid = i < len;
+    const float inv = valid ? 1.0f / l_run[hrow] : 0.f;
+    __nv_bfloat16* orow = obase + static_cast<size_t>(i) * d;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const float x = valid ? o[nt][2 * hrow] * inv : 0.f, y = valid ? o[nt][2 * hrow + 1] * inv : 0.f;
+      *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t) = pack_bf16x2(x, y);
+    }
+  }
+}
+
+// Row(s) of the global token(s): full attention softmax_j((q_g / sqrt(dk)) . k_j) v_j, no positional
+// terms.  grid (H, B), 128 threads; scores staged in shared memory (T_max floats).
+__global__ void __launch_bounds__(128)
+global_row_attention_kernel(const AttnDev p) {
+  extern __shared__ float gs[];                      // [T_max] scores, then [4] reduction scratch
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int len = p.enc_len[b];
+  if (len <= 0) return;
+  const int d = p.H * DK;
+  const size_t ld = static_cast<size_t>(3) * d;
+  const __nv_bfloat16* qrow = p.qkv + (static_cast<size_t>(b) * p.T_max) * ld + h * DK;   // query = frame 0
+  const __nv_bfloat16* kbase = qrow + d;
+  const __nv_bfloat16* vbase = qrow + 2 * d;
+  const float scale = rsqrtf(static_cast<float>(DK));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* red = gs + p.T_max;
+  const float2 q0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * lane));
+  const float2 q1 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * lane + 2));
+  float mx = -INFINITY;
+  for (int j = warp; j < len; j += 4) {
+    const uint2 kk = *reinterpret_cast<const uint2*>(kbase + static_cast<size_t>(j) * ld + 4 * lane);
+    const float2 k0 = unpack_bf16x2(kk.x), k1 = unpack_bf16x2(kk.y);
+    float dot = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+    dot = warp_sum(dot) * scale;
+    if (lane == 0) gs[j] = dot;
+    mx = fmaxf(mx, dot);
+  }
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < len; j += blockDim.x) { const float e = __expf(gs[j] - mx); gs[j] = e; sum += e; }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+  // thread c owns output dim c: sum_j p_j v[j][c]  (coalesced 256 B rows)
+  const int c = threadIdx.x;
+  float acc = 0.f;
+  for (int j = 0; j < len; ++j) acc = fmaf(gs[j], __bfloat162float(vbase[static_cast<size_t>(j) * ld + c]), acc);
+  p.out[(static_cast<size_t>(b) * p.T_max) * d + h * DK + c] = __float2bfloat16_rn(acc * inv);
+}
+
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  if (a.dk != DK || a.n_global < 0 || a.n_global > 1) return cudaErrorInvalidValue;
+  AttnDev p;
+  p.qkv = static_cast<const __nv_bfloat16*>(a.qkv); p.pos = static_cast<const __nv_bfloat16*>(a.pos);
+  p.bias_u = a.bias_u; p.bias_v = a.bias_v; p.out = static_cast<__nv_bfloat16*>(a.out); p.enc_len = a.enc_len;
+  p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right; p.n_global = a.n_global;
+  p.n_rel = a.w_left + a.w_right + 1;
+  p.n_rel_pad = ((p.n_rel + KT - 1) / KT) * KT;
+  const size_t smem = static_cast<size_t>(4) * QT * LDS * 2 + static_cast<size_t>(QT) * (p.n_rel_pad + 1) * 4 + QT * 4;
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(global_row_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const dim3 grid((a.T_max + QT - 1) / QT, a.H, a.B);
+  local_attention_kernel<<<grid, 128, smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (a.n_global > 0) {
+    const size_t gsmem = (static_cast<size_t>(a.T_max) + 8) * sizeof(float);
+    if (gsmem > 200 * 1024) return cudaErrorInvalidValue;
+    global_row_attention_kernel<<<dim3(a.H, a.B), 128, gsmem, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+}  // namespace rs

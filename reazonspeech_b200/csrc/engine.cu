@@ -1,0 +1,467 @@
+// C ABI of the engine (include/rs_engine.h): weight table lookup, workspace planning and the
+// launch sequence of the FastConformer-RNNT path.  Host-side orchestration only; every device
+// operation is one of the sm_100a kernels declared in kernels.h.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rs_engine.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+struct Tensor { const void* p = nullptr; int dtype = 0; int64_t numel = 0; };
+
+struct FeTablesHost {   // must match rs::FeTables in frontend.cu
+  const float* window; const float* tw256; const float* tw512;
+  const int32_t* mel_start; const int32_t* mel_count; const float* mel_w;
+};
+
+struct LayerW {
+  const float *ln_ff1_g, *ln_ff1_b, *ff1_b1, *ff1_b2;
+  const void *ff1_w1, *ff1_w2;
+  const float *ln_att_g, *ln_att_b, *bqkv, *att_u, *att_v, *bo;
+  const void *wqkv, *att_pos, *wo;
+  const float *ln_conv_g, *ln_conv_b, *pw1_b, *dw_w, *dw_shift, *pw2_b;
+  const void *pw1_w, *pw2_w;
+  const float *ln_ff2_g, *ln_ff2_b, *ff2_b1, *ff2_b2;
+  const void *ff2_w1, *ff2_w2;
+  const float *ln_out_g, *ln_out_b;
+};
+
+struct Plan {           // workspace offsets (bytes) for one (B, L_max)
+  int B, L_max, F_max, T1, F1, T2, F2, T3, F3, M;
+  size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, enc, encp;
+  size_t tokens, frames, ntok, total;
+};
+
+inline int conv_len(int n) { return (n - 1) / 2 + 1; }
+
+}  // namespace
+
+struct rs_engine {
+  rs_model_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  std::map<std::string, Tensor> w;
+  FeTablesHost fe;
+  struct { const float *c0w, *c0b, *d1w, *d1b, *p1b, *d2w, *d2b, *p2b, *ob; const void *p1w, *p2w, *ow; } sub;
+  std::vector<LayerW> layers;
+  struct { const void *enc_w, *out_w, *lstm_w, *pred_w; const float *enc_b, *out_b, *embed, *lstm_b, *pred_b; } dec;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int U_cap = 0;
+  mutable char err[512] = "";
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[9] = {};
+  bool ev_ok = false;
+  float stage_ms[8] = {};
+};
+
+namespace {
+
+int fail(const rs_engine* e, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(e ? e->err : g_create_error, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define RS_CUDA(e, call)                                                                   \
+  do {                                                                                     \
+    cudaError_t _c = (call);                                                               \
+    if (_c != cudaSuccess) return fail((e), RS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_c)); \
+  } while (0)
+
+size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
+  const rs_model_config& c = e->cfg;
+  Plan p{};
+  p.B = B; p.L_max = L_max;
+  p.F_max = L_max / c.n_window_stride + 1;
+  p.T1 = conv_len(p.F_max); p.F1 = conv_len(c.n_mels);
+  p.T2 = conv_len(p.T1); p.F2 = conv_len(p.F1);
+  p.T3 = conv_len(p.T2); p.F3 = conv_len(p.F2);
+  p.M = B * p.T3;
+  const size_t C = c.sub_channels, d = c.d_model;
+  const size_t wide = static_cast<size_t>(c.d_ff) > 3 * d ? c.d_ff : 3 * d;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  p.wav = take(static_cast<size_t>(B) * L_max * 4);
+  p.len = take(static_cast<size_t>(B) * 4);
+  p.mel = take(static_cast<size_t>(B) * p.F_max * c.n_mels * 4);
+  p.mel_len = take(static_cast<size_t>(B) * 4);
+  p.enc_len = take(static_cast<size_t>(B) * 4);
+  p.sub1 = take(static_cast<size_t>(B) * p.T2 * p.F2 * C * 2);
+  p.sub2 = take(static_cast<size_t>(B) * p.T2 * p.F2 * C * 2);
+  p.sub3 = take(static_cast<size_t>(B) * p.T3 * p.F3 * C * 2);
+  p.sub4 = take(static_cast<size_t>(B) * p.T3 * p.F3 * C * 2);
+  p.x = take(static_cast<size_t>(p.M) * d * 4);
+  p.xn = take(static_cast<size_t>(p.M) * d * 2);
+  p.hbuf = take(static_cast<size_t>(p.M) * wide * 2);
+  p.abuf = take(static_cast<size_t>(p.M) * d * 2);
+  p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
+  p.enc = take(static_cast<size_t>(p.M) * d * 4);
+  p.encp = take(static_cast<size_t>(p.M) * c.joint_hidden * 4);
+  p.tokens = take(static_cast<size_t>(B) * U_max * 4);
+  p.frames = take(static_cast<size_t>(B) * U_max * 4);
+  p.ntok = take(static_cast<size_t>(B) * 4);
+  p.total = off;
+  return p;
+}
+
+template <typename T>
+T* at(const rs_engine* e, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(e->ws) + off); }
+
+int need(rs_engine* e, const char* name, int dtype, int64_t numel, const void** out) {
+  auto it = e->w.find(name);
+  if (it == e->w.end()) return fail(e, RS_ERR_MISSING_WEIGHT, "weight '%s' missing from the table", name);
+  if (it->second.dtype != dtype || it->second.numel != numel)
+    return fail(e, RS_ERR_MISSING_WEIGHT, "weight '%s': dtype/numel (%d, %lld) != expected (%d, %lld)", name,
+                it->second.dtype, (long long)it->second.numel, dtype, (long long)numel);
+  *out = it->second.p;
+  return RS_OK;
+}
+
+#define NEED(field, name, dt, n)                                                   \
+  do {                                                                             \
+    const void* _p;                                                                \
+    int _r = need(e, (name), (dt), (n), &_p);                                      \
+    if (_r != RS_OK) return _r;                                                    \
+    field = static_cast<decltype(field)>(_p);                                      \
+  } while (0)
+
+int bind_weights(rs_engine* e) {
+  const rs_model_config& c = e->cfg;
+  const int64_t d = c.d_model, ff = c.d_ff, C = c.sub_channels, H = c.n_heads, dk = d / H;
+  const int64_t n_rel = c.att_left + c.att_right + 1, k = c.conv_kernel;
+  const int64_t F3 = conv_len(conv_len(conv_len(c.n_mels)));
+  NEED(e->fe.window, "fe.window", RS_F32, c.n_fft);
+  NEED(e->fe.tw256, "fe.tw256", RS_F32, c.n_fft);
+  NEED(e->fe.tw512, "fe.tw512", RS_F32, c.n_fft + 2);
+  NEED(e->fe.mel_start, "fe.mel_start", RS_I32, c.n_mels);
+  NEED(e->fe.mel_count, "fe.mel_count", RS_I32, c.n_mels);
+  NEED(e->fe.mel_w, "fe.mel_w", RS_F32, static_cast<int64_t>(c.n_mels) * 40);
+  NEED(e->sub.c0w, "sub.conv0.w", RS_F32, C * 9); NEED(e->sub.c0b, "sub.conv0.b", RS_F32, C);
+  NEED(e->sub.d1w, "sub.dw1.w", RS_F32, C * 9); NEED(e->sub.d1b, "sub.dw1.b", RS_F32, C);
+  NEED(e->sub.p1w, "sub.pw1.w", RS_BF16, C * C); NEED(e->sub.p1b, "sub.pw1.b", RS_F32, C);
+  NEED(e->sub.d2w, "sub.dw2.w", RS_F32, C * 9); NEED(e->sub.d2b, "sub.dw2.b", RS_F32, C);
+  NEED(e->sub.p2w, "sub.pw2.w", RS_BF16, C * C); NEED(e->sub.p2b, "sub.pw2.b", RS_F32, C);
+  NEED(e->sub.ow, "sub.out.w", RS_BF16, d * F3 * C); NEED(e->sub.ob, "sub.out.b", RS_F32, d);
+  e->layers.resize(c.n_layers);
+  for (int i = 0; i < c.n_layers; ++i) {
+    LayerW& L = e->layers[i];
+    char nm[64];
+    auto N = [&](const char* s) { snprintf(nm, sizeof nm, "L%d.%s", i, s); return nm; };
+    NEED(L.ln_ff1_g, N("ln_ff1.g"), RS_F32, d); NEED(L.ln_ff1_b, N("ln_ff1.b"), RS_F32, d);
+    NEED(L.ff1_w1, N("ff1.w1"), RS_BF16, ff * d); NEED(L.ff1_b1, N("ff1.b1"), RS_F32, ff);
+    NEED(L.ff1_w2, N("ff1.w2"), RS_BF16, d * ff); NEED(L.ff1_b2, N("ff1.b2"), RS_F32, d);
+    NEED(L.ln_att_g, N("ln_att.g"), RS_F32, d); NEED(L.ln_att_b, N("ln_att.b"), RS_F32, d);
+    NEED(L.wqkv, N("att.wqkv"), RS_BF16, 3 * d * d); NEED(L.bqkv, N("att.bqkv"), RS_F32, 3 * d);
+    NEED(L.att_pos, N("att.pos"), RS_BF16, H * n_rel * dk);
+    NEED(L.att_u, N("att.u"), RS_F32, d); NEED(L.att_v, N("att.v"), RS_F32, d);
+    NEED(L.wo, N("att.wo"), RS_BF16, d * d); NEED(L.bo, N("att.bo"), RS_F32, d);
+    NEED(L.ln_conv_g, N("ln_conv.g"), RS_F32, d); NEED(L.ln_conv_b, N("ln_conv.b"), RS_F32, d);
+    NEED(L.pw1_w, N("conv.pw1.w"), RS_BF16, 2 * d * d); NEED(L.pw1_b, N("conv.pw1.b"), RS_F32, 2 * d);
+    NEED(L.dw_w, N("conv.dw.w"), RS_F32, k * d); NEED(L.dw_shift, N("conv.dw.shift"), RS_F32, d);
+    NEED(L.pw2_w, N("conv.pw2.w"), RS_BF16, d * d); NEED(L.pw2_b, N("conv.pw2.b"), RS_F32, d);
+    NEED(L.ln_ff2_g, N("ln_ff2.g"), RS_F32, d); NEED(L.ln_ff2_b, N("ln_ff2.b"), RS_F32, d);
+    NEED(L.ff2_w1, N("ff2.w1"), RS_BF16, ff * d); NEED(L.ff2_b1, N("ff2.b1"), RS_F32, ff);
+    NEED(L.ff2_w2, N("ff2.w2"), RS_BF16, d * ff); NEED(L.ff2_b2, N("ff2.b2"), RS_F32, d);
+    NEED(L.ln_out_g, N("ln_out.g"), RS_F32, d); NEED(L.ln_out_b, N("ln_out.b"), RS_F32, d);
+  }
+  const int64_t Hj = c.joint_hidden, Hp = c.pred_hidden, NC = c.vocab_size + 1;
+  NEED(e->dec.enc_w, "joint.enc.w", RS_BF16, Hj * d); NEED(e->dec.enc_b, "joint.enc.b", RS_F32, Hj);
+  NEED(e->dec.out_w, "joint.out.w", RS_BF16, NC * Hj); NEED(e->dec.out_b, "joint.out.b", RS_F32, NC);
+  NEED(e->dec.embed, "pred.embed", RS_F32, NC * Hp);
+  NEED(e->dec.lstm_w, "pred.lstm.w", RS_BF16, 4 * Hp * 2 * Hp); NEED(e->dec.lstm_b, "pred.lstm.b", RS_F32, 4 * Hp);
+  NEED(e->dec.pred_w, "joint.pred.w", RS_BF16, Hj * Hp); NEED(e->dec.pred_b, "joint.pred.b", RS_F32, Hj);
+  return RS_OK;
+}
+
+__global__ void enc_len_kernel(const int32_t* __restrict__ mel_len, int32_t* __restrict__ enc_len, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int n = mel_len[b];
+  for (int i = 0; i < 3; ++i) n = (n - 1) / 2 + 1;
+  enc_len[b] = n;
+}
+
+int gemm(rs_engine* e, const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N,
+         int K, int epi, float alpha, cudaStream_t s) {
+  rs::GemmArgs g{a, w, bias, resid, out, M, N, K, epi, alpha};
+  char msg[256] = "";
+  cudaError_t c = rs::launch_gemm(g, e->num_sms, s, msg);
+  if (c != cudaSuccess) return fail(e, RS_ERR_CUDA, "gemm: %s", msg);
+  e->launches++;
+  return RS_OK;
+}
+
+#define RS_TRY(x) do { int _r = (x); if (_r != RS_OK) return _r; } while (0)
+#define RS_K(e, call, n)                                                                       \
+  do {                                                                                         \
+    cudaError_t _c = (call);                                                                   \
+    if (_c != cudaSuccess) return fail((e), RS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_c)); \
+    (e)->launches += (n);                                                                      \
+  } while (0)
+
+int check_ws(rs_engine* e, const Plan& p) {
+  if (e->ws == nullptr) return fail(e, RS_ERR_WORKSPACE, "no workspace set (rs_set_workspace)");
+  if (p.total > e->ws_bytes)
+    return fail(e, RS_ERR_WORKSPACE, "workspace too small: need %zu bytes for B=%d L_max=%d, have %zu", p.total, p.B, p.L_max, e->ws_bytes);
+  return RS_OK;
+}
+
+void mark(rs_engine* e, int i, cudaStream_t s) {
+  if (e->timing && e->ev_ok) cudaEventRecord(e->ev[i], s);
+}
+
+int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, cudaStream_t s) {
+  const rs_model_config& c = e->cfg;
+  RS_K(e, rs::launch_logmel(wav, len, B, L_max, mel, mel_len, nullptr, &e->fe, c.n_mels, c.n_window_stride, c.n_fft,
+                           c.n_window_size, c.preemph, c.log_zero_guard, c.norm_eps, s), 2);
+  return RS_OK;
+}
+
+int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, float* enc, int32_t* enc_len,
+              int n_layers, cudaStream_t s) {
+  const rs_model_config& c = e->cfg;
+  const int d = c.d_model, C = c.sub_channels, M = p.M, B = p.B;
+  if (n_layers < 0 || n_layers > c.n_layers) n_layers = c.n_layers;
+  enc_len_kernel<<<(B + 127) / 128, 128, 0, s>>>(mel_len, enc_len, B);
+  RS_K(e, cudaGetLastError(), 1);
+  // ---- ConvSubsampling
+  rs::SubsampleArgs sa{mel, mel_len, B, p.F_max, c.n_mels, C, e->sub.c0w, e->sub.c0b, e->sub.d1w, e->sub.d1b,
+                       at<void>(e, p.sub1), p.T1, p.F1, p.T2, p.F2};
+  RS_K(e, rs::launch_sub_conv0_dw1(sa, s), 1);
+  RS_TRY(gemm(e, at<void>(e, p.sub1), e->sub.p1w, e->sub.p1b, nullptr, at<void>(e, p.sub2), B * p.T2 * p.F2, C, C,
+              RS_EPI_BIAS_RELU_BF16, 1.f, s));
+  RS_K(e, rs::launch_sub_dw(at<void>(e, p.sub2), at<void>(e, p.sub3), e->sub.d2w, e->sub.d2b, mel_len, 2, B, p.T2, p.F2,
+                            p.T3, p.F3, C, s), 1);
+  RS_TRY(gemm(e, at<void>(e, p.sub3), e->sub.p2w, e->sub.p2b, nullptr, at<void>(e, p.sub4), B * p.T3 * p.F3, C, C,
+              RS_EPI_BIAS_RELU_BF16, 1.f, s));
+  float* x = at<float>(e, p.x);
+  RS_TRY(gemm(e, at<void>(e, p.sub4), e->sub.ow, e->sub.ob, nullptr, x, M, d, p.F3 * C, RS_EPI_BIAS_F32, c.xscale, s));
+  mark(e, 2, s);
+  // ---- Conformer layers
+  void* xn = at<void>(e, p.xn); void* hb = at<void>(e, p.hbuf); void* ab = at<void>(e, p.abuf); void* cb = at<void>(e, p.cbuf);
+  if (n_layers > 0) {
+    const LayerW& L0 = e->layers[0];
+    RS_K(e, rs::launch_layernorm(x, L0.ln_ff1_g, L0.ln_ff1_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+  }
+  for (int i = 0; i < n_layers; ++i) {
+    const LayerW& L = e->layers[i];
+    RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
+    RS_TRY(gemm(e, hb, L.ff1_w2, L.ff1_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
+    RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
+    rs::AttnArgs aa{hb, L.att_pos, L.att_u, L.att_v, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
+    RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
+    RS_TRY(gemm(e, ab, L.wo, L.bo, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
+    RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f, s));
+    RS_K(e, rs::launch_conv_dw(ab, cb, L.dw_w, L.dw_shift, enc_len, B, p.T3, d, c.conv_kernel, s), 1);
+    RS_TRY(gemm(e, cb, L.pw2_w, L.pw2_b, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
+    RS_K(e, rs::launch_layernorm(x, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.ff2_w1, L.ff2_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
+    RS_TRY(gemm(e, hb, L.ff2_w2, L.ff2_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
+    if (i + 1 < n_layers) {   // norm_out chained with the next layer's norm_feed_forward1
+      const LayerW& Ln = e->layers[i + 1];
+      RS_K(e, rs::launch_layernorm(x, L.ln_out_g, L.ln_out_b, x, xn, Ln.ln_ff1_g, Ln.ln_ff1_b, M, d, c.ln_eps, s), 1);
+    } else {
+      RS_K(e, rs::launch_layernorm(x, L.ln_out_g, L.ln_out_b, enc, nullptr, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    }
+  }
+  if (n_layers == 0) RS_CUDA(e, cudaMemcpyAsync(enc, x, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, s));
+  RS_K(e, rs::launch_zero_pad_rows(enc, enc_len, B, p.T3, d, s), 1);
+  return RS_OK;
+}
+
+int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_len, int T_max, int32_t* tokens,
+              int32_t* frames, int32_t* ntok, int U_max, cudaStream_t s) {
+  const rs_model_config& c = e->cfg;
+  const int M = p.B * T_max;
+  RS_K(e, rs::launch_f32_to_bf16(enc, at<void>(e, p.xn), static_cast<int64_t>(M) * c.d_model, s), 1);
+  RS_TRY(gemm(e, at<void>(e, p.xn), e->dec.enc_w, e->dec.enc_b, nullptr, at<void>(e, p.encp), M, c.joint_hidden, c.d_model,
+              RS_EPI_BIAS_F32, 1.f, s));
+  mark(e, 4, s);
+  rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b,
+                    e->dec.pred_w, e->dec.pred_b, tokens, frames, ntok, p.B, T_max, c.joint_hidden, c.pred_hidden,
+                    c.vocab_size, U_max, c.max_symbols};
+  RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
+  return RS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n_weights, int device, rs_engine** out) {
+  if (cfg == nullptr || weights == nullptr || out == nullptr) return fail(nullptr, RS_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n_fft != 512) return fail(nullptr, RS_ERR_UNSUPPORTED, "n_fft=%d unsupported (frontend kernel is built for 512)", cfg->n_fft);
+  if (cfg->d_model % cfg->n_heads || cfg->d_model / cfg->n_heads != 128)
+    return fail(nullptr, RS_ERR_UNSUPPORTED, "d_model/n_heads must be 128 (got %d/%d)", cfg->d_model, cfg->n_heads);
+  if (cfg->d_model != 256 && cfg->d_model != 512 && cfg->d_model != 1024)
+    return fail(nullptr, RS_ERR_UNSUPPORTED, "d_model=%d unsupported (256/512/1024)", cfg->d_model);
+  if (cfg->conv_kernel != 9) return fail(nullptr, RS_ERR_UNSUPPORTED, "conv_kernel=%d unsupported (9)", cfg->conv_kernel);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, RS_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU path", cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(nullptr, RS_ERR_INVALID_ARG, "device %d out of range (%d devices)", device, ndev);
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return fail(nullptr, RS_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(ce));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) return fail(nullptr, RS_ERR_UNSUPPORTED, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  rs_engine* e = new rs_engine();
+  e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount;
+  for (int i = 0; i < n_weights; ++i) e->w[weights[i].name] = Tensor{weights[i].dev_ptr, weights[i].dtype, weights[i].numel};
+  int r = bind_weights(e);
+  if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }
+  e->ev_ok = true;
+  for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) e->ev_ok = false;
+  *out = e;
+  return RS_OK;
+}
+
+void rs_engine_destroy(rs_engine* e) {
+  if (e == nullptr) return;
+  if (e->ev_ok) for (auto& ev : e->ev) cudaEventDestroy(ev);
+  delete e;
+}
+
+const char* rs_last_error(const rs_engine* e) { return e ? e->err : g_create_error; }
+
+int rs_workspace_bytes(const rs_engine* e, int B, int L_max, size_t* bytes) {
+  if (e == nullptr || bytes == nullptr || B <= 0 || L_max <= 0) return fail(e, RS_ERR_INVALID_ARG, "bad arguments");
+  // token capacity: max_symbols per encoder frame is the hard upper bound of the greedy loop
+  const int T = conv_len(conv_len(conv_len(L_max / e->cfg.n_window_stride + 1)));
+  *bytes = make_plan(e, B, L_max, T * e->cfg.max_symbols).total;
+  return RS_OK;
+}
+
+int rs_set_workspace(rs_engine* e, void* dev_ptr, size_t bytes) {
+  if (e == nullptr) return RS_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(dev_ptr) & 255) return fail(e, RS_ERR_INVALID_ARG, "workspace must be 256-byte aligned");
+  e->ws = dev_ptr; e->ws_bytes = bytes;
+  return RS_OK;
+}
+
+int rs_mel_frames(const rs_engine* e, int n) { return n / e->cfg.n_window_stride + 1; }
+int rs_enc_frames(const rs_engine* e, int n) { return conv_len(conv_len(conv_len(rs_mel_frames(e, n)))); }
+
+int rs_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, void* stream) {
+  if (!e || !wav || !len || !mel || !mel_len || B <= 0 || L_max <= 0) return fail(e, RS_ERR_INVALID_ARG, "rs_logmel: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  return do_logmel(e, wav, len, B, L_max, mel, mel_len, static_cast<cudaStream_t>(stream));
+}
+
+int rs_encode(rs_engine* e, const float* mel, const int32_t* mel_len, int B, int F_max, float* enc, int32_t* enc_len,
+              int n_layers, void* stream) {
+  if (!e || !mel || !mel_len || !enc || !enc_len || B <= 0 || F_max <= 0) return fail(e, RS_ERR_INVALID_ARG, "rs_encode: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  const int L_max = (F_max - 1) * e->cfg.n_window_stride;
+  Plan p = make_plan(e, B, L_max, 1);
+  RS_TRY(check_ws(e, p));
+  return do_encode(e, p, mel, mel_len, enc, enc_len, n_layers, static_cast<cudaStream_t>(stream));
+}
+
+int rs_rnnt_greedy(rs_engine* e, const float* enc, const int32_t* enc_len, int B, int T_max, int32_t* tokens,
+                   int32_t* frames, int32_t* n_tok, int U_max, void* stream) {
+  if (!e || !enc || !enc_len || !tokens || !frames || !n_tok || B <= 0 || T_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_rnnt_greedy: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  Plan p{};
+  // only xn / encp are touched: size them for M = B*T_max rows
+  p.B = B; p.M = B * T_max;
+  size_t off = 0;
+  p.xn = off; off = align_up(off + static_cast<size_t>(p.M) * e->cfg.d_model * 2);
+  p.encp = off; off = align_up(off + static_cast<size_t>(p.M) * e->cfg.joint_hidden * 4);
+  p.total = off; p.L_max = 0;
+  RS_TRY(check_ws(e, p));
+  return do_greedy(e, p, enc, enc_len, T_max, tokens, frames, n_tok, U_max, static_cast<cudaStream_t>(stream));
+}
+
+int rs_transcribe_device(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, int32_t* tokens,
+                         int32_t* frames, int32_t* n_tok, int U_max, void* stream) {
+  if (!e || !wav || !len || !tokens || !frames || !n_tok || B <= 0 || L_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_device: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan p = make_plan(e, B, L_max, U_max);
+  RS_TRY(check_ws(e, p));
+  mark(e, 0, s);
+  RS_TRY(do_logmel(e, wav, len, B, L_max, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), s));
+  mark(e, 1, s);
+  RS_TRY(do_encode(e, p, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s));
+  mark(e, 3, s);
+  RS_TRY(do_greedy(e, p, at<float>(e, p.enc), at<int32_t>(e, p.enc_len), p.T3, tokens, frames, n_tok, U_max, s));
+  mark(e, 5, s);
+  return RS_OK;
+}
+
+int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_host, int B, int L_max,
+                        int32_t* tokens_host, int32_t* frames_host, int32_t* n_tok_host, int U_max, void* stream) {
+  if (!e || !wav_host || !len_host || !tokens_host || !frames_host || !n_tok_host || B <= 0 || L_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_batch: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan p = make_plan(e, B, L_max, U_max);
+  RS_TRY(check_ws(e, p));
+  RS_CUDA(e, cudaMemcpyAsync(at<float>(e, p.wav), wav_host, static_cast<size_t>(B) * L_max * 4, cudaMemcpyHostToDevice, s));
+  RS_CUDA(e, cudaMemcpyAsync(at<int32_t>(e, p.len), len_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
+  RS_TRY(rs_transcribe_device(e, at<float>(e, p.wav), at<int32_t>(e, p.len), B, L_max, at<int32_t>(e, p.tokens),
+                              at<int32_t>(e, p.frames), at<int32_t>(e, p.ntok), U_max, s));
+  RS_CUDA(e, cudaMemcpyAsync(tokens_host, at<int32_t>(e, p.tokens), static_cast<size_t>(B) * U_max * 4, cudaMemcpyDeviceToHost, s));
+  RS_CUDA(e, cudaMemcpyAsync(frames_host, at<int32_t>(e, p.frames), static_cast<size_t>(B) * U_max * 4, cudaMemcpyDeviceToHost, s));
+  RS_CUDA(e, cudaMemcpyAsync(n_tok_host, at<int32_t>(e, p.ntok), static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
+  RS_CUDA(e, cudaStreamSynchronize(s));
+  return RS_OK;
+}
+
+int rs_gemm_bf16(rs_engine* e, const void* a, const void* w, const float* bias, const float* resid, void* out, int M,
+                 int N, int K, int epilogue, float alpha, void* stream) {
+  if (!e || !a || !w || !out) return fail(e, RS_ERR_INVALID_ARG, "rs_gemm_bf16: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  return gemm(e, a, w, bias, resid, out, M, N, K, epilogue, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int rs_layernorm(rs_engine* e, const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
+                 int rows, int d, void* stream) {
+  if (!e || !x || !gamma || !beta) return fail(e, RS_ERR_INVALID_ARG, "rs_layernorm: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  RS_K(e, rs::launch_layernorm(x, gamma, beta, out_f32, out_bf16, nullptr, nullptr, rows, d, e->cfg.ln_eps,
+                               static_cast<cudaStream_t>(stream)), 1);
+  return RS_OK;
+}
+
+int64_t rs_launch_count(const rs_engine* e) { return e ? e->launches : 0; }
+
+int rs_enable_stage_timing(rs_engine* e, int on) {
+  if (!e) return RS_ERR_INVALID_ARG;
+  e->timing = on != 0;
+  return RS_OK;
+}
+
+// Stages: [0] log-mel, [1] subsampling, [2] conformer layers, [3] f32->bf16 + joint.enc GEMM, [4] greedy decode.
+int rs_stage_times_ms(const rs_engine* e, float* ms) {
+  if (!e || !ms || !e->ev_ok) return RS_ERR_INVALID_ARG;
+  for (int i = 0; i < 8; ++i) ms[i] = 0.f;
+  if (cudaEventSynchronize(e->ev[5]) != cudaSuccess) return RS_ERR_CUDA;
+  for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], e->ev[i], e->ev[i + 1]);
+  return RS_OK;
+}
+
+}  // extern "C"

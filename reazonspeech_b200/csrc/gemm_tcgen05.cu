@@ -1,0 +1,296 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  out = epi(A[M,K] * W[N,K]^T)
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor 2-D tiles (128B swizzle) -> smem ring
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma (UMMA 128 x BN x 16), fp32
+//                              accumulators in TMEM, two accumulator stages (2*BN columns)
+//   warps 2..9  epilogue       tcgen05.ld TMEM -> registers -> bias / activation / GLU /
+//                              residual -> vectorised global stores; overlaps the next tile's MMAs
+//
+// Covers every dense contraction of the FastConformer encoder: FFN W1/W2,
+// fused QKV, attention out-proj, conv pointwise 1/2, the subsampling 1x1 convs and out-linear,
+// and the joint's encoder projection.  Replaces the cuBLAS fp32 GEMMs NeMo dispatches under
+// model.transcribe (pkg/nemo-asr/src/transcribe.py:48-53).
+#include <cuda.h>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rs_engine.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rs {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 32 * (2 + kEpiWarps);
+constexpr int kABytes = BM * BK * 2;   // 16 KiB
+
+struct GemmDev {
+  const float* bias;
+  const float* resid;
+  void* out;
+  int M, N, K;
+  int epilogue;
+  float alpha;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;                       // power of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled operand tiles need 1024 B alignment.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+
+  const int warp = warp_id_uniform();
+  const int lane = lane_id();
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          tma_load_2d(smem_a(stage), &tm_a, kb * BK, m0, full_bar(stage));
+          tma_load_2d(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_a(stage));
+          const uint64_t db = umma_desc_k_sw128(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the >>4 address field
+            umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                     // smem slot reusable when these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));                         // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;                        // which interleaved 32-column chunks
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+        const int col0 = n0 + chunk * 32;
+        if (col0 >= p.N) break;                              // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (row_ok) {
+        switch (p.epilogue) {
+          case RS_EPI_BIAS_BF16:
+          case RS_EPI_BIAS_RELU_BF16:
+          case RS_EPI_BIAS_SWISH_BF16: {
+            if (p.epilogue == RS_EPI_BIAS_RELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            } else if (p.epilogue == RS_EPI_BIAS_SWISH_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.N + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            break;
+          }
+          case RS_EPI_BIAS_GLU_BF16: {
+            // columns [0,16) of the chunk are values, [16,32) the matching gates (weights interleaved at pack time)
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = v[j] * sigmoidf_fast(v[16 + j]);
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * (p.N / 2) + col0 / 2);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              o[j] = make_uint4(pack_bf16x2(g[8 * j], g[8 * j + 1]), pack_bf16x2(g[8 * j + 2], g[8 * j + 3]),
+                                pack_bf16x2(g[8 * j + 4], g[8 * j + 5]), pack_bf16x2(g[8 * j + 6], g[8 * j + 7]));
+            break;
+          }
+          case RS_EPI_RESID_F32: {
+            const float4* rs4 = reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.N + col0);
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.N + col0);
+            float4 rr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(rr[j].x + p.alpha * v[4 * j], rr[j].y + p.alpha * v[4 * j + 1],
+                                 rr[j].z + p.alpha * v[4 * j + 2], rr[j].w + p.alpha * v[4 * j + 3]);
+            break;
+          }
+          default: {  // RS_EPI_BIAS_F32
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.N + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
+            break;
+          }
+        }
+        }
+        __syncwarp();                                        // reconverge before the next .aligned tcgen05.ld
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] -> 2-D map with a (box_rows x 64) box and 128B swizzle.
+static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, char* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { snprintf(err, 256, "cuTensorMapEncodeTiled entry point unavailable"); return false; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, 256, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols); return false; }
+  return true;
+}
+
+template <int BN>
+static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  CUtensorMap tm_a, tm_b;
+  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, BM, err)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, BN, err)) return cudaErrorInvalidValue;
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha};
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) snprintf(err, 256, "gemm launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
+  return e;
+}
+
+cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.K % BK != 0 || g.N % 32 != 0) {
+    snprintf(err, 256, "gemm shape unsupported: M=%d N=%d K=%d (need K%%64==0, N%%32==0)", g.M, g.N, g.K);
+    return cudaErrorInvalidValue;
+  }
+  if ((reinterpret_cast<uintptr_t>(g.a) | reinterpret_cast<uintptr_t>(g.w) | reinterpret_cast<uintptr_t>(g.out)) & 15u) {
+    snprintf(err, 256, "gemm operands must be 16-byte aligned");
+    return cudaErrorInvalidValue;
+  }
+  if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
+  // Widest tile that still yields at least ~one wave of tiles; narrow N uses a narrower tile.
+  if (g.N >= 256 && g.N % 256 == 0) return launch_bn<256>(g, num_sms, stream, err);
+  if (g.N >= 128 && g.N % 128 == 0) return launch_bn<128>(g, num_sms, stream, err);
+  return launch_bn<64>(g, num_sms, stream, err);
+}
+
+}  // namespace rs

@@ -1,0 +1,77 @@
+// Host-side launch interface of the sm_100a kernels (internal to librs_engine.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rs {
+
+struct GemmArgs {
+  const void* a;       // bf16 [M,K] row-major
+  const void* w;       // bf16 [N,K] row-major (nn.Linear layout)
+  const float* bias;   // f32 [N] or nullptr
+  const float* resid;  // f32 [M,N] for RS_EPI_RESID_F32
+  void* out;
+  int M, N, K;
+  int epilogue;        // rs_epilogue
+  float alpha;
+};
+// Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
+cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
+
+struct FrontendTables;   // device tables of the log-mel frontend (window, twiddles, sparse mel)
+cudaError_t launch_logmel(const float* wav, const int32_t* len, int B, int L_max, float* mel,
+                          int32_t* mel_len, float* partials, const void* tables, int n_mels,
+                          int hop, int n_fft, int win, float preemph, float guard, float eps,
+                          cudaStream_t stream);
+
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out_f32,
+                             void* out_bf16, const float* gamma2, const float* beta2, int rows, int d,
+                             float eps, cudaStream_t stream);
+
+struct SubsampleArgs {
+  const float* mel; const int32_t* mel_len; int B, F_max, n_mels, C;
+  const float* w0; const float* b0;      // conv.0  [C,9], [C]
+  const float* wd1; const float* bd1;    // conv.2  [C,9], [C]
+  void* out1;                            // bf16 [B,T2,F2,C]
+  int T1, F1, T2, F2;
+};
+cudaError_t launch_sub_conv0_dw1(const SubsampleArgs& a, cudaStream_t stream);
+// depthwise 3x3 s2 on channels-last bf16 [B,Tin,Fin,C] (rows t >= len_in(b) read as zero)
+cudaError_t launch_sub_dw(const void* in, void* out, const float* w, const float* b, const int32_t* mel_len,
+                          int len_shift, int B, int Tin, int Fin, int Tout, int Fout, int C, cudaStream_t stream);
+
+// GLU output u bf16 [B*T_max, d] -> depthwise conv (k taps, BN folded) -> swish -> bf16
+cudaError_t launch_conv_dw(const void* u, void* out, const float* w /*[k,d]*/, const float* shift /*[d]*/,
+                           const int32_t* enc_len, int B, int T_max, int d, int k, cudaStream_t stream);
+
+struct AttnArgs {
+  const void* qkv;       // bf16 [B*T_max, 3*d]: q | k | v
+  const void* pos;       // bf16 [H, n_rel, dk]  (linear_pos of the relative table)
+  const float* bias_u;   // f32 [H, dk]
+  const float* bias_v;   // f32 [H, dk]
+  void* out;             // bf16 [B*T_max, d]
+  const int32_t* enc_len;
+  int B, T_max, H, dk, w_left, w_right, n_global;
+};
+cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+struct DecodeArgs {
+  const float* enc_proj;      // f32 [B*T_max, Hj]  (joint.enc applied to every frame)
+  const int32_t* enc_len;
+  const void* w_out;          // bf16 [V+1, Hj]
+  const float* b_out;         // f32 [V+1]
+  const float* embed;         // f32 [V+1, Hp]
+  const void* w_lstm;         // bf16 [4*Hp, 2*Hp]  (W_ih | W_hh, gate order i,f,g,o)
+  const float* b_lstm;        // f32 [4*Hp]  (b_ih + b_hh)
+  const void* w_pred;         // bf16 [Hj, Hp]
+  const float* b_pred;        // f32 [Hj]
+  int32_t* tokens; int32_t* frames; int32_t* n_tok;
+  int B, T_max, Hj, Hp, V, U_max, max_symbols;
+};
+cudaError_t launch_rnnt_greedy(const DecodeArgs& a, int num_sms, cudaStream_t stream);
+
+// small utility kernels
+cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);
+cudaError_t launch_zero_pad_rows(float* x, const int32_t* len, int B, int T_max, int d, cudaStream_t stream);
+
+}  // namespace rs

@@ -1,0 +1,360 @@
+"""ctypes binding of librs_engine.so (include/rs_engine.h) + weight packing.
+
+PyTorch is used for device memory, streams and the one-time weight repack only; every
+operation on the inference path is a hand-written sm_100a kernel behind the C ABI.  There
+is deliberately no CPU or eager-PyTorch fallback: if the library or a B200 is missing the
+constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .config import ModelConfig, conv_out_len, xscale
+from .weights import StateDict, hann_window, mel_filterbank, rel_pos_table
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librs_engine.so")
+MEL_MAX_W = 40
+
+EPI_BIAS_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_SWISH_BF16, EPI_BIAS_GLU_BF16, EPI_RESID_F32, EPI_BIAS_F32 = range(6)
+
+
+class RsModelConfig(C.Structure):
+    _fields_ = [
+        ("sample_rate", C.c_int32), ("n_window_size", C.c_int32), ("n_window_stride", C.c_int32),
+        ("n_fft", C.c_int32), ("n_mels", C.c_int32),
+        ("preemph", C.c_float), ("log_zero_guard", C.c_float), ("norm_eps", C.c_float),
+        ("n_layers", C.c_int32), ("d_model", C.c_int32), ("n_heads", C.c_int32), ("d_ff", C.c_int32),
+        ("conv_kernel", C.c_int32), ("sub_channels", C.c_int32),
+        ("att_left", C.c_int32), ("att_right", C.c_int32), ("global_tokens", C.c_int32),
+        ("xscale", C.c_float), ("ln_eps", C.c_float),
+        ("vocab_size", C.c_int32), ("pred_hidden", C.c_int32), ("joint_hidden", C.c_int32), ("max_symbols", C.c_int32),
+    ]
+
+
+class RsTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("dev_ptr", C.c_void_p), ("dtype", C.c_int32), ("numel", C.c_int64)]
+
+
+_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.int32: 2}
+_lib = None
+
+EXPORTS = [
+    "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
+    "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
+    "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
+    "rs_stage_times_ms",
+]
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen librs_engine.so (building it with nvcc first if it is absent and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        if not build_if_missing:
+            raise FileNotFoundError(_LIB_PATH)
+        from .build import build
+        build()
+    lib = C.CDLL(_LIB_PATH)
+    vp, ip, i32p, f32p = C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    lib.rs_engine_create.argtypes = [C.POINTER(RsModelConfig), C.POINTER(RsTensor), ip, ip, C.POINTER(vp)]
+    lib.rs_engine_create.restype = ip
+    lib.rs_engine_destroy.argtypes = [vp]
+    lib.rs_engine_destroy.restype = None
+    lib.rs_last_error.argtypes = [vp]
+    lib.rs_last_error.restype = C.c_char_p
+    lib.rs_workspace_bytes.argtypes = [vp, ip, ip, C.POINTER(C.c_size_t)]
+    lib.rs_set_workspace.argtypes = [vp, vp, C.c_size_t]
+    lib.rs_mel_frames.argtypes = [vp, ip]
+    lib.rs_enc_frames.argtypes = [vp, ip]
+    lib.rs_logmel.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp]
+    lib.rs_encode.argtypes = [vp, vp, vp, ip, ip, vp, vp, ip, vp]
+    lib.rs_rnnt_greedy.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_transcribe_device.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_transcribe_batch.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, C.c_float, vp]
+    lib.rs_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, vp]
+    lib.rs_launch_count.argtypes = [vp]
+    lib.rs_launch_count.restype = C.c_int64
+    lib.rs_enable_stage_timing.argtypes = [vp, ip]
+    lib.rs_stage_times_ms.argtypes = [vp, f32p]
+    for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode",
+               "rs_rnnt_greedy", "rs_transcribe_device", "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm",
+               "rs_enable_stage_timing", "rs_stage_times_ms"):
+        getattr(lib, fn).restype = ip
+    _lib = lib
+    return lib
+
+
+# --------------------------------------------------------------------------------------
+# Weight packing (NeMo state dict -> the engine's named device tensors)
+# --------------------------------------------------------------------------------------
+def glu_interleave_index(d: int) -> torch.Tensor:
+    """Row permutation of pointwise_conv1 so that each 32-column GEMM chunk holds 16 value rows
+    followed by their 16 gate rows (RS_EPI_BIAS_GLU_BF16)."""
+    blk = torch.arange(d // 16).repeat_interleave(32)
+    within = torch.arange(32).repeat(d // 16)
+    return torch.where(within < 16, blk * 16 + within, d + blk * 16 + within - 16)
+
+
+def frontend_tables(cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    if cfg.n_fft != 512:
+        raise ValueError("frontend kernel is built for n_fft == 512")
+    win = torch.zeros(cfg.n_fft, dtype=torch.float32)
+    lo = (cfg.n_fft - cfg.n_window_size) // 2
+    win[lo:lo + cfg.n_window_size] = hann_window(cfg)
+    k = np.arange(cfg.n_fft // 2, dtype=np.float64)
+    tw256 = np.stack([np.cos(2 * np.pi * k / 256), -np.sin(2 * np.pi * k / 256)], axis=1)
+    k2 = np.arange(cfg.n_fft // 2 + 1, dtype=np.float64)
+    tw512 = np.stack([np.cos(2 * np.pi * k2 / 512), -np.sin(2 * np.pi * k2 / 512)], axis=1)
+    fb = mel_filterbank(cfg).numpy()
+    start = np.zeros(cfg.n_mels, dtype=np.int32)
+    count = np.zeros(cfg.n_mels, dtype=np.int32)
+    w = np.zeros((cfg.n_mels, MEL_MAX_W), dtype=np.float32)
+    for m in range(cfg.n_mels):
+        nz = np.nonzero(fb[m])[0]
+        if len(nz) == 0:
+            continue
+        s, e = int(nz[0]), int(nz[-1])
+        if e - s + 1 > MEL_MAX_W:
+            raise ValueError(f"mel filter {m} spans {e - s + 1} bins > {MEL_MAX_W}")
+        start[m], count[m] = s, e - s + 1
+        w[m, : e - s + 1] = fb[m, s:e + 1]
+    return {
+        "fe.window": win, "fe.tw256": torch.from_numpy(tw256.astype(np.float32)).reshape(-1),
+        "fe.tw512": torch.from_numpy(tw512.astype(np.float32)).reshape(-1),
+        "fe.mel_start": torch.from_numpy(start), "fe.mel_count": torch.from_numpy(count),
+        "fe.mel_w": torch.from_numpy(w).reshape(-1),
+    }
+
+
+def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    """NeMo-named fp32 state dict -> packed host tensors (bf16 GEMM weights, folded BN, ...)."""
+    bf = lambda t: t.to(torch.bfloat16).contiguous()
+    f32 = lambda t: t.to(torch.float32).contiguous()
+    out: Dict[str, torch.Tensor] = dict(frontend_tables(cfg))
+    d, H, dk, Cc = cfg.d_model, cfg.n_heads, cfg.d_head, cfg.sub_channels
+    pe = "encoder.pre_encode."
+    out["sub.conv0.w"] = f32(sd[pe + "conv.0.weight"].reshape(Cc, 9)); out["sub.conv0.b"] = f32(sd[pe + "conv.0.bias"])
+    out["sub.dw1.w"] = f32(sd[pe + "conv.2.weight"].reshape(Cc, 9)); out["sub.dw1.b"] = f32(sd[pe + "conv.2.bias"])
+    out["sub.pw1.w"] = bf(sd[pe + "conv.3.weight"].reshape(Cc, Cc)); out["sub.pw1.b"] = f32(sd[pe + "conv.3.bias"])
+    out["sub.dw2.w"] = f32(sd[pe + "conv.5.weight"].reshape(Cc, 9)); out["sub.dw2.b"] = f32(sd[pe + "conv.5.bias"])
+    out["sub.pw2.w"] = bf(sd[pe + "conv.6.weight"].reshape(Cc, Cc)); out["sub.pw2.b"] = f32(sd[pe + "conv.6.bias"])
+    F3 = cfg.sub_freq
+    # NeMo flattens [C, F3] channel-major (index c*F3+f); the engine's activations are [F3, C]
+    out["sub.out.w"] = bf(sd[pe + "out.weight"].view(d, Cc, F3).permute(0, 2, 1).reshape(d, F3 * Cc))
+    out["sub.out.b"] = f32(sd[pe + "out.bias"])
+    table = rel_pos_table(cfg)
+    glu_idx = glu_interleave_index(d)
+    for i in range(cfg.n_layers):
+        p, o = f"encoder.layers.{i}.", f"L{i}."
+        for src, dst in (("norm_feed_forward1", "ln_ff1"), ("norm_self_att", "ln_att"), ("norm_conv", "ln_conv"),
+                         ("norm_feed_forward2", "ln_ff2"), ("norm_out", "ln_out")):
+            out[o + dst + ".g"] = f32(sd[p + src + ".weight"]); out[o + dst + ".b"] = f32(sd[p + src + ".bias"])
+        for src, dst in (("feed_forward1", "ff1"), ("feed_forward2", "ff2")):
+            out[o + dst + ".w1"] = bf(sd[p + src + ".linear1.weight"]); out[o + dst + ".b1"] = f32(sd[p + src + ".linear1.bias"])
+            out[o + dst + ".w2"] = bf(sd[p + src + ".linear2.weight"]); out[o + dst + ".b2"] = f32(sd[p + src + ".linear2.bias"])
+        a = p + "self_attn."
+        out[o + "att.wqkv"] = bf(torch.cat([sd[a + "linear_q.weight"], sd[a + "linear_k.weight"], sd[a + "linear_v.weight"]], 0))
+        out[o + "att.bqkv"] = f32(torch.cat([sd[a + "linear_q.bias"], sd[a + "linear_k.bias"], sd[a + "linear_v.bias"]], 0))
+        pos = torch.nn.functional.linear(table, sd[a + "linear_pos.weight"])          # input independent: once at load
+        out[o + "att.pos"] = bf(pos.view(cfg.n_rel, H, dk).permute(1, 0, 2))
+        out[o + "att.u"] = f32(sd[a + "pos_bias_u"].reshape(-1)); out[o + "att.v"] = f32(sd[a + "pos_bias_v"].reshape(-1))
+        out[o + "att.wo"] = bf(sd[a + "linear_out.weight"]); out[o + "att.bo"] = f32(sd[a + "linear_out.bias"])
+        c = p + "conv."
+        out[o + "conv.pw1.w"] = bf(sd[c + "pointwise_conv1.weight"][:, :, 0][glu_idx])
+        out[o + "conv.pw1.b"] = f32(sd[c + "pointwise_conv1.bias"][glu_idx])
+        s = sd[c + "batch_norm.weight"] / torch.sqrt(sd[c + "batch_norm.running_var"] + cfg.bn_eps)
+        out[o + "conv.dw.w"] = f32((sd[c + "depthwise_conv.weight"][:, 0, :] * s[:, None]).T)
+        out[o + "conv.dw.shift"] = f32((sd[c + "depthwise_conv.bias"] - sd[c + "batch_norm.running_mean"]) * s + sd[c + "batch_norm.bias"])
+        out[o + "conv.pw2.w"] = bf(sd[c + "pointwise_conv2.weight"][:, :, 0]); out[o + "conv.pw2.b"] = f32(sd[c + "pointwise_conv2.bias"])
+    l = "decoder.prediction.dec_rnn.lstm."
+    out["joint.enc.w"] = bf(sd["joint.enc.weight"]); out["joint.enc.b"] = f32(sd["joint.enc.bias"])
+    out["joint.out.w"] = bf(sd["joint.joint_net.2.weight"]); out["joint.out.b"] = f32(sd["joint.joint_net.2.bias"])
+    out["pred.embed"] = f32(sd["decoder.prediction.embed.weight"])
+    out["pred.lstm.w"] = bf(torch.cat([sd[l + "weight_ih_l0"], sd[l + "weight_hh_l0"]], 1))
+    out["pred.lstm.b"] = f32(sd[l + "bias_ih_l0"] + sd[l + "bias_hh_l0"])
+    out["joint.pred.w"] = bf(sd["joint.pred.weight"]); out["joint.pred.b"] = f32(sd["joint.pred.bias"])
+    return out
+
+
+def to_rs_config(cfg: ModelConfig) -> RsModelConfig:
+    return RsModelConfig(
+        cfg.sample_rate, cfg.n_window_size, cfg.n_window_stride, cfg.n_fft, cfg.n_mels,
+        cfg.preemph, cfg.log_zero_guard, cfg.norm_eps,
+        cfg.n_layers, cfg.d_model, cfg.n_heads, cfg.d_ff, cfg.conv_kernel, cfg.sub_channels,
+        cfg.att_left, cfg.att_right, cfg.global_tokens, xscale(cfg), cfg.ln_eps,
+        cfg.vocab_size, cfg.pred_hidden, cfg.joint_hidden, cfg.max_symbols)
+
+
+# --------------------------------------------------------------------------------------
+# Engine
+# --------------------------------------------------------------------------------------
+class Engine:
+    """One engine per device: packed weights + workspace + the C-ABI handle."""
+
+    def __init__(self, cfg: ModelConfig, state_dict: StateDict, device: str = "cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("reazonspeech_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"device {device!r}: the B200 engine has no CPU path")
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.dev_index)
+        packed = pack_weights(state_dict, cfg)
+        self.weights = {k: v.to(self.device) for k, v in packed.items()}
+        self._names = [k.encode() for k in self.weights]
+        arr = (RsTensor * len(self.weights))()
+        for i, (k, v) in enumerate(self.weights.items()):
+            arr[i] = RsTensor(self._names[i], v.data_ptr(), _DTYPES[v.dtype], v.numel())
+        self._rs_cfg = to_rs_config(cfg)
+        h = C.c_void_p()
+        rc = self.lib.rs_engine_create(C.byref(self._rs_cfg), arr, len(self.weights), self.dev_index, C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"rs_engine_create failed ({rc}): {self.lib.rs_last_error(None).decode()}")
+        self.h = h
+        self._ws: Optional[torch.Tensor] = None
+        self._ws_key: Tuple[int, int] = (0, 0)
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h:
+            self.lib.rs_engine_destroy(h)
+            self.h = None
+
+    # -- helpers
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.rs_last_error(self.h).decode()}")
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def ensure_workspace(self, B: int, L_max: int):
+        if self._ws is not None and B <= self._ws_key[0] and L_max <= self._ws_key[1]:
+            return
+        B2, L2 = max(B, self._ws_key[0]), max(L_max, self._ws_key[1])
+        n = C.c_size_t()
+        self._check(self.lib.rs_workspace_bytes(self.h, B2, L2, C.byref(n)), "rs_workspace_bytes")
+        self._ws = None
+        self._ws = torch.empty(n.value + 256, dtype=torch.uint8, device=self.device)
+        ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        self._check(self.lib.rs_set_workspace(self.h, ptr, n.value), "rs_set_workspace")
+        self._ws_key = (B2, L2)
+
+    def mel_frames(self, n: int) -> int:
+        return self.lib.rs_mel_frames(self.h, n)
+
+    def enc_frames(self, n: int) -> int:
+        return self.lib.rs_enc_frames(self.h, n)
+
+    def u_max(self, L_max: int) -> int:
+        return self.enc_frames(L_max) * self.cfg.max_symbols
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.rs_launch_count(self.h))
+
+    # -- stages (device tensors in, device tensors out)
+    def log_mel(self, wav: torch.Tensor, lens: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        B, L = wav.shape
+        assert wav.dtype == torch.float32 and wav.is_contiguous() and lens.dtype == torch.int32
+        F = self.mel_frames(L)
+        mel = torch.empty(B, F, self.cfg.n_mels, dtype=torch.float32, device=self.device)
+        mel_len = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.rs_logmel(self.h, wav.data_ptr(), lens.data_ptr(), B, L, mel.data_ptr(), mel_len.data_ptr(),
+                                       self._stream()), "rs_logmel")
+        return mel, mel_len
+
+    def encode(self, mel: torch.Tensor, mel_len: torch.Tensor, n_layers: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
+        B, F, _ = mel.shape
+        L = (F - 1) * self.cfg.n_window_stride
+        self.ensure_workspace(B, L)
+        T = conv_out_len(conv_out_len(conv_out_len(F)))
+        enc = torch.empty(B, T, self.cfg.d_model, dtype=torch.float32, device=self.device)
+        enc_len = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.rs_encode(self.h, mel.data_ptr(), mel_len.data_ptr(), B, F, enc.data_ptr(), enc_len.data_ptr(),
+                                       n_layers, self._stream()), "rs_encode")
+        return enc, enc_len
+
+    def greedy(self, enc: torch.Tensor, enc_len: torch.Tensor, U_max: Optional[int] = None):
+        B, T, _ = enc.shape
+        assert enc.dtype == torch.float32 and enc.is_contiguous()
+        self.ensure_workspace(B, (T * 8 + 8) * self.cfg.n_window_stride)
+        U = U_max or T * self.cfg.max_symbols
+        tokens = torch.zeros(B, U, dtype=torch.int32, device=self.device)
+        frames = torch.zeros(B, U, dtype=torch.int32, device=self.device)
+        ntok = torch.zeros(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.rs_rnnt_greedy(self.h, enc.data_ptr(), enc_len.data_ptr(), B, T, tokens.data_ptr(),
+                                            frames.data_ptr(), ntok.data_ptr(), U, self._stream()), "rs_rnnt_greedy")
+        return tokens, frames, ntok
+
+    def transcribe_device(self, wav: torch.Tensor, lens: torch.Tensor, U_max: Optional[int] = None, out=None):
+        B, L = wav.shape
+        self.ensure_workspace(B, L)
+        U = U_max or self.u_max(L)
+        if out is None:
+            out = (torch.zeros(B, U, dtype=torch.int32, device=self.device),
+                   torch.zeros(B, U, dtype=torch.int32, device=self.device),
+                   torch.zeros(B, dtype=torch.int32, device=self.device))
+        tokens, frames, ntok = out
+        self._check(self.lib.rs_transcribe_device(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(),
+                                                  frames.data_ptr(), ntok.data_ptr(), U, self._stream()), "rs_transcribe_device")
+        return tokens, frames, ntok
+
+    def transcribe_host(self, wav: torch.Tensor, lens: torch.Tensor, U_max: Optional[int] = None, out=None):
+        """wav: host float32 [B, L] (pinned for speed), lens: host int32 [B] -> host tokens/frames/n_tok."""
+        B, L = wav.shape
+        assert wav.device.type == "cpu" and wav.dtype == torch.float32 and wav.is_contiguous()
+        self.ensure_workspace(B, L)
+        U = U_max or self.u_max(L)
+        if out is None:
+            out = (torch.zeros(B, U, dtype=torch.int32).pin_memory(), torch.zeros(B, U, dtype=torch.int32).pin_memory(),
+                   torch.zeros(B, dtype=torch.int32).pin_memory())
+        tokens, frames, ntok = out
+        self._check(self.lib.rs_transcribe_batch(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(),
+                                                 frames.data_ptr(), ntok.data_ptr(), U, self._stream()), "rs_transcribe_batch")
+        return tokens, frames, ntok
+
+    # -- kernel seams
+    def gemm(self, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
+             resid: Optional[torch.Tensor] = None, alpha: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        M, K = a.shape
+        N = w.shape[0]
+        assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.is_contiguous() and w.is_contiguous()
+        if out is None:
+            if epilogue in (EPI_RESID_F32, EPI_BIAS_F32):
+                out = torch.empty(M, N, dtype=torch.float32, device=self.device)
+            elif epilogue == EPI_BIAS_GLU_BF16:
+                out = torch.empty(M, N // 2, dtype=torch.bfloat16, device=self.device)
+            else:
+                out = torch.empty(M, N, dtype=torch.bfloat16, device=self.device)
+        self._check(self.lib.rs_gemm_bf16(self.h, a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                          resid.data_ptr() if resid is not None else None, out.data_ptr(), M, N, K,
+                                          epilogue, alpha, self._stream()), "rs_gemm_bf16")
+        return out
+
+    def layernorm(self, x: torch.Tensor, g: torch.Tensor, b: torch.Tensor, bf16_out: bool = True) -> torch.Tensor:
+        rows, d = x.shape
+        out = torch.empty(rows, d, dtype=torch.bfloat16 if bf16_out else torch.float32, device=self.device)
+        self._check(self.lib.rs_layernorm(self.h, x.data_ptr(), g.data_ptr(), b.data_ptr(),
+                                          None if bf16_out else out.data_ptr(), out.data_ptr() if bf16_out else None,
+                                          rows, d, self._stream()), "rs_layernorm")
+        return out
+
+    def enable_stage_timing(self, on: bool = True):
+        self._check(self.lib.rs_enable_stage_timing(self.h, int(on)), "rs_enable_stage_timing")
+
+    def stage_times_ms(self) -> Dict[str, float]:
+        ms = (C.c_float * 8)()
+        self._check(self.lib.rs_stage_times_ms(self.h, ms), "rs_stage_times_ms")
+        return dict(zip(("logmel", "subsample", "layers", "enc_proj", "decode"), [float(v) for v in ms[:5]]))

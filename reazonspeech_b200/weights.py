@@ -1,0 +1,212 @@
+"""Checkpoint handling: NeMo state-dict naming, seeded synthetic weights, ``.nemo`` reader.
+
+The reference obtains its weights through
+``EncDecRNNTBPEModel.from_pretrained('reazon-research/reazonspeech-nemo-v2')``
+(pkg/nemo-asr/src/transcribe.py:26-28).  Neither NeMo nor the checkpoint is reachable
+offline, so every test and the benchmark run on *seeded random weights of the same
+shapes*, keyed by the same state-dict names NeMo uses -- a real ``model_weights.ckpt``
+drops in through :func:`load_nemo_archive` without touching anything downstream.
+
+Synthetic weights are rounded to bf16-representable values on purpose: the engine keeps
+GEMM weights in bf16, so with representable weights the CPU oracle and the engine
+evaluate *the same model* and the only deviation left is activation rounding.
+"""
+from __future__ import annotations
+
+import io
+import math
+import tarfile
+from typing import Dict
+
+import numpy as np
+import torch
+
+from .config import ModelConfig
+
+StateDict = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# Fixed (non-learned) tables of the frontend / positional encoding
+# --------------------------------------------------------------------------------------
+def hann_window(cfg: ModelConfig) -> torch.Tensor:
+    """Symmetric Hann (torch.hann_window(periodic=False)), float32, length n_window_size."""
+    n = cfg.n_window_size
+    k = torch.arange(n, dtype=torch.float64)
+    return (0.5 - 0.5 * torch.cos(2.0 * math.pi * k / (n - 1))).to(torch.float32)
+
+
+def _hz_to_mel_slaney(f: np.ndarray) -> np.ndarray:
+    f = np.asarray(f, dtype=np.float64)
+    f_sp = 200.0 / 3
+    mels = f / f_sp
+    min_log_hz, min_log_mel = 1000.0, 1000.0 / f_sp
+    logstep = math.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, mels)
+
+
+def _mel_to_hz_slaney(m: np.ndarray) -> np.ndarray:
+    m = np.asarray(m, dtype=np.float64)
+    f_sp = 200.0 / 3
+    min_log_hz, min_log_mel = 1000.0, 1000.0 / f_sp
+    logstep = math.log(6.4) / 27.0
+    return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+
+def mel_filterbank(cfg: ModelConfig) -> torch.Tensor:
+    """Slaney-scale, slaney-normalised triangular filterbank, float32 [n_mels, n_freq].
+
+    Restates librosa.filters.mel(sr, n_fft, n_mels, fmin=0, fmax=sr/2, htk=False,
+    norm='slaney'), which NeMo's FilterbankFeatures uses for ``self.fb``."""
+    sr, n_fft, n_mels = cfg.sample_rate, cfg.n_fft, cfg.n_mels
+    fftfreqs = np.linspace(0.0, sr / 2.0, cfg.n_freq)
+    mel_pts = np.linspace(_hz_to_mel_slaney(0.0), _hz_to_mel_slaney(sr / 2.0), n_mels + 2)
+    hz_pts = _mel_to_hz_slaney(mel_pts)
+    fdiff = np.diff(hz_pts)
+    ramps = hz_pts[:, None] - fftfreqs[None, :]
+    fb = np.zeros((n_mels, cfg.n_freq), dtype=np.float64)
+    for i in range(n_mels):
+        lower = -ramps[i] / fdiff[i]
+        upper = ramps[i + 2] / fdiff[i + 1]
+        fb[i] = np.maximum(0.0, np.minimum(lower, upper))
+    enorm = 2.0 / (hz_pts[2:n_mels + 2] - hz_pts[:n_mels])
+    fb *= enorm[:, None]
+    return torch.from_numpy(fb.astype(np.float32))
+
+
+def rel_pos_table(cfg: ModelConfig) -> torch.Tensor:
+    """LocalAttRelPositionalEncoding table, float32 [n_rel, d_model].
+
+    Row c holds the sinusoid of relative position (att_left - c): positions run from
+    +left down to -right, interleaved sin/cos with the 10000^(-2i/d) frequencies."""
+    pos = torch.arange(cfg.att_left, -cfg.att_right - 1, -1, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, cfg.d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / cfg.d_model))
+    pe = torch.zeros(pos.shape[0], cfg.d_model, dtype=torch.float32)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+# --------------------------------------------------------------------------------------
+# State-dict schema (NeMo names)
+# --------------------------------------------------------------------------------------
+def state_dict_shapes(cfg: ModelConfig) -> Dict[str, tuple]:
+    d, h, dk, ff, k = cfg.d_model, cfg.n_heads, cfg.d_head, cfg.d_ff, cfg.conv_kernel
+    c = cfg.sub_channels
+    s: Dict[str, tuple] = {}
+    pe = "encoder.pre_encode."
+    s[pe + "conv.0.weight"] = (c, 1, 3, 3); s[pe + "conv.0.bias"] = (c,)
+    for dw, pw in ((2, 3), (5, 6)):
+        s[pe + f"conv.{dw}.weight"] = (c, 1, 3, 3); s[pe + f"conv.{dw}.bias"] = (c,)
+        s[pe + f"conv.{pw}.weight"] = (c, c, 1, 1); s[pe + f"conv.{pw}.bias"] = (c,)
+    s[pe + "out.weight"] = (d, cfg.sub_out_dim); s[pe + "out.bias"] = (d,)
+    for i in range(cfg.n_layers):
+        p = f"encoder.layers.{i}."
+        for ln in ("norm_feed_forward1", "norm_self_att", "norm_conv", "norm_feed_forward2", "norm_out"):
+            s[p + ln + ".weight"] = (d,); s[p + ln + ".bias"] = (d,)
+        for f in ("feed_forward1", "feed_forward2"):
+            s[p + f + ".linear1.weight"] = (ff, d); s[p + f + ".linear1.bias"] = (ff,)
+            s[p + f + ".linear2.weight"] = (d, ff); s[p + f + ".linear2.bias"] = (d,)
+        for l in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            s[p + f"self_attn.{l}.weight"] = (d, d); s[p + f"self_attn.{l}.bias"] = (d,)
+        s[p + "self_attn.linear_pos.weight"] = (d, d)
+        s[p + "self_attn.pos_bias_u"] = (h, dk); s[p + "self_attn.pos_bias_v"] = (h, dk)
+        s[p + "conv.pointwise_conv1.weight"] = (2 * d, d, 1); s[p + "conv.pointwise_conv1.bias"] = (2 * d,)
+        s[p + "conv.depthwise_conv.weight"] = (d, 1, k); s[p + "conv.depthwise_conv.bias"] = (d,)
+        for b in ("weight", "bias", "running_mean", "running_var"):
+            s[p + "conv.batch_norm." + b] = (d,)
+        s[p + "conv.pointwise_conv2.weight"] = (d, d, 1); s[p + "conv.pointwise_conv2.bias"] = (d,)
+    hp, hj = cfg.pred_hidden, cfg.joint_hidden
+    s["decoder.prediction.embed.weight"] = (cfg.n_classes, hp)
+    lstm = "decoder.prediction.dec_rnn.lstm."
+    s[lstm + "weight_ih_l0"] = (4 * hp, hp); s[lstm + "weight_hh_l0"] = (4 * hp, hp)
+    s[lstm + "bias_ih_l0"] = (4 * hp,); s[lstm + "bias_hh_l0"] = (4 * hp,)
+    s["joint.enc.weight"] = (hj, d); s["joint.enc.bias"] = (hj,)
+    s["joint.pred.weight"] = (hj, hp); s["joint.pred.bias"] = (hj,)
+    s["joint.joint_net.2.weight"] = (cfg.n_classes, hj); s["joint.joint_net.2.bias"] = (cfg.n_classes,)
+    return s
+
+
+def _bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_rate: float = 0.75) -> StateDict:
+    """Seeded synthetic checkpoint with NeMo's names and shapes (float32, bf16-representable).
+
+    Linear / conv weights ~ N(0, gain/fan_in) (variance preserving; gain 2 ahead of a ReLU)
+    so the time-varying part of the signal survives 24 layers instead of collapsing onto
+    the biases, small biases, LayerNorm gains near 1, BatchNorm running stats near (0, 1).
+    The blank logit bias is calibrated so greedy decoding emits blank on roughly ``blank_rate`` of the joint evaluations --
+    untrained logits would otherwise emit ``max_symbols`` tokens on every frame, which is
+    not the decode load a trained model presents."""
+    g = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    for name, shape in state_dict_shapes(cfg).items():
+        leaf = name.rsplit(".", 1)[-1]
+        if "norm" in name and leaf == "weight":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif "norm" in name and leaf == "bias":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "running_mean":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif leaf == "running_var":
+            t = 0.5 + torch.rand(shape, generator=g)
+        elif leaf in ("pos_bias_u", "pos_bias_v"):
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif name == "decoder.prediction.embed.weight":
+            t = torch.randn(shape, generator=g)
+            t[cfg.blank] = 0.0                      # padding_idx == blank (blank_as_pad)
+        else:
+            if len(shape) == 1:                     # a bias
+                t = 0.02 * torch.randn(shape, generator=g)
+            else:
+                fan_in = int(np.prod(shape[1:]))
+                gain = 2.0 if "pre_encode.conv" in name else 1.0
+                if name == "joint.pred.weight":     # let the label history move the logits as
+                    gain = 8.0                      # much as the acoustics do (|h_lstm| is small)
+                t = torch.randn(shape, generator=g) * math.sqrt(gain / fan_in)
+        sd[name] = _bf16_round(t.to(torch.float32))
+    # --- calibrate the blank bias on synthetic joint activations ---
+    n = 4096
+    a = torch.randn(n, cfg.joint_hidden, generator=g) * 1.0 + torch.randn(n, cfg.joint_hidden, generator=g) * 0.8
+    logits = torch.relu(a) @ sd["joint.joint_net.2.weight"].T + sd["joint.joint_net.2.bias"]
+    best_other = logits[:, : cfg.blank].max(dim=1).values - logits[:, cfg.blank]
+    shift = torch.quantile(best_other, blank_rate).item()
+    b = sd["joint.joint_net.2.bias"].clone()
+    b[cfg.blank] += shift
+    sd["joint.joint_net.2.bias"] = _bf16_round(b)
+    return sd
+
+
+# --------------------------------------------------------------------------------------
+# .nemo archive reader
+# --------------------------------------------------------------------------------------
+def load_nemo_archive(path: str):
+    """Read a ``.nemo`` archive: returns (ModelConfig, state_dict, tokenizer_model_bytes | None).
+
+    A ``.nemo`` file is a (possibly gzipped) tar holding ``model_config.yaml``,
+    ``model_weights.ckpt`` (a torch state dict) and ``*_tokenizer.model`` (SentencePiece)."""
+    import yaml
+    cfg_d, sd, tok = None, None, None
+    with tarfile.open(path, "r:*") as tar:
+        for m in tar.getmembers():
+            base = m.name.rsplit("/", 1)[-1]
+            if base == "model_config.yaml":
+                cfg_d = yaml.safe_load(tar.extractfile(m).read())
+            elif base == "model_weights.ckpt":
+                sd = torch.load(io.BytesIO(tar.extractfile(m).read()), map_location="cpu", weights_only=True)
+            elif base.endswith("tokenizer.model"):
+                tok = tar.extractfile(m).read()
+    if cfg_d is None or sd is None:
+        raise ValueError(f"{path}: not a .nemo archive (model_config.yaml / model_weights.ckpt missing)")
+    cfg = ModelConfig.from_nemo_yaml(cfg_d)
+    want = state_dict_shapes(cfg)
+    sd = {k: v.to(torch.float32) for k, v in sd.items() if k in want}
+    missing = [k for k in want if k not in sd]
+    if missing:
+        raise ValueError(f"{path}: checkpoint lacks {len(missing)} tensors, e.g. {missing[:3]}")
+    for k, shp in want.items():
+        if tuple(sd[k].shape) != tuple(shp):
+            raise ValueError(f"{path}: {k} has shape {tuple(sd[k].shape)}, expected {shp}")
+    return cfg, sd, tok
