@@ -122,6 +122,12 @@ int64_t rs_launch_count(const rs_engine* e);
 /* Per-stage device time of the last rs_transcribe_* call when timing was enabled. */
 int rs_enable_stage_timing(rs_engine* e, int on);
 int rs_stage_times_ms(const rs_engine* e, float* ms /*[8]*/);
+/* Per-launch CUDA-event timing of the tcgen05 GEMM (the dominant kernel): while enabled every GEMM
+ * launch is bracketed by two events on its stream.  rs_gemm_timing() synchronises, returns the summed
+ * device time, the summed algorithmic FLOPs (2*M*N*K) and the launch count since it was enabled or
+ * last read, and resets the accumulators. */
+int rs_enable_gemm_timing(rs_engine* e, int on);
+int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches);
 
 #ifdef __cplusplus
 }

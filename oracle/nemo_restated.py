@@ -224,12 +224,22 @@ def rnnt_greedy(enc: torch.Tensor, sd: StateDict, cfg: ModelConfig, emulate: boo
     hp = cfg.pred_hidden
     res = GreedyResult()
     ep = joint_enc_proj(_q(enc, emulate), sd)
+    n_threads = torch.get_num_threads()
+    torch.set_num_threads(1)            # the token loop is matrix-vector work; threads only add sync cost
+    try:
+        return _greedy_loop(ep, sd, cfg, res)
+    finally:
+        torch.set_num_threads(n_threads)
+
+
+def _greedy_loop(ep, sd, cfg, res):
+    hp = cfg.pred_hidden
     emb = sd["decoder.prediction.embed.weight"]
     h = torch.zeros(hp); c = torch.zeros(hp)
     h_new, c_new = lstm_step(torch.zeros(hp), h, c, sd)                            # SOS step
     pp = F.linear(h_new, sd["joint.pred.weight"], sd["joint.pred.bias"])
     W, b = sd["joint.joint_net.2.weight"], sd["joint.joint_net.2.bias"]
-    for t in range(enc.shape[0]):
+    for t in range(ep.shape[0]):
         for _ in range(cfg.max_symbols):
             logits = F.linear(torch.relu(ep[t] + pp), W, b)
             top2 = torch.topk(logits, 2)

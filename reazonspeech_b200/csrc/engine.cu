@@ -64,6 +64,10 @@ struct rs_engine {
   cudaEvent_t ev[9] = {};
   bool ev_ok = false;
   float stage_ms[8] = {};
+  bool gemm_timing = false;
+  std::vector<cudaEvent_t> gemm_ev;     // pairs
+  size_t gemm_ev_used = 0;
+  double gemm_flops = 0.0;
 };
 
 namespace {
@@ -201,8 +205,23 @@ int gemm(rs_engine* e, const void* a, const void* w, const float* bias, const fl
          int K, int epi, float alpha, cudaStream_t s) {
   rs::GemmArgs g{a, w, bias, resid, out, M, N, K, epi, alpha};
   char msg[256] = "";
+  bool timed = false;
+  if (e->gemm_timing) {
+    if (e->gemm_ev_used + 2 > e->gemm_ev.size()) {
+      const size_t old = e->gemm_ev.size();
+      e->gemm_ev.resize(old + 512);
+      for (size_t i = old; i < e->gemm_ev.size(); ++i) cudaEventCreate(&e->gemm_ev[i]);
+    }
+    cudaEventRecord(e->gemm_ev[e->gemm_ev_used], s);
+    timed = true;
+  }
   cudaError_t c = rs::launch_gemm(g, e->num_sms, s, msg);
   if (c != cudaSuccess) return fail(e, RS_ERR_CUDA, "gemm: %s", msg);
+  if (timed) {
+    cudaEventRecord(e->gemm_ev[e->gemm_ev_used + 1], s);
+    e->gemm_ev_used += 2;
+    e->gemm_flops += 2.0 * M * static_cast<double>(N) * K;
+  }
   e->launches++;
   return RS_OK;
 }
@@ -339,6 +358,7 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
 void rs_engine_destroy(rs_engine* e) {
   if (e == nullptr) return;
   if (e->ev_ok) for (auto& ev : e->ev) cudaEventDestroy(ev);
+  for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -461,6 +481,30 @@ int rs_stage_times_ms(const rs_engine* e, float* ms) {
   for (int i = 0; i < 8; ++i) ms[i] = 0.f;
   if (cudaEventSynchronize(e->ev[5]) != cudaSuccess) return RS_ERR_CUDA;
   for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], e->ev[i], e->ev[i + 1]);
+  return RS_OK;
+}
+
+int rs_enable_gemm_timing(rs_engine* e, int on) {
+  if (!e) return RS_ERR_INVALID_ARG;
+  e->gemm_timing = on != 0;
+  e->gemm_ev_used = 0;
+  e->gemm_flops = 0.0;
+  return RS_OK;
+}
+
+int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches) {
+  if (!e || !ms || !flops || !launches) return RS_ERR_INVALID_ARG;
+  double total = 0.0;
+  if (e->gemm_ev_used > 0) {
+    RS_CUDA(e, cudaEventSynchronize(e->gemm_ev[e->gemm_ev_used - 1]));
+    for (size_t i = 0; i + 1 < e->gemm_ev_used; i += 2) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, e->gemm_ev[i], e->gemm_ev[i + 1]);
+      total += t;
+    }
+  }
+  *ms = total; *flops = e->gemm_flops; *launches = static_cast<int64_t>(e->gemm_ev_used / 2);
+  e->gemm_ev_used = 0; e->gemm_flops = 0.0;
   return RS_OK;
 }
 

@@ -48,7 +48,7 @@ EXPORTS = [
     "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
     "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
-    "rs_stage_times_ms",
+    "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing",
 ]
 
 
@@ -85,9 +85,11 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_launch_count.restype = C.c_int64
     lib.rs_enable_stage_timing.argtypes = [vp, ip]
     lib.rs_stage_times_ms.argtypes = [vp, f32p]
+    lib.rs_enable_gemm_timing.argtypes = [vp, ip]
+    lib.rs_gemm_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode",
                "rs_rnnt_greedy", "rs_transcribe_device", "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm",
-               "rs_enable_stage_timing", "rs_stage_times_ms"):
+               "rs_enable_stage_timing", "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing"):
         getattr(lib, fn).restype = ip
     _lib = lib
     return lib
@@ -353,6 +355,15 @@ class Engine:
 
     def enable_stage_timing(self, on: bool = True):
         self._check(self.lib.rs_enable_stage_timing(self.h, int(on)), "rs_enable_stage_timing")
+
+    def enable_gemm_timing(self, on: bool = True):
+        self._check(self.lib.rs_enable_gemm_timing(self.h, int(on)), "rs_enable_gemm_timing")
+
+    def gemm_timing(self):
+        """(summed device ms, summed algorithmic FLOPs, launches) of the tcgen05 GEMM since enabled / last read."""
+        ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self.lib.rs_gemm_timing(self.h, C.byref(ms), C.byref(fl), C.byref(n)), "rs_gemm_timing")
+        return ms.value, fl.value, n.value
 
     def stage_times_ms(self) -> Dict[str, float]:
         ms = (C.c_float * 8)()

@@ -16,7 +16,7 @@ from __future__ import annotations
 import io
 import math
 import tarfile
-from typing import Dict
+from typing import Dict, Optional
 
 import numpy as np
 import torch
@@ -131,50 +131,65 @@ def _bf16_round(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_rate: float = 0.75) -> StateDict:
+# Blank-bias shifts measured on a B200 with scripts/calibrate_blank.py (greedy emission rate of about
+# one token per three encoder frames on the synthetic clip set); keyed by (config signature, seed).
+CALIBRATED_BLANK_SHIFT: Dict[tuple, float] = {
+    ((2, 256, 127, 128, 128), 0): 2.03125,          # ModelConfig.tiny(), CPU oracle, rate 0.26 tokens/frame
+}
+
+
+def _cfg_key(cfg: ModelConfig) -> tuple:
+    return (cfg.n_layers, cfg.d_model, cfg.vocab_size, cfg.pred_hidden, cfg.joint_hidden)
+
+
+def random_state_dict(cfg: ModelConfig, seed: int = 0, blank_rate: float = 0.75,
+                      blank_shift: Optional[float] = None) -> StateDict:
     """Seeded synthetic checkpoint with NeMo's names and shapes (float32, bf16-representable).
 
     Linear / conv weights ~ N(0, gain/fan_in) (variance preserving; gain 2 ahead of a ReLU)
     so the time-varying part of the signal survives 24 layers instead of collapsing onto
     the biases, small biases, LayerNorm gains near 1, BatchNorm running stats near (0, 1).
-    The blank logit bias is calibrated so greedy decoding emits blank on roughly ``blank_rate`` of the joint evaluations --
-    untrained logits would otherwise emit ``max_symbols`` tokens on every frame, which is
-    not the decode load a trained model presents."""
-    g = torch.Generator().manual_seed(seed)
+    The blank logit bias is shifted so greedy decoding emits at a speech-like rate instead of
+    ``max_symbols`` tokens on every frame (untrained logits put blank at 1/3001; SURVEY.md
+    section 8d): ``blank_shift`` if given, else the value measured for this (config, seed) in
+    CALIBRATED_BLANK_SHIFT, else a quantile heuristic on synthetic joint activations."""
     sd: StateDict = {}
-    for name, shape in state_dict_shapes(cfg).items():
+    for idx, (name, shape) in enumerate(state_dict_shapes(cfg).items()):
+        rng = np.random.default_rng([seed, idx])
+        randn = lambda: torch.from_numpy(rng.standard_normal(shape, dtype=np.float32))
         leaf = name.rsplit(".", 1)[-1]
         if "norm" in name and leaf == "weight":
-            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+            t = 1.0 + 0.1 * randn()
         elif "norm" in name and leaf == "bias":
-            t = 0.1 * torch.randn(shape, generator=g)
+            t = 0.1 * randn()
         elif leaf == "running_mean":
-            t = 0.1 * torch.randn(shape, generator=g)
+            t = 0.1 * randn()
         elif leaf == "running_var":
-            t = 0.5 + torch.rand(shape, generator=g)
+            t = 0.5 + torch.from_numpy(rng.random(shape, dtype=np.float32))
         elif leaf in ("pos_bias_u", "pos_bias_v"):
-            t = 0.1 * torch.randn(shape, generator=g)
+            t = 0.1 * randn()
         elif name == "decoder.prediction.embed.weight":
-            t = torch.randn(shape, generator=g)
+            t = randn()
             t[cfg.blank] = 0.0                      # padding_idx == blank (blank_as_pad)
+        elif len(shape) == 1:                       # a bias
+            t = 0.02 * randn()
         else:
-            if len(shape) == 1:                     # a bias
-                t = 0.02 * torch.randn(shape, generator=g)
-            else:
-                fan_in = int(np.prod(shape[1:]))
-                gain = 2.0 if "pre_encode.conv" in name else 1.0
-                if name == "joint.pred.weight":     # let the label history move the logits as
-                    gain = 8.0                      # much as the acoustics do (|h_lstm| is small)
-                t = torch.randn(shape, generator=g) * math.sqrt(gain / fan_in)
+            fan_in = int(np.prod(shape[1:]))
+            gain = 2.0 if "pre_encode.conv" in name else 1.0
+            if name == "joint.pred.weight":         # let the label history move the logits as
+                gain = 8.0                          # much as the acoustics do (|h_lstm| is small)
+            t = randn() * math.sqrt(gain / fan_in)
         sd[name] = _bf16_round(t.to(torch.float32))
-    # --- calibrate the blank bias on synthetic joint activations ---
-    n = 4096
-    a = torch.randn(n, cfg.joint_hidden, generator=g) * 1.0 + torch.randn(n, cfg.joint_hidden, generator=g) * 0.8
-    logits = torch.relu(a) @ sd["joint.joint_net.2.weight"].T + sd["joint.joint_net.2.bias"]
-    best_other = logits[:, : cfg.blank].max(dim=1).values - logits[:, cfg.blank]
-    shift = torch.quantile(best_other, blank_rate).item()
+    if blank_shift is None:
+        blank_shift = CALIBRATED_BLANK_SHIFT.get((_cfg_key(cfg), seed))
+    if blank_shift is None:
+        rng = np.random.default_rng([seed, 10 ** 6])
+        a = torch.from_numpy(rng.standard_normal((4096, cfg.joint_hidden), dtype=np.float32)) * 1.28
+        logits = torch.relu(a) @ sd["joint.joint_net.2.weight"].T + sd["joint.joint_net.2.bias"]
+        best_other = logits[:, : cfg.blank].max(dim=1).values - logits[:, cfg.blank]
+        blank_shift = torch.quantile(best_other, blank_rate).item()
     b = sd["joint.joint_net.2.bias"].clone()
-    b[cfg.blank] += shift
+    b[cfg.blank] += blank_shift
     sd["joint.joint_net.2.bias"] = _bf16_round(b)
     return sd
 

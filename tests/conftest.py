@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run under gpurun)")
+    from oracle.cpu_threads import tune_threads
+    tune_threads(16)
 
 
 @pytest.fixture(scope="session")
