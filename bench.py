@@ -51,7 +51,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except OSError:
@@ -155,7 +155,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
@@ -205,12 +205,12 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident timed region (`value`)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                      # nvidia-smi needs a few hundred ms to start: begin before the warm-up
     for _ in range(args.warmup):
         eng.transcribe_device(wav_dev, len_dev, U, out_dev)
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -4,12 +4,15 @@
 // oracle/nemo_restated.py::local_attention_core.
 //
 // One CTA = 64 query rows of one (utterance, head); 4 warps x 16 rows, flash-style online
-// softmax in fp32, bf16 mma.sync m16n8k16 for QK^T, Q P^T and PV.  The positional term
-// (q+v).p[rel] is computed once per query tile for all 2w+1 relative offsets into shared memory
-// and added to each key tile through the skewed index rel = j - i + w_left (no rel-shift pass,
-// no [T,T] score tensor in HBM).  Only key tiles intersecting [i-w_left, i+w_right] are
-// visited, so cost is linear in T (long-form audio).  The global token enters as the initial
-// state of the online softmax; its own row (full attention) is a separate small kernel.
+// softmax in fp32, bf16 mma.sync m16n8k16 for QK^T and PV.  The positional term
+// BD[i][c] = (q_i + v).p[c] for all 2w+1 relative offsets c is produced beforehand by ONE batched
+// tcgen05 GEMM over all heads (A = q columns of the QKV buffer, W = linear_pos table, bias =
+// v.p[c]); this kernel adds it to each key tile through the skewed index c = j - i + w_left
+// (no rel-shift pass, no [T,T] score tensor in HBM).  With BD out of the kernel the CTA needs
+// 53 KB of shared memory, so 3-4 CTAs share an SM and hide each other's load / mma latency.
+// Only key tiles intersecting [i-w_left, i+w_right] are visited, so cost is linear in T
+// (long-form audio).  The global token enters as the initial state of the online softmax; its
+// own row (full attention) is a separate small kernel.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -33,9 +36,9 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 struct AttnDev {
-  const __nv_bfloat16* qkv; const __nv_bfloat16* pos; const float* bias_u; const float* bias_v;
+  const __nv_bfloat16* qkv; const float* bd; const float* bias_u;
   __nv_bfloat16* out; const int32_t* enc_len;
-  int T_max, H, w_left, w_right, n_global, n_rel, n_rel_pad;
+  int T_max, H, w_left, w_right, n_global, n_rel_pad;
 };
 
 // Copy 64 rows x 128 bf16 (row stride `ld` elements, rows >= valid read as zero) into padded smem.
@@ -48,16 +51,13 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
   }
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 3)
 local_attention_kernel(const AttnDev p) {
   extern __shared__ __align__(16) uint8_t at_smem[];
   __nv_bfloat16* sQU = reinterpret_cast<__nv_bfloat16*>(at_smem);
-  __nv_bfloat16* sQV = sQU + QT * LDS;
-  __nv_bfloat16* sK = sQV + QT * LDS;
+  __nv_bfloat16* sK = sQU + QT * LDS;
   __nv_bfloat16* sV = sK + KT * LDS;
-  float* sBD = reinterpret_cast<float*>(sV + KT * LDS);
-  const int bdld = p.n_rel_pad + 1;
-  float* sG = sBD + QT * bdld;                      // [QT] global-key score (already scaled)
+  float* sG = reinterpret_cast<float*>(sV + KT * LDS);   // [QT] global-key score (already scaled)
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const int len = p.enc_len[b];
@@ -79,23 +79,20 @@ local_attention_kernel(const AttnDev p) {
     return;
   }
 
-  // ---- phase 0: Q tile -> (q+u), (q+v) in bf16; global-key scores
+  // ---- phase 0: Q tile -> (q+u) in bf16; global-key scores
   for (int id = threadIdx.x; id < QT * 16; id += blockDim.x) {
     const int r = id >> 4, c = (id & 15) * 8;
     uint4 raw = make_uint4(0, 0, 0, 0);
     if (q0 + r < p.T_max) raw = *reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * ld + c);
     const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    uint32_t qu[4], qv[4];
+    uint32_t qu[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 q2 = unpack_bf16x2(w[i]);
       const float2 u2 = *reinterpret_cast<const float2*>(p.bias_u + h * DK + c + 2 * i);
-      const float2 v2 = *reinterpret_cast<const float2*>(p.bias_v + h * DK + c + 2 * i);
       qu[i] = pack_bf16x2(q2.x + u2.x, q2.y + u2.y);
-      qv[i] = pack_bf16x2(q2.x + v2.x, q2.y + v2.y);
     }
     *reinterpret_cast<uint4*>(sQU + r * LDS + c) = make_uint4(qu[0], qu[1], qu[2], qu[3]);
-    *reinterpret_cast<uint4*>(sQV + r * LDS + c) = make_uint4(qv[0], qv[1], qv[2], qv[3]);
   }
   if (p.n_global > 0) {
     const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;     // 2 threads per row, 64 dims each
@@ -120,42 +117,11 @@ local_attention_kernel(const AttnDev p) {
   __syncthreads();
 
   const int r0 = warp * 16;
-  const uint32_t sQU_a = smem_u32(sQU), sQV_a = smem_u32(sQV), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+  const uint32_t sQU_a = smem_u32(sQU), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
   // per-lane ldmatrix offsets (bytes)
   const uint32_t a_off = ((r0 + (lane & 15)) * LDS + (lane >> 4) * 8) * 2;             // A: rows r0.., k-halves
   const uint32_t b_off = ((((lane >> 4) & 1) * 8 + (lane & 7)) * LDS + ((lane >> 3) & 1) * 8) * 2;   // B (K-major rows)
   const uint32_t v_off = ((((lane >> 3) & 1) * 8 + (lane & 7)) * LDS + ((lane >> 4) & 1) * 8) * 2;   // B via .trans (V)
-
-  // ---- phase 1: BD[i][c] = (q_i + v) . p[c] for all relative offsets c, fp32 in smem
-  const __nv_bfloat16* pbase = p.pos + static_cast<size_t>(h) * p.n_rel * DK;
-  for (int pc = 0; pc < p.n_rel_pad / KT; ++pc) {
-    __syncthreads();
-    load_tile(sK, pbase + static_cast<size_t>(pc) * KT * DK, DK, min(KT, p.n_rel - pc * KT));
-    __syncthreads();
-    float acc[8][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-#pragma unroll
-    for (int ks = 0; ks < DK / 16; ++ks) {
-      uint32_t a[4];
-      ldsm_x4(sQV_a + a_off + ks * 32, a[0], a[1], a[2], a[3]);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(sK_a + b_off + (np * 16 * LDS) * 2 + ks * 32, b0, b1, b2, b3);
-        mma_bf16(acc[2 * np], a, b0, b1);
-        mma_bf16(acc[2 * np + 1], a, b2, b3);
-      }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int c = pc * KT + nt * 8 + 2 * t;
-      sBD[(r0 + g) * bdld + c] = acc[nt][0];
-      sBD[(r0 + g) * bdld + c + 1] = acc[nt][1];
-      sBD[(r0 + g + 8) * bdld + c] = acc[nt][2];
-      sBD[(r0 + g + 8) * bdld + c + 1] = acc[nt][3];
-    }
-  }
 
   // ---- phase 2: online softmax over the key tiles that intersect the band
   float o[16][4];
@@ -175,6 +141,9 @@ local_attention_kernel(const AttnDev p) {
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
   }
+  // BD rows of the two query rows this thread owns (skewed read: column j - i + w_left)
+  const float* bd_lo = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_lo, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
+  const float* bd_hi = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_hi, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
   const int j_first = max(0, q0 - p.w_left);
   const int j_last = min(len - 1, q0 + QT - 1 + p.w_right);
   for (int kt = j_first / KT; kt <= j_last / KT; ++kt) {
@@ -183,6 +152,18 @@ local_attention_kernel(const AttnDev p) {
     load_tile(sK, kbase + static_cast<size_t>(j0) * ld, ld, min(KT, p.T_max - j0));
     load_tile(sV, vbase + static_cast<size_t>(j0) * ld, ld, min(KT, p.T_max - j0));
     __syncthreads();
+    // positional terms for this key tile: issued before the QK^T mma chain so the L2 latency hides behind it
+    float bdv[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + nt * 8 + 2 * t + (e & 1);
+        const int rel = j - ((e < 2) ? i_lo : i_hi);
+        const bool ok = (j < len) && (rel >= -p.w_left) && (rel <= p.w_right);
+        bdv[nt][e] = ok ? __ldg(((e < 2) ? bd_lo : bd_hi) + rel + p.w_left) : 0.f;
+      }
+    }
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f; }
@@ -209,7 +190,7 @@ local_attention_kernel(const AttnDev p) {
         const int rel = j - i;
         const bool ok = (j < len) && (rel >= -p.w_left) && (rel <= p.w_right);
         float v = -INFINITY;
-        if (ok) v = (s[nt][e] + sBD[(i - q0) * bdld + rel + p.w_left]) * scale;
+        if (ok) v = (s[nt][e] + bdv[nt][e]) * scale;
         s[nt][e] = v;
         mx[e >> 1] = fmaxf(mx[e >> 1], v);
       }
@@ -316,26 +297,39 @@ global_row_attention_kernel(const AttnDev p) {
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
-  // thread c owns output dim c: sum_j p_j v[j][c]  (coalesced 256 B rows)
-  const int c = threadIdx.x;
-  float acc = 0.f;
-  for (int j = 0; j < len; ++j) acc = fmaf(gs[j], __bfloat162float(vbase[static_cast<size_t>(j) * ld + c]), acc);
-  p.out[(static_cast<size_t>(b) * p.T_max) * d + h * DK + c] = __float2bfloat16_rn(acc * inv);
+  // each warp accumulates a strided subset of the keys (lane = 4 output dims), then the warps are summed
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int j = warp; j < len; j += 4) {
+    const uint2 vv = *reinterpret_cast<const uint2*>(vbase + static_cast<size_t>(j) * ld + 4 * lane);
+    const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y);
+    const float pj = gs[j];
+    a0 = fmaf(pj, v0.x, a0); a1 = fmaf(pj, v0.y, a1); a2 = fmaf(pj, v1.x, a2); a3 = fmaf(pj, v1.y, a3);
+  }
+  __syncthreads();                                   // everyone is done reading gs
+  float4* part = reinterpret_cast<float4*>(gs);      // [4 warps][32 lanes]
+  part[warp * 32 + lane] = make_float4(a0, a1, a2, a3);
+  __syncthreads();
+  if (warp == 0) {
+    const float4 x0 = part[lane], x1 = part[32 + lane], x2 = part[64 + lane], x3 = part[96 + lane];
+    const float r0 = ((x0.x + x1.x) + (x2.x + x3.x)) * inv, r1 = ((x0.y + x1.y) + (x2.y + x3.y)) * inv;
+    const float r2 = ((x0.z + x1.z) + (x2.z + x3.z)) * inv, r3 = ((x0.w + x1.w) + (x2.w + x3.w)) * inv;
+    *reinterpret_cast<uint2*>(p.out + (static_cast<size_t>(b) * p.T_max) * d + h * DK + 4 * lane) =
+        make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
+  }
 }
 
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.dk != DK || a.n_global < 0 || a.n_global > 1) return cudaErrorInvalidValue;
   AttnDev p;
-  p.qkv = static_cast<const __nv_bfloat16*>(a.qkv); p.pos = static_cast<const __nv_bfloat16*>(a.pos);
-  p.bias_u = a.bias_u; p.bias_v = a.bias_v; p.out = static_cast<__nv_bfloat16*>(a.out); p.enc_len = a.enc_len;
+  p.qkv = static_cast<const __nv_bfloat16*>(a.qkv); p.bd = a.bd;
+  p.bias_u = a.bias_u; p.out = static_cast<__nv_bfloat16*>(a.out); p.enc_len = a.enc_len;
   p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right; p.n_global = a.n_global;
-  p.n_rel = a.w_left + a.w_right + 1;
-  p.n_rel_pad = ((p.n_rel + KT - 1) / KT) * KT;
-  const size_t smem = static_cast<size_t>(4) * QT * LDS * 2 + static_cast<size_t>(QT) * (p.n_rel_pad + 1) * 4 + QT * 4;
-  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  p.n_rel_pad = a.n_rel_pad;
+  if (a.n_rel_pad < a.w_left + a.w_right + 1) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(3) * QT * LDS * 2 + QT * 4;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(global_row_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
@@ -346,7 +340,7 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.n_global > 0) {
-    const size_t gsmem = (static_cast<size_t>(a.T_max) + 8) * sizeof(float);
+    const size_t gsmem = (static_cast<size_t>(a.T_max > 512 ? a.T_max : 512) + 8) * sizeof(float);
     if (gsmem > 200 * 1024) return cudaErrorInvalidValue;
     global_row_attention_kernel<<<dim3(a.H, a.B), 128, gsmem, stream>>>(p);
     e = cudaGetLastError();

@@ -53,6 +53,33 @@ __device__ __forceinline__ float row_dot(const __nv_bfloat16* __restrict__ wrow,
   return acc;
 }
 
+// Two rows at once: 2*NCH independent 16 B loads in flight per lane (the GEMV is bound by
+// memory-level parallelism against ~1 us of L2 latency, not by bandwidth or FMAs).
+template <int NCH>
+__device__ __forceinline__ void row_dot2(const __nv_bfloat16* __restrict__ w0, const __nv_bfloat16* __restrict__ w1,
+                                         const float* __restrict__ x, int hl, float& r0, float& r1) {
+  uint4 a[NCH], b[NCH];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) { a[i] = ldg_nc_v4(w0 + (hl + 16 * i) * 8); b[i] = ldg_nc_v4(w1 + (hl + 16 * i) * 8); }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const float4 x0 = *reinterpret_cast<const float4*>(x + (hl + 16 * i) * 8);
+    const float4 x1 = *reinterpret_cast<const float4*>(x + (hl + 16 * i) * 8 + 4);
+    s0 = fmaf(bf16_lo(a[i].x), x0.x, s0); s0 = fmaf(bf16_hi(a[i].x), x0.y, s0);
+    s0 = fmaf(bf16_lo(a[i].y), x0.z, s0); s0 = fmaf(bf16_hi(a[i].y), x0.w, s0);
+    s0 = fmaf(bf16_lo(a[i].z), x1.x, s0); s0 = fmaf(bf16_hi(a[i].z), x1.y, s0);
+    s0 = fmaf(bf16_lo(a[i].w), x1.z, s0); s0 = fmaf(bf16_hi(a[i].w), x1.w, s0);
+    s1 = fmaf(bf16_lo(b[i].x), x0.x, s1); s1 = fmaf(bf16_hi(b[i].x), x0.y, s1);
+    s1 = fmaf(bf16_lo(b[i].y), x0.z, s1); s1 = fmaf(bf16_hi(b[i].y), x0.w, s1);
+    s1 = fmaf(bf16_lo(b[i].z), x1.x, s1); s1 = fmaf(bf16_hi(b[i].z), x1.y, s1);
+    s1 = fmaf(bf16_lo(b[i].w), x1.z, s1); s1 = fmaf(bf16_hi(b[i].w), x1.w, s1);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  r0 = s0; r1 = s1;
+}
+
 template <int NCH_J, int NCH_L, int NCH_P>
 __global__ void __launch_bounds__(kDecThreads, 1)
 rnnt_greedy_kernel(const DecodeDev p) {
@@ -92,13 +119,17 @@ rnnt_greedy_kernel(const DecodeDev p) {
   // One LSTM step on s_x[xb] (embed part already filled) followed by pred_proj; leaves h in s_x[xb^1].
   auto lstm_and_pred = [&]() {
     const float* x = s_x + xb * 2 * Hp;
-    for (int base = 0; base < 4 * us; base += kDecUnits) {          // warp-uniform trip count
-      const bool ok = base + unit < 4 * us;
-      const int r = ok ? base + unit : 4 * us - 1;
-      const int gate = r / us, u = r % us;
-      const int row = gate * Hp + u_begin + u;
-      const float v = row_dot<NCH_L>(p.w_lstm + static_cast<size_t>(row) * (2 * Hp), x, hl);
-      if (ok && hl == 0) s_gate[gate * us + u] = v + __ldg(p.b_lstm + row);
+    for (int base = 0; base < 4 * us; base += 2 * kDecUnits) {      // warp-uniform trip count, two rows per pass
+      const int ra = base + unit, rb = base + kDecUnits + unit;
+      const bool oka = ra < 4 * us, okb = rb < 4 * us;
+      const int qa = oka ? ra : 4 * us - 1, qb = okb ? rb : 4 * us - 1;
+      const int rowa = (qa / us) * Hp + u_begin + qa % us, rowb = (qb / us) * Hp + u_begin + qb % us;
+      float va, vb;
+      row_dot2<NCH_L>(p.w_lstm + static_cast<size_t>(rowa) * (2 * Hp), p.w_lstm + static_cast<size_t>(rowb) * (2 * Hp), x, hl, va, vb);
+      if (hl == 0) {
+        if (oka) s_gate[qa] = va + __ldg(p.b_lstm + rowa);
+        if (okb) s_gate[qb] = vb + __ldg(p.b_lstm + rowb);
+      }
     }
     __syncthreads();
     for (int u = tid; u < us; u += kDecThreads) {
@@ -136,11 +167,15 @@ rnnt_greedy_kernel(const DecodeDev p) {
     __syncthreads();
     // ---- partial argmax over this CTA's vocabulary rows
     float best = -INFINITY; int best_i = 0x7fffffff;
-    for (int base = j_begin; base < j_end; base += kDecUnits) {      // warp-uniform trip count
-      const bool ok = base + unit < j_end;
-      const int row = ok ? base + unit : j_end - 1;
-      const float v = row_dot<NCH_J>(p.w_out + static_cast<size_t>(row) * Hj, s_g, hl) + __ldg(p.b_out + row);
-      if (ok && v > best) { best = v; best_i = row; }   // rows visited in increasing order: first max wins
+    for (int base = j_begin; base < j_end; base += 2 * kDecUnits) {  // warp-uniform trip count, two rows per pass
+      const int ra = base + unit, rb = base + kDecUnits + unit;
+      const bool oka = ra < j_end, okb = rb < j_end;
+      const int rowa = oka ? ra : j_end - 1, rowb = okb ? rb : j_end - 1;
+      float va, vb;
+      row_dot2<NCH_J>(p.w_out + static_cast<size_t>(rowa) * Hj, p.w_out + static_cast<size_t>(rowb) * Hj, s_g, hl, va, vb);
+      va += __ldg(p.b_out + rowa); vb += __ldg(p.b_out + rowb);
+      if (oka && va > best) { best = va; best_i = rowa; }   // rows visited in increasing order: first max wins
+      if (okb && vb > best) { best = vb; best_i = rowb; }
     }
     if (hl == 0) { s_uval[unit] = best; s_uidx[unit] = best_i; }
     __syncthreads();

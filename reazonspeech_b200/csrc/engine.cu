@@ -27,7 +27,7 @@ struct FeTablesHost {   // must match rs::FeTables in frontend.cu
 struct LayerW {
   const float *ln_ff1_g, *ln_ff1_b, *ff1_b1, *ff1_b2;
   const void *ff1_w1, *ff1_w2;
-  const float *ln_att_g, *ln_att_b, *bqkv, *att_u, *att_v, *bo;
+  const float *ln_att_g, *ln_att_b, *bqkv, *att_u, *att_bdbias, *bo;
   const void *wqkv, *att_pos, *wo;
   const float *ln_conv_g, *ln_conv_b, *pw1_b, *dw_w, *dw_shift, *pw2_b;
   const void *pw1_w, *pw2_w;
@@ -38,7 +38,8 @@ struct LayerW {
 
 struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   int B, L_max, F_max, T1, F1, T2, F2, T3, F3, M;
-  size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, enc, encp;
+  size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, enc, encp;
+  int n_rel_pad;
   size_t tokens, frames, ntok, total;
 };
 
@@ -115,6 +116,8 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.hbuf = take(static_cast<size_t>(p.M) * wide * 2);
   p.abuf = take(static_cast<size_t>(p.M) * d * 2);
   p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
+  p.n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32;
+  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * p.n_rel_pad * 4);
   p.enc = take(static_cast<size_t>(p.M) * d * 4);
   p.encp = take(static_cast<size_t>(p.M) * c.joint_hidden * 4);
   p.tokens = take(static_cast<size_t>(B) * U_max * 4);
@@ -148,7 +151,7 @@ int need(rs_engine* e, const char* name, int dtype, int64_t numel, const void** 
 int bind_weights(rs_engine* e) {
   const rs_model_config& c = e->cfg;
   const int64_t d = c.d_model, ff = c.d_ff, C = c.sub_channels, H = c.n_heads, dk = d / H;
-  const int64_t n_rel = c.att_left + c.att_right + 1, k = c.conv_kernel;
+  const int64_t n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32, k = c.conv_kernel;
   const int64_t F3 = conv_len(conv_len(conv_len(c.n_mels)));
   NEED(e->fe.window, "fe.window", RS_F32, c.n_fft);
   NEED(e->fe.tw256, "fe.tw256", RS_F32, c.n_fft);
@@ -172,8 +175,8 @@ int bind_weights(rs_engine* e) {
     NEED(L.ff1_w2, N("ff1.w2"), RS_BF16, d * ff); NEED(L.ff1_b2, N("ff1.b2"), RS_F32, d);
     NEED(L.ln_att_g, N("ln_att.g"), RS_F32, d); NEED(L.ln_att_b, N("ln_att.b"), RS_F32, d);
     NEED(L.wqkv, N("att.wqkv"), RS_BF16, 3 * d * d); NEED(L.bqkv, N("att.bqkv"), RS_F32, 3 * d);
-    NEED(L.att_pos, N("att.pos"), RS_BF16, H * n_rel * dk);
-    NEED(L.att_u, N("att.u"), RS_F32, d); NEED(L.att_v, N("att.v"), RS_F32, d);
+    NEED(L.att_pos, N("att.pos"), RS_BF16, H * n_rel_pad * dk);
+    NEED(L.att_u, N("att.u"), RS_F32, d); NEED(L.att_bdbias, N("att.bdbias"), RS_F32, H * n_rel_pad);
     NEED(L.wo, N("att.wo"), RS_BF16, d * d); NEED(L.bo, N("att.bo"), RS_F32, d);
     NEED(L.ln_conv_g, N("ln_conv.g"), RS_F32, d); NEED(L.ln_conv_b, N("ln_conv.b"), RS_F32, d);
     NEED(L.pw1_w, N("conv.pw1.w"), RS_BF16, 2 * d * d); NEED(L.pw1_b, N("conv.pw1.b"), RS_F32, 2 * d);
@@ -201,9 +204,16 @@ __global__ void enc_len_kernel(const int32_t* __restrict__ mel_len, int32_t* __r
   enc_len[b] = n;
 }
 
+int gemm_args(rs_engine* e, const rs::GemmArgs& g, cudaStream_t s);
+
 int gemm(rs_engine* e, const void* a, const void* w, const float* bias, const float* resid, void* out, int M, int N,
          int K, int epi, float alpha, cudaStream_t s) {
   rs::GemmArgs g{a, w, bias, resid, out, M, N, K, epi, alpha};
+  return gemm_args(e, g, s);
+}
+
+int gemm_args(rs_engine* e, const rs::GemmArgs& g, cudaStream_t s) {
+  const int M = g.M, N = g.N, K = g.K;
   char msg[256] = "";
   bool timed = false;
   if (e->gemm_timing) {
@@ -220,7 +230,7 @@ int gemm(rs_engine* e, const void* a, const void* w, const float* bias, const fl
   if (timed) {
     cudaEventRecord(e->gemm_ev[e->gemm_ev_used + 1], s);
     e->gemm_ev_used += 2;
-    e->gemm_flops += 2.0 * M * static_cast<double>(N) * K;
+    e->gemm_flops += 2.0 * M * static_cast<double>(N) * K * (g.n_batch > 0 ? g.n_batch : 1);
   }
   e->launches++;
   return RS_OK;
@@ -284,7 +294,13 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     RS_TRY(gemm(e, hb, L.ff1_w2, L.ff1_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
-    rs::AttnArgs aa{hb, L.att_pos, L.att_u, L.att_v, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
+    {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
+      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F32, 1.f};
+      g.lda = 3 * d; g.ldo = c.n_heads * p.n_rel_pad; g.n_batch = c.n_heads;
+      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad;
+      RS_TRY(gemm_args(e, g, s));
+    }
+    rs::AttnArgs aa{hb, at<float>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
     RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
     RS_TRY(gemm(e, ab, L.wo, L.bo, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
     RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);

@@ -34,6 +34,10 @@ struct GemmDev {
   int M, N, K;
   int epilogue;
   float alpha;
+  int ldo;              // output (and residual) row stride in elements
+  // optional batching along columns (one launch for all attention heads): batch b reads A columns
+  // [b*a_col_stride, +K), W rows [b*w_row_stride, +N), bias + b*bias_stride, writes columns + b*out_col_stride
+  int n_batch, a_col_stride, w_row_stride, bias_stride, out_col_stride;
 };
 
 template <int BN>
@@ -65,7 +69,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const int lane = lane_id();
   const int num_m = (p.M + BM - 1) / BM;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  const int tiles_per_batch = num_m * num_n;
+  const int num_tiles = tiles_per_batch * p.n_batch;
   const int num_k = p.K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -87,12 +92,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        const int bt = tile / tiles_per_batch, tl = tile % tiles_per_batch;
+        const int m0 = (tl / num_n) * BM, n0 = (tl % num_n) * BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-          tma_load_2d(smem_a(stage), &tm_a, kb * BK, m0, full_bar(stage));
-          tma_load_2d(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
+          tma_load_2d(smem_a(stage), &tm_a, bt * p.a_col_stride + kb * BK, m0, full_bar(stage));
+          tma_load_2d(smem_b(stage), &tm_b, kb * BK, bt * p.w_row_stride + n0, full_bar(stage));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -133,8 +139,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      const int bt = tile / tiles_per_batch, tl = tile % tiles_per_batch;
+      const int m0 = (tl / num_n) * BM, n0 = (tl % num_n) * BN;
       const int row = m0 + q * 32 + lane;
+      const size_t orow = static_cast<size_t>(row) * p.ldo + bt * p.out_col_stride;
       const bool row_ok = row < p.M;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -149,7 +157,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(b4 + j);
@@ -168,7 +176,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
             }
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.N + col0);
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
@@ -180,7 +188,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             float g[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) g[j] = v[j] * sigmoidf_fast(v[16 + j]);
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * (p.N / 2) + col0 / 2);
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0 / 2);
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               o[j] = make_uint4(pack_bf16x2(g[8 * j], g[8 * j + 1]), pack_bf16x2(g[8 * j + 2], g[8 * j + 3]),
@@ -188,8 +196,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             break;
           }
           case RS_EPI_RESID_F32: {
-            const float4* rs4 = reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.N + col0);
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.N + col0);
+            const float4* rs4 = reinterpret_cast<const float4*>(p.resid + orow + col0);
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
             float4 rr[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
@@ -200,7 +208,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             break;
           }
           default: {  // RS_EPI_BIAS_F32
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.N + col0);
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               o[j] = make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
@@ -242,11 +250,11 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 row-major [rows, cols] -> 2-D map with a (box_rows x 64) box and 128B swizzle.
-static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, char* err) {
+static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, char* err) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { snprintf(err, 256, "cuTensorMapEncodeTiled entry point unavailable"); return false; }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
+  cuuint64_t strides[1] = {ld * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -266,10 +274,15 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
     attr_set = true;
   }
   CUtensorMap tm_a, tm_b;
-  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, BM, err)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, BN, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha};
-  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+  const int nb = g.n_batch > 0 ? g.n_batch : 1;
+  const int lda = g.lda > 0 ? g.lda : g.K;
+  const int a_cols = nb > 1 ? (nb - 1) * g.a_col_stride + g.K : g.K;
+  const int w_rows = nb > 1 ? (nb - 1) * g.w_row_stride + g.N : g.N;
+  const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
+  if (!make_tmap_bf16(&tm_a, g.a, g.M, a_cols, lda, BM, err)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tm_b, g.w, w_rows, g.K, g.K, BN, err)) return cudaErrorInvalidValue;
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride};
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();

@@ -14,6 +14,9 @@ struct GemmArgs {
   int M, N, K;
   int epilogue;        // rs_epilogue
   float alpha;
+  // optional: A row stride (elements, default K), output row stride (default N), column batching
+  int lda = 0, ldo = 0;
+  int n_batch = 1, a_col_stride = 0, w_row_stride = 0, bias_stride = 0, out_col_stride = 0;
 };
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
@@ -46,9 +49,9 @@ cudaError_t launch_conv_dw(const void* u, void* out, const float* w /*[k,d]*/, c
 
 struct AttnArgs {
   const void* qkv;       // bf16 [B*T_max, 3*d]: q | k | v
-  const void* pos;       // bf16 [H, n_rel, dk]  (linear_pos of the relative table)
+  const float* bd;       // f32 [B*T_max, H, n_rel_pad]: (q + v_bias) . p[c], from the batched tcgen05 GEMM
+  int n_rel_pad;
   const float* bias_u;   // f32 [H, dk]
-  const float* bias_v;   // f32 [H, dk]
   void* out;             // bf16 [B*T_max, d]
   const int32_t* enc_len;
   int B, T_max, H, dk, w_left, w_right, n_global;

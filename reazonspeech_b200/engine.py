@@ -167,8 +167,13 @@ def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
         out[o + "att.wqkv"] = bf(torch.cat([sd[a + "linear_q.weight"], sd[a + "linear_k.weight"], sd[a + "linear_v.weight"]], 0))
         out[o + "att.bqkv"] = f32(torch.cat([sd[a + "linear_q.bias"], sd[a + "linear_k.bias"], sd[a + "linear_v.bias"]], 0))
         pos = torch.nn.functional.linear(table, sd[a + "linear_pos.weight"])          # input independent: once at load
-        out[o + "att.pos"] = bf(pos.view(cfg.n_rel, H, dk).permute(1, 0, 2))
-        out[o + "att.u"] = f32(sd[a + "pos_bias_u"].reshape(-1)); out[o + "att.v"] = f32(sd[a + "pos_bias_v"].reshape(-1))
+        n_rel_pad = (cfg.n_rel + 31) // 32 * 32
+        pos_h = torch.zeros(H, n_rel_pad, dk)
+        pos_h[:, : cfg.n_rel] = pos.view(cfg.n_rel, H, dk).permute(1, 0, 2)
+        out[o + "att.pos"] = bf(pos_h)                                                 # B operand of the batched BD GEMM
+        # (q + v).p = q.p + v.p: the second term is input independent -> the GEMM's bias
+        out[o + "att.bdbias"] = f32((out[o + "att.pos"].float() * sd[a + "pos_bias_v"][:, None, :]).sum(-1).reshape(-1))
+        out[o + "att.u"] = f32(sd[a + "pos_bias_u"].reshape(-1))
         out[o + "att.wo"] = bf(sd[a + "linear_out.weight"]); out[o + "att.bo"] = f32(sd[a + "linear_out.bias"])
         c = p + "conv."
         out[o + "conv.pw1.w"] = bf(sd[c + "pointwise_conv1.weight"][:, :, 0][glu_idx])

@@ -1,0 +1,115 @@
+"""Produce reazonspeech_b200/data/synth_calib_<config>_seed<seed>.json for the seeded synthetic
+checkpoint (see weights.random_state_dict): (1) the time-average of the encoder output on a
+calibration clip set -> joint.enc bias that cancels it, (2) a power-of-two joint.enc gain bringing
+the time-varying part of enc_proj to about unit standard deviation, (3) the blank-bias shift giving
+a greedy emission rate of about one token per three encoder frames.  A deterministic function of the
+seeded weights; it shapes the decode load of the benchmark only and is not part of the engine.
+
+    python scripts/calibrate_synthetic.py --config tiny     # CPU, through the oracle
+    python scripts/calibrate_synthetic.py --config full     # on a B200, through the engine
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from reazonspeech_b200.config import ModelConfig
+from reazonspeech_b200.synth import synth_clip
+from reazonspeech_b200.weights import _bf16_round, apply_calibration, calibration_path, random_state_dict
+
+TARGET = 1.0 / 3.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="tiny", choices=["tiny", "full"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    cfg = ModelConfig.tiny() if a.config == "tiny" else ModelConfig()
+    sd = random_state_dict(cfg, a.seed, calibrate=False)
+    secs = (6.0, 9.0, 12.0, 7.0) if a.config == "tiny" else (30.0, 30.0, 30.0, 30.0)
+    waves = [np.pad(synth_clip(100 + i, s), 8000) for i, s in enumerate(secs)]
+    n_frames = [cfg.enc_frames(len(w)) for w in waves]
+    W, b0 = sd["joint.enc.weight"].clone(), sd["joint.enc.bias"].clone()
+    bout0 = sd["joint.joint_net.2.bias"].clone()
+
+    if a.config == "tiny":
+        from oracle import nemo_restated as O
+        torch.set_num_threads(1)
+        with torch.no_grad():
+            encs = [O.encoder(O.log_mel(torch.from_numpy(w), cfg), sd, cfg) for w in waves]
+        valid = torch.cat(encs)
+        eng = None
+    else:
+        from reazonspeech_b200.engine import Engine
+        eng = Engine(cfg, sd, "cuda:0")
+        L = max(len(w) for w in waves)
+        x = torch.zeros(len(waves), L)
+        for i, w in enumerate(waves):
+            x[i, : len(w)] = torch.from_numpy(w)
+        lens = torch.tensor([len(w) for w in waves], dtype=torch.int32).cuda()
+        x = x.cuda()
+        mel, mel_len = eng.log_mel(x, lens)
+        enc, enc_len = eng.encode(mel, mel_len)
+        torch.cuda.synchronize()
+        enc = enc.cpu()
+        valid = torch.cat([enc[i, : n_frames[i]] for i in range(len(waves))])
+
+    dc = valid.mean(0)
+    ac = valid - dc
+    ep_ac = ac @ W.T
+    print(f"enc: |dc| rms {dc.pow(2).mean().sqrt():.3f}, ac rms {ac.pow(2).mean().sqrt():.3f}; enc_proj ac std {ep_ac.std():.4f}")
+    k = int(round(math.log2(1.0 / float(ep_ac.std()))))
+    gain = 2.0 ** k
+    bias = _bf16_round(b0 - gain * (W @ dc))
+    calib = {"joint_enc_gain_log2": k, "joint_enc_bias": bias.tolist(), "blank_shift": 0.0}
+
+    def install(shift):
+        calib["blank_shift"] = shift
+        s2 = dict(sd)
+        s2["joint.enc.weight"], s2["joint.enc.bias"], s2["joint.joint_net.2.bias"] = W.clone(), b0.clone(), bout0.clone()
+        apply_calibration(s2, cfg, calib)
+        return s2
+
+    if eng is None:
+        def rate(shift):
+            s2 = install(shift)
+            return sum(len(O.rnnt_greedy(e, s2, cfg).tokens) for e in encs) / sum(n_frames)
+    else:
+        def rate(shift):
+            s2 = install(shift)
+            eng.weights["joint.enc.w"].copy_(s2["joint.enc.weight"].to(torch.bfloat16))
+            eng.weights["joint.enc.b"].copy_(s2["joint.enc.bias"])
+            eng.weights["joint.out.b"].copy_(s2["joint.joint_net.2.bias"])
+            _, _, ntok = eng.transcribe_device(x, lens)
+            torch.cuda.synchronize()
+            return float(ntok.sum()) / sum(n_frames)
+
+    curve = {s: rate(s) for s in np.arange(-2.0, 8.01, 0.5)}
+    print("rate curve:", {float(k2): round(v, 3) for k2, v in curve.items()})
+    lo, hi = -4.0, 10.0
+    for _ in range(20):
+        mid = 0.5 * (lo + hi)
+        if rate(mid) > TARGET:
+            lo = mid
+        else:
+            hi = mid
+    cands = [float(_bf16_round(torch.tensor(v))) for v in (lo, hi, 0.5 * (lo + hi))]
+    best = min(cands, key=lambda v: abs(rate(v) - TARGET))
+    calib["blank_shift"] = best
+    calib["rate"] = rate(best)
+    calib["note"] = f"config={a.config} seed={a.seed}; clips={list(secs)} s; produced by scripts/calibrate_synthetic.py"
+    out = a.out or calibration_path(cfg, a.seed)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    json.dump(calib, open(out, "w"))
+    print(json.dumps({k2: v for k2, v in calib.items() if k2 != "joint_enc_bias"}), "->", out)
+
+
+if __name__ == "__main__":
+    main()
