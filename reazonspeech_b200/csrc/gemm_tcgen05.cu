@@ -12,6 +12,7 @@
 // model.transcribe (pkg/nemo-asr/src/transcribe.py:48-53).
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/rs_engine.h"
@@ -48,6 +49,73 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN;                       // power of two >= 32
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// Fused epilogue of one 32-column chunk of one accumulator row: bias, activation / GLU / residual, store.
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], bool row_ok, size_t orow, int col0, int bt) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (row_ok) {
+        switch (p.epilogue) {
+          case RS_EPI_BIAS_BF16:
+          case RS_EPI_BIAS_RELU_BF16:
+          case RS_EPI_BIAS_SWISH_BF16: {
+            if (p.epilogue == RS_EPI_BIAS_RELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+            } else if (p.epilogue == RS_EPI_BIAS_SWISH_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
+            }
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            break;
+          }
+          case RS_EPI_BIAS_GLU_BF16: {
+            // columns [0,16) of the chunk are values, [16,32) the matching gates (weights interleaved at pack time)
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = v[j] * sigmoidf_fast(v[16 + j]);
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0 / 2);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              o[j] = make_uint4(pack_bf16x2(g[8 * j], g[8 * j + 1]), pack_bf16x2(g[8 * j + 2], g[8 * j + 3]),
+                                pack_bf16x2(g[8 * j + 4], g[8 * j + 5]), pack_bf16x2(g[8 * j + 6], g[8 * j + 7]));
+            break;
+          }
+          case RS_EPI_RESID_F32: {
+            const float4* rs4 = reinterpret_cast<const float4*>(p.resid + orow + col0);
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
+            float4 rr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(rr[j].x + p.alpha * v[4 * j], rr[j].y + p.alpha * v[4 * j + 1],
+                                 rr[j].z + p.alpha * v[4 * j + 2], rr[j].w + p.alpha * v[4 * j + 3]);
+            break;
+          }
+          default: {  // RS_EPI_BIAS_F32
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
+            break;
+          }
+        }
+        }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -153,69 +221,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if (row_ok) {
-        switch (p.epilogue) {
-          case RS_EPI_BIAS_BF16:
-          case RS_EPI_BIAS_RELU_BF16:
-          case RS_EPI_BIAS_SWISH_BF16: {
-            if (p.epilogue == RS_EPI_BIAS_RELU_BF16) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-            } else if (p.epilogue == RS_EPI_BIAS_SWISH_BF16) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
-            }
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            break;
-          }
-          case RS_EPI_BIAS_GLU_BF16: {
-            // columns [0,16) of the chunk are values, [16,32) the matching gates (weights interleaved at pack time)
-            float g[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = v[j] * sigmoidf_fast(v[16 + j]);
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0 / 2);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              o[j] = make_uint4(pack_bf16x2(g[8 * j], g[8 * j + 1]), pack_bf16x2(g[8 * j + 2], g[8 * j + 3]),
-                                pack_bf16x2(g[8 * j + 4], g[8 * j + 5]), pack_bf16x2(g[8 * j + 6], g[8 * j + 7]));
-            break;
-          }
-          case RS_EPI_RESID_F32: {
-            const float4* rs4 = reinterpret_cast<const float4*>(p.resid + orow + col0);
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
-            float4 rr[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = make_float4(rr[j].x + p.alpha * v[4 * j], rr[j].y + p.alpha * v[4 * j + 1],
-                                 rr[j].z + p.alpha * v[4 * j + 2], rr[j].w + p.alpha * v[4 * j + 3]);
-            break;
-          }
-          default: {  // RS_EPI_BIAS_F32
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
-            break;
-          }
-        }
-        }
+        epilogue_store(p, r, row_ok, orow, col0, bt);
         __syncwarp();                                        // reconverge before the next .aligned tcgen05.ld
       }
       tcgen05_fence_before();
@@ -229,6 +235,147 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------- 2-CTA variant
+// Cluster of two CTAs (an SM pair) computes a 256 x BN tile with tcgen05.mma.cta_group::2: each CTA
+// stages its own 128 rows of A and HALF of the W tile, the leader's single thread issues UMMA
+// 256 x BN x 16 reading both halves.  Per CTA and k-block that is 32 KB of L2->smem traffic for the
+// MACs the 1-CTA kernel feeds with 48 KB, which matters because at 128 x 256 tiles the 1-CTA kernel
+// is bound by L2 bandwidth (87 FLOP/B against ~12 TB/s), not by the tensor pipe; it also leaves room
+// for a 6-deep ring.  Barriers: full[] on the leader (both producers arrive, both TMAs credit it),
+// empty[] / tmem_full[] per CTA (commit multicast to both), tmem_empty[] on the leader.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBHalfBytes;
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+
+  const int warp = warp_id_uniform();
+  const int lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);          // 256-row cluster tiles
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;
+  const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  cluster_sync_all();                                        // peer barriers exist before any remote arrive / 2-SM alloc
+  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cid; tile < num_tiles; tile += ncl) {
+        const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
+        const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          tma_load_2d_2sm(smem_a(stage), &tm_a, kb * BK, m0, full_bar(stage));
+          tma_load_2d_2sm(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(full_bar(stage), 0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_a(stage));
+          const uint64_t db = umma_desc_k_sw128(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own TMEM half)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    int it = 0;
+    for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (tile % num_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      const size_t orow = static_cast<size_t>(row) * p.ldo;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+        const int col0 = n0 + chunk * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+        tmem_ld_wait();
+        epilogue_store(p, r, row_ok, orow, col0, 0);
+        __syncwarp();
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                                        // both CTAs done with TMEM and with each other's barriers
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -290,7 +437,37 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   return e;
 }
 
+template <int BN>
+static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  CUtensorMap tm_a, tm_b;
+  const int lda = g.lda > 0 ? g.lda : g.K;
+  const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
+  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0};
+  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+  int clusters = num_sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  gemm_bf16_tn_2cta_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) snprintf(err, 256, "gemm 2cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
+  return e;
+}
+
+static int g_gemm_mode = -1;   // RS_GEMM_MODE: 0 = 1-CTA kernels only, 1 (default) = 2-CTA pairs where the shape allows
+
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  if (g_gemm_mode < 0) {
+    const char* m = getenv("RS_GEMM_MODE");
+    g_gemm_mode = m ? atoi(m) : 1;
+  }
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.K % BK != 0 || g.N % 32 != 0) {
     snprintf(err, 256, "gemm shape unsupported: M=%d N=%d K=%d (need K%%64==0, N%%32==0)", g.M, g.N, g.K);
     return cudaErrorInvalidValue;
@@ -300,6 +477,8 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
+  if (g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0 && g.M >= 1024)
+    return launch_2cta<256>(g, num_sms, stream, err);
   // Widest tile that still yields at least ~one wave of tiles; narrow N uses a narrower tile.
   if (g.N >= 256 && g.N % 256 == 0) return launch_bn<256>(g, num_sms, stream, err);
   if (g.N >= 128 && g.N % 128 == 0) return launch_bn<128>(g, num_sms, stream, err);

@@ -93,15 +93,16 @@ def main():
 
     curve = {s: rate(s) for s in np.arange(-2.0, 8.01, 0.5)}
     print("rate curve:", {float(k2): round(v, 3) for k2, v in curve.items()})
-    lo, hi = -4.0, 10.0
-    for _ in range(20):
-        mid = 0.5 * (lo + hi)
-        if rate(mid) > TARGET:
-            lo = mid
-        else:
-            hi = mid
-    cands = [float(_bf16_round(torch.tensor(v))) for v in (lo, hi, 0.5 * (lo + hi))]
-    best = min(cands, key=lambda v: abs(rate(v) - TARGET))
+    # the blank bias is stored in bf16: scan every representable value between the coarse bracket
+    xs = sorted(curve)
+    lo = max([s for s in xs if curve[s] > TARGET], default=xs[0])
+    hi = min([s for s in xs if s > lo and curve[s] <= TARGET], default=xs[-1])
+    base = float(bout0[cfg.blank])
+    vals = sorted({float(_bf16_round(torch.tensor(base + v))) - base for v in np.arange(lo, hi + 1e-6, 1.0 / 128)})
+    fine = {v: rate(v) for v in vals}
+    print("fine scan:", {round(k2, 4): round(v, 3) for k2, v in fine.items()})
+    ok = {k2: v for k2, v in fine.items() if v > 0}
+    best = min(ok, key=lambda k2: abs(math.log(ok[k2] / TARGET)))
     calib["blank_shift"] = best
     calib["rate"] = rate(best)
     calib["note"] = f"config={a.config} seed={a.seed}; clips={list(secs)} s; produced by scripts/calibrate_synthetic.py"

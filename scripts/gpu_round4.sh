@@ -6,3 +6,4 @@ echo "=== calibrate full"; timeout -k 10 900 python scripts/calibrate_synthetic.
 cp gpurun_out/synth_calib_full.json reazonspeech_b200/data/synth_calib_24x1024_v3000_p640_j640_seed0.json
 echo "=== full-model tests"; timeout -k 10 1500 python -m pytest tests/test_gpu_full_model.py -m gpu -q -s -x -p no:cacheprovider > gpurun_out/full_model.log 2>&1; echo "exit $?"; tail -n 12 gpurun_out/full_model.log
 echo "=== bench"; timeout -k 10 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
+echo "=== launch list"; timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 460 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "exit $?"

@@ -45,18 +45,10 @@ def test_full_model_encoder_and_tokens(full):
         T = ref.shape[0]
         rel = ((enc[i, :T].cpu().double() - ref.double()).norm() / ref.double().norm()).item()
         n = int(ntok[i])
-        got = tokens[i, :n].cpu().tolist()
         print(f"utt{i}: T={T} enc rel-L2 {rel:.3e}; {n} tokens (oracle {len(emu.tokens)}), oracle min margin {min(emu.margins):.3e}")
         assert int(enc_len[i]) == T and rel < 2e-2
-        if got != emu.tokens:
-            div = next((j for j, (a, b) in enumerate(zip(got, emu.tokens)) if a != b), min(len(got), len(emu.tokens)))
-            emitted, margin = 0, None
-            for j, k in enumerate(emu.decisions):
-                if emitted == div:
-                    margin = min(emu.margins[max(0, j - 1): j + 2]); break
-                emitted += k != cfg.blank
-            print(f"utt{i}: diverges at token {div}, oracle margin there {margin}")
-            assert margin is not None and margin < 5e-2
+        from test_gpu_kernels import check_tokens_against_oracle
+        check_tokens_against_oracle(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), emu, T, cfg, 5e-2, f"utt{i}")
 
 
 def test_full_batch_properties(full):
