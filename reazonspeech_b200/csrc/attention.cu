@@ -41,6 +41,19 @@ struct AttnDev {
   int T_max, H, w_left, w_right, n_global, n_rel_pad;
 };
 
+// Asynchronous copy (cp.async, 16 B, L2-only) of 64 rows x 128 bf16 into padded smem; rows >= valid are zero-filled.
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, size_t ld, int valid_rows) {
+  for (int id = threadIdx.x; id < 64 * 16; id += blockDim.x) {
+    const int r = id >> 4, c = (id & 15) * 8;
+    const bool ok = r < valid_rows;
+    const __nv_bfloat16* src = g + static_cast<size_t>(ok ? r : 0) * ld + c;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(s + r * LDS + c)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // Copy 64 rows x 128 bf16 (row stride `ld` elements, rows >= valid read as zero) into padded smem.
 __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16* g, size_t ld, int valid_rows) {
   for (int id = threadIdx.x; id < 64 * 16; id += blockDim.x) {
@@ -51,13 +64,14 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
   }
 }
 
-__global__ void __launch_bounds__(128, 3)
+constexpr int kKvStages = 2;      // K/V tile ring (cp.async prefetch of the next key tile during the current one)
+
+__global__ void __launch_bounds__(128, 2)
 local_attention_kernel(const AttnDev p) {
   extern __shared__ __align__(16) uint8_t at_smem[];
   __nv_bfloat16* sQU = reinterpret_cast<__nv_bfloat16*>(at_smem);
-  __nv_bfloat16* sK = sQU + QT * LDS;
-  __nv_bfloat16* sV = sK + KT * LDS;
-  float* sG = reinterpret_cast<float*>(sV + KT * LDS);   // [QT] global-key score (already scaled)
+  __nv_bfloat16* sKV = sQU + QT * LDS;                    // [stages][K tile | V tile]
+  float* sG = reinterpret_cast<float*>(sKV + kKvStages * 2 * KT * LDS);   // [QT] global-key score (already scaled)
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const int len = p.enc_len[b];
@@ -117,7 +131,7 @@ local_attention_kernel(const AttnDev p) {
   __syncthreads();
 
   const int r0 = warp * 16;
-  const uint32_t sQU_a = smem_u32(sQU), sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+  const uint32_t sQU_a = smem_u32(sQU), sKV_a = smem_u32(sKV);
   // per-lane ldmatrix offsets (bytes)
   const uint32_t a_off = ((r0 + (lane & 15)) * LDS + (lane >> 4) * 8) * 2;             // A: rows r0.., k-halves
   const uint32_t b_off = ((((lane >> 4) & 1) * 8 + (lane & 7)) * LDS + ((lane >> 3) & 1) * 8) * 2;   // B (K-major rows)
@@ -146,12 +160,21 @@ local_attention_kernel(const AttnDev p) {
   const float* bd_hi = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_hi, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
   const int j_first = max(0, q0 - p.w_left);
   const int j_last = min(len - 1, q0 + QT - 1 + p.w_right);
-  for (int kt = j_first / KT; kt <= j_last / KT; ++kt) {
+  const int kt_first = j_first / KT, kt_last = j_last / KT;
+  auto prefetch = [&](int kt, int st) {
+    const int jj = kt * KT;
+    __nv_bfloat16* dst = sKV + st * 2 * KT * LDS;
+    load_tile_async(dst, kbase + static_cast<size_t>(jj) * ld, ld, min(KT, p.T_max - jj));
+    load_tile_async(dst + KT * LDS, vbase + static_cast<size_t>(jj) * ld, ld, min(KT, p.T_max - jj));
+    cp_async_commit();
+  };
+  prefetch(kt_first, 0);
+  for (int kt = kt_first; kt <= kt_last; ++kt) {
     const int j0 = kt * KT;
+    const int st = (kt - kt_first) & 1;
+    if (kt < kt_last) { prefetch(kt + 1, st ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    load_tile(sK, kbase + static_cast<size_t>(j0) * ld, ld, min(KT, p.T_max - j0));
-    load_tile(sV, vbase + static_cast<size_t>(j0) * ld, ld, min(KT, p.T_max - j0));
-    __syncthreads();
+    const uint32_t sK_a = sKV_a + st * 2 * KT * LDS * 2, sV_a = sK_a + KT * LDS * 2;
     // positional terms for this key tile: issued before the QK^T mma chain so the L2 latency hides behind it
     float bdv[8][4];
 #pragma unroll
@@ -243,6 +266,7 @@ local_attention_kernel(const AttnDev p) {
         mma_bf16(o[2 * np + 1], a, b2, b3);
       }
     }
+    __syncthreads();                                   // all warps done with this stage before it is refilled
   }
   // ---- write back
 #pragma unroll
@@ -262,9 +286,9 @@ local_attention_kernel(const AttnDev p) {
 
 // Row(s) of the global token(s): full attention softmax_j((q_g / sqrt(dk)) . k_j) v_j, no positional
 // terms.  grid (H, B), 128 threads; scores staged in shared memory (T_max floats).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 global_row_attention_kernel(const AttnDev p) {
-  extern __shared__ float gs[];                      // [T_max] scores, then [4] reduction scratch
+  extern __shared__ __align__(16) float gs[];        // [T_max] scores, then [8] reduction scratch
   const int h = blockIdx.x, b = blockIdx.y;
   const int len = p.enc_len[b];
   if (len <= 0) return;
@@ -279,40 +303,67 @@ global_row_attention_kernel(const AttnDev p) {
   const float2 q0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * lane));
   const float2 q1 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * lane + 2));
   float mx = -INFINITY;
-  for (int j = warp; j < len; j += 4) {
-    const uint2 kk = *reinterpret_cast<const uint2*>(kbase + static_cast<size_t>(j) * ld + 4 * lane);
-    const float2 k0 = unpack_bf16x2(kk.x), k1 = unpack_bf16x2(kk.y);
-    float dot = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
-    dot = warp_sum(dot) * scale;
-    if (lane == 0) gs[j] = dot;
-    mx = fmaxf(mx, dot);
+  constexpr int NW = 8;                               // warps per CTA
+  for (int j0 = warp; j0 < len; j0 += 4 * NW) {       // four keys in flight per warp
+    uint2 kk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = min(j0 + u * NW, len - 1);
+      kk[u] = *reinterpret_cast<const uint2*>(kbase + static_cast<size_t>(j) * ld + 4 * lane);
+    }
+    float dot[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 k0 = unpack_bf16x2(kk[u].x), k1 = unpack_bf16x2(kk[u].y);
+      dot[u] = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * NW;
+      if (j < len) { const float v = dot[u] * scale; if (lane == 0) gs[j] = v; mx = fmaxf(mx, v); }
+    }
   }
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
   __syncthreads();
   float sum = 0.f;
   for (int j = threadIdx.x; j < len; j += blockDim.x) { const float e = __expf(gs[j] - mx); gs[j] = e; sum += e; }
   sum = warp_sum(sum);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
-  const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+  const float inv = 1.0f / (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
   // each warp accumulates a strided subset of the keys (lane = 4 output dims), then the warps are summed
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int j = warp; j < len; j += 4) {
-    const uint2 vv = *reinterpret_cast<const uint2*>(vbase + static_cast<size_t>(j) * ld + 4 * lane);
-    const float2 v0 = unpack_bf16x2(vv.x), v1 = unpack_bf16x2(vv.y);
-    const float pj = gs[j];
-    a0 = fmaf(pj, v0.x, a0); a1 = fmaf(pj, v0.y, a1); a2 = fmaf(pj, v1.x, a2); a3 = fmaf(pj, v1.y, a3);
+  for (int j0 = warp; j0 < len; j0 += 4 * NW) {
+    uint2 vv[4]; float pj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * NW;
+      const int jc = min(j, len - 1);
+      vv[u] = *reinterpret_cast<const uint2*>(vbase + static_cast<size_t>(jc) * ld + 4 * lane);
+      pj[u] = j < len ? gs[jc] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 v0 = unpack_bf16x2(vv[u].x), v1 = unpack_bf16x2(vv[u].y);
+      a0 = fmaf(pj[u], v0.x, a0); a1 = fmaf(pj[u], v0.y, a1); a2 = fmaf(pj[u], v1.x, a2); a3 = fmaf(pj[u], v1.y, a3);
+    }
   }
   __syncthreads();                                   // everyone is done reading gs
-  float4* part = reinterpret_cast<float4*>(gs);      // [4 warps][32 lanes]
+  float4* part = reinterpret_cast<float4*>(gs);      // [NW warps][32 lanes]
   part[warp * 32 + lane] = make_float4(a0, a1, a2, a3);
   __syncthreads();
   if (warp == 0) {
-    const float4 x0 = part[lane], x1 = part[32 + lane], x2 = part[64 + lane], x3 = part[96 + lane];
-    const float r0 = ((x0.x + x1.x) + (x2.x + x3.x)) * inv, r1 = ((x0.y + x1.y) + (x2.y + x3.y)) * inv;
-    const float r2 = ((x0.z + x1.z) + (x2.z + x3.z)) * inv, r3 = ((x0.w + x1.w) + (x2.w + x3.w)) * inv;
+    float4 acc = part[lane];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { const float4 x = part[w * 32 + lane]; acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
+    const float r0 = acc.x * inv, r1 = acc.y * inv, r2 = acc.z * inv, r3 = acc.w * inv;
     *reinterpret_cast<uint2*>(p.out + (static_cast<size_t>(b) * p.T_max) * d + h * DK + 4 * lane) =
         make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
   }
@@ -326,10 +377,10 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right; p.n_global = a.n_global;
   p.n_rel_pad = a.n_rel_pad;
   if (a.n_rel_pad < a.w_left + a.w_right + 1) return cudaErrorInvalidValue;
-  const size_t smem = static_cast<size_t>(3) * QT * LDS * 2 + QT * 4;
+  const size_t smem = static_cast<size_t>(1 + 2 * kKvStages) * QT * LDS * 2 + QT * 4;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(global_row_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
@@ -340,9 +391,9 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.n_global > 0) {
-    const size_t gsmem = (static_cast<size_t>(a.T_max > 512 ? a.T_max : 512) + 8) * sizeof(float);
+    const size_t gsmem = (static_cast<size_t>(a.T_max > 1024 ? a.T_max : 1024) + 8) * sizeof(float);
     if (gsmem > 200 * 1024) return cudaErrorInvalidValue;
-    global_row_attention_kernel<<<dim3(a.H, a.B), 128, gsmem, stream>>>(p);
+    global_row_attention_kernel<<<dim3(a.H, a.B), 256, gsmem, stream>>>(p);
     e = cudaGetLastError();
   }
   return e;

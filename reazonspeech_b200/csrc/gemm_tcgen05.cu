@@ -51,7 +51,15 @@ struct GemmCfg {
 };
 
 // Fused epilogue of one 32-column chunk of one accumulator row: bias, activation / GLU / residual, store.
-__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], bool row_ok, size_t orow, int col0, int bt) {
+__device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, size_t orow, int col0, float4 (&rr)[8]) {
+  if (on) {
+    const float4* rs4 = reinterpret_cast<const float4*>(p.resid + orow + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
+  }
+}
+
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], bool row_ok, size_t orow, int col0, int bt, const float4 (&rr)[8]) {
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -95,11 +103,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
             break;
           }
           case RS_EPI_RESID_F32: {
-            const float4* rs4 = reinterpret_cast<const float4*>(p.resid + orow + col0);
             float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
-            float4 rr[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               o[j] = make_float4(rr[j].x + p.alpha * v[4 * j], rr[j].y + p.alpha * v[4 * j + 1],
@@ -212,16 +216,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int row = m0 + q * 32 + lane;
       const size_t orow = static_cast<size_t>(row) * p.ldo + bt * p.out_col_stride;
       const bool row_ok = row < p.M;
+      // residual of the first chunk is fetched while the tile's MMAs are still running
+      const bool pre = row_ok && p.epilogue == RS_EPI_RESID_F32;
+      float4 rr[8], cur[8];
+      resid_prefetch(p, pre && n0 + half * 32 < p.N, orow, n0 + half * 32, rr);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int chunk = half; chunk < BN / 32; chunk += 2) {
         const int col0 = n0 + chunk * 32;
         if (col0 >= p.N) break;                              // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+        resid_prefetch(p, pre && chunk + 2 < BN / 32 && col0 + 64 < p.N, orow, col0 + 64, rr);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store(p, r, row_ok, orow, col0, bt);
+        epilogue_store(p, r, row_ok, orow, col0, bt, cur);
         __syncwarp();                                        // reconverge before the next .aligned tcgen05.ld
       }
       tcgen05_fence_before();
@@ -352,15 +363,21 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const int row = m0 + q * 32 + lane;
       const size_t orow = static_cast<size_t>(row) * p.ldo;
       const bool row_ok = row < p.M;
+      const bool pre = row_ok && p.epilogue == RS_EPI_RESID_F32;
+      float4 rr[8], cur[8];
+      resid_prefetch(p, pre, orow, n0 + half * 32, rr);       // overlaps the tile's MMAs
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int chunk = half; chunk < BN / 32; chunk += 2) {
         const int col0 = n0 + chunk * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+        resid_prefetch(p, pre && chunk + 2 < BN / 32, orow, col0 + 64, rr);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store(p, r, row_ok, orow, col0, 0);
+        epilogue_store(p, r, row_ok, orow, col0, 0, cur);
         __syncwarp();
       }
       tcgen05_fence_before();

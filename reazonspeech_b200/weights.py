@@ -190,6 +190,9 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, calibrate: bool = True) -
             gain = 2.0 if "pre_encode.conv" in name else 1.0
             if name == "joint.pred.weight":         # let the label history move the logits as
                 gain = 8.0                          # much as the acoustics do (|h_lstm| is small)
+            if name.endswith("weight_hh_l0"):       # weak recurrence: the predictor state is mostly a function
+                gain = 0.1                          # of the last token, so greedy decoding cannot lock into the
+                                                    # emit-the-same-token fixed points an untrained LSTM has
             t = randn() * math.sqrt(gain / fan_in)
         sd[name] = _bf16_round(t.to(torch.float32))
     if calibrate:
