@@ -150,6 +150,35 @@ def apply_calibration(sd: StateDict, cfg: ModelConfig, calib: dict) -> None:
     sd["joint.joint_net.2.bias"] = _bf16_round(b)
 
 
+def _structure_predictor(sd: StateDict, cfg: ModelConfig, suppress: float = 16.0, decay_logit: float = 2.2) -> None:
+    """Give the synthetic prediction network the one behaviour greedy RNN-T decoding relies on in a trained
+    model: having emitted a token, stop preferring it.  An untrained LSTM instead has states in which some
+    token keeps winning on every frame (decoding then emits max_symbols tokens per frame for the rest of the
+    clip).  Construction (still an ordinary embedding + LSTM + linear, only the values are chosen):
+      embed[k] = -suppress * W_out[k];  LSTM: input gate ~1, output gate ~1, forget gate sigmoid(2.2) ~ 0.9,
+      candidate g = tanh(embed + small noise);  joint.pred ~ identity (+ small noise).
+    so pred_proj ~ -suppress * sum_i 0.9^i W_out[k_{-i}]: the logits of the most recently emitted tokens are
+    pushed down, everything else is perturbed only by the small random terms."""
+    hp, hj = cfg.pred_hidden, cfg.joint_hidden
+    if hp != hj:
+        return                                           # construction needs the two widths to agree (640 == 640)
+    l = "decoder.prediction.dec_rnn.lstm."
+    w_out = sd["joint.joint_net.2.weight"]
+    emb = -suppress * w_out.clone()
+    emb[cfg.blank] = 0.0
+    sd["decoder.prediction.embed.weight"] = _bf16_round(emb)
+    w_ih = 0.02 * sd[l + "weight_ih_l0"] * math.sqrt(hp)            # small noise everywhere ...
+    w_ih[2 * hp:3 * hp] += torch.eye(hp)                             # ... identity on the candidate (g) block
+    sd[l + "weight_ih_l0"] = _bf16_round(w_ih)
+    sd[l + "weight_hh_l0"] = _bf16_round(0.02 * sd[l + "weight_hh_l0"] * math.sqrt(hp))
+    b = torch.zeros(4 * hp)
+    b[0 * hp:1 * hp] = 3.0                                           # input gate open
+    b[1 * hp:2 * hp] = decay_logit                                   # forget gate: memory of recent tokens decays
+    b[3 * hp:4 * hp] = 3.0                                           # output gate open
+    sd[l + "bias_ih_l0"] = _bf16_round(b)
+    sd["joint.pred.weight"] = _bf16_round(torch.eye(hj, hp) + 0.02 * sd["joint.pred.weight"] * math.sqrt(hp))
+
+
 def random_state_dict(cfg: ModelConfig, seed: int = 0, calibrate: bool = True) -> StateDict:
     """Seeded synthetic checkpoint with NeMo's names and shapes (float32, bf16-representable).
 
@@ -162,9 +191,11 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, calibrate: bool = True) -
     tokens on every frame.  With ``calibrate`` the stored calibration for this (config, seed)
     (``data/synth_calib_*.json``, produced by scripts/calibrate_synthetic.py from the seeded weights)
     is applied: joint.enc's bias cancels the DC component of the encoder output and its gain is a
-    power of two bringing the time-varying part to unit scale, and the blank bias is shifted so the
+    power of two bringing the time-varying part to a fixed scale, and the blank bias is shifted so the
     greedy emission rate is about one token per three frames -- the decode LOAD of speech
-    (SURVEY.md section 8d).  It shapes the workload only; oracle and engine see identical tensors."""
+    (SURVEY.md section 8d).  The prediction network is structured (see _structure_predictor) so that
+    an emitted token is suppressed afterwards, as in a trained model.  All of this shapes the workload
+    only; oracle and engine see identical tensors."""
     sd: StateDict = {}
     for idx, (name, shape) in enumerate(state_dict_shapes(cfg).items()):
         rng = np.random.default_rng([seed, idx])
@@ -188,13 +219,9 @@ def random_state_dict(cfg: ModelConfig, seed: int = 0, calibrate: bool = True) -
         else:
             fan_in = int(np.prod(shape[1:]))
             gain = 2.0 if "pre_encode.conv" in name else 1.0
-            if name == "joint.pred.weight":         # let the label history move the logits as
-                gain = 8.0                          # much as the acoustics do (|h_lstm| is small)
-            if name.endswith("weight_hh_l0"):       # weak recurrence: the predictor state is mostly a function
-                gain = 0.1                          # of the last token, so greedy decoding cannot lock into the
-                                                    # emit-the-same-token fixed points an untrained LSTM has
             t = randn() * math.sqrt(gain / fan_in)
         sd[name] = _bf16_round(t.to(torch.float32))
+    _structure_predictor(sd, cfg)
     if calibrate:
         import json
         import os

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--config", default="tiny", choices=["tiny", "full"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default=None)
-    ap.add_argument("--ac-target", type=float, default=0.5, help="std of the time-varying part of enc_proj after the gain")
+    ap.add_argument("--ac-target", type=float, default=1.0, help="std of the time-varying part of enc_proj after the gain")
     a = ap.parse_args()
     cfg = ModelConfig.tiny() if a.config == "tiny" else ModelConfig()
     sd = random_state_dict(cfg, a.seed, calibrate=False)
