@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -40,7 +41,7 @@ struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   int B, L_max, F_max, T1, F1, T2, F2, T3, F3, M;
   size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, enc, encp;
   int n_rel_pad;
-  size_t tokens, frames, ntok, total;
+  size_t tokens, frames, ntok, dec_ws, total;
 };
 
 inline int conv_len(int n) { return (n - 1) / 2 + 1; }
@@ -123,6 +124,7 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.tokens = take(static_cast<size_t>(B) * U_max * 4);
   p.frames = take(static_cast<size_t>(B) * U_max * 4);
   p.ntok = take(static_cast<size_t>(B) * 4);
+  p.dec_ws = take(rs::rnnt_batched_workspace_bytes(B, c.joint_hidden, c.pred_hidden, e->num_sms));
   p.total = off;
   return p;
 }
@@ -333,7 +335,12 @@ int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_
   rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b,
                     e->dec.pred_w, e->dec.pred_b, tokens, frames, ntok, p.B, T_max, c.joint_hidden, c.pred_hidden,
                     c.vocab_size, U_max, c.max_symbols};
-  RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
+  // B >= 8: batched weights-stationary cooperative kernel; fewer: one cluster per utterance (RS_DECODE_MODE overrides)
+  const char* m = getenv("RS_DECODE_MODE");      // 0/unset: automatic, 1: per-utterance clusters, 2: batched
+  const int mode = m ? atoi(m) : 0;
+  const bool batched = mode == 2 || (mode == 0 && p.B >= 8);
+  if (batched) RS_K(e, rs::launch_rnnt_greedy_batched(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
+  else RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
   return RS_OK;
 }
 
@@ -425,6 +432,7 @@ int rs_rnnt_greedy(rs_engine* e, const float* enc, const int32_t* enc_len, int B
   size_t off = 0;
   p.xn = off; off = align_up(off + static_cast<size_t>(p.M) * e->cfg.d_model * 2);
   p.encp = off; off = align_up(off + static_cast<size_t>(p.M) * e->cfg.joint_hidden * 4);
+  p.dec_ws = off; off = align_up(off + rs::rnnt_batched_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms));
   p.total = off; p.L_max = 0;
   RS_TRY(check_ws(e, p));
   return do_greedy(e, p, enc, enc_len, T_max, tokens, frames, n_tok, U_max, static_cast<cudaStream_t>(stream));

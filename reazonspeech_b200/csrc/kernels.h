@@ -72,6 +72,9 @@ struct DecodeArgs {
   int B, T_max, Hj, Hp, V, U_max, max_symbols;
 };
 cudaError_t launch_rnnt_greedy(const DecodeArgs& a, int num_sms, cudaStream_t stream);
+// batched, weights-stationary variant (decode_batched.cu); workspace from rnnt_batched_workspace_bytes()
+size_t rnnt_batched_workspace_bytes(int B, int Hj, int Hp, int num_sms);
+cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream);
 
 // small utility kernels
 cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);

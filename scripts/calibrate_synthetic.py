@@ -103,14 +103,14 @@ def main():
     # the blank bias is stored in bf16: scan every representable value between the coarse bracket
     xs = sorted(curve)
     lo = max([s for s in xs if curve[s] > TARGET], default=xs[0])
-    hi = min([s for s in xs if s > lo and curve[s] <= TARGET], default=xs[-1])
+    hi = min([s for s in xs if s > lo and curve[s] <= 0.3 * TARGET], default=xs[-1])   # wide enough to satisfy the worst-clip bound
     base = float(bout0[cfg.blank])
     vals = sorted({float(_bf16_round(torch.tensor(base + v))) - base for v in np.arange(lo, hi + 1e-6, 1.0 / 128)})
     fine, fine_worst = {}, {}
     for v in vals:
         fine[v] = rate(v); fine_worst[v] = worst[0]
     print("fine scan (mean rate, worst clip):", {round(k2, 4): (round(v, 3), round(fine_worst[k2], 2)) for k2, v in fine.items()})
-    ok = {k2: v for k2, v in fine.items() if v > 0 and fine_worst[k2] <= 3.0} or {k2: v for k2, v in fine.items() if v > 0}
+    ok = {k2: v for k2, v in fine.items() if v > 0 and fine_worst[k2] <= 1.0} or {k2: v for k2, v in fine.items() if v > 0}
     best = min(ok, key=lambda k2: abs(math.log(ok[k2] / TARGET)))
     calib["blank_shift"] = best
     calib["rate"] = rate(best)

@@ -161,9 +161,12 @@ def test_encoder_vs_oracle(tiny_engine, tiny_cfg, tiny_sd, n_layers):
 
 
 # ------------------------------------------------------------------------------------ decode
-def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd):
-    """Decode kernel alone: fed the ORACLE's encoder output, tokens and frames must be identical."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd, mode, monkeypatch):
+    """Decode kernels alone (1: one cluster per utterance, 2: batched weights-stationary grid): fed the
+    ORACLE's encoder output, tokens and frames must be identical."""
     from oracle import nemo_restated as O
+    monkeypatch.setenv("RS_DECODE_MODE", mode)
     eng = tiny_engine
     waves = [padded(synth_clip(6, 4.0)), padded(synth_clip(7, 2.5)), padded(synth_clip(8, 6.0))]
     refs, encs = [], []
