@@ -126,6 +126,7 @@ int rs_stage_times_ms(const rs_engine* e, float* ms /*[8]*/);
  * launch is bracketed by two events on its stream.  rs_gemm_timing() synchronises, returns the summed
  * device time, the summed algorithmic FLOPs (2*M*N*K) and the launch count since it was enabled or
  * last read, and resets the accumulators. */
+int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* out8);   /* profiling aid, see engine.cu */
 int rs_enable_gemm_timing(rs_engine* e, int on);
 int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches);
 

@@ -39,6 +39,7 @@ struct BatchedDev {
   float* hbuf;              // [2][B][Hp]
   float* ppbuf;             // [B][Hj]
   unsigned int* counter;    // grid barrier
+  long long* prof;          // [8] cycle counters of CTA 0 (phase J, barrier, reduce, phase L, barrier, phase P, barrier, iterations)
   int B, T_max, Hj, Hp, V, U_max, max_symbols;
   int rows_j, units, rows_p;   // per-CTA slice sizes
 };
@@ -117,6 +118,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
   __syncthreads();
 
   unsigned int target = 0;
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto tick = [&](int slot, long long& t0) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; } };
+  long long tk = clock64();
 
   // LSTM step + pred_proj for the utterances listed in s_emit[0..n_emit): token s_tok[b], state parity s_par[b].
   auto lstm_and_pred = [&]() {
@@ -171,7 +175,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
         }
       }
     }
+    tick(3, tk);
     grid_barrier(p.counter, target, G);
+    tick(4, tk);
     // ---- phase P (state parity flips for the utterances that stepped)
     for (int e = tid; e < n_emit; e += kBdThreads) s_par[s_emit[e]] ^= 1;
     __syncthreads();
@@ -199,7 +205,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
         }
       }
     }
+    tick(5, tk);
     grid_barrier(p.counter, target, G);
+    tick(6, tk);
   };
 
   lstm_and_pred();                                // SOS: every utterance steps once on the blank (zero) embedding
@@ -262,7 +270,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
       if (lane == 0 && oka) __stcg(p.partial + static_cast<size_t>(ba) * G + cta, make_int2(__float_as_int(best), bi));
       if (lane == 1 && okb) __stcg(p.partial + static_cast<size_t>(bb) * G + cta, make_int2(__float_as_int(best), bi));
     }
+    tick(0, tk);
     grid_barrier(p.counter, target, G);
+    tick(1, tk);
     // ---- reduce partials -> token per active utterance; advance the (t, symbols) state (identically in every CTA)
     for (int b = warp; b < B; b += kBdWarps) {
       const bool act = s_t[b] < p.enc_len[b];
@@ -304,10 +314,13 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     }
     __syncthreads();
     const int n_active = s_cnt[1];
+    tick(2, tk);
+    prof[7] += 1;
     if (s_cnt[0] > 0) lstm_and_pred();
     if (n_active == 0) break;
   }
   if (cta == 0) for (int b = tid; b < B; b += kBdThreads) p.n_tok[b] = s_n[b];
+  if (cta == 0 && tid == 0) for (int i = 0; i < 8; ++i) p.prof[i] = prof[i];
 }
 
 size_t rnnt_batched_workspace_bytes(int B, int Hj, int Hp, int num_sms) {
@@ -340,6 +353,7 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
   p.hbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(2) * a.B * a.Hp * 4;
   p.ppbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(a.B) * a.Hj * 4;
   p.counter = reinterpret_cast<unsigned int*>(ws);
+  p.prof = reinterpret_cast<long long*>(ws + 64);
   p.B = a.B; p.T_max = a.T_max; p.Hj = a.Hj; p.Hp = a.Hp; p.V = a.V; p.U_max = a.U_max; p.max_symbols = a.max_symbols;
   p.rows_j = (a.V + 1 + G - 1) / G;
   p.units = (a.Hp + G - 1) / G;

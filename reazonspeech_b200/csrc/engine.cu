@@ -508,6 +508,18 @@ int rs_stage_times_ms(const rs_engine* e, float* ms) {
   return RS_OK;
 }
 
+// Debug: cycle counters of the batched decode kernel's CTA 0 from the last rs_transcribe_* call for (B, L_max):
+// phase J, barrier, token reduce, phase L, barrier, phase P, barrier, iterations.  Synchronises the device.
+int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* out8) {
+  if (!e || !out8) return RS_ERR_INVALID_ARG;
+  Plan p = make_plan(e, B, L_max, U_max);
+  RS_CUDA(e, cudaDeviceSynchronize());
+  const size_t off = p.dec_ws + static_cast<size_t>(B) * e->num_sms * 8 + static_cast<size_t>(2) * B * e->cfg.pred_hidden * 4 +
+                     static_cast<size_t>(B) * e->cfg.joint_hidden * 4 + 64;
+  RS_CUDA(e, cudaMemcpy(out8, static_cast<char*>(e->ws) + off, 64, cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
 int rs_enable_gemm_timing(rs_engine* e, int on) {
   if (!e) return RS_ERR_INVALID_ARG;
   e->gemm_timing = on != 0;

@@ -45,80 +45,115 @@ template <int BN>
 struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int kTmemCols = 2 * BN;                       // power of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 32 * 36 * 4 * 8 /*epilogue staging*/;
 };
 
-// Fused epilogue of one 32-column chunk of one accumulator row: bias, activation / GLU / residual, store.
-__device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, size_t orow, int col0, float4 (&rr)[8]) {
+// Fused epilogue of one 32-row x 32-column chunk (one epilogue warp): bias, activation / GLU / residual, store.
+// tcgen05.ld hands every lane one ROW of the chunk; storing that directly would touch 32 different cache
+// lines per instruction.  The chunk is therefore transposed through a per-warp staging buffer in shared
+// memory so that each global access instruction covers whole 128-byte lines (fp32: 4 rows x 128 B,
+// bf16: 8 rows x 64 B), and the residual is read -- and prefetched during the MMAs -- in that same
+// coalesced ownership.
+constexpr int kStageLd = 36;                                   // floats per staged row (144 B: 16 B-aligned, conflict-free)
+constexpr int kStageBytesPerWarp = 32 * kStageLd * 4;
+constexpr int kStageBytesTotal = kEpiWarps * kStageBytesPerWarp;
+
+__device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int tile_row0, int lane, int col0, int bt, float4 (&rr)[8]) {
   if (on) {
-    const float4* rs4 = reinterpret_cast<const float4*>(p.resid + orow + col0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rr[j] = rs4[j];
+    for (int i = 0; i < 8; ++i) {
+      const int row = tile_row0 + i * 4 + (lane >> 3);
+      rr[i] = row < p.M ? *reinterpret_cast<const float4*>(p.resid + static_cast<size_t>(row) * p.ldo + bt * p.out_col_stride + col0 + (lane & 7) * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
 }
 
-__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], bool row_ok, size_t orow, int col0, int bt, const float4 (&rr)[8]) {
-        float v[32];
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
+                                               int col0, int bt, const float4 (&rr)[8]) {
+  float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-          }
-        }
-        if (row_ok) {
-        switch (p.epilogue) {
-          case RS_EPI_BIAS_BF16:
-          case RS_EPI_BIAS_RELU_BF16:
-          case RS_EPI_BIAS_SWISH_BF16: {
-            if (p.epilogue == RS_EPI_BIAS_RELU_BF16) {
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
+  uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
+  switch (p.epilogue) {
+    case RS_EPI_BIAS_BF16:
+    case RS_EPI_BIAS_RELU_BF16:
+    case RS_EPI_BIAS_SWISH_BF16: {
+      if (p.epilogue == RS_EPI_BIAS_RELU_BF16) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-            } else if (p.epilogue == RS_EPI_BIAS_SWISH_BF16) {
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      } else if (p.epilogue == RS_EPI_BIAS_SWISH_BF16) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
-            }
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0);
+        for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
+      }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            break;
-          }
-          case RS_EPI_BIAS_GLU_BF16: {
-            // columns [0,16) of the chunk are values, [16,32) the matching gates (weights interleaved at pack time)
-            float g[16];
+      for (int j = 0; j < 4; ++j)                              // staged row = 16 words, row stride 20 words
+        *reinterpret_cast<uint4*>(stage_u + lane * 20 + 4 * j) =
+            make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+      __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = v[j] * sigmoidf_fast(v[16 + j]);
-            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + orow + col0 / 2);
+      for (int i = 0; i < 4; ++i) {                            // 8 rows x 64 B per instruction
+        const int rl = i * 8 + (lane >> 2), cw = (lane & 3) * 4;
+        const int row = tile_row0 + rl;
+        const uint4 a = *reinterpret_cast<const uint4*>(stage_u + rl * 20 + cw);
+        if (row < p.M)
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 + cw * 2) = a;
+      }
+      break;
+    }
+    case RS_EPI_BIAS_GLU_BF16: {
+      // columns [0,16) of the chunk are values, [16,32) the matching gates (weights interleaved at pack time)
+      float g[16];
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-              o[j] = make_uint4(pack_bf16x2(g[8 * j], g[8 * j + 1]), pack_bf16x2(g[8 * j + 2], g[8 * j + 3]),
-                                pack_bf16x2(g[8 * j + 4], g[8 * j + 5]), pack_bf16x2(g[8 * j + 6], g[8 * j + 7]));
-            break;
-          }
-          case RS_EPI_RESID_F32: {
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
+      for (int j = 0; j < 16; ++j) g[j] = v[j] * sigmoidf_fast(v[16 + j]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = make_float4(rr[j].x + p.alpha * v[4 * j], rr[j].y + p.alpha * v[4 * j + 1],
-                                 rr[j].z + p.alpha * v[4 * j + 2], rr[j].w + p.alpha * v[4 * j + 3]);
-            break;
-          }
-          default: {  // RS_EPI_BIAS_F32
-            float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + orow + col0);
+      for (int j = 0; j < 2; ++j)                              // staged row = 8 words, row stride 12 words
+        *reinterpret_cast<uint4*>(stage_u + lane * 12 + 4 * j) =
+            make_uint4(pack_bf16x2(g[8 * j], g[8 * j + 1]), pack_bf16x2(g[8 * j + 2], g[8 * j + 3]),
+                       pack_bf16x2(g[8 * j + 4], g[8 * j + 5]), pack_bf16x2(g[8 * j + 6], g[8 * j + 7]));
+      __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
-            break;
-          }
-        }
-        }
+      for (int i = 0; i < 2; ++i) {                            // 16 rows x 32 B per instruction
+        const int rl = i * 16 + (lane >> 1), cw = (lane & 1) * 4;
+        const int row = tile_row0 + rl;
+        const uint4 a = *reinterpret_cast<const uint4*>(stage_u + rl * 12 + cw);
+        if (row < p.M)
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 / 2 + cw * 2) = a;
+      }
+      break;
+    }
+    default: {  // RS_EPI_RESID_F32 / RS_EPI_BIAS_F32
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * j) =
+            make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
+      __syncwarp();
+      const bool add = p.epilogue == RS_EPI_RESID_F32;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                            // 4 rows x 128 B per instruction
+        const int rl = i * 4 + (lane >> 3), cw = (lane & 7) * 4;
+        const int row = tile_row0 + rl;
+        float4 a = *reinterpret_cast<const float4*>(stage + rl * kStageLd + cw);
+        if (add) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
+        if (row < p.M)
+          *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 + cw) = a;
+      }
+      break;
+    }
+  }
+  __syncwarp();                                                // staging buffer reusable; reconverged for the next tcgen05.ld
 }
 
 template <int BN>
@@ -134,6 +169,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));   // generic pointer to the staging area
   auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
 
@@ -207,19 +243,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                                  // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;                        // which interleaved 32-column chunks
+    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * kStageBytesPerWarp);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int bt = tile / tiles_per_batch, tl = tile % tiles_per_batch;
       const int m0 = (tl / num_n) * BM, n0 = (tl % num_n) * BN;
-      const int row = m0 + q * 32 + lane;
-      const size_t orow = static_cast<size_t>(row) * p.ldo + bt * p.out_col_stride;
-      const bool row_ok = row < p.M;
+      const int tile_row0 = m0 + q * 32;
       // residual of the first chunk is fetched while the tile's MMAs are still running
-      const bool pre = row_ok && p.epilogue == RS_EPI_RESID_F32;
+      const bool pre = p.epilogue == RS_EPI_RESID_F32;
       float4 rr[8], cur[8];
-      resid_prefetch(p, pre && n0 + half * 32 < p.N, orow, n0 + half * 32, rr);
+      resid_prefetch(p, pre && n0 + half * 32 < p.N, tile_row0, lane, n0 + half * 32, bt, rr);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -228,12 +263,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         if (col0 >= p.N) break;                              // warp-uniform
 #pragma unroll
         for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-        resid_prefetch(p, pre && chunk + 2 < BN / 32 && col0 + 64 < p.N, orow, col0 + 64, rr);
+        resid_prefetch(p, pre && chunk + 2 < BN / 32 && col0 + 64 < p.N, tile_row0, lane, col0 + 64, bt, rr);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store(p, r, row_ok, orow, col0, bt, cur);
-        __syncwarp();                                        // reconverge before the next .aligned tcgen05.ld
+        epilogue_store(p, r, stage, tile_row0, lane, col0, bt, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -261,9 +295,9 @@ template <int BN>
 struct Gemm2Cfg {
   static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? 5 : 7;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 32 * 36 * 4 * 8 /*epilogue staging*/;
 };
 
 template <int BN>
@@ -278,6 +312,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));   // generic pointer to the staging area
   auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
 
@@ -355,17 +390,16 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     // ------------------------------------------------------------------ epilogue warps (both CTAs, own TMEM half)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * kStageBytesPerWarp);
     int it = 0;
     for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (tile % num_n) * BN;
-      const int row = m0 + q * 32 + lane;
-      const size_t orow = static_cast<size_t>(row) * p.ldo;
-      const bool row_ok = row < p.M;
-      const bool pre = row_ok && p.epilogue == RS_EPI_RESID_F32;
+      const int tile_row0 = m0 + q * 32;
+      const bool pre = p.epilogue == RS_EPI_RESID_F32;
       float4 rr[8], cur[8];
-      resid_prefetch(p, pre, orow, n0 + half * 32, rr);       // overlaps the tile's MMAs
+      resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -373,12 +407,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         const int col0 = n0 + chunk * 32;
 #pragma unroll
         for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-        resid_prefetch(p, pre && chunk + 2 < BN / 32, orow, col0 + 64, rr);
+        resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store(p, r, row_ok, orow, col0, 0, cur);
-        __syncwarp();
+        epilogue_store(p, r, stage, tile_row0, lane, col0, 0, cur);
       }
       tcgen05_fence_before();
       __syncwarp();

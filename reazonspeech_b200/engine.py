@@ -48,7 +48,7 @@ EXPORTS = [
     "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
     "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
-    "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing",
+    "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
 ]
 
 
@@ -85,6 +85,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_launch_count.restype = C.c_int64
     lib.rs_enable_stage_timing.argtypes = [vp, ip]
     lib.rs_stage_times_ms.argtypes = [vp, f32p]
+    lib.rs_debug_decode_cycles.argtypes = [vp, ip, ip, ip, C.POINTER(C.c_int64)]
+    lib.rs_debug_decode_cycles.restype = ip
     lib.rs_enable_gemm_timing.argtypes = [vp, ip]
     lib.rs_gemm_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode",
@@ -360,6 +362,11 @@ class Engine:
 
     def enable_stage_timing(self, on: bool = True):
         self._check(self.lib.rs_enable_stage_timing(self.h, int(on)), "rs_enable_stage_timing")
+
+    def decode_cycles(self, B: int, L_max: int, U_max: int):
+        out = (C.c_int64 * 8)()
+        self._check(self.lib.rs_debug_decode_cycles(self.h, B, L_max, U_max, out), "rs_debug_decode_cycles")
+        return dict(zip(("phase_j", "barrier_a", "reduce", "phase_l", "barrier_b", "phase_p", "barrier_c", "iterations"), [int(v) for v in out]))
 
     def enable_gemm_timing(self, on: bool = True):
         self._check(self.lib.rs_enable_gemm_timing(self.h, int(on)), "rs_enable_gemm_timing")

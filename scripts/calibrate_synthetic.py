@@ -110,7 +110,7 @@ def main():
     for v in vals:
         fine[v] = rate(v); fine_worst[v] = worst[0]
     print("fine scan (mean rate, worst clip):", {round(k2, 4): (round(v, 3), round(fine_worst[k2], 2)) for k2, v in fine.items()})
-    ok = {k2: v for k2, v in fine.items() if v > 0 and fine_worst[k2] <= 1.0} or {k2: v for k2, v in fine.items() if v > 0}
+    ok = {k2: v for k2, v in fine.items() if v > 0 and fine_worst[k2] <= 0.6} or {k2: v for k2, v in fine.items() if v > 0}
     best = min(ok, key=lambda k2: abs(math.log(ok[k2] / TARGET)))
     calib["blank_shift"] = best
     calib["rate"] = rate(best)
