@@ -26,9 +26,10 @@
 
 namespace rs {
 
-constexpr int kBdThreads = 512;
+constexpr int kBdThreads = 256;
 constexpr int kBdWarps = kBdThreads / 32;
-constexpr int kRowBlk = 16;                 // joint rows accumulated per register block
+constexpr int kRowBlk = 8;                  // joint rows accumulated per register block
+constexpr int kUpw = 4;                     // utterances per warp in phase J (W rows are read once per 4 utterances)
 
 struct BatchedDev {
   const float* enc_proj; const int32_t* enc_len;
@@ -145,14 +146,14 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
         for (int r = 0; r < 32; ++r) {
           if (r < 4 * p.units) {                  // warp-uniform
             const uint2* wr = reinterpret_cast<const uint2*>(s_wlstm + static_cast<size_t>(r) * 2 * Hp + lane * 2 * KP);
-            float a = 0.f;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 2 * KP / 4; ++i) {
               const uint2 w = wr[i];
-              a = fmaf(bf16_lo(w.x), x[4 * i], a); a = fmaf(bf16_hi(w.x), x[4 * i + 1], a);
-              a = fmaf(bf16_lo(w.y), x[4 * i + 2], a); a = fmaf(bf16_hi(w.y), x[4 * i + 3], a);
+              a0 = fmaf(bf16_lo(w.x), x[4 * i], a0); a1 = fmaf(bf16_hi(w.x), x[4 * i + 1], a1);
+              a2 = fmaf(bf16_lo(w.y), x[4 * i + 2], a2); a3 = fmaf(bf16_hi(w.y), x[4 * i + 3], a3);
             }
-            acc[r] = a;
+            acc[r] = (a0 + a1) + (a2 + a3);
           }
         }
         warp_reduce_scatter<32>(acc, lane);       // lane l now holds the total of gate row l
@@ -213,49 +214,55 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
   lstm_and_pred();                                // SOS: every utterance steps once on the blank (zero) embedding
 
   for (;;) {
-    // ---- phase J: partial argmax over this CTA's vocabulary rows, two utterances per warp
-    for (int base = 0; base < B; base += 2 * kBdWarps) {
-      const int ba = base + 2 * warp, bb = ba + 1;
-      const bool oka = ba < B && s_t[ba] < p.enc_len[ba];
-      const bool okb = bb < B && s_t[bb] < p.enc_len[bb];
-      float ga[KJ], gb[KJ];
-      {
-        const float* epa = p.enc_proj + (static_cast<size_t>(oka ? ba : 0) * p.T_max + (oka ? s_t[ba] : 0)) * Hj + lane * KJ;
-        const float* epb = p.enc_proj + (static_cast<size_t>(okb ? bb : 0) * p.T_max + (okb ? s_t[bb] : 0)) * Hj + lane * KJ;
-        const float* ppa = p.ppbuf + static_cast<size_t>(oka ? ba : 0) * Hj + lane * KJ;
-        const float* ppb = p.ppbuf + static_cast<size_t>(okb ? bb : 0) * Hj + lane * KJ;
+    // ---- phase J: partial argmax over this CTA's vocabulary rows, kUpw utterances per warp
+    for (int base = 0; base < B; base += kUpw * kBdWarps) {
+      int bu[kUpw]; bool ok[kUpw];
+      float g[kUpw][KJ];
+#pragma unroll
+      for (int u = 0; u < kUpw; ++u) {
+        bu[u] = base + kUpw * warp + u;
+        ok[u] = bu[u] < B && s_t[bu[u]] < p.enc_len[bu[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < kUpw; ++u) {
+        const int b = ok[u] ? bu[u] : 0, t = ok[u] ? s_t[b] : 0;
+        const float* ep = p.enc_proj + (static_cast<size_t>(b) * p.T_max + t) * Hj + lane * KJ;
+        const float* pp = p.ppbuf + static_cast<size_t>(b) * Hj + lane * KJ;
 #pragma unroll
         for (int i = 0; i < KJ / 4; ++i) {
-          const float4 e0 = __ldg(reinterpret_cast<const float4*>(epa) + i), q0 = ldcg4(ppa + 4 * i);
-          const float4 e1 = __ldg(reinterpret_cast<const float4*>(epb) + i), q1 = ldcg4(ppb + 4 * i);
-          ga[4 * i] = fmaxf(e0.x + q0.x, 0.f); ga[4 * i + 1] = fmaxf(e0.y + q0.y, 0.f);
-          ga[4 * i + 2] = fmaxf(e0.z + q0.z, 0.f); ga[4 * i + 3] = fmaxf(e0.w + q0.w, 0.f);
-          gb[4 * i] = fmaxf(e1.x + q1.x, 0.f); gb[4 * i + 1] = fmaxf(e1.y + q1.y, 0.f);
-          gb[4 * i + 2] = fmaxf(e1.z + q1.z, 0.f); gb[4 * i + 3] = fmaxf(e1.w + q1.w, 0.f);
+          const float4 e0 = __ldg(reinterpret_cast<const float4*>(ep) + i), q0 = ldcg4(pp + 4 * i);
+          g[u][4 * i] = fmaxf(e0.x + q0.x, 0.f); g[u][4 * i + 1] = fmaxf(e0.y + q0.y, 0.f);
+          g[u][4 * i + 2] = fmaxf(e0.z + q0.z, 0.f); g[u][4 * i + 3] = fmaxf(e0.w + q0.w, 0.f);
         }
       }
-      // after the reduce-scatter lane l holds ONE total: row (l >> 1) of the block for utterance (l & 1)
+      // after the reduce-scatter lane l holds ONE total: row (l >> 2) of the block for utterance (l & 3)
       float best = -INFINITY;
       int bi = 0x7fffffff;
       for (int rb = 0; rb < nj; rb += kRowBlk) {
-        float acc[2 * kRowBlk];
+        float acc[kUpw * kRowBlk];
 #pragma unroll
         for (int r = 0; r < kRowBlk; ++r) {
-          float a = 0.f, c = 0.f;
+          float a[kUpw];
+#pragma unroll
+          for (int u = 0; u < kUpw; ++u) a[u] = 0.f;
           if (rb + r < nj) {                                   // warp-uniform
             const uint2* wr = reinterpret_cast<const uint2*>(s_wout + static_cast<size_t>(rb + r) * Hj + lane * KJ);
 #pragma unroll
             for (int i = 0; i < KJ / 4; ++i) {
               const uint2 w = wr[i];
               const float w0 = bf16_lo(w.x), w1 = bf16_hi(w.x), w2 = bf16_lo(w.y), w3 = bf16_hi(w.y);
-              a = fmaf(w0, ga[4 * i], a); a = fmaf(w1, ga[4 * i + 1], a); a = fmaf(w2, ga[4 * i + 2], a); a = fmaf(w3, ga[4 * i + 3], a);
-              c = fmaf(w0, gb[4 * i], c); c = fmaf(w1, gb[4 * i + 1], c); c = fmaf(w2, gb[4 * i + 2], c); c = fmaf(w3, gb[4 * i + 3], c);
+#pragma unroll
+              for (int u = 0; u < kUpw; ++u) {
+                a[u] = fmaf(w0, g[u][4 * i], a[u]); a[u] = fmaf(w1, g[u][4 * i + 1], a[u]);
+                a[u] = fmaf(w2, g[u][4 * i + 2], a[u]); a[u] = fmaf(w3, g[u][4 * i + 3], a[u]);
+              }
             }
           }
-          acc[2 * r] = a; acc[2 * r + 1] = c;
+#pragma unroll
+          for (int u = 0; u < kUpw; ++u) acc[kUpw * r + u] = a[u];
         }
-        warp_reduce_scatter<2 * kRowBlk>(acc, lane);
-        const int r = rb + (lane >> 1);
+        warp_reduce_scatter<kUpw * kRowBlk>(acc, lane);
+        const int r = rb + (lane >> 2);
         if (r < nj) {
           const int row = j0 + r;
           const float v = acc[0] + __ldg(p.b_out + row);
@@ -263,12 +270,13 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
         }
       }
 #pragma unroll
-      for (int o = 16; o > 1; o >>= 1) {                       // lanes of equal parity = same utterance
+      for (int o = 16; o >= kUpw; o >>= 1) {                   // lanes with equal (lane & 3) = same utterance
         const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
       }
-      if (lane == 0 && oka) __stcg(p.partial + static_cast<size_t>(ba) * G + cta, make_int2(__float_as_int(best), bi));
-      if (lane == 1 && okb) __stcg(p.partial + static_cast<size_t>(bb) * G + cta, make_int2(__float_as_int(best), bi));
+#pragma unroll
+      for (int u = 0; u < kUpw; ++u)
+        if (lane == u && ok[u]) __stcg(p.partial + static_cast<size_t>(bu[u]) * G + cta, make_int2(__float_as_int(best), bi));
     }
     tick(0, tk);
     grid_barrier(p.counter, target, G);
@@ -278,10 +286,16 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
       const bool act = s_t[b] < p.enc_len[b];
       if (!act) { if (lane == 0) s_tok[b] = -1; continue; }     // warp-uniform
       float best = -INFINITY; int bi = 0x7fffffff;
-      for (int c = lane; c < G; c += 32) {
-        const int2 v = __ldcg(p.partial + static_cast<size_t>(b) * G + c);
-        const float f = __int_as_float(v.x);
-        if (f > best || (f == best && v.y < bi)) { best = f; bi = v.y; }
+      int2 pv[8];                                              // all loads in flight first (G <= 256)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = lane + 32 * i;
+        pv[i] = c < G ? __ldcg(p.partial + static_cast<size_t>(b) * G + c) : make_int2(__float_as_int(-INFINITY), 0x7fffffff);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float f = __int_as_float(pv[i].x);
+        if (f > best || (f == best && pv[i].y < bi)) { best = f; bi = pv[i].y; }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -358,7 +372,7 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
   p.rows_j = (a.V + 1 + G - 1) / G;
   p.units = (a.Hp + G - 1) / G;
   p.rows_p = (a.Hj + G - 1) / G;
-  if (4 * p.units > 32) return cudaErrorInvalidValue;
+  if (4 * p.units > 32 || G > 256) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.hbuf, 0, static_cast<size_t>(2) * a.B * a.Hp * 4 + static_cast<size_t>(a.B) * a.Hj * 4 + 256, stream);
   if (e != cudaSuccess) return e;
   const size_t smem = (static_cast<size_t>(p.rows_j) * a.Hj + static_cast<size_t>(4 * p.units) * 2 * a.Hp + static_cast<size_t>(p.rows_p) * a.Hp) * 2 +

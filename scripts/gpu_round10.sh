@@ -1,0 +1,6 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+mkdir -p gpurun_out
+echo "=== decode tests"; timeout -k 10 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -s -k "teacher or end_to_end" -p no:cacheprovider 2>&1 | tail -6
+echo "=== full-model tests"; timeout -k 10 1500 python -m pytest tests/test_gpu_full_model.py -m gpu -q -s -x -p no:cacheprovider > gpurun_out/full_model.log 2>&1; echo "exit $?"; tail -n 6 gpurun_out/full_model.log
+echo "=== bench"; timeout -k 10 1200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/bench.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['config']['tokens_per_clip'], d['roofline']['achieved'], d['roofline']['gemm_ms_per_step'], d['decode_cycles_cta0'])"; tail -3 gpurun_out/bench.err
