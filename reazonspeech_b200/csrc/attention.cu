@@ -285,10 +285,11 @@ local_attention_kernel(const AttnDev p) {
 }
 
 // Row(s) of the global token(s): full attention softmax_j((q_g / sqrt(dk)) . k_j) v_j, no positional
-// terms.  grid (H, B), 128 threads; scores staged in shared memory (T_max floats).
+// terms.  grid (H, B), 256 threads.  Scores: one key per thread (16 independent 16-byte loads in flight
+// per thread); weighted sum of V: 4 key groups x 64 dim pairs, unrolled by 8.
 __global__ void __launch_bounds__(256)
 global_row_attention_kernel(const AttnDev p) {
-  extern __shared__ __align__(16) float gs[];        // [T_max] scores, then [8] reduction scratch
+  extern __shared__ __align__(16) float gs[];        // [T_max] scores | [8] reduction scratch | [128] q
   const int h = blockIdx.x, b = blockIdx.y;
   const int len = p.enc_len[b];
   if (len <= 0) return;
@@ -298,74 +299,64 @@ global_row_attention_kernel(const AttnDev p) {
   const __nv_bfloat16* kbase = qrow + d;
   const __nv_bfloat16* vbase = qrow + 2 * d;
   const float scale = rsqrtf(static_cast<float>(DK));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* red = gs + p.T_max;
-  const float2 q0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * lane));
-  const float2 q1 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * lane + 2));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t_pad = ((p.T_max > 1024 ? p.T_max : 1024) + 3) & ~3;
+  float* red = gs + t_pad;
+  float* sq = red + 8;
+  if (tid < DK) sq[tid] = __bfloat162float(qrow[tid]) * scale;
+  __syncthreads();
   float mx = -INFINITY;
-  constexpr int NW = 8;                               // warps per CTA
-  for (int j0 = warp; j0 < len; j0 += 4 * NW) {       // four keys in flight per warp
-    uint2 kk[4];
+  for (int j = tid; j < len; j += 256) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ld);
+    uint4 kk[16];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = min(j0 + u * NW, len - 1);
-      kk[u] = *reinterpret_cast<const uint2*>(kbase + static_cast<size_t>(j) * ld + 4 * lane);
+    for (int i = 0; i < 16; ++i) kk[i] = __ldg(kr + i);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 qa = *reinterpret_cast<const float4*>(sq + 8 * i), qb = *reinterpret_cast<const float4*>(sq + 8 * i + 4);
+      d0 = fmaf(bf16_lo(kk[i].x), qa.x, d0); d1 = fmaf(bf16_hi(kk[i].x), qa.y, d1);
+      d2 = fmaf(bf16_lo(kk[i].y), qa.z, d2); d3 = fmaf(bf16_hi(kk[i].y), qa.w, d3);
+      d0 = fmaf(bf16_lo(kk[i].z), qb.x, d0); d1 = fmaf(bf16_hi(kk[i].z), qb.y, d1);
+      d2 = fmaf(bf16_lo(kk[i].w), qb.z, d2); d3 = fmaf(bf16_hi(kk[i].w), qb.w, d3);
     }
-    float dot[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float2 k0 = unpack_bf16x2(kk[u].x), k1 = unpack_bf16x2(kk[u].y);
-      dot[u] = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * NW;
-      if (j < len) { const float v = dot[u] * scale; if (lane == 0) gs[j] = v; mx = fmaxf(mx, v); }
-    }
+    const float v = (d0 + d1) + (d2 + d3);
+    gs[j] = v;
+    mx = fmaxf(mx, v);
   }
+  mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
   mx = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
   __syncthreads();
   float sum = 0.f;
-  for (int j = threadIdx.x; j < len; j += blockDim.x) { const float e = __expf(gs[j] - mx); gs[j] = e; sum += e; }
+  for (int j = tid; j < len; j += 256) { const float e = __expf(gs[j] - mx); gs[j] = e; sum += e; }
   sum = warp_sum(sum);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   const float inv = 1.0f / (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
-  // each warp accumulates a strided subset of the keys (lane = 4 output dims), then the warps are summed
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int j0 = warp; j0 < len; j0 += 4 * NW) {
-    uint2 vv[4]; float pj[4];
+  const int kg = tid >> 6, cp = tid & 63;            // key group (4), dim pair (64)
+  float a0 = 0.f, a1 = 0.f;
+  for (int j0 = kg; j0 < len; j0 += 32) {
+    uint32_t vv[8]; float pj[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * NW;
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + 4 * u;
       const int jc = min(j, len - 1);
-      vv[u] = *reinterpret_cast<const uint2*>(vbase + static_cast<size_t>(jc) * ld + 4 * lane);
+      vv[u] = __ldg(reinterpret_cast<const uint32_t*>(vbase + static_cast<size_t>(jc) * ld) + cp);
       pj[u] = j < len ? gs[jc] : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float2 v0 = unpack_bf16x2(vv[u].x), v1 = unpack_bf16x2(vv[u].y);
-      a0 = fmaf(pj[u], v0.x, a0); a1 = fmaf(pj[u], v0.y, a1); a2 = fmaf(pj[u], v1.x, a2); a3 = fmaf(pj[u], v1.y, a3);
-    }
+    for (int u = 0; u < 8; ++u) { a0 = fmaf(pj[u], bf16_lo(vv[u]), a0); a1 = fmaf(pj[u], bf16_hi(vv[u]), a1); }
   }
   __syncthreads();                                   // everyone is done reading gs
-  float4* part = reinterpret_cast<float4*>(gs);      // [NW warps][32 lanes]
-  part[warp * 32 + lane] = make_float4(a0, a1, a2, a3);
+  float2* part = reinterpret_cast<float2*>(gs);      // [4 key groups][64 dim pairs]
+  part[kg * 64 + cp] = make_float2(a0, a1);
   __syncthreads();
-  if (warp == 0) {
-    float4 acc = part[lane];
-#pragma unroll
-    for (int w = 1; w < NW; ++w) { const float4 x = part[w * 32 + lane]; acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
-    const float r0 = acc.x * inv, r1 = acc.y * inv, r2 = acc.z * inv, r3 = acc.w * inv;
-    *reinterpret_cast<uint2*>(p.out + (static_cast<size_t>(b) * p.T_max) * d + h * DK + 4 * lane) =
-        make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
+  if (tid < 64) {
+    const float2 x0 = part[tid], x1 = part[64 + tid], x2 = part[128 + tid], x3 = part[192 + tid];
+    const float r0 = ((x0.x + x1.x) + (x2.x + x3.x)) * inv, r1 = ((x0.y + x1.y) + (x2.y + x3.y)) * inv;
+    *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(b) * p.T_max) * d + h * DK + 2 * tid) = pack_bf16x2(r0, r1);
   }
 }
 
@@ -391,7 +382,7 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.n_global > 0) {
-    const size_t gsmem = (static_cast<size_t>(a.T_max > 1024 ? a.T_max : 1024) + 8) * sizeof(float);
+    const size_t gsmem = (static_cast<size_t>(((a.T_max > 1024 ? a.T_max : 1024) + 3) & ~3) + 8 + DK) * sizeof(float);
     if (gsmem > 200 * 1024) return cudaErrorInvalidValue;
     global_row_attention_kernel<<<dim3(a.H, a.B), 256, gsmem, stream>>>(p);
     e = cudaGetLastError();

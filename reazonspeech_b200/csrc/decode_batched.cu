@@ -120,6 +120,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
 
   unsigned int target = 0;
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long jprof[3] = {0, 0, 0};   // inside phase J: operand loads, row loop + reduce, argmax + store
   auto tick = [&](int slot, long long& t0) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; } };
   long long tk = clock64();
 
@@ -235,6 +236,11 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
           g[u][4 * i + 2] = fmaxf(e0.z + q0.z, 0.f); g[u][4 * i + 3] = fmaxf(e0.w + q0.w, 0.f);
         }
       }
+      if (cta == 0 && tid == 0) { float sink = 0.f;
+#pragma unroll
+        for (int u = 0; u < kUpw; ++u) sink += g[u][0] + g[u][KJ - 1];
+        if (sink == 123456.f) jprof[2] += 1;                     // forces the loads to complete before the timestamp
+        const long long t1 = clock64(); jprof[0] += t1 - tk; tk = t1; }
       // after the reduce-scatter lane l holds ONE total: row (l >> 2) of the block for utterance (l & 3)
       float best = -INFINITY;
       int bi = 0x7fffffff;
@@ -269,6 +275,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
           if (v > best) { best = v; bi = row; }                 // blocks visited in increasing row order
         }
       }
+      if (cta == 0 && tid == 0) { if (best == 123456.f) jprof[2] += 1; const long long t1 = clock64(); jprof[1] += t1 - tk; tk = t1; }
 #pragma unroll
       for (int o = 16; o >= kUpw; o >>= 1) {                   // lanes with equal (lane & 3) = same utterance
         const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
@@ -334,7 +341,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     if (n_active == 0) break;
   }
   if (cta == 0) for (int b = tid; b < B; b += kBdThreads) p.n_tok[b] = s_n[b];
-  if (cta == 0 && tid == 0) for (int i = 0; i < 8; ++i) p.prof[i] = prof[i];
+  if (cta == 0 && tid == 0) { for (int i = 0; i < 8; ++i) p.prof[i] = prof[i]; p.prof[8] = jprof[0]; p.prof[9] = jprof[1]; p.prof[10] = jprof[2]; }
 }
 
 size_t rnnt_batched_workspace_bytes(int B, int Hj, int Hp, int num_sms) {

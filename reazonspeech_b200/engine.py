@@ -364,9 +364,9 @@ class Engine:
         self._check(self.lib.rs_enable_stage_timing(self.h, int(on)), "rs_enable_stage_timing")
 
     def decode_cycles(self, B: int, L_max: int, U_max: int):
-        out = (C.c_int64 * 8)()
+        out = (C.c_int64 * 12)()
         self._check(self.lib.rs_debug_decode_cycles(self.h, B, L_max, U_max, out), "rs_debug_decode_cycles")
-        return dict(zip(("phase_j", "barrier_a", "reduce", "phase_l", "barrier_b", "phase_p", "barrier_c", "iterations"), [int(v) for v in out]))
+        return dict(zip(("phase_j", "barrier_a", "reduce", "phase_l", "barrier_b", "phase_p", "barrier_c", "iterations", "j_loads", "j_rows", "j_misc", "_"), [int(v) for v in out]))
 
     def enable_gemm_timing(self, on: bool = True):
         self._check(self.lib.rs_enable_gemm_timing(self.h, int(on)), "rs_enable_gemm_timing")
