@@ -101,7 +101,8 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
   int* s_t = reinterpret_cast<int*>(s_c + static_cast<size_t>(B) * p.units);        // [B]
   int* s_sym = s_t + B; int* s_n = s_sym + B; int* s_par = s_n + B; int* s_tok = s_par + B;
   int* s_emit = s_tok + B;                                                            // [B] compact list
-  int* s_cnt = s_emit + B;                                                            // [2]: n_emit, n_active
+  int* s_len = s_emit + B;                                                            // [B] enc_len copy
+  int* s_cnt = s_len + B;                                                            // [2]: n_emit, n_active
 
   for (int i = tid; i < nj * Hj / 8; i += kBdThreads)
     reinterpret_cast<uint4*>(s_wout)[i] = reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0) * Hj)[i];
@@ -114,7 +115,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
   for (int i = tid; i < np * Hp / 8; i += kBdThreads)
     reinterpret_cast<uint4*>(s_wpred)[i] = reinterpret_cast<const uint4*>(p.w_pred + static_cast<size_t>(p0) * Hp)[i];
   for (int i = tid; i < B * p.units; i += kBdThreads) s_c[i] = 0.f;
-  for (int b = tid; b < B; b += kBdThreads) { s_t[b] = 0; s_sym[b] = 0; s_n[b] = 0; s_par[b] = 0; s_tok[b] = blank; s_emit[b] = b; }
+  for (int b = tid; b < B; b += kBdThreads) { s_t[b] = 0; s_sym[b] = 0; s_n[b] = 0; s_par[b] = 0; s_tok[b] = blank; s_emit[b] = b; s_len[b] = p.enc_len[b]; }
   if (tid == 0) { s_cnt[0] = B; s_cnt[1] = 0; }
   __syncthreads();
 
@@ -129,8 +130,8 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     const int n_emit = s_cnt[0];
     // ---- phase L
     if (nu > 0) {
-      for (int e = warp; e < n_emit; e += kBdWarps) {
-        const int b = s_emit[e];
+      for (int eq = warp; eq < n_emit; eq += kBdWarps) {
+        const int b = s_emit[(eq + cta) % n_emit];
         const int k = s_tok[b], par = s_par[b];
         float x[2 * KP];                          // lane slice of (embed[k] | h_b): 2*Hp/32 contiguous values
         const float* src = (lane < 16) ? p.embed + static_cast<size_t>(k) * Hp + lane * 2 * KP
@@ -184,8 +185,8 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     for (int e = tid; e < n_emit; e += kBdThreads) s_par[s_emit[e]] ^= 1;
     __syncthreads();
     if (np > 0) {
-      for (int e = warp; e < n_emit; e += kBdWarps) {
-        const int b = s_emit[e];
+      for (int eq = warp; eq < n_emit; eq += kBdWarps) {
+        const int b = s_emit[(eq + cta) % n_emit];
         float hv[KP];
         const float* src = p.hbuf + (static_cast<size_t>(s_par[b]) * B + b) * Hp + lane * KP;
 #pragma unroll
@@ -219,21 +220,32 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     for (int base = 0; base < B; base += kUpw * kBdWarps) {
       int bu[kUpw]; bool ok[kUpw];
       float g[kUpw][KJ];
+      // every CTA needs the same B activation rows; rotating which warp takes which utterance by the CTA
+      // index keeps the 148 CTAs from requesting the same L2 lines at the same instant (hot-spotting)
 #pragma unroll
       for (int u = 0; u < kUpw; ++u) {
-        bu[u] = base + kUpw * warp + u;
-        ok[u] = bu[u] < B && s_t[bu[u]] < p.enc_len[bu[u]];
+        bu[u] = base + (kUpw * warp + u + 5 * cta) % (kUpw * kBdWarps);
+        ok[u] = bu[u] < B && s_t[bu[u]] < s_len[bu[u]];
       }
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < kUpw; ++u) any |= ok[u];
+      if (!any) continue;                                      // warp-uniform: nothing active in this group
 #pragma unroll
       for (int u = 0; u < kUpw; ++u) {
-        const int b = ok[u] ? bu[u] : 0, t = ok[u] ? s_t[b] : 0;
-        const float* ep = p.enc_proj + (static_cast<size_t>(b) * p.T_max + t) * Hj + lane * KJ;
-        const float* pp = p.ppbuf + static_cast<size_t>(b) * Hj + lane * KJ;
+        if (ok[u]) {                                           // warp-uniform
+          const int b = bu[u], t = s_t[b];
+          const float* ep = p.enc_proj + (static_cast<size_t>(b) * p.T_max + t) * Hj + lane * KJ;
+          const float* pp = p.ppbuf + static_cast<size_t>(b) * Hj + lane * KJ;
 #pragma unroll
-        for (int i = 0; i < KJ / 4; ++i) {
-          const float4 e0 = __ldg(reinterpret_cast<const float4*>(ep) + i), q0 = ldcg4(pp + 4 * i);
-          g[u][4 * i] = fmaxf(e0.x + q0.x, 0.f); g[u][4 * i + 1] = fmaxf(e0.y + q0.y, 0.f);
-          g[u][4 * i + 2] = fmaxf(e0.z + q0.z, 0.f); g[u][4 * i + 3] = fmaxf(e0.w + q0.w, 0.f);
+          for (int i = 0; i < KJ / 4; ++i) {
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(ep) + i), q0 = ldcg4(pp + 4 * i);
+            g[u][4 * i] = fmaxf(e0.x + q0.x, 0.f); g[u][4 * i + 1] = fmaxf(e0.y + q0.y, 0.f);
+            g[u][4 * i + 2] = fmaxf(e0.z + q0.z, 0.f); g[u][4 * i + 3] = fmaxf(e0.w + q0.w, 0.f);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < KJ; ++i) g[u][i] = 0.f;
         }
       }
       if (cta == 0 && tid == 0) { float sink = 0.f;
@@ -289,8 +301,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     grid_barrier(p.counter, target, G);
     tick(1, tk);
     // ---- reduce partials -> token per active utterance; advance the (t, symbols) state (identically in every CTA)
-    for (int b = warp; b < B; b += kBdWarps) {
-      const bool act = s_t[b] < p.enc_len[b];
+    for (int bq = warp; bq < B; bq += kBdWarps) {
+      const int b = (bq + 3 * cta) % B;                         // rotated per CTA (see phase J)
+      const bool act = s_t[b] < s_len[b];
       if (!act) { if (lane == 0) s_tok[b] = -1; continue; }     // warp-uniform
       float best = -INFINITY; int bi = 0x7fffffff;
       int2 pv[8];                                              // all loads in flight first (G <= 256)
@@ -329,7 +342,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
       int ne = 0, na = 0;
       for (int b = 0; b < B; ++b) {
         if (s_tok[b] >= 0) s_emit[ne++] = b;
-        if (s_t[b] < p.enc_len[b]) ++na;
+        if (s_t[b] < s_len[b]) ++na;
       }
       s_cnt[0] = ne; s_cnt[1] = na;
     }
@@ -383,7 +396,7 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
   cudaError_t e = cudaMemsetAsync(p.hbuf, 0, static_cast<size_t>(2) * a.B * a.Hp * 4 + static_cast<size_t>(a.B) * a.Hj * 4 + 256, stream);
   if (e != cudaSuccess) return e;
   const size_t smem = (static_cast<size_t>(p.rows_j) * a.Hj + static_cast<size_t>(4 * p.units) * 2 * a.Hp + static_cast<size_t>(p.rows_p) * a.Hp) * 2 +
-                      static_cast<size_t>(a.B) * p.units * 4 + static_cast<size_t>(a.B) * 6 * 4 + 64;
+                      static_cast<size_t>(a.B) * p.units * 4 + static_cast<size_t>(a.B) * 7 * 4 + 64;
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   if (a.Hj == 640 && a.Hp == 640) return launch_bd<20, 20>(p, G, smem, stream);
   if (a.Hj == 128 && a.Hp == 128) return launch_bd<4, 4>(p, G, smem, stream);
