@@ -95,10 +95,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
 
   // ---- shared memory carve-up
   __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(bsm);                    // [rows_j][Hj]
-  __nv_bfloat16* s_wpred = s_wout + static_cast<size_t>(p.rows_j) * Hj;             // [rows_p][Hp]
-  float* s_wlstm = reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * Hp);   // [4*units][2*Hp] fp32, gate-major
-  float* s_gates = s_wlstm + static_cast<size_t>(4 * p.units) * 2 * Hp;             // [B][4][units] pre-activations
-  float* s_c = s_gates + static_cast<size_t>(B) * 4 * p.units;                       // [B][units]
+  __nv_bfloat16* s_wlstm = s_wout + static_cast<size_t>(p.rows_j) * Hj;             // [4*units][2*Hp]  (gate-major)
+  __nv_bfloat16* s_wpred = s_wlstm + static_cast<size_t>(4 * p.units) * 2 * Hp;     // [rows_p][Hp]
+  float* s_c = reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * Hp);   // [B][units]
   int* s_t = reinterpret_cast<int*>(s_c + static_cast<size_t>(B) * p.units);        // [B]
   int* s_sym = s_t + B; int* s_n = s_sym + B; int* s_par = s_n + B; int* s_tok = s_par + B;
   int* s_emit = s_tok + B;                                                            // [B] compact list
@@ -109,9 +108,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     reinterpret_cast<uint4*>(s_wout)[i] = reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0) * Hj)[i];
   for (int r = 0; r < 4 * nu; ++r) {
     const int gate = r / nu, u = r % nu;
-    const __nv_bfloat16* src = p.w_lstm + (static_cast<size_t>(gate) * Hp + u0 + u) * 2 * Hp;
-    float* dst = s_wlstm + static_cast<size_t>(gate * p.units + u) * 2 * Hp;
-    for (int i = tid; i < 2 * Hp; i += kBdThreads) dst[i] = __bfloat162float(src[i]);   // exact widening, once
+    const uint4* src = reinterpret_cast<const uint4*>(p.w_lstm + (static_cast<size_t>(gate) * Hp + u0 + u) * 2 * Hp);
+    uint4* dst = reinterpret_cast<uint4*>(s_wlstm + static_cast<size_t>(gate * p.units + u) * 2 * Hp);
+    for (int i = tid; i < 2 * Hp / 8; i += kBdThreads) dst[i] = src[i];
   }
   for (int i = tid; i < np * Hp / 8; i += kBdThreads)
     reinterpret_cast<uint4*>(s_wpred)[i] = reinterpret_cast<const uint4*>(p.w_pred + static_cast<size_t>(p0) * Hp)[i];
@@ -129,11 +128,9 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
   // LSTM step + pred_proj for the utterances listed in s_emit[0..n_emit): token s_tok[b], state parity s_par[b].
   auto lstm_and_pred = [&]() {
     const int n_emit = s_cnt[0];
-    // ---- phase L: work item = (emitting utterance, gate): the rows of one gate for the CTA's units.
-    // Spreading an utterance over four warps keeps the phase short when only a few utterances emitted.
+    // ---- phase L
     if (nu > 0) {
-      for (int item = warp; item < 4 * n_emit; item += kBdWarps) {
-        const int eq = item >> 2, gate = item & 3;
+      for (int eq = warp; eq < n_emit; eq += kBdWarps) {
         const int b = s_emit[(eq + cta) % n_emit];
         const int k = s_tok[b], par = s_par[b];
         float x[2 * KP];                          // lane slice of (embed[k] | h_b): 2*Hp/32 contiguous values
@@ -144,30 +141,42 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
           const float4 v = ldcg4(src + 4 * i);
           x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
-        for (int u = 0; u < nu; ++u) {
-          const float4* wr = reinterpret_cast<const float4*>(s_wlstm + static_cast<size_t>(gate * p.units + u) * 2 * Hp + lane * 2 * KP);
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float acc[32];
 #pragma unroll
-          for (int i = 0; i < 2 * KP / 4; ++i) {
-            const float4 w = wr[i];
-            a0 = fmaf(w.x, x[4 * i], a0); a1 = fmaf(w.y, x[4 * i + 1], a1);
-            a2 = fmaf(w.z, x[4 * i + 2], a2); a3 = fmaf(w.w, x[4 * i + 3], a3);
+        for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          if (r < 4 * p.units) {                  // warp-uniform
+            const uint2* wr = reinterpret_cast<const uint2*>(s_wlstm + static_cast<size_t>(r) * 2 * Hp + lane * 2 * KP);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 2 * KP / 4; ++i) {
+              const uint2 w = wr[i];
+              a0 = fmaf(bf16_lo(w.x), x[4 * i], a0); a1 = fmaf(bf16_hi(w.x), x[4 * i + 1], a1);
+              a2 = fmaf(bf16_lo(w.y), x[4 * i + 2], a2); a3 = fmaf(bf16_hi(w.y), x[4 * i + 3], a3);
+            }
+            acc[r] = (a0 + a1) + (a2 + a3);
           }
-          const float tot = warp_sum((a0 + a1) + (a2 + a3));
-          if (lane == 0) s_gates[(eq * 4 + gate) * p.units + u] = tot + __ldg(p.b_lstm + gate * Hp + u0 + u);
+        }
+        warp_reduce_scatter<32>(acc, lane);       // lane l now holds the total of gate row l
+        const float tot = acc[0];
+        // gather the four gates of unit (lane) into lanes 0..nu-1
+        const int uu = lane < nu ? lane : 0;
+        const float gi = __shfl_sync(0xffffffffu, tot, 0 * p.units + uu);
+        const float gf = __shfl_sync(0xffffffffu, tot, 1 * p.units + uu);
+        const float gg = __shfl_sync(0xffffffffu, tot, 2 * p.units + uu);
+        const float go = __shfl_sync(0xffffffffu, tot, 3 * p.units + uu);
+        if (lane < nu) {
+          const int unit = u0 + lane;
+          const float ig = sigmoidf_accurate(gi + __ldg(p.b_lstm + unit));
+          const float fg = sigmoidf_accurate(gf + __ldg(p.b_lstm + Hp + unit));
+          const float cg = tanhf(gg + __ldg(p.b_lstm + 2 * Hp + unit));
+          const float og = sigmoidf_accurate(go + __ldg(p.b_lstm + 3 * Hp + unit));
+          const float c2 = fg * s_c[b * p.units + lane] + ig * cg;
+          s_c[b * p.units + lane] = c2;
+          __stcg(p.hbuf + (static_cast<size_t>(par ^ 1) * B + b) * Hp + unit, og * tanhf(c2));
         }
       }
-    }
-    __syncthreads();
-    for (int i = tid; i < n_emit * nu; i += kBdThreads) {     // cell update of (utterance, unit)
-      const int eq = i / nu, u = i % nu;
-      const int b = s_emit[(eq + cta) % n_emit];
-      const float* gt = s_gates + eq * 4 * p.units;
-      const float ig = sigmoidf_accurate(gt[u]), fg = sigmoidf_accurate(gt[p.units + u]);
-      const float cg = tanhf(gt[2 * p.units + u]), og = sigmoidf_accurate(gt[3 * p.units + u]);
-      const float c2 = fg * s_c[b * p.units + u] + ig * cg;
-      s_c[b * p.units + u] = c2;
-      __stcg(p.hbuf + (static_cast<size_t>(s_par[b] ^ 1) * B + b) * Hp + u0 + u, og * tanhf(c2));
     }
     tick(3, tk);
     grid_barrier(p.counter, target, G);
@@ -292,53 +301,39 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
     grid_barrier(p.counter, target, G);
     tick(1, tk);
     // ---- reduce partials -> token per active utterance; advance the (t, symbols) state (identically in every CTA)
-    for (int bq0 = warp; bq0 < B; bq0 += 4 * kBdWarps) {        // four utterances per warp with all their loads in flight
-      int bl[4]; bool act[4]; int2 pv[4][5];
+    for (int bq = warp; bq < B; bq += kBdWarps) {
+      const int b = (bq + 3 * cta) % B;                         // rotated per CTA (see phase J)
+      const bool act = s_t[b] < s_len[b];
+      if (!act) { if (lane == 0) s_tok[b] = -1; continue; }     // warp-uniform
+      float best = -INFINITY; int bi = 0x7fffffff;
+      int2 pv[8];                                              // all loads in flight first (G <= 256)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int bq = bq0 + u * kBdWarps;
-        bl[u] = bq < B ? (bq + 3 * cta) % B : 0;                // rotated per CTA (see phase J)
-        act[u] = bq < B && s_t[bl[u]] < s_len[bl[u]];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int c = lane + 32 * i;
-          pv[u][i] = (act[u] && c < G) ? __ldcg(p.partial + static_cast<size_t>(bl[u]) * G + c) : make_int2(__float_as_int(-INFINITY), 0x7fffffff);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int c = lane + 32 * i;
+        pv[i] = c < G ? __ldcg(p.partial + static_cast<size_t>(b) * G + c) : make_int2(__float_as_int(-INFINITY), 0x7fffffff);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int b = bl[u];
-        if (bq0 + u * kBdWarps >= B) continue;                   // warp-uniform
-        if (!act[u]) { if (lane == 0) s_tok[b] = -1; continue; } // warp-uniform
-        float best = -INFINITY; int bi = 0x7fffffff;
+      for (int i = 0; i < 8; ++i) {
+        const float f = __int_as_float(pv[i].x);
+        if (f > best || (f == best && pv[i].y < bi)) { best = f; bi = pv[i].y; }
+      }
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const float f = __int_as_float(pv[u][i].x);
-          if (f > best || (f == best && pv[u][i].y < bi)) { best = f; bi = pv[u][i].y; }
-        }
-        for (int c = lane + 160; c < G; c += 32) {               // G > 160 (not on B200): remaining partials
-          const int2 v = __ldcg(p.partial + static_cast<size_t>(b) * G + c);
-          const float f = __int_as_float(v.x);
-          if (f > best || (f == best && v.y < bi)) { best = f; bi = v.y; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-        }
-        if (lane == 0) {
-          const int k = bi;
-          if (k == blank) { s_t[b] += 1; s_sym[b] = 0; s_tok[b] = -1; }
-          else {
-            const int n = s_n[b];
-            if (cta == 0 && n < p.U_max) {
-              p.tokens[static_cast<size_t>(b) * p.U_max + n] = k;
-              p.frames[static_cast<size_t>(b) * p.U_max + n] = s_t[b];
-            }
-            s_n[b] = n + 1;
-            s_tok[b] = k;
-            if (++s_sym[b] >= p.max_symbols) { s_t[b] += 1; s_sym[b] = 0; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        const int k = bi;
+        if (k == blank) { s_t[b] += 1; s_sym[b] = 0; s_tok[b] = -1; }
+        else {
+          const int n = s_n[b];
+          if (cta == 0 && n < p.U_max) {
+            p.tokens[static_cast<size_t>(b) * p.U_max + n] = k;
+            p.frames[static_cast<size_t>(b) * p.U_max + n] = s_t[b];
           }
+          s_n[b] = n + 1;
+          s_tok[b] = k;
+          if (++s_sym[b] >= p.max_symbols) { s_t[b] += 1; s_sym[b] = 0; }
         }
       }
     }
@@ -400,9 +395,8 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
   if (4 * p.units > 32 || G > 256) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.hbuf, 0, static_cast<size_t>(2) * a.B * a.Hp * 4 + static_cast<size_t>(a.B) * a.Hj * 4 + 256, stream);
   if (e != cudaSuccess) return e;
-  const size_t smem = (static_cast<size_t>(p.rows_j) * a.Hj + static_cast<size_t>(p.rows_p) * a.Hp) * 2 +
-                      static_cast<size_t>(4 * p.units) * 2 * a.Hp * 4 + static_cast<size_t>(a.B) * 5 * p.units * 4 +
-                      static_cast<size_t>(a.B) * 7 * 4 + 64;
+  const size_t smem = (static_cast<size_t>(p.rows_j) * a.Hj + static_cast<size_t>(4 * p.units) * 2 * a.Hp + static_cast<size_t>(p.rows_p) * a.Hp) * 2 +
+                      static_cast<size_t>(a.B) * p.units * 4 + static_cast<size_t>(a.B) * 7 * 4 + 64;
   if (smem > 220 * 1024) return cudaErrorInvalidValue;
   if (a.Hj == 640 && a.Hp == 640) return launch_bd<20, 20>(p, G, smem, stream);
   if (a.Hj == 128 && a.Hp == 128) return launch_bd<4, 4>(p, G, smem, stream);
