@@ -251,7 +251,7 @@ def main():
     torch.cuda.synchronize(dev)
     stages = eng.stage_times_ms()
     eng.enable_stage_timing(False)
-    decode_prof = eng.decode_cycles(B, L, U) if B >= 8 and os.environ.get("RS_DECODE_MODE", "0") in ("0", "2") else None
+    decode_prof = eng.decode_cycles(B, L, U) if os.environ.get("RS_DECODE_MODE", "0") != "1" else None
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
                 "kernel": "gemm_bf16_tn_kernel (tcgen05.mma, all encoder/joint GEMMs)", "peak_source": f"{src} bf16_tflops_sustained",

@@ -335,10 +335,12 @@ int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_
   rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b,
                     e->dec.pred_w, e->dec.pred_b, tokens, frames, ntok, p.B, T_max, c.joint_hidden, c.pred_hidden,
                     c.vocab_size, U_max, c.max_symbols};
-  // B >= 8: batched weights-stationary cooperative kernel; fewer: one cluster per utterance (RS_DECODE_MODE overrides)
+  // One decode kernel for every batch size (batched, weights-stationary): an utterance's logits are then
+  // accumulated in the same order whether it is decoded alone or inside a batch, so results do not depend
+  // on batch composition.  RS_DECODE_MODE=1 selects the cluster-per-utterance kernel (latency experiments).
   const char* m = getenv("RS_DECODE_MODE");      // 0/unset: automatic, 1: per-utterance clusters, 2: batched
   const int mode = m ? atoi(m) : 0;
-  const bool batched = mode == 2 || (mode == 0 && p.B >= 8);
+  const bool batched = mode != 1;
   if (batched) RS_K(e, rs::launch_rnnt_greedy_batched(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
   else RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
   return RS_OK;

@@ -527,7 +527,8 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
-  if (g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0 && g.M >= 1024)
+  // kernel choice depends on N only (never on M): a row's result must not depend on the batch it sits in
+  if (g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0)
     return launch_2cta<256>(g, num_sms, stream, err);
   // Widest tile that still yields at least ~one wave of tiles; narrow N uses a narrower tile.
   if (g.N >= 256 && g.N % 256 == 0) return launch_bn<256>(g, num_sms, stream, err);
