@@ -10,8 +10,9 @@
 // of enc_proj / pred_proj rows from L2 instead of streaming 3.8 MB of weights per utterance, so the
 // cost per iteration is set by three grid barriers and is almost independent of B.
 //
-//   phase J  every CTA: partial argmax of W_out[slice] relu(enc_proj[b,t_b] + pred_proj[b]) for all b
-//   barrier  -> every CTA reduces the partials to the same token k_b, updates (t_b, symbols_b), emits
+//   phase J  every CTA: argmax over W_out[slice] relu(enc_proj[b,t_b] + pred_proj[b]) for all b, folded into a
+//            grid-wide 64-bit red.max per utterance (logit bits | complemented row index)
+//   barrier  -> every CTA reads the same token k_b, updates (t_b, symbols_b), emits
 //   phase L  utterances that emitted: LSTM gates of the CTA's units on (embed[k_b], h_b) -> new h slice
 //   barrier
 //   phase P  utterances that emitted: pred_proj rows of the CTA from the new h
@@ -36,7 +37,7 @@ struct BatchedDev {
   const __nv_bfloat16* w_out; const float* b_out; const float* embed;
   const __nv_bfloat16* w_lstm; const float* b_lstm; const __nv_bfloat16* w_pred; const float* b_pred;
   int32_t* tokens; int32_t* frames; int32_t* n_tok;
-  int2* partial;            // [B][G] (float bits of the best logit, global row index)
+  unsigned long long* best; // [3][B] packed (ordered logit bits << 32 | ~row): grid-wide argmax by red.max, 3-deep ring
   float* hbuf;              // [2][B][Hp]
   float* ppbuf;             // [B][Hj]
   unsigned int* counter;    // grid barrier
@@ -120,6 +121,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
   __syncthreads();
 
   unsigned int target = 0;
+  int iter = 0;
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long jprof[3] = {0, 0, 0};   // inside phase J: operand loads, row loop + reduce, argmax + store
   auto tick = [&](int slot, long long& t0) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; } };
@@ -295,48 +297,39 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
       }
 #pragma unroll
       for (int u = 0; u < kUpw; ++u)
-        if (lane == u && ok[u]) __stcg(p.partial + static_cast<size_t>(bu[u]) * G + cta, make_int2(__float_as_int(best), bi));
+        if (lane == u && ok[u]) {
+          // grid-wide argmax without a gather: order-preserving float bits in the high word, complemented row
+          // index in the low word (ties -> lower row), one fire-and-forget 64-bit max per (CTA, utterance)
+          unsigned int fb = __float_as_uint(best);
+          fb = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+          const unsigned long long packed = (static_cast<unsigned long long>(fb) << 32) | (0xffffffffu - static_cast<unsigned int>(bi));
+          asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p.best + static_cast<size_t>(iter % 3) * B + bu[u]), "l"(packed) : "memory");
+        }
     }
     tick(0, tk);
     grid_barrier(p.counter, target, G);
     tick(1, tk);
-    // ---- reduce partials -> token per active utterance; advance the (t, symbols) state (identically in every CTA)
-    for (int bq = warp; bq < B; bq += kBdWarps) {
-      const int b = (bq + 3 * cta) % B;                         // rotated per CTA (see phase J)
-      const bool act = s_t[b] < s_len[b];
-      if (!act) { if (lane == 0) s_tok[b] = -1; continue; }     // warp-uniform
-      float best = -INFINITY; int bi = 0x7fffffff;
-      int2 pv[8];                                              // all loads in flight first (G <= 256)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = lane + 32 * i;
-        pv[i] = c < G ? __ldcg(p.partial + static_cast<size_t>(b) * G + c) : make_int2(__float_as_int(-INFINITY), 0x7fffffff);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float f = __int_as_float(pv[i].x);
-        if (f > best || (f == best && pv[i].y < bi)) { best = f; bi = pv[i].y; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
-      if (lane == 0) {
-        const int k = bi;
-        if (k == blank) { s_t[b] += 1; s_sym[b] = 0; s_tok[b] = -1; }
-        else {
-          const int n = s_n[b];
-          if (cta == 0 && n < p.U_max) {
-            p.tokens[static_cast<size_t>(b) * p.U_max + n] = k;
-            p.frames[static_cast<size_t>(b) * p.U_max + n] = s_t[b];
-          }
-          s_n[b] = n + 1;
-          s_tok[b] = k;
-          if (++s_sym[b] >= p.max_symbols) { s_t[b] += 1; s_sym[b] = 0; }
+    // ---- token per active utterance from the packed maxima; advance the (t, symbols) state (identically in every CTA)
+    for (int b = tid; b < B; b += kBdThreads) {
+      if (!(s_t[b] < s_len[b])) { s_tok[b] = -1; continue; }
+      const unsigned long long v = __ldcg(p.best + static_cast<size_t>(iter % 3) * B + b);
+      const int k = static_cast<int>(0xffffffffu - static_cast<unsigned int>(v & 0xffffffffull));
+      if (k == blank) { s_t[b] += 1; s_sym[b] = 0; s_tok[b] = -1; }
+      else {
+        const int n = s_n[b];
+        if (cta == 0 && n < p.U_max) {
+          p.tokens[static_cast<size_t>(b) * p.U_max + n] = k;
+          p.frames[static_cast<size_t>(b) * p.U_max + n] = s_t[b];
         }
+        s_n[b] = n + 1;
+        s_tok[b] = k;
+        if (++s_sym[b] >= p.max_symbols) { s_t[b] += 1; s_sym[b] = 0; }
       }
     }
+    // the slot that iteration iter+2 will use was last read two barriers ago: clear it now (visible through the
+    // next barrier, which precedes that iteration's red.max)
+    if (cta == 0) for (int b = tid; b < B; b += kBdThreads) __stcg(p.best + static_cast<size_t>((iter + 2) % 3) * B + b, 0ull);
+    ++iter;
     __syncthreads();
     if (tid == 0) {                                // compact list of the utterances that emitted (ordered by b)
       int ne = 0, na = 0;
@@ -358,7 +351,7 @@ rnnt_greedy_batched_kernel(const BatchedDev p) {
 }
 
 size_t rnnt_batched_workspace_bytes(int B, int Hj, int Hp, int num_sms) {
-  return static_cast<size_t>(B) * num_sms * sizeof(int2) + static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + 256;
+  return static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + static_cast<size_t>(3) * B * 8 + 256;
 }
 
 template <int KJ, int KP>
@@ -383,9 +376,9 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
   p.w_pred = static_cast<const __nv_bfloat16*>(a.w_pred); p.b_pred = a.b_pred;
   p.tokens = a.tokens; p.frames = a.frames; p.n_tok = a.n_tok;
   char* ws = static_cast<char*>(workspace);
-  p.partial = reinterpret_cast<int2*>(ws); ws += static_cast<size_t>(a.B) * G * sizeof(int2);
   p.hbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(2) * a.B * a.Hp * 4;
   p.ppbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(a.B) * a.Hj * 4;
+  p.best = reinterpret_cast<unsigned long long*>(ws); ws += static_cast<size_t>(3) * a.B * 8;
   p.counter = reinterpret_cast<unsigned int*>(ws);
   p.prof = reinterpret_cast<long long*>(ws + 64);
   p.B = a.B; p.T_max = a.T_max; p.Hj = a.Hj; p.Hp = a.Hp; p.V = a.V; p.U_max = a.U_max; p.max_symbols = a.max_symbols;
@@ -393,7 +386,7 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
   p.units = (a.Hp + G - 1) / G;
   p.rows_p = (a.Hj + G - 1) / G;
   if (4 * p.units > 32 || G > 256) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(p.hbuf, 0, static_cast<size_t>(2) * a.B * a.Hp * 4 + static_cast<size_t>(a.B) * a.Hj * 4 + 256, stream);
+  cudaError_t e = cudaMemsetAsync(p.hbuf, 0, static_cast<size_t>(2) * a.B * a.Hp * 4 + static_cast<size_t>(a.B) * a.Hj * 4 + static_cast<size_t>(3) * a.B * 8 + 256, stream);
   if (e != cudaSuccess) return e;
   const size_t smem = (static_cast<size_t>(p.rows_j) * a.Hj + static_cast<size_t>(4 * p.units) * 2 * a.Hp + static_cast<size_t>(p.rows_p) * a.Hp) * 2 +
                       static_cast<size_t>(a.B) * p.units * 4 + static_cast<size_t>(a.B) * 7 * 4 + 64;

@@ -516,8 +516,8 @@ int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* o
   if (!e || !out8) return RS_ERR_INVALID_ARG;
   Plan p = make_plan(e, B, L_max, U_max);
   RS_CUDA(e, cudaDeviceSynchronize());
-  const size_t off = p.dec_ws + static_cast<size_t>(B) * e->num_sms * 8 + static_cast<size_t>(2) * B * e->cfg.pred_hidden * 4 +
-                     static_cast<size_t>(B) * e->cfg.joint_hidden * 4 + 64;
+  const size_t off = p.dec_ws + static_cast<size_t>(2) * B * e->cfg.pred_hidden * 4 + static_cast<size_t>(B) * e->cfg.joint_hidden * 4 +
+                     static_cast<size_t>(3) * B * 8 + 64;
   RS_CUDA(e, cudaMemcpy(out8, static_cast<char*>(e->ws) + off, 96, cudaMemcpyDeviceToHost));
   return RS_OK;
 }
