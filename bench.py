@@ -253,7 +253,10 @@ def main():
     eng.enable_stage_timing(False)
     decode_prof = eng.decode_cycles(B, L, U) if os.environ.get("RS_DECODE_MODE", "0") != "1" else None
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": None,
+    # DRAM bytes per launch of the dominant kernel: mean of dram__bytes_read.sum + dram__bytes_write.sum over the
+    # eight consecutive launches of the `ncu --set full` capture in profiles/r01_v2_gemm_ncu.md (not re-measured here)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": 1.011e8,
+                "traffic_source": "profiles/r01_v2_gemm_ncu.md (mean over 8 launches, bytes)",
                 "kernel": "gemm_bf16_tn_kernel (tcgen05.mma, all encoder/joint GEMMs)", "peak_source": f"{src} bf16_tflops_sustained",
                 "launches_per_step": g_n // max(args.steps, 1), "gemm_ms_per_step": g_ms / max(args.steps, 1),
                 "algorithmic_gflop_per_step": g_flops / max(args.steps, 1) / 1e9,
