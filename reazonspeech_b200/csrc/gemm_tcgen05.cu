@@ -134,6 +134,20 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       }
       break;
     }
+    case RS_EPI_BIAS_F32_SKEW: {
+      // positional term of the local attention: row r is stored shifted by (r % 64) + 64 columns, so that the
+      // 64-query attention tile finds the value for key j at the same column j - q0 + w_left + 64 in every row
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      for (int rl = 0; rl < 32; ++rl) {                        // one row (128 contiguous bytes) per instruction
+        const int row = tile_row0 + rl;
+        if (row < p.M)
+          static_cast<float*>(p.out)[static_cast<size_t>(row) * p.ldo + col_off + col0 + lane + (row & 63) + 64] = stage[rl * kStageLd + lane];
+      }
+      break;
+    }
     default: {  // RS_EPI_RESID_F32 / RS_EPI_BIAS_F32
 #pragma unroll
       for (int j = 0; j < 8; ++j)
