@@ -299,7 +299,7 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
       rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F32_SKEW, 1.f};
       g.lda = 3 * d; g.ldo = c.n_heads * (p.n_rel_pad + 128); g.n_batch = c.n_heads;
-      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad + 128;
+      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad + 128; g.rows_per_seq = p.T3;
       RS_TRY(gemm_args(e, g, s));
     }
     rs::AttnArgs aa{hb, at<float>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};

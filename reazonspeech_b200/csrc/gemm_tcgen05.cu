@@ -39,6 +39,7 @@ struct GemmDev {
   // optional batching along columns (one launch for all attention heads): batch b reads A columns
   // [b*a_col_stride, +K), W rows [b*w_row_stride, +N), bias + b*bias_stride, writes columns + b*out_col_stride
   int n_batch, a_col_stride, w_row_stride, bias_stride, out_col_stride;
+  int rows_per_seq;     // RS_EPI_BIAS_F32_SKEW: rows per utterance (the skew is taken on the frame index row % rows_per_seq)
 };
 
 template <int BN>
@@ -144,7 +145,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       for (int rl = 0; rl < 32; ++rl) {                        // one row (128 contiguous bytes) per instruction
         const int row = tile_row0 + rl;
         if (row < p.M)
-          static_cast<float*>(p.out)[static_cast<size_t>(row) * p.ldo + col_off + col0 + lane + (row & 63) + 64] = stage[rl * kStageLd + lane];
+          static_cast<float*>(p.out)[static_cast<size_t>(row) * p.ldo + col_off + col0 + lane + ((row % p.rows_per_seq) & 63) + 64] = stage[rl * kStageLd + lane];
       }
       break;
     }
@@ -492,7 +493,7 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, a_cols, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, w_rows, g.K, g.K, BN, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride};
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride, g.rows_per_seq > 0 ? g.rows_per_seq : 1 << 30};
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
@@ -515,7 +516,7 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0};
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.rows_per_seq > 0 ? g.rows_per_seq : 1 << 30};
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
