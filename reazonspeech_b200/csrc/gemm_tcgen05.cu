@@ -142,10 +142,13 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       __syncwarp();
+      int t = tile_row0 % p.rows_per_seq;                      // frame index of the chunk's first row
+      float* o = static_cast<float*>(p.out) + static_cast<size_t>(tile_row0) * p.ldo + col_off + col0 + lane + 64;
+#pragma unroll 4
       for (int rl = 0; rl < 32; ++rl) {                        // one row (128 contiguous bytes) per instruction
-        const int row = tile_row0 + rl;
-        if (row < p.M)
-          static_cast<float*>(p.out)[static_cast<size_t>(row) * p.ldo + col_off + col0 + lane + ((row % p.rows_per_seq) & 63) + 64] = stage[rl * kStageLd + lane];
+        if (tile_row0 + rl < p.M) o[(t & 63)] = stage[rl * kStageLd + lane];
+        o += p.ldo;
+        if (++t == p.rows_per_seq) t = 0;
       }
       break;
     }
