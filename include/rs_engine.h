@@ -68,8 +68,7 @@ typedef enum rs_epilogue {
   RS_EPI_BIAS_SWISH_BF16 = 2, /* out_bf16[M,N]   = swish(acc + bias)                           */
   RS_EPI_BIAS_GLU_BF16 = 3,   /* out_bf16[M,N/2] = a * sigmoid(g); W rows interleaved 16/16    */
   RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias)   */
-  RS_EPI_BIAS_F32 = 5,        /* out_f32[M,N]    = alpha * (acc + bias)                        */
-  RS_EPI_BIAS_F32_SKEW = 6    /* as 5, row r stored shifted right by (r % 64) + 64 columns (attention positional term) */
+  RS_EPI_BIAS_F32 = 5         /* out_f32[M,N]    = alpha * (acc + bias)                        */
 } rs_epilogue;
 
 /* ---- lifetime -------------------------------------------------------------------------- */

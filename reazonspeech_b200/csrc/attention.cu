@@ -155,12 +155,9 @@ local_attention_kernel(const AttnDev p) {
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
   }
-  // Positional rows of the two query rows this thread owns.  The GEMM stored row i shifted by (i % 64) + 64
-  // columns, so the value for key j sits at column j - q0 + w_left + 64 in EVERY row of this 64-query tile:
-  // the tile's window is rectangular and pairs (j, j+1) are aligned 8-byte loads.
-  const size_t bd_ld = static_cast<size_t>(p.H) * (p.n_rel_pad + 128);
-  const float* bd_lo = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_lo, p.T_max - 1)) * bd_ld + static_cast<size_t>(h) * (p.n_rel_pad + 128) + (p.w_left + 64 - q0);
-  const float* bd_hi = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_hi, p.T_max - 1)) * bd_ld + static_cast<size_t>(h) * (p.n_rel_pad + 128) + (p.w_left + 64 - q0);
+  // BD rows of the two query rows this thread owns (skewed read: column j - i + w_left)
+  const float* bd_lo = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_lo, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
+  const float* bd_hi = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_hi, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
   const int j_first = max(0, q0 - p.w_left);
   const int j_last = min(len - 1, q0 + QT - 1 + p.w_right);
   const int kt_first = j_first / KT, kt_last = j_last / KT;
@@ -182,10 +179,13 @@ local_attention_kernel(const AttnDev p) {
     float bdv[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int j = j0 + nt * 8 + 2 * t;                       // even: (j, j+1) is an aligned pair (w_left even)
-      const float2 lo = __ldg(reinterpret_cast<const float2*>(bd_lo + j));
-      const float2 hi = __ldg(reinterpret_cast<const float2*>(bd_hi + j));
-      bdv[nt][0] = lo.x; bdv[nt][1] = lo.y; bdv[nt][2] = hi.x; bdv[nt][3] = hi.y;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + nt * 8 + 2 * t + (e & 1);
+        const int rel = j - ((e < 2) ? i_lo : i_hi);
+        const bool ok = (j < len) && (rel >= -p.w_left) && (rel <= p.w_right);
+        bdv[nt][e] = ok ? __ldg(((e < 2) ? bd_lo : bd_hi) + rel + p.w_left) : 0.f;
+      }
     }
     float s[8][4];
 #pragma unroll
@@ -367,7 +367,7 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.bias_u = a.bias_u; p.out = static_cast<__nv_bfloat16*>(a.out); p.enc_len = a.enc_len;
   p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right; p.n_global = a.n_global;
   p.n_rel_pad = a.n_rel_pad;
-  if (a.n_rel_pad < a.w_left + a.w_right + 1 || (a.w_left & 1)) return cudaErrorInvalidValue;
+  if (a.n_rel_pad < a.w_left + a.w_right + 1) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(1 + 2 * kKvStages) * QT * LDS * 2 + QT * 4;
   static bool attr = false;
   if (!attr) {

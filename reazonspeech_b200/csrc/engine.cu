@@ -118,7 +118,7 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.abuf = take(static_cast<size_t>(p.M) * d * 2);
   p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
   p.n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32;
-  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * (p.n_rel_pad + 128) * 4 + 4096);   // skewed rows: + (r % 64) + 64 columns; slack for tile-granular reads
+  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * p.n_rel_pad * 4);
   p.enc = take(static_cast<size_t>(p.M) * d * 4);
   p.encp = take(static_cast<size_t>(p.M) * c.joint_hidden * 4);
   p.tokens = take(static_cast<size_t>(B) * U_max * 4);
@@ -297,9 +297,9 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
     {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
-      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F32_SKEW, 1.f};
-      g.lda = 3 * d; g.ldo = c.n_heads * (p.n_rel_pad + 128); g.n_batch = c.n_heads;
-      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad + 128; g.rows_per_seq = p.T3;
+      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F32, 1.f};
+      g.lda = 3 * d; g.ldo = c.n_heads * p.n_rel_pad; g.n_batch = c.n_heads;
+      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad;
       RS_TRY(gemm_args(e, g, s));
     }
     rs::AttnArgs aa{hb, at<float>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};

@@ -39,7 +39,6 @@ struct GemmDev {
   // optional batching along columns (one launch for all attention heads): batch b reads A columns
   // [b*a_col_stride, +K), W rows [b*w_row_stride, +N), bias + b*bias_stride, writes columns + b*out_col_stride
   int n_batch, a_col_stride, w_row_stride, bias_stride, out_col_stride;
-  int rows_per_seq;     // RS_EPI_BIAS_F32_SKEW: rows per utterance (the skew is taken on the frame index row % rows_per_seq)
 };
 
 template <int BN>
@@ -132,23 +131,6 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
         const uint4 a = *reinterpret_cast<const uint4*>(stage_u + rl * 12 + cw);
         if (row < p.M)
           *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 / 2 + cw * 2) = a;
-      }
-      break;
-    }
-    case RS_EPI_BIAS_F32_SKEW: {
-      // positional term of the local attention: row r is stored shifted by (r % 64) + 64 columns, so that the
-      // 64-query attention tile finds the value for key j at the same column j - q0 + w_left + 64 in every row
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      int t = tile_row0 % p.rows_per_seq;                      // frame index of the chunk's first row
-      float* o = static_cast<float*>(p.out) + static_cast<size_t>(tile_row0) * p.ldo + col_off + col0 + lane + 64;
-#pragma unroll 4
-      for (int rl = 0; rl < 32; ++rl) {                        // one row (128 contiguous bytes) per instruction
-        if (tile_row0 + rl < p.M) o[(t & 63)] = stage[rl * kStageLd + lane];
-        o += p.ldo;
-        if (++t == p.rows_per_seq) t = 0;
       }
       break;
     }
@@ -496,7 +478,7 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, a_cols, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, w_rows, g.K, g.K, BN, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride, g.rows_per_seq > 0 ? g.rows_per_seq : 1 << 30};
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride};
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
@@ -519,7 +501,7 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.rows_per_seq > 0 ? g.rows_per_seq : 1 << 30};
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0};
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;

@@ -17,7 +17,6 @@ struct GemmArgs {
   // optional: A row stride (elements, default K), output row stride (default N), column batching
   int lda = 0, ldo = 0;
   int n_batch = 1, a_col_stride = 0, w_row_stride = 0, bias_stride = 0, out_col_stride = 0;
-  int rows_per_seq = 0;   // RS_EPI_BIAS_F32_SKEW: rows per utterance (T_max)
 };
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
