@@ -81,45 +81,58 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
 // depthwise conv); t < 0 is the conv's own zero padding.  BatchNorm(eval) is folded at pack time:
 // w'[j][c] = w[c][j] * gamma/sqrt(var+eps),  shift[c] = (bias - mean) * gamma/sqrt(var+eps) + beta.
 template <int KW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 conv_dw_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out, const float* __restrict__ w,
                const float* __restrict__ shift, const int32_t* __restrict__ len, int T_max, int d, int tile_t) {
+  // four channels per thread (8-byte loads), four output frames per step: the four new input rows of a
+  // step are requested together, the (KW-1+4)-row window lives in registers.
   constexpr int PAD = (KW - 1) / 2;
+  constexpr int UN = 4;
   const int b = blockIdx.z;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= d) return;
   const int t0 = blockIdx.y * tile_t;
   const int n = len[b];
   const int t_end = min(t0 + tile_t, T_max);
-  float2 wt[KW];
+  float4 wt[KW];
 #pragma unroll
-  for (int j = 0; j < KW; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(j) * d + c));
-  const float2 sh = __ldg(reinterpret_cast<const float2*>(shift + c));
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(u + (static_cast<size_t>(b) * T_max) * d + c);
-  const size_t stride = static_cast<size_t>(d) / 2;   // in uint32 (bf16x2) units
-  auto load = [&](int t) -> float2 {
-    if (t < 0 || t >= n) return make_float2(0.f, 0.f);
-    return unpack_bf16x2(__ldg(base + static_cast<size_t>(t) * stride));
+  for (int j = 0; j < KW; ++j) wt[j] = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(j) * d + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+  const __nv_bfloat16* base = u + (static_cast<size_t>(b) * T_max) * d + c;
+  auto load = [&](int t) -> float4 {
+    if (t < 0 || t >= n) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(base + static_cast<size_t>(t) * d));
+    return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
   };
-  float2 win[KW];
+  float4 win[KW - 1 + UN];
 #pragma unroll
-  for (int j = 0; j < KW - 1; ++j) win[j + 1] = load(t0 - PAD + j);
-  for (int t = t0; t < t_end; ++t) {
+  for (int j = 0; j < KW - 1; ++j) win[j] = load(t0 - PAD + j);
+  for (int t = t0; t < t_end; t += UN) {
 #pragma unroll
-    for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
-    win[KW - 1] = load(t + PAD);
-    float ax = sh.x, ay = sh.y;
+    for (int q = 0; q < UN; ++q) win[KW - 1 + q] = load(t + q + PAD);
 #pragma unroll
-    for (int j = 0; j < KW; ++j) { ax = fmaf(win[j].x, wt[j].x, ax); ay = fmaf(win[j].y, wt[j].y, ay); }
-    *reinterpret_cast<uint32_t*>(out + (static_cast<size_t>(b) * T_max + t) * d + c) = pack_bf16x2(swishf_fast(ax), swishf_fast(ay));
+    for (int q = 0; q < UN; ++q) {
+      float4 a = sh;
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        a.x = fmaf(win[q + j].x, wt[j].x, a.x); a.y = fmaf(win[q + j].y, wt[j].y, a.y);
+        a.z = fmaf(win[q + j].z, wt[j].z, a.z); a.w = fmaf(win[q + j].w, wt[j].w, a.w);
+      }
+      if (t + q < t_end)
+        *reinterpret_cast<uint2*>(out + (static_cast<size_t>(b) * T_max + t + q) * d + c) =
+            make_uint2(pack_bf16x2(swishf_fast(a.x), swishf_fast(a.y)), pack_bf16x2(swishf_fast(a.z), swishf_fast(a.w)));
+    }
+#pragma unroll
+    for (int j = 0; j < KW - 1; ++j) win[j] = win[j + UN];
   }
 }
 
 cudaError_t launch_conv_dw(const void* u, void* out, const float* w, const float* shift, const int32_t* enc_len,
                            int B, int T_max, int d, int k, cudaStream_t stream) {
-  if (k != 9 || (d & 1)) return cudaErrorInvalidValue;
-  const int tile_t = 32;
-  const dim3 block(128), grid((d / 2 + 127) / 128, (T_max + tile_t - 1) / tile_t, B);
+  if (k != 9 || (d & 3)) return cudaErrorInvalidValue;
+  const int tile_t = 16;
+  const int threads = d / 4 < 256 ? d / 4 : 256;
+  const dim3 block(threads), grid((d / 4 + threads - 1) / threads, (T_max + tile_t - 1) / tile_t, B);
   conv_dw_kernel<9><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
                                                 w, shift, enc_len, T_max, d, tile_t);
   return cudaGetLastError();

@@ -124,17 +124,20 @@ __global__ void __launch_bounds__(128)
 sub_dw_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ w,
               const float* __restrict__ bias, const int32_t* __restrict__ mel_len, int len_shift, int Tin, int Fin,
               int Tout, int Fout, int C) {
+  // eight channels per thread: one 16-byte load per tap
   const int b = blockIdx.z, t = blockIdx.y;
   int lin = mel_len[b];
   for (int i = 0; i < len_shift; ++i) lin = conv_len(lin);
   const int lout = conv_len(lin);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // over Fout * C/2
-  const int c2 = C / 2;
-  if (idx >= Fout * c2) return;
-  const int f = idx / c2, c = (idx % c2) * 2;
-  uint32_t* o = reinterpret_cast<uint32_t*>(out + ((static_cast<size_t>(b) * Tout + t) * Fout + f) * C + c);
-  if (t >= lout) { *o = 0u; return; }
-  float ax = __ldg(bias + c), ay = __ldg(bias + c + 1);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // over Fout * C/8
+  const int c8 = C / 8;
+  if (idx >= Fout * c8) return;
+  const int f = idx / c8, c = (idx % c8) * 8;
+  uint4* o = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Tout + t) * Fout + f) * C + c);
+  if (t >= lout) { *o = make_uint4(0u, 0u, 0u, 0u); return; }
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = __ldg(bias + c + k);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int ti = 2 * t - 1 + i;
@@ -143,17 +146,22 @@ sub_dw_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ 
     for (int j = 0; j < 3; ++j) {
       const int fi = 2 * f - 1 + j;
       if (fi < 0 || fi >= Fin) continue;
-      const float2 v = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(in + ((static_cast<size_t>(b) * Tin + ti) * Fin + fi) * C + c)));
-      ax = fmaf(v.x, __ldg(w + c * 9 + i * 3 + j), ax);
-      ay = fmaf(v.y, __ldg(w + (c + 1) * 9 + i * 3 + j), ay);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * Tin + ti) * Fin + fi) * C + c));
+      const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a[2 * k] = fmaf(bf16_lo(vw[k]), __ldg(w + (c + 2 * k) * 9 + i * 3 + j), a[2 * k]);
+        a[2 * k + 1] = fmaf(bf16_hi(vw[k]), __ldg(w + (c + 2 * k + 1) * 9 + i * 3 + j), a[2 * k + 1]);
+      }
     }
   }
-  *o = pack_bf16x2(ax, ay);
+  *o = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
 }
 
 cudaError_t launch_sub_dw(const void* in, void* out, const float* w, const float* b, const int32_t* mel_len, int len_shift,
                           int B, int Tin, int Fin, int Tout, int Fout, int C, cudaStream_t stream) {
-  const int work = Fout * (C / 2);
+  if (C % 8) return cudaErrorInvalidValue;
+  const int work = Fout * (C / 8);
   const dim3 grid((work + 127) / 128, Tout, B);
   sub_dw_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), w, b,
                                           mel_len, len_shift, Tin, Fin, Tout, Fout, C);
