@@ -83,9 +83,15 @@ const char* rs_last_error(const rs_engine* e);
 int rs_workspace_bytes(const rs_engine* e, int B, int L_max, size_t* bytes);
 int rs_set_workspace(rs_engine* e, void* dev_ptr, size_t bytes);
 
-/* ---- shape arithmetic (FilterbankFeatures.get_seq_len, ConvSubsampling.calc_length) ----- */
+/* ---- shape arithmetic --------------------------------------------------------------------
+ * rs_mel_frames / rs_enc_frames: TENSOR time sizes for a buffer of n_samples (frames of the centred
+ * STFT = n/hop + 1, and ConvSubsampling.calc_length applied to it three times): what callers allocate.
+ * rs_mel_valid / rs_enc_valid: the VALID lengths of an utterance of n_samples
+ * (FilterbankFeatures.get_seq_len = n/hop, then calc_length x3): what mel_len / enc_len will hold. */
 int rs_mel_frames(const rs_engine* e, int n_samples);
 int rs_enc_frames(const rs_engine* e, int n_samples);
+int rs_mel_valid(const rs_engine* e, int n_samples);
+int rs_enc_valid(const rs_engine* e, int n_samples);
 
 /* ---- stages (each is also a parity-test seam) --------------------------------------------- */
 /* N1 AudioToMelSpectrogramPreprocessor: wav f32[B,L_max] + len -> mel f32[B,F_max,n_mels]

@@ -6,13 +6,21 @@ THIS IS TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and t
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
 package ``reazonspeech_b200`` never does.
 
-PARITY UNPINNED.  The arithmetic of this path lives in the third-party dependency
-``nemo_toolkit[asr] >= 2.6.1`` (pkg/nemo-asr/pyproject.toml:13), which is absent from
-/root/reference, cannot be imported in the build container, and for which the reference
-ships no tests, golden vectors or fixtures.  What follows restates
-NeMo's published algorithm module by module from the upstream sources named in each
-docstring; it has not been diffed against a NeMo run.  Every place where upstream
-behaviour is recalled rather than verified is marked (R).
+PARITY: PINNED FOR N1-N7 AGAINST A THIRD-PARTY PORT OF NeMo, UNPINNED FOR THE REST.  The arithmetic
+of this path lives in ``nemo_toolkit[asr] >= 2.6.1`` (pkg/nemo-asr/pyproject.toml:13), which is absent
+from /root/reference and cannot be imported offline, and the reference ships no tests, golden vectors
+or fixtures for it.  What the image does ship is ``transformers.models.parakeet``,
+NVIDIA's port of NeMo's FilterbankFeatures + FastConformer encoder: tests/golden/make_parakeet_golden.py
+runs it on seeded weights/clips and tests/test_oracle_parakeet.py holds this file to its outputs
+(log-mel incl. the get_seq_len = L // hop length convention and the masked final frame, dw_striding
+subsampling, xscale, relative positional encoding + rel_shift, MHSA, convolution module, macaron FFN,
+LayerNorm order: encoder output relative L2 1e-5).  Parakeet has full relative-position attention only,
+so the pin covers the local-attention code path with T <= w + 1 and no global token.  NOT covered, and
+still recalled (R) rather than verified: the global-token wiring of
+RelPositionMultiHeadAttentionLongformer, and the RNN-T prediction network / joint / greedy loop
+(``max_symbols``) -- standard LSTM-transducer arithmetic restated from NeMo's modules/rnnt.py.
+The reference-owned ``decode_hypothesis`` is pinned separately by importing the reference's decode.py
+(tests/golden/make_decode_golden.py).
 
 Semantics are batch=1, exactly as the reference calls NeMo (transcribe.py:48-50): every
 function takes ONE utterance with no padding.  ``emulate`` switches on bf16 rounding of
@@ -43,7 +51,12 @@ def _q(x: torch.Tensor, emulate: bool) -> torch.Tensor:
 #     (nemo/collections/asr/parts/preprocessing/features.py)
 # --------------------------------------------------------------------------------------
 def log_mel(wave: torch.Tensor, cfg: ModelConfig, independent_fb: bool = False) -> torch.Tensor:
-    """float32[L] -> float32[n_mels, F], F = L // hop + 1 (all frames valid at batch=1).
+    """float32[L] -> float32[n_mels, F], F = L // hop: the VALID frames (``get_seq_len``).
+
+    The centred STFT yields L // hop + 1 frames; NeMo's length is one less, the final frame is
+    masked to zero, stays out of the statistics, and every later stage masks by length -- which at
+    batch=1 is the same as dropping it here (pinned against transformers' Parakeet port of NeMo,
+    tests/test_oracle_parakeet.py).
 
     preemph -> torch.stft(center=True, zero pad (R: "constant"; identical to "reflect" on
     transcribe() inputs, whose 0.5 s edges are silence -- audio.py:80-82)) -> |X| -> **2 ->
@@ -64,6 +77,7 @@ def log_mel(wave: torch.Tensor, cfg: ModelConfig, independent_fb: bool = False) 
     mel = torch.matmul(fb, power)
     mel = torch.log(mel + cfg.log_zero_guard)
     assert mel.shape[1] == cfg.mel_frames(wave.numel())
+    mel = mel[:, : cfg.mel_valid(wave.numel())]
     mean = mel.mean(dim=1, keepdim=True)
     std = mel.std(dim=1, keepdim=True) + cfg.norm_eps          # unbiased (N-1)
     return (mel - mean) / std

@@ -84,11 +84,20 @@ class ModelConfig:
         return self.att_left + self.att_right + 1
 
     def mel_frames(self, n_samples: int) -> int:
-        """FilterbankFeatures.get_seq_len with center=True: L // hop + 1."""
+        """Frames the centred STFT produces (the feature TENSOR's time size): L // hop + 1."""
         return n_samples // self.n_window_stride + 1
 
+    def mel_valid(self, n_samples: int) -> int:
+        """FilterbankFeatures.get_seq_len (NeMo 2.x): floor((L + 2*(n_fft//2) - n_fft) / hop) = L // hop.
+
+        One less than the STFT's frame count: the final frame is masked to zero and excluded from
+        the normalisation statistics.  Pinned by transformers' Parakeet port of NeMo
+        (feature_extraction_parakeet.py ``features_lengths``; tests/golden/make_parakeet_golden.py)."""
+        return (n_samples + 2 * (self.n_fft // 2) - self.n_fft) // self.n_window_stride
+
     def enc_frames(self, n_samples: int) -> int:
-        t = self.mel_frames(n_samples)
+        """Valid encoder frames: ConvSubsampling.calc_length applied three times to ``mel_valid``."""
+        t = self.mel_valid(n_samples)
         for _ in range(3):
             t = conv_out_len(t)
         return t

@@ -406,6 +406,8 @@ int rs_set_workspace(rs_engine* e, void* dev_ptr, size_t bytes) {
 
 int rs_mel_frames(const rs_engine* e, int n) { return n / e->cfg.n_window_stride + 1; }
 int rs_enc_frames(const rs_engine* e, int n) { return conv_len(conv_len(conv_len(rs_mel_frames(e, n)))); }
+int rs_mel_valid(const rs_engine* e, int n) { return (n + 2 * (e->cfg.n_fft / 2) - e->cfg.n_fft) / e->cfg.n_window_stride; }
+int rs_enc_valid(const rs_engine* e, int n) { return conv_len(conv_len(conv_len(rs_mel_valid(e, n)))); }
 
 int rs_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, void* stream) {
   if (!e || !wav || !len || !mel || !mel_len || B <= 0 || L_max <= 0) return fail(e, RS_ERR_INVALID_ARG, "rs_logmel: bad arguments");

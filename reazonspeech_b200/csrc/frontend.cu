@@ -38,7 +38,9 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, in
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * kFramesPerBlock;
   const int n = len[b];
-  const int n_frames = n / hop + 1;
+  // valid frames = FilterbankFeatures.get_seq_len = n / hop (n_fft even): one less than the centred STFT yields;
+  // NeMo masks that final frame to zero and keeps it out of the statistics (config.py::mel_valid)
+  const int n_frames = n / hop;
   if (blockIdx.x == 0 && threadIdx.x == 0) mel_len[b] = n_frames;
   if (f0 >= n_frames) return;
 

@@ -46,7 +46,7 @@ _lib = None
 
 EXPORTS = [
     "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
-    "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
+    "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
 ]
@@ -74,6 +74,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_set_workspace.argtypes = [vp, vp, C.c_size_t]
     lib.rs_mel_frames.argtypes = [vp, ip]
     lib.rs_enc_frames.argtypes = [vp, ip]
+    lib.rs_mel_valid.argtypes = [vp, ip]
+    lib.rs_enc_valid.argtypes = [vp, ip]
     lib.rs_logmel.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp]
     lib.rs_encode.argtypes = [vp, vp, vp, ip, ip, vp, vp, ip, vp]
     lib.rs_rnnt_greedy.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
@@ -89,7 +91,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_debug_decode_cycles.restype = ip
     lib.rs_enable_gemm_timing.argtypes = [vp, ip]
     lib.rs_gemm_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-    for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_logmel", "rs_encode",
+    for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode",
                "rs_rnnt_greedy", "rs_transcribe_device", "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm",
                "rs_enable_stage_timing", "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing"):
         getattr(lib, fn).restype = ip

@@ -14,7 +14,7 @@ from reazonspeech_b200.weights import mel_filterbank, random_state_dict, rel_pos
 
 def test_shape_arithmetic_matches_survey():
     c = ModelConfig()
-    assert c.mel_frames(496000) == 3101 and c.enc_frames(496000) == 388
+    assert c.mel_frames(496000) == 3101 and c.mel_valid(496000) == 3100 and c.enc_frames(496000) == 388
     assert [conv_out_len(n) for n in (3101, 1551, 776)] == [1551, 776, 388]
     assert c.sub_freq == 10 and c.sub_out_dim == 2560 and c.n_rel == 257
 
@@ -34,7 +34,7 @@ def test_mel_filterbank_matches_torchaudio(tiny_cfg):
 
 def test_log_mel_statistics(tiny_cfg):
     m = O.log_mel(torch.from_numpy(np.pad(synth_clip(1, 2.0), 8000)), tiny_cfg)
-    assert m.shape == (80, tiny_cfg.mel_frames(48000))
+    assert m.shape == (80, tiny_cfg.mel_valid(48000)) and tiny_cfg.mel_valid(48000) == tiny_cfg.mel_frames(48000) - 1
     assert m.mean(1).abs().max() < 1e-4 and (m.std(1) - 1).abs().max() < 1e-3
 
 
