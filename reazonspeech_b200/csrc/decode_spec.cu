@@ -1,0 +1,554 @@
+// Windowed ("blank-run speculative") batched RNN-T greedy decode on the legacy tensor path.
+//
+// Same algorithm and results as decode_batched.cu / decode.cu (NeMo GreedyRNNTInfer._greedy_decode,
+// RNNTDecoder.predict, RNNTJoint.joint; the reference reaches it at pkg/nemo-asr/src/transcribe.py:48-53),
+// reorganised around two facts about greedy transducer decoding:
+//
+//  1. A blank leaves the prediction-network state untouched, so the joint of the NEXT frames can be
+//     evaluated against the same state before the current decision is known.  Every iteration scores a
+//     window of kFrames consecutive frames per utterance; the utterance then consumes the window up to and
+//     including its first non-blank frame (all-blank window: kFrames frames in one iteration).  The decision
+//     sequence is exactly the sequential one; the number of lock-step iterations drops from max(T + U) to
+//     about max(U + (T - U)/kFrames).
+//  2. With kFrames x B rows per iteration the joint is a real (small) GEMM.  The CTAs form a 2-D grid,
+//     kGroups utterance groups x S vocabulary slices: a CTA keeps its ~82 rows of W_out in shared memory
+//     for the whole decode and multiplies them with the relu(enc_proj + pred_proj) rows of its group
+//     (32 rows per pass) on mma.sync m16n8k16.  Activations stay fp32-exact: every fp32 value is split into
+//     three bf16 terms (hi + mid + lo = 24 mantissa bits), the weights are bf16 already, accumulation is
+//     fp32 - the products are the same as an fp32 FMA's, only the summation order differs.
+//     The LSTM step and joint.pred of the utterances that emitted are the same kind of GEMM (rows =
+//     utterances, K split over the warps, A fragments loaded straight from L2).
+//
+//   phase J  kGroups x S CTAs: window logits of the CTA's vocabulary slice -> per (utterance, frame) a grid-wide
+//            64-bit red.max of (ordered logit bits | ~row)
+//   barrier  -> every CTA reads the window's tokens, advances (t, symbols), emits
+//   phase L  utterances that emitted: LSTM gates of the CTA's units -> new h slice
+//   barrier
+//   phase P  utterances that emitted: pred_proj rows of the CTA from the new h
+//   barrier
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rs {
+
+constexpr int kSpThreads = 256;
+constexpr int kSpWarps = kSpThreads / 32;
+constexpr int kFrames = 4;                       // frames scored per utterance and iteration
+constexpr int kGroups = 4;                       // utterance groups (utterance b belongs to group b % kGroups)
+constexpr int kPassRows = 32;                    // (utterance, frame) rows per pass: two m16 tiles
+constexpr int kPassUtts = kPassRows / kFrames;
+constexpr int kMaxTilesPerWarp = 3;              // vocabulary n8-tiles per warp (4 warps share an m16 tile)
+
+struct SpecDev {
+  const float* enc_proj; const int32_t* enc_len;
+  const __nv_bfloat16* w_out; const float* b_out; const float* embed;
+  const __nv_bfloat16* w_lstm; const float* b_lstm; const __nv_bfloat16* w_pred; const float* b_pred;
+  int32_t* tokens; int32_t* frames; int32_t* n_tok;
+  unsigned long long* best;   // [3][B][kFrames] packed (ordered logit bits << 32 | ~row), 3-deep ring
+  float* hbuf;                // [2][B][Hp]
+  float* ppbuf;               // [B][Hj]
+  unsigned int* counter;      // grid barrier
+  long long* prof;            // [12] cycle counters of CTA 0
+  int B, T_max, V, U_max, max_symbols;
+  int S, rows_j, units, rows_p;
+};
+
+__device__ __forceinline__ void sp_grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// fp32 pair -> three bf16 pairs with hi + mid + lo == x exactly (8 + 8 + 8 mantissa bits)
+__device__ __forceinline__ void split3(float2 x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  hi = pack_bf16x2(x.x, x.y);
+  const float r0 = x.x - bf16_lo(hi), r1 = x.y - bf16_hi(hi);
+  mid = pack_bf16x2(r0, r1);
+  lo = pack_bf16x2(r0 - bf16_lo(mid), r1 - bf16_hi(mid));
+}
+
+__device__ __forceinline__ float2 ldcg2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float4 ldcg4s(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ unsigned long long pack_best(float v, int row) {
+  unsigned int fb = __float_as_uint(v);
+  fb = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);           // order-preserving
+  return (static_cast<unsigned long long>(fb) << 32) | (0xffffffffu - static_cast<unsigned int>(row));   // ties -> lower row
+}
+
+template <int HJ, int HP>
+__global__ void __launch_bounds__(kSpThreads, 1)
+rnnt_greedy_spec_kernel(const SpecDev p) {
+  constexpr int KH = HJ / 2;                 // joint k-half staged in shared memory at a time
+  constexpr int GS = KH + 8;                 // s_g row stride in floats   (stride % 32 == 8: conflict-free LDS.64 fragments)
+  constexpr int WS = HJ + 8;                 // W_out / W_pred row stride in bf16 (word stride % 32 == 4: conflict-free B fragments)
+  constexpr int LS = 2 * HP + 8;             // W_lstm row stride in bf16
+  constexpr int KS_H = KH / 16;              // k16 steps per joint half
+  constexpr int KSW_L = (2 * HP / 16) / kSpWarps;   // k16 steps per warp, LSTM
+  constexpr int KSW_P = (HP / 16) / kSpWarps;       // k16 steps per warp, joint.pred
+  constexpr int V4_ROW = KH / 4;             // float4 per staged row
+  constexpr int PER = (kPassRows * V4_ROW + kSpThreads - 1) / kSpThreads;
+  constexpr int G_FLOATS = (kPassRows * GS > kSpWarps * 16 * 24) ? kPassRows * GS : kSpWarps * 16 * 24;   // s_g doubles as the L / P reduction buffer
+  static_assert(HJ % 32 == 0 && (2 * HP / 16) % kSpWarps == 0 && (HP / 16) % kSpWarps == 0, "shape");
+
+  extern __shared__ __align__(16) uint8_t ssm[];
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int NC = p.V + 1, blank = p.V, B = p.B;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+
+  // ---- slices owned by this CTA
+  const int grp = cta / p.S, slice = cta % p.S;
+  const bool has_j = grp < kGroups;
+  const int j0 = min(NC, slice * p.rows_j), j1 = min(NC, j0 + p.rows_j);
+  const int nj = has_j ? j1 - j0 : 0;
+  const int n_tiles = (p.rows_j + 7) / 8;
+  const int u0 = min(HP, cta * p.units), u1 = min(HP, u0 + p.units);
+  const int nu = u1 - u0;
+  const int p0 = min(HJ, cta * p.rows_p), p1 = min(HJ, p0 + p.rows_p);
+  const int np = p1 - p0;
+
+  // ---- shared memory carve-up.  B fragments of a partial last n8-tile read past the end of a weight array
+  // into the next one; those columns are masked, and every array is followed by at least 8 more rows of bytes.
+  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(ssm);                      // [rows_j][WS]
+  __nv_bfloat16* s_wlstm = s_wout + static_cast<size_t>(p.rows_j) * WS;               // [4*units][LS] gate-major
+  __nv_bfloat16* s_wpred = s_wlstm + static_cast<size_t>(4 * p.units) * LS;           // [rows_p][WS']  (WS' = HP + 8)
+  float* s_g = reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8));   // [32][GS]; also the L / P reduction buffer
+  float* s_bout = s_g + G_FLOATS;                                                    // [n_tiles*8], -inf beyond nj
+  float* s_c = s_bout + n_tiles * 8;                                                 // [B][units]
+  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_c + ((static_cast<size_t>(B) * p.units + 1) & ~static_cast<size_t>(1)));   // [32][4]
+  int* s_t = reinterpret_cast<int*>(s_best + kPassRows * 4);
+  int* s_sym = s_t + B; int* s_n = s_sym + B; int* s_par = s_n + B; int* s_tok = s_par + B;
+  int* s_emit = s_tok + B; int* s_len = s_emit + B;
+  int* s_cnt = s_len + B;                                                            // [0] n_emit, [1] n_active, [2..2+8) warp counts x2
+
+  {
+    const uint32_t zero = 0;
+    // W_out slice (rows beyond nj zero-filled)
+    for (int i = tid; i < p.rows_j * (HJ / 8); i += kSpThreads) {
+      const int r = i / (HJ / 8), c = i % (HJ / 8);
+      uint4 v = make_uint4(zero, zero, zero, zero);
+      if (r < nj) v = reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c];
+      *reinterpret_cast<uint4*>(s_wout + static_cast<size_t>(r) * WS + c * 8) = v;
+    }
+    for (int i = tid; i < 4 * p.units * (2 * HP / 8); i += kSpThreads) {
+      const int r = i / (2 * HP / 8), c = i % (2 * HP / 8);
+      const int gate = r / p.units, u = r % p.units;
+      uint4 v = make_uint4(zero, zero, zero, zero);
+      if (u < nu) v = reinterpret_cast<const uint4*>(p.w_lstm + (static_cast<size_t>(gate) * HP + u0 + u) * 2 * HP)[c];
+      *reinterpret_cast<uint4*>(s_wlstm + static_cast<size_t>(r) * LS + c * 8) = v;
+    }
+    for (int i = tid; i < p.rows_p * (HP / 8); i += kSpThreads) {
+      const int r = i / (HP / 8), c = i % (HP / 8);
+      uint4 v = make_uint4(zero, zero, zero, zero);
+      if (r < np) v = reinterpret_cast<const uint4*>(p.w_pred + static_cast<size_t>(p0 + r) * HP)[c];
+      *reinterpret_cast<uint4*>(s_wpred + static_cast<size_t>(r) * (HP + 8) + c * 8) = v;
+    }
+    for (int i = tid; i < n_tiles * 8; i += kSpThreads) s_bout[i] = i < nj ? p.b_out[j0 + i] : -INFINITY;
+    for (int i = tid; i < B * p.units; i += kSpThreads) s_c[i] = 0.f;
+    for (int b = tid; b < B; b += kSpThreads) {
+      s_t[b] = 0; s_sym[b] = 0; s_n[b] = 0; s_par[b] = 0; s_tok[b] = blank; s_emit[b] = b; s_len[b] = p.enc_len[b];
+    }
+    if (tid == 0) { s_cnt[0] = B; s_cnt[1] = 0; }
+  }
+  __syncthreads();
+
+  unsigned int target = 0;
+  int iter = 0;
+  long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  auto tick = [&](int slot, long long& t0) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; } };
+  long long tk = clock64();
+
+  // ------------------------------------------------------------------------------------------------
+  // LSTM step + joint.pred for the utterances listed in s_emit[0..n_emit): token s_tok[b], state parity s_par[b]
+  // ------------------------------------------------------------------------------------------------
+  auto lstm_and_pred = [&]() {
+    const int n_emit = s_cnt[0];
+    float* red = s_g;                                  // [warps][16][24]
+    // ---- phase L: gates[utterance][4*units] = (embed[k] | h) . W_lstm[slice]^T, K split over the warps
+    if (nu > 0) {
+      const int kw = (warp + cta) % kSpWarps;          // which k-range this warp takes (rotated per CTA against L2 hot-spotting)
+      for (int m0 = 0; m0 < n_emit; m0 += 16) {
+        const int ea = m0 + gid, eb = ea + 8;
+        const bool va = ea < n_emit, vb = eb < n_emit;
+        const int ba = va ? s_emit[ea] : 0, bb = vb ? s_emit[eb] : 0;
+        const float* emb_a = p.embed + static_cast<size_t>(va ? s_tok[ba] : 0) * HP;
+        const float* emb_b = p.embed + static_cast<size_t>(vb ? s_tok[bb] : 0) * HP;
+        const float* h_a = p.hbuf + (static_cast<size_t>(s_par[ba]) * B + ba) * HP;
+        const float* h_b = p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * HP;
+        float2 xa[KSW_L][2], xb[KSW_L][2];
+#pragma unroll
+        for (int i = 0; i < KSW_L; ++i) {
+          const int ks = kw * KSW_L + i;
+          const bool in_e = ks < HP / 16;
+          const int off = (in_e ? ks : ks - HP / 16) * 16 + tig * 2;
+          const float* pa = (in_e ? emb_a : h_a) + off;
+          const float* pb = (in_e ? emb_b : h_b) + off;
+          xa[i][0] = va ? ldcg2(pa) : make_float2(0.f, 0.f); xa[i][1] = va ? ldcg2(pa + 8) : make_float2(0.f, 0.f);
+          xb[i][0] = vb ? ldcg2(pb) : make_float2(0.f, 0.f); xb[i][1] = vb ? ldcg2(pb + 8) : make_float2(0.f, 0.f);
+        }
+        float acc[3][4];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+#pragma unroll
+        for (int i = 0; i < KSW_L; ++i) {
+          const int ks = kw * KSW_L + i;
+          uint32_t ah[4], am[4], al[4];
+          split3(xa[i][0], ah[0], am[0], al[0]); split3(xb[i][0], ah[1], am[1], al[1]);
+          split3(xa[i][1], ah[2], am[2], al[2]); split3(xb[i][1], ah[3], am[3], al[3]);
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {
+            if (n * 8 < 4 * p.units) {                 // warp-uniform
+              const __nv_bfloat16* wr = s_wlstm + static_cast<size_t>(n * 8 + gid) * LS + ks * 16 + tig * 2;
+              const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+              mma_bf16_16816(acc[n], ah, b0, b1); mma_bf16_16816(acc[n], am, b0, b1); mma_bf16_16816(acc[n], al, b0, b1);
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+          float* r0 = red + (warp * 16 + gid) * 24 + n * 8 + tig * 2;
+          r0[0] = acc[n][0]; r0[1] = acc[n][1]; r0[8 * 24] = acc[n][2]; r0[8 * 24 + 1] = acc[n][3];
+        }
+        __syncthreads();
+        if (tid < 16 * nu) {
+          const int el = tid / nu, u = tid % nu, e = m0 + el;
+          if (e < n_emit) {
+            const int b = s_emit[e], unit = u0 + u;
+            float gsum[4];
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate) {
+              float s = 0.f;
+#pragma unroll
+              for (int w = 0; w < kSpWarps; ++w) s += red[(w * 16 + el) * 24 + gate * p.units + u];
+              gsum[gate] = s + __ldg(p.b_lstm + gate * HP + unit);
+            }
+            const float ig = sigmoidf_accurate(gsum[0]), fg = sigmoidf_accurate(gsum[1]);
+            const float cg = tanhf(gsum[2]), og = sigmoidf_accurate(gsum[3]);
+            const float c2 = fg * s_c[b * p.units + u] + ig * cg;
+            s_c[b * p.units + u] = c2;
+            __stcg(p.hbuf + (static_cast<size_t>(s_par[b] ^ 1) * B + b) * HP + unit, og * tanhf(c2));
+          }
+        }
+        __syncthreads();
+      }
+    }
+    tick(3, tk);
+    sp_grid_barrier(p.counter, target, G);
+    tick(4, tk);
+    // ---- phase P (state parity flips for the utterances that stepped)
+    for (int e = tid; e < n_emit; e += kSpThreads) s_par[s_emit[e]] ^= 1;
+    __syncthreads();
+    if (np > 0) {
+      const int kw = (warp + cta) % kSpWarps;
+      for (int m0 = 0; m0 < n_emit; m0 += 16) {
+        const int ea = m0 + gid, eb = ea + 8;
+        const bool va = ea < n_emit, vb = eb < n_emit;
+        const int ba = va ? s_emit[ea] : 0, bb = vb ? s_emit[eb] : 0;
+        const float* h_a = p.hbuf + (static_cast<size_t>(s_par[ba]) * B + ba) * HP;
+        const float* h_b = p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * HP;
+        float2 xa[KSW_P][2], xb[KSW_P][2];
+#pragma unroll
+        for (int i = 0; i < KSW_P; ++i) {
+          const int off = (kw * KSW_P + i) * 16 + tig * 2;
+          xa[i][0] = va ? ldcg2(h_a + off) : make_float2(0.f, 0.f); xa[i][1] = va ? ldcg2(h_a + off + 8) : make_float2(0.f, 0.f);
+          xb[i][0] = vb ? ldcg2(h_b + off) : make_float2(0.f, 0.f); xb[i][1] = vb ? ldcg2(h_b + off + 8) : make_float2(0.f, 0.f);
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < KSW_P; ++i) {
+          const int ks = kw * KSW_P + i;
+          uint32_t ah[4], am[4], al[4];
+          split3(xa[i][0], ah[0], am[0], al[0]); split3(xb[i][0], ah[1], am[1], al[1]);
+          split3(xa[i][1], ah[2], am[2], al[2]); split3(xb[i][1], ah[3], am[3], al[3]);
+          const __nv_bfloat16* wr = s_wpred + static_cast<size_t>(gid) * (HP + 8) + ks * 16 + tig * 2;
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+          mma_bf16_16816(acc, ah, b0, b1); mma_bf16_16816(acc, am, b0, b1); mma_bf16_16816(acc, al, b0, b1);
+        }
+        {
+          float* r0 = red + (warp * 16 + gid) * 8 + tig * 2;
+          r0[0] = acc[0]; r0[1] = acc[1]; r0[8 * 8] = acc[2]; r0[8 * 8 + 1] = acc[3];
+        }
+        __syncthreads();
+        if (tid < 16 * np) {
+          const int el = tid / np, r = tid % np, e = m0 + el;
+          if (e < n_emit) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSpWarps; ++w) s += red[(w * 16 + el) * 8 + r];
+            __stcg(p.ppbuf + static_cast<size_t>(s_emit[e]) * HJ + p0 + r, s + __ldg(p.b_pred + p0 + r));
+          }
+        }
+        __syncthreads();
+      }
+    }
+    tick(5, tk);
+    sp_grid_barrier(p.counter, target, G);
+    tick(6, tk);
+  };
+
+  lstm_and_pred();                                // SOS: every utterance steps once on the blank (zero) embedding
+
+  const int bg_max = (B + kGroups - 1) / kGroups;            // utterances in the largest group
+  const int n_pass = (bg_max + kPassUtts - 1) / kPassUtts;
+  const int mt = warp & 1, ng = warp >> 1;                   // this warp's m16 tile and n8-tile residue class
+
+  for (;;) {
+    // ---- phase J
+    if (has_j) {
+      for (int pass = 0; pass < n_pass; ++pass) {
+        // row r = (utterance ul of the pass, frame j of its window); lane r evaluates row r's validity for the ballot
+        int row_b, row_t;
+        {
+          const int e = pass * kPassUtts + lane / kFrames, b = grp + kGroups * e, j = lane % kFrames;
+          const bool ok = b < B && s_t[b] + j < s_len[b];
+          row_b = ok ? b : -1; row_t = ok ? s_t[b] + j : 0;
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, row_b >= 0);
+        if (mask == 0u) continue;                             // identical in every warp of the CTA
+        float4 gv[PER];
+        auto load_half = [&](int h) {
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int idx = tid + kSpThreads * i;
+            gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int r = min(idx / V4_ROW, kPassRows - 1), c4 = idx % V4_ROW;
+            const int b = __shfl_sync(0xffffffffu, row_b, r);       // every warp holds the row table, lane r = row r
+            const int t = __shfl_sync(0xffffffffu, row_t, r);
+            if (idx < kPassRows * V4_ROW) {
+              if (b >= 0) {
+                const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.enc_proj + (static_cast<size_t>(b) * p.T_max + t) * HJ + h * KH) + c4);
+                const float4 q4 = ldcg4s(p.ppbuf + static_cast<size_t>(b) * HJ + h * KH + 4 * c4);
+                gv[i] = make_float4(fmaxf(e4.x + q4.x, 0.f), fmaxf(e4.y + q4.y, 0.f), fmaxf(e4.z + q4.z, 0.f), fmaxf(e4.w + q4.w, 0.f));
+              }
+            }
+          }
+        };
+        auto store_half = [&]() {
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int idx = tid + kSpThreads * i;
+            if (idx < kPassRows * V4_ROW) {
+              const int r = idx / V4_ROW, c4 = idx % V4_ROW;
+              *reinterpret_cast<float4*>(s_g + r * GS + 4 * c4) = gv[i];
+            }
+          }
+        };
+        float acc[kMaxTilesPerWarp][4];
+#pragma unroll
+        for (int n = 0; n < kMaxTilesPerWarp; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+        const bool tile_on = ((mask >> (mt * 16)) & 0xffffu) != 0u;
+        auto mma_half = [&](int h) {
+          if (!tile_on) return;
+          const float* ga = s_g + (mt * 16 + gid) * GS + tig * 2;
+#pragma unroll 4
+          for (int ks = 0; ks < KS_H; ++ks) {
+            const float2 x0 = *reinterpret_cast<const float2*>(ga + ks * 16);
+            const float2 x1 = *reinterpret_cast<const float2*>(ga + 8 * GS + ks * 16);
+            const float2 x2 = *reinterpret_cast<const float2*>(ga + ks * 16 + 8);
+            const float2 x3 = *reinterpret_cast<const float2*>(ga + 8 * GS + ks * 16 + 8);
+            uint32_t ah[4], am[4], al[4];
+            split3(x0, ah[0], am[0], al[0]); split3(x1, ah[1], am[1], al[1]);
+            split3(x2, ah[2], am[2], al[2]); split3(x3, ah[3], am[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < kMaxTilesPerWarp; ++n) {
+              const int nt = ng + 4 * n;
+              if (nt < n_tiles) {                            // warp-uniform
+                const __nv_bfloat16* wr = s_wout + static_cast<size_t>(nt * 8 + gid) * WS + h * KH + ks * 16 + tig * 2;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+                mma_bf16_16816(acc[n], ah, b0, b1); mma_bf16_16816(acc[n], am, b0, b1); mma_bf16_16816(acc[n], al, b0, b1);
+              }
+            }
+          }
+        };
+        long long tj = 0;
+        if (cta == 0 && tid == 0) tj = clock64();
+        auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
+        load_half(0);
+        store_half();
+        __syncthreads();
+        jtick(8);
+        load_half(1);                                         // in flight under the MMAs of half 0
+        mma_half(0);
+        __syncthreads();
+        store_half();
+        __syncthreads();
+        mma_half(1);
+        jtick(9);
+        // ---- argmax of this warp's columns per row, then across the 4 lanes of a row, then across the 4 warps of the tile
+        {
+          float bv[2] = {-INFINITY, -INFINITY};
+          int bi[2] = {0x7fffffff, 0x7fffffff};
+#pragma unroll
+          for (int n = 0; n < kMaxTilesPerWarp; ++n) {
+            const int nt = ng + 4 * n;
+            if (nt < n_tiles) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int col = nt * 8 + tig * 2 + (q & 1), hrow = q >> 1;
+                const float v = acc[n][q] + s_bout[col];
+                if (col < nj && (v > bv[hrow] || (v == bv[hrow] && j0 + col < bi[hrow]))) { bv[hrow] = v; bi[hrow] = j0 + col; }
+              }
+            }
+          }
+#pragma unroll
+          for (int hrow = 0; hrow < 2; ++hrow) {
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, bv[hrow], o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi[hrow], o);
+              if (ov > bv[hrow] || (ov == bv[hrow] && oi < bi[hrow])) { bv[hrow] = ov; bi[hrow] = oi; }
+            }
+            if (tig == 0) s_best[(mt * 16 + hrow * 8 + gid) * 4 + ng] = (bi[hrow] != 0x7fffffff) ? pack_best(bv[hrow], bi[hrow]) : 0ull;
+          }
+        }
+        __syncthreads();
+        if (warp == 0 && row_b >= 0) {
+          unsigned long long m = s_best[lane * 4];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) { const unsigned long long o = s_best[lane * 4 + q]; m = o > m ? o : m; }
+          asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p.best + (static_cast<size_t>(iter % 3) * B + row_b) * kFrames + (lane % kFrames)), "l"(m) : "memory");
+        }
+        jtick(10);
+        // s_best / s_g are rewritten only after the next pass's first __syncthreads pair; the reads above are by warp 0
+        // before it reaches that barrier
+      }
+    }
+    tick(0, tk);
+    sp_grid_barrier(p.counter, target, G);
+    tick(1, tk);
+    // ---- consume the window (identically in every CTA): blanks advance t, the first non-blank emits and ends the window
+    for (int b = tid; b < B; b += kSpThreads) {
+      int t = s_t[b];
+      const int len = s_len[b];
+      int tok = -1;
+      if (t < len) {
+        const int nv = min(kFrames, len - t);
+        int sym = s_sym[b];
+        const unsigned long long* bp = p.best + (static_cast<size_t>(iter % 3) * B + b) * kFrames;
+        for (int j = 0; j < nv; ++j) {
+          const unsigned long long v = __ldcg(bp + j);
+          const int k = static_cast<int>(0xffffffffu - static_cast<unsigned int>(v & 0xffffffffull));
+          if (k == blank) { t += 1; sym = 0; continue; }
+          const int n = s_n[b];
+          if (cta == 0 && n < p.U_max) {
+            p.tokens[static_cast<size_t>(b) * p.U_max + n] = k;
+            p.frames[static_cast<size_t>(b) * p.U_max + n] = t;
+          }
+          s_n[b] = n + 1;
+          tok = k;
+          if (++sym >= p.max_symbols) { t += 1; sym = 0; }
+          break;
+        }
+        s_t[b] = t; s_sym[b] = sym;
+      }
+      s_tok[b] = tok;
+    }
+    // the slot that iteration iter+2 will use was last read two barriers ago: clear it now (visible through the
+    // next barrier, which precedes that iteration's red.max)
+    if (cta == 0) for (int i = tid; i < B * kFrames; i += kSpThreads) __stcg(p.best + static_cast<size_t>((iter + 2) % 3) * B * kFrames + i, 0ull);
+    ++iter;
+    __syncthreads();
+    // ---- ordered compaction of the utterances that emitted; count of the still-active ones
+    {
+      int run_e = 0, run_a = 0;
+      for (int base = 0; base < B; base += kSpThreads) {
+        const int b = base + tid;
+        const bool em = b < B && s_tok[b] >= 0, ac = b < B && s_t[b] < s_len[b];
+        const unsigned me = __ballot_sync(0xffffffffu, em), ma = __ballot_sync(0xffffffffu, ac);
+        if (lane == 0) { s_cnt[2 + warp] = __popc(me); s_cnt[2 + kSpWarps + warp] = __popc(ma); }
+        __syncthreads();
+        int before = 0, tot_e = 0, tot_a = 0;
+#pragma unroll
+        for (int w = 0; w < kSpWarps; ++w) {
+          const int c = s_cnt[2 + w];
+          if (w < warp) before += c;
+          tot_e += c; tot_a += s_cnt[2 + kSpWarps + w];
+        }
+        if (em) s_emit[run_e + before + __popc(me & ((1u << lane) - 1u))] = b;
+        run_e += tot_e; run_a += tot_a;
+        __syncthreads();
+      }
+      if (tid == 0) { s_cnt[0] = run_e; s_cnt[1] = run_a; }
+      __syncthreads();
+    }
+    const int n_active = s_cnt[1];
+    tick(2, tk);
+    prof[7] += 1;
+    if (s_cnt[0] > 0) lstm_and_pred();
+    if (n_active == 0) break;
+  }
+  if (cta == 0) for (int b = tid; b < B; b += kSpThreads) p.n_tok[b] = s_n[b];
+  if (cta == 0 && tid == 0) for (int i = 0; i < 12; ++i) p.prof[i] = prof[i];
+}
+
+// workspace: hbuf | ppbuf | (3*B*8 pad, keeps the counter/prof offset of decode_batched.cu) | counter + prof (256 B) | best
+size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int /*num_sms*/) {
+  return static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + static_cast<size_t>(3) * B * 8 + 256 +
+         static_cast<size_t>(3) * B * kFrames * 8;
+}
+
+template <int HJ, int HP>
+static cudaError_t launch_sp(SpecDev p, int grid, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(rnnt_greedy_spec_kernel<HJ, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_greedy_spec_kernel<HJ, HP>, kSpThreads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+  void* args[] = {&p};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_spec_kernel<HJ, HP>), dim3(grid), dim3(kSpThreads), args, smem, stream);
+}
+
+cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream) {
+  if (a.B <= 0 || num_sms < kGroups) return cudaErrorInvalidValue;
+  const int G = num_sms;
+  SpecDev p;
+  p.enc_proj = a.enc_proj; p.enc_len = a.enc_len;
+  p.w_out = static_cast<const __nv_bfloat16*>(a.w_out); p.b_out = a.b_out; p.embed = a.embed;
+  p.w_lstm = static_cast<const __nv_bfloat16*>(a.w_lstm); p.b_lstm = a.b_lstm;
+  p.w_pred = static_cast<const __nv_bfloat16*>(a.w_pred); p.b_pred = a.b_pred;
+  p.tokens = a.tokens; p.frames = a.frames; p.n_tok = a.n_tok;
+  char* ws = static_cast<char*>(workspace);
+  p.hbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(2) * a.B * a.Hp * 4;
+  p.ppbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(a.B) * a.Hj * 4;
+  ws += static_cast<size_t>(3) * a.B * 8;
+  p.counter = reinterpret_cast<unsigned int*>(ws);
+  p.prof = reinterpret_cast<long long*>(ws + 64);
+  ws += 256;
+  p.best = reinterpret_cast<unsigned long long*>(ws);
+  p.B = a.B; p.T_max = a.T_max; p.V = a.V; p.U_max = a.U_max; p.max_symbols = a.max_symbols;
+  p.S = G / kGroups;
+  p.rows_j = (a.V + 1 + p.S - 1) / p.S;
+  p.units = (a.Hp + G - 1) / G;
+  p.rows_p = (a.Hj + G - 1) / G;
+  const int n_tiles = (p.rows_j + 7) / 8;
+  if (n_tiles > 4 * kMaxTilesPerWarp || 4 * p.units > 24 || p.rows_p > 8 || 16 * p.units > kSpThreads) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, rnnt_spec_workspace_bytes(a.B, a.Hj, a.Hp, num_sms), stream);
+  if (e != cudaSuccess) return e;
+  const size_t gs = a.Hj / 2 + 8;
+  const size_t g_floats = kPassRows * gs > static_cast<size_t>(kSpWarps) * 16 * 24 ? kPassRows * gs : static_cast<size_t>(kSpWarps) * 16 * 24;
+  size_t smem = (static_cast<size_t>(p.rows_j) * (a.Hj + 8) + static_cast<size_t>(4 * p.units) * (2 * a.Hp + 8) +
+                 static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
+  smem += (g_floats + n_tiles * 8 + ((static_cast<size_t>(a.B) * p.units + 1) & ~static_cast<size_t>(1))) * 4;
+  smem += kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 7 * 4 + (2 + 2 * kSpWarps) * 4 + 64;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640>(p, G, smem, stream);
+  if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128>(p, G, smem, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace rs

@@ -90,6 +90,12 @@ int fail(const rs_engine* e, int code, const char* fmt, ...) {
 
 size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
+inline size_t dec_ws_bytes(const rs_engine* e, int B) {   // the decode kernels share one region: size it for the larger
+  const size_t a = rs::rnnt_batched_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms);
+  const size_t b = rs::rnnt_spec_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms);
+  return a > b ? a : b;
+}
+
 Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   const rs_model_config& c = e->cfg;
   Plan p{};
@@ -124,7 +130,7 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.tokens = take(static_cast<size_t>(B) * U_max * 4);
   p.frames = take(static_cast<size_t>(B) * U_max * 4);
   p.ntok = take(static_cast<size_t>(B) * 4);
-  p.dec_ws = take(rs::rnnt_batched_workspace_bytes(B, c.joint_hidden, c.pred_hidden, e->num_sms));
+  p.dec_ws = take(dec_ws_bytes(e, B));
   p.total = off;
   return p;
 }
@@ -335,14 +341,15 @@ int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_
   rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b,
                     e->dec.pred_w, e->dec.pred_b, tokens, frames, ntok, p.B, T_max, c.joint_hidden, c.pred_hidden,
                     c.vocab_size, U_max, c.max_symbols};
-  // One decode kernel for every batch size (batched, weights-stationary): an utterance's logits are then
-  // accumulated in the same order whether it is decoded alone or inside a batch, so results do not depend
-  // on batch composition.  RS_DECODE_MODE=1 selects the cluster-per-utterance kernel (latency experiments).
-  const char* m = getenv("RS_DECODE_MODE");      // 0/unset: automatic, 1: per-utterance clusters, 2: batched
+  // One decode kernel for every batch size (windowed, weights-stationary, decode_spec.cu): an utterance's logits
+  // are accumulated in the same order whether it is decoded alone or inside a batch, so results do not depend on
+  // batch composition.  RS_DECODE_MODE selects the earlier kernels for A/B measurements:
+  //   0/unset/3: windowed tensor-path kernel, 1: one cluster per utterance, 2: batched one-frame-per-iteration kernel
+  const char* m = getenv("RS_DECODE_MODE");
   const int mode = m ? atoi(m) : 0;
-  const bool batched = mode != 1;
-  if (batched) RS_K(e, rs::launch_rnnt_greedy_batched(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
-  else RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
+  if (mode == 1) RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
+  else if (mode == 2) RS_K(e, rs::launch_rnnt_greedy_batched(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
+  else RS_K(e, rs::launch_rnnt_greedy_spec(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
   return RS_OK;
 }
 
@@ -436,7 +443,7 @@ int rs_rnnt_greedy(rs_engine* e, const float* enc, const int32_t* enc_len, int B
   size_t off = 0;
   p.xn = off; off = align_up(off + static_cast<size_t>(p.M) * e->cfg.d_model * 2);
   p.encp = off; off = align_up(off + static_cast<size_t>(p.M) * e->cfg.joint_hidden * 4);
-  p.dec_ws = off; off = align_up(off + rs::rnnt_batched_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms));
+  p.dec_ws = off; off = align_up(off + dec_ws_bytes(e, B));
   p.total = off; p.L_max = 0;
   RS_TRY(check_ws(e, p));
   return do_greedy(e, p, enc, enc_len, T_max, tokens, frames, n_tok, U_max, static_cast<cudaStream_t>(stream));

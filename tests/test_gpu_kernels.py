@@ -161,10 +161,10 @@ def test_encoder_vs_oracle(tiny_engine, tiny_cfg, tiny_sd, n_layers):
 
 
 # ------------------------------------------------------------------------------------ decode
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
 def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd, mode, monkeypatch):
-    """Decode kernels alone (1: one cluster per utterance, 2: batched weights-stationary grid): fed the
-    ORACLE's encoder output, tokens and frames must be identical."""
+    """Decode kernels alone (1: one cluster per utterance, 2: batched weights-stationary grid, 3: windowed
+    tensor-path grid = the default): fed the ORACLE's encoder output, tokens and frames must be identical."""
     from oracle import nemo_restated as O
     monkeypatch.setenv("RS_DECODE_MODE", mode)
     eng = tiny_engine
@@ -188,6 +188,34 @@ def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd, mode, monkeypatch
         assert n == len(r.tokens)
         assert tokens[i, :n].cpu().tolist() == r.tokens
         assert frames[i, :n].cpu().tolist() == r.frames
+
+
+@pytest.mark.parametrize("B", [1, 3, 5, 33, 70])
+def test_windowed_decode_equals_sequential_kernel(tiny_engine, tiny_cfg, B, monkeypatch):
+    """The windowed kernel (4 frames per iteration, utterance groups x vocabulary slices, bf16x3 tensor path)
+    against the one-frame-per-iteration fp32 kernel on random encoder outputs, ragged lengths (incl. a
+    zero-length utterance), batch sizes that are not multiples of the group count and span several passes:
+    tokens, frames and counts identical."""
+    eng = tiny_engine
+    g = torch.Generator().manual_seed(B)
+    T = 61
+    enc = torch.randn(B, T, tiny_cfg.d_model, generator=g) * 2.0
+    enc_len = torch.randint(1, T + 1, (B,), generator=g, dtype=torch.int32)
+    enc_len[0] = T
+    if B > 2:
+        enc_len[2] = 0
+    outs = {}
+    for mode in ("2", "3"):
+        monkeypatch.setenv("RS_DECODE_MODE", mode)
+        t, f, n = eng.greedy(enc.cuda(), enc_len.cuda())
+        torch.cuda.synchronize()
+        outs[mode] = (t.cpu(), f.cpu(), n.cpu())
+    n2, n3 = outs["2"][2], outs["3"][2]
+    print("tokens per utterance:", n3.tolist()[:12], "lens", enc_len.tolist()[:12])
+    assert torch.equal(n2, n3)
+    for b in range(B):
+        n = int(n2[b])
+        assert torch.equal(outs["2"][0][b, :n], outs["3"][0][b, :n]) and torch.equal(outs["2"][1][b, :n], outs["3"][1][b, :n]), f"utt {b}"
 
 
 def decisions_from(tokens, frames, T, max_symbols, blank):
