@@ -133,7 +133,8 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   int* s_t = reinterpret_cast<int*>(s_best + kPassRows * 4);
   int* s_sym = s_t + B; int* s_n = s_sym + B; int* s_par = s_n + B; int* s_tok = s_par + B;
   int* s_emit = s_tok + B; int* s_len = s_emit + B;
-  int* s_cnt = s_len + B;                                                            // [0] n_emit, [1] n_active, [2..2+8) warp counts x2
+  int* s_act = s_len + B;                                                            // ordered list of the utterances with frames left
+  int* s_cnt = s_act + B;                                                            // [0] n_emit, [1] n_active, [2..2+8) warp counts x2
 
   {
     const uint32_t zero = 0;
@@ -300,21 +301,53 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
     tick(6, tk);
   };
 
-  lstm_and_pred();                                // SOS: every utterance steps once on the blank (zero) embedding
+  // ordered compaction of the utterances that emitted (s_emit) and of those with frames left (s_act)
+  auto compact = [&]() {
+    int run_e = 0, run_a = 0;
+    for (int base = 0; base < B; base += kSpThreads) {
+      const int b = base + tid;
+      const bool em = b < B && s_tok[b] >= 0, ac = b < B && s_t[b] < s_len[b];
+      const unsigned me = __ballot_sync(0xffffffffu, em), ma = __ballot_sync(0xffffffffu, ac);
+      if (lane == 0) { s_cnt[2 + warp] = __popc(me); s_cnt[2 + kSpWarps + warp] = __popc(ma); }
+      __syncthreads();
+      int bef_e = 0, bef_a = 0, tot_e = 0, tot_a = 0;
+#pragma unroll
+      for (int w = 0; w < kSpWarps; ++w) {
+        const int ce = s_cnt[2 + w], ca = s_cnt[2 + kSpWarps + w];
+        if (w < warp) { bef_e += ce; bef_a += ca; }
+        tot_e += ce; tot_a += ca;
+      }
+      const unsigned below = (1u << lane) - 1u;
+      if (em) s_emit[run_e + bef_e + __popc(me & below)] = b;
+      if (ac) s_act[run_a + bef_a + __popc(ma & below)] = b;
+      run_e += tot_e; run_a += tot_a;
+      __syncthreads();
+    }
+    if (tid == 0) { s_cnt[0] = run_e; s_cnt[1] = run_a; }
+    __syncthreads();
+  };
 
-  const int bg_max = (B + kGroups - 1) / kGroups;            // utterances in the largest group
-  const int n_pass = (bg_max + kPassUtts - 1) / kPassUtts;
+  lstm_and_pred();                                // SOS: every utterance steps once on the blank (zero) embedding
+  for (int b = tid; b < B; b += kSpThreads) s_tok[b] = -1;
+  __syncthreads();
+  compact();
+
   const int mt = warp & 1, ng = warp >> 1;                   // this warp's m16 tile and n8-tile residue class
 
   for (;;) {
     // ---- phase J
     if (has_j) {
+      // the active utterances are dealt round-robin to the groups every iteration (any group can serve any utterance:
+      // all hold the full vocabulary), so the groups stay balanced while utterances finish at different times
+      const int n_act = s_cnt[1];
+      const int n_pass = ((n_act + kGroups - 1) / kGroups + kPassUtts - 1) / kPassUtts;
       for (int pass = 0; pass < n_pass; ++pass) {
         // row r = (utterance ul of the pass, frame j of its window); lane r evaluates row r's validity for the ballot
         int row_b, row_t;
         {
-          const int e = pass * kPassUtts + lane / kFrames, b = grp + kGroups * e, j = lane % kFrames;
-          const bool ok = b < B && s_t[b] + j < s_len[b];
+          const int e = pass * kPassUtts + lane / kFrames, ai = grp + kGroups * e, j = lane % kFrames;
+          const int b = ai < n_act ? s_act[ai] : 0;
+          const bool ok = ai < n_act && s_t[b] + j < s_len[b];
           row_b = ok ? b : -1; row_t = ok ? s_t[b] + j : 0;
         }
         const unsigned mask = __ballot_sync(0xffffffffu, row_b >= 0);
@@ -438,9 +471,14 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
       if (t < len) {
         const int nv = min(kFrames, len - t);
         int sym = s_sym[b];
-        const unsigned long long* bp = p.best + (static_cast<size_t>(iter % 3) * B + b) * kFrames;
-        for (int j = 0; j < nv; ++j) {
-          const unsigned long long v = __ldcg(bp + j);
+        const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(p.best + (static_cast<size_t>(iter % 3) * B + b) * kFrames);
+        static_assert(kFrames == 4, "window read as two 16-byte loads");
+        const ulonglong2 w01 = __ldcg(bp), w23 = __ldcg(bp + 1);
+        const unsigned long long win[kFrames] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+        for (int j = 0; j < kFrames; ++j) {
+          if (j >= nv) break;
+          const unsigned long long v = win[j];
           const int k = static_cast<int>(0xffffffffu - static_cast<unsigned int>(v & 0xffffffffull));
           if (k == blank) { t += 1; sym = 0; continue; }
           const int n = s_n[b];
@@ -462,29 +500,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
     if (cta == 0) for (int i = tid; i < B * kFrames; i += kSpThreads) __stcg(p.best + static_cast<size_t>((iter + 2) % 3) * B * kFrames + i, 0ull);
     ++iter;
     __syncthreads();
-    // ---- ordered compaction of the utterances that emitted; count of the still-active ones
-    {
-      int run_e = 0, run_a = 0;
-      for (int base = 0; base < B; base += kSpThreads) {
-        const int b = base + tid;
-        const bool em = b < B && s_tok[b] >= 0, ac = b < B && s_t[b] < s_len[b];
-        const unsigned me = __ballot_sync(0xffffffffu, em), ma = __ballot_sync(0xffffffffu, ac);
-        if (lane == 0) { s_cnt[2 + warp] = __popc(me); s_cnt[2 + kSpWarps + warp] = __popc(ma); }
-        __syncthreads();
-        int before = 0, tot_e = 0, tot_a = 0;
-#pragma unroll
-        for (int w = 0; w < kSpWarps; ++w) {
-          const int c = s_cnt[2 + w];
-          if (w < warp) before += c;
-          tot_e += c; tot_a += s_cnt[2 + kSpWarps + w];
-        }
-        if (em) s_emit[run_e + before + __popc(me & ((1u << lane) - 1u))] = b;
-        run_e += tot_e; run_a += tot_a;
-        __syncthreads();
-      }
-      if (tid == 0) { s_cnt[0] = run_e; s_cnt[1] = run_a; }
-      __syncthreads();
-    }
+    compact();
     const int n_active = s_cnt[1];
     tick(2, tk);
     prof[7] += 1;
@@ -497,7 +513,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 
 // workspace: hbuf | ppbuf | (3*B*8 pad, keeps the counter/prof offset of decode_batched.cu) | counter + prof (256 B) | best
 size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int /*num_sms*/) {
-  return static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + static_cast<size_t>(3) * B * 8 + 256 +
+  return static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + static_cast<size_t>(3) * B * 8 + 256 + 16 +
          static_cast<size_t>(3) * B * kFrames * 8;
 }
 
@@ -529,6 +545,7 @@ cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int nu
   p.counter = reinterpret_cast<unsigned int*>(ws);
   p.prof = reinterpret_cast<long long*>(ws + 64);
   ws += 256;
+  ws += (16 - (reinterpret_cast<uintptr_t>(ws) & 15)) & 15;       // the window is read with 16-byte loads
   p.best = reinterpret_cast<unsigned long long*>(ws);
   p.B = a.B; p.T_max = a.T_max; p.V = a.V; p.U_max = a.U_max; p.max_symbols = a.max_symbols;
   p.S = G / kGroups;
@@ -544,7 +561,7 @@ cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int nu
   size_t smem = (static_cast<size_t>(p.rows_j) * (a.Hj + 8) + static_cast<size_t>(4 * p.units) * (2 * a.Hp + 8) +
                  static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
   smem += (g_floats + n_tiles * 8 + ((static_cast<size_t>(a.B) * p.units + 1) & ~static_cast<size_t>(1))) * 4;
-  smem += kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 7 * 4 + (2 + 2 * kSpWarps) * 4 + 64;
+  smem += kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 8 * 4 + (2 + 2 * kSpWarps) * 4 + 64;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640>(p, G, smem, stream);
   if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128>(p, G, smem, stream);

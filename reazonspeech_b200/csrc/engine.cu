@@ -70,6 +70,12 @@ struct rs_engine {
   std::vector<cudaEvent_t> gemm_ev;     // pairs
   size_t gemm_ev_used = 0;
   double gemm_flops = 0.0;
+  // rs_transcribe_batch: host->device copies run on their own stream in utterance chunks so the frontend of
+  // chunk i overlaps the copy of chunk i+1
+  static constexpr int kCopyChunks = 8;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[kCopyChunks + 1] = {};
+  bool copy_ok = false;
 };
 
 namespace {
@@ -270,17 +276,25 @@ int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_m
   return RS_OK;
 }
 
+int do_sub_conv0(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, int b0, int nb, cudaStream_t s) {
+  const rs_model_config& c = e->cfg;
+  const int C = c.sub_channels;
+  rs::SubsampleArgs sa{mel + static_cast<size_t>(b0) * p.F_max * c.n_mels, mel_len + b0, nb, p.F_max, c.n_mels, C,
+                       e->sub.c0w, e->sub.c0b, e->sub.d1w, e->sub.d1b,
+                       at<uint16_t>(e, p.sub1) + static_cast<size_t>(b0) * p.T2 * p.F2 * C, p.T1, p.F1, p.T2, p.F2};
+  RS_K(e, rs::launch_sub_conv0_dw1(sa, s), 1);
+  return RS_OK;
+}
+
 int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, float* enc, int32_t* enc_len,
-              int n_layers, cudaStream_t s) {
+              int n_layers, cudaStream_t s, bool conv0_done = false) {
   const rs_model_config& c = e->cfg;
   const int d = c.d_model, C = c.sub_channels, M = p.M, B = p.B;
   if (n_layers < 0 || n_layers > c.n_layers) n_layers = c.n_layers;
   enc_len_kernel<<<(B + 127) / 128, 128, 0, s>>>(mel_len, enc_len, B);
   RS_K(e, cudaGetLastError(), 1);
   // ---- ConvSubsampling
-  rs::SubsampleArgs sa{mel, mel_len, B, p.F_max, c.n_mels, C, e->sub.c0w, e->sub.c0b, e->sub.d1w, e->sub.d1b,
-                       at<void>(e, p.sub1), p.T1, p.F1, p.T2, p.F2};
-  RS_K(e, rs::launch_sub_conv0_dw1(sa, s), 1);
+  if (!conv0_done) RS_TRY(do_sub_conv0(e, p, mel, mel_len, 0, B, s));
   RS_TRY(gemm(e, at<void>(e, p.sub1), e->sub.p1w, e->sub.p1b, nullptr, at<void>(e, p.sub2), B * p.T2 * p.F2, C, C,
               RS_EPI_BIAS_RELU_BF16, 1.f, s));
   RS_K(e, rs::launch_sub_dw(at<void>(e, p.sub2), at<void>(e, p.sub3), e->sub.d2w, e->sub.d2b, mel_len, 2, B, p.T2, p.F2,
@@ -383,6 +397,8 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }
   e->ev_ok = true;
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) e->ev_ok = false;
+  e->copy_ok = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& ev : e->copy_ev) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) e->copy_ok = false;
   *out = e;
   return RS_OK;
 }
@@ -390,6 +406,8 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
 void rs_engine_destroy(rs_engine* e) {
   if (e == nullptr) return;
   if (e->ev_ok) for (auto& ev : e->ev) cudaEventDestroy(ev);
+  for (auto& ev : e->copy_ev) if (ev) cudaEventDestroy(ev);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
   delete e;
 }
@@ -475,10 +493,41 @@ int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Plan p = make_plan(e, B, L_max, U_max);
   RS_TRY(check_ws(e, p));
-  RS_CUDA(e, cudaMemcpyAsync(at<float>(e, p.wav), wav_host, static_cast<size_t>(B) * L_max * 4, cudaMemcpyHostToDevice, s));
-  RS_CUDA(e, cudaMemcpyAsync(at<int32_t>(e, p.len), len_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
-  RS_TRY(rs_transcribe_device(e, at<float>(e, p.wav), at<int32_t>(e, p.len), B, L_max, at<int32_t>(e, p.tokens),
-                              at<int32_t>(e, p.frames), at<int32_t>(e, p.ntok), U_max, s));
+  float* wav = at<float>(e, p.wav);
+  int32_t* len = at<int32_t>(e, p.len);
+  float* mel = at<float>(e, p.mel);
+  int32_t* mel_len = at<int32_t>(e, p.mel_len);
+  const int n_chunks = (e->copy_ok && B >= 2 * rs_engine::kCopyChunks) ? rs_engine::kCopyChunks : 1;
+  if (n_chunks == 1) {
+    RS_CUDA(e, cudaMemcpyAsync(wav, wav_host, static_cast<size_t>(B) * L_max * 4, cudaMemcpyHostToDevice, s));
+    RS_CUDA(e, cudaMemcpyAsync(len, len_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
+    RS_TRY(rs_transcribe_device(e, wav, len, B, L_max, at<int32_t>(e, p.tokens), at<int32_t>(e, p.frames),
+                                at<int32_t>(e, p.ntok), U_max, s));
+  } else {
+    // copies on the copy stream, chunk by chunk; log-mel and the first (fused) subsampling conv of a chunk start as
+    // soon as its samples have landed.  The copy stream first waits for everything already queued on the caller's
+    // stream (the workspace may still be in use by an earlier asynchronous call).
+    const int per = (B + n_chunks - 1) / n_chunks;
+    RS_CUDA(e, cudaEventRecord(e->copy_ev[n_chunks], s));
+    RS_CUDA(e, cudaStreamWaitEvent(e->copy_stream, e->copy_ev[n_chunks], 0));
+    RS_CUDA(e, cudaMemcpyAsync(len, len_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, e->copy_stream));
+    for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+      const int nb = (B - b0 < per) ? B - b0 : per;
+      RS_CUDA(e, cudaMemcpyAsync(wav + static_cast<size_t>(b0) * L_max, wav_host + static_cast<size_t>(b0) * L_max,
+                                 static_cast<size_t>(nb) * L_max * 4, cudaMemcpyHostToDevice, e->copy_stream));
+      RS_CUDA(e, cudaEventRecord(e->copy_ev[c], e->copy_stream));
+    }
+    for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
+      const int nb = (B - b0 < per) ? B - b0 : per;
+      RS_CUDA(e, cudaStreamWaitEvent(s, e->copy_ev[c], 0));
+      RS_TRY(do_logmel(e, wav + static_cast<size_t>(b0) * L_max, len + b0, nb, L_max,
+                       mel + static_cast<size_t>(b0) * p.F_max * e->cfg.n_mels, mel_len + b0, s));
+      RS_TRY(do_sub_conv0(e, p, mel, mel_len, b0, nb, s));
+    }
+    RS_TRY(do_encode(e, p, mel, mel_len, at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s, true));
+    RS_TRY(do_greedy(e, p, at<float>(e, p.enc), at<int32_t>(e, p.enc_len), p.T3, at<int32_t>(e, p.tokens),
+                     at<int32_t>(e, p.frames), at<int32_t>(e, p.ntok), U_max, s));
+  }
   RS_CUDA(e, cudaMemcpyAsync(tokens_host, at<int32_t>(e, p.tokens), static_cast<size_t>(B) * U_max * 4, cudaMemcpyDeviceToHost, s));
   RS_CUDA(e, cudaMemcpyAsync(frames_host, at<int32_t>(e, p.frames), static_cast<size_t>(B) * U_max * 4, cudaMemcpyDeviceToHost, s));
   RS_CUDA(e, cudaMemcpyAsync(n_tok_host, at<int32_t>(e, p.ntok), static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));

@@ -262,3 +262,21 @@ def test_end_to_end_tokens(tiny_engine, tiny_cfg, tiny_sd):
                                              tiny_cfg.enc_frames(len(w)), tiny_cfg, 5e-2, f"utt{i}")
     print(f"exact decision sequences: {exact}/{len(waves)}")
     assert exact >= len(waves) // 2
+
+
+@pytest.mark.parametrize("B", [16, 19])
+def test_host_entry_chunked_copies_equal_device_entry(tiny_engine, B):
+    """rs_transcribe_batch overlaps its host->device copies with the frontend in utterance chunks (B >= 16):
+    the result must be bit-identical to rs_transcribe_device on the same batch (ragged lengths, a batch size
+    that does not divide into the chunk count)."""
+    eng = tiny_engine
+    waves = [padded(synth_clip(60 + i, 0.6 + 0.37 * (i % 7))) for i in range(B)]
+    x, lens = pad_batch(waves, "cpu")
+    th, fh, nh = eng.transcribe_host(x.pin_memory(), lens)
+    td, fd, nd = eng.transcribe_device(x.cuda(), lens.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(nh, nd.cpu())
+    for b in range(B):
+        n = int(nh[b])
+        assert torch.equal(th[b, :n], td[b, :n].cpu()) and torch.equal(fh[b, :n], fd[b, :n].cpu())
+    assert int(nh.sum()) > 0
