@@ -252,6 +252,11 @@ def main():
     stages = eng.stage_times_ms()
     eng.enable_stage_timing(False)
     decode_prof = eng.decode_cycles(B, L, U) if os.environ.get("RS_DECODE_MODE", "0") != "1" else None
+    # per-kernel device time inside the pipeline (event pair around every launch; one extra, untimed step)
+    eng.kernel_timing(True)
+    eng.transcribe_device(wav_dev, len_dev, U, out_dev)
+    kernel_ms = {k: {"launches": n, "ms": round(ms, 4)} for k, (n, ms) in sorted(eng.kernel_timing().items(), key=lambda kv: -kv[1][1])}
+    eng.kernel_timing(False)
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     # DRAM bytes per launch of the dominant kernel: mean of dram__bytes_read.sum + dram__bytes_write.sum over the
     # eight consecutive launches of the `ncu --set full` capture in profiles/r01_v2_gemm_ncu.md (not re-measured here)
@@ -280,7 +285,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
-        "roofline": roofline, "stage_ms": stages, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
+        "roofline": roofline, "stage_ms": stages, "kernel_ms": kernel_ms, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
     }), flush=True)
 
 

@@ -68,7 +68,8 @@ typedef enum rs_epilogue {
   RS_EPI_BIAS_SWISH_BF16 = 2, /* out_bf16[M,N]   = swish(acc + bias)                           */
   RS_EPI_BIAS_GLU_BF16 = 3,   /* out_bf16[M,N/2] = a * sigmoid(g); W rows interleaved 16/16    */
   RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias)   */
-  RS_EPI_BIAS_F32 = 5         /* out_f32[M,N]    = alpha * (acc + bias)                        */
+  RS_EPI_BIAS_F32 = 5,        /* out_f32[M,N]    = alpha * (acc + bias)                        */
+  RS_EPI_BIAS_F16 = 6         /* out_f16[M,N]    = acc + bias  (IEEE half: attention positional scores) */
 } rs_epilogue;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -135,6 +136,11 @@ int rs_stage_times_ms(const rs_engine* e, float* ms /*[8]*/);
 int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* out8);   /* profiling aid, see engine.cu */
 int rs_enable_gemm_timing(rs_engine* e, int on);
 int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches);
+/* Per-kernel CUDA-event timing of EVERY launch inside the real pipeline (warm caches, back-to-back launches, unlike
+ * the cold, serialised launches ncu reports).  rs_kernel_timing() synchronises the device and writes one line per
+ * kernel name, "name<TAB>launches<TAB>total_ms", into buf; the log is reset. */
+int rs_enable_kernel_timing(rs_engine* e, int on);
+int rs_kernel_timing(rs_engine* e, char* buf, int buf_bytes);
 
 #ifdef __cplusplus
 }

@@ -123,6 +123,8 @@ def local_attention_core(q, k, v, p, u, vb, cfg: ModelConfig, emulate: bool = Fa
     qv = _q(q + vb[:, None, :], emulate)
     ac = torch.matmul(qu, k.transpose(1, 2))                                      # [H,T,T]
     bd_rel = torch.matmul(qv, p.transpose(1, 2))                                  # [H,T,n_rel]
+    if emulate:                                                                   # the engine stores this term in IEEE half
+        bd_rel = bd_rel.to(torch.float16).to(torch.float32)
     i = torch.arange(T)[:, None]
     j = torch.arange(T)[None, :]
     rel = j - i

@@ -36,7 +36,7 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 struct AttnDev {
-  const __nv_bfloat16* qkv; const float* bd; const float* bias_u;
+  const __nv_bfloat16* qkv; const __half* bd; const float* bias_u;
   __nv_bfloat16* out; const int32_t* enc_len;
   int T_max, H, w_left, w_right, n_global, n_rel_pad;
 };
@@ -156,8 +156,8 @@ local_attention_kernel(const AttnDev p) {
     for (int nt = 0; nt < 16; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
   }
   // BD rows of the two query rows this thread owns (skewed read: column j - i + w_left)
-  const float* bd_lo = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_lo, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
-  const float* bd_hi = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_hi, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
+  const __half* bd_lo = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_lo, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
+  const __half* bd_hi = p.bd + (static_cast<size_t>(b) * p.T_max + min(i_hi, p.T_max - 1)) * (static_cast<size_t>(p.H) * p.n_rel_pad) + static_cast<size_t>(h) * p.n_rel_pad;
   const int j_first = max(0, q0 - p.w_left);
   const int j_last = min(len - 1, q0 + QT - 1 + p.w_right);
   const int kt_first = j_first / KT, kt_last = j_last / KT;
@@ -184,7 +184,7 @@ local_attention_kernel(const AttnDev p) {
         const int j = j0 + nt * 8 + 2 * t + (e & 1);
         const int rel = j - ((e < 2) ? i_lo : i_hi);
         const bool ok = (j < len) && (rel >= -p.w_left) && (rel <= p.w_right);
-        bdv[nt][e] = ok ? __ldg(((e < 2) ? bd_lo : bd_hi) + rel + p.w_left) : 0.f;
+        bdv[nt][e] = ok ? __half2float(__ldg(((e < 2) ? bd_lo : bd_hi) + rel + p.w_left)) : 0.f;
       }
     }
     float s[8][4];
@@ -363,7 +363,7 @@ global_row_attention_kernel(const AttnDev p) {
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.dk != DK || a.n_global < 0 || a.n_global > 1) return cudaErrorInvalidValue;
   AttnDev p;
-  p.qkv = static_cast<const __nv_bfloat16*>(a.qkv); p.bd = a.bd;
+  p.qkv = static_cast<const __nv_bfloat16*>(a.qkv); p.bd = static_cast<const __half*>(a.bd);
   p.bias_u = a.bias_u; p.out = static_cast<__nv_bfloat16*>(a.out); p.enc_len = a.enc_len;
   p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right; p.n_global = a.n_global;
   p.n_rel_pad = a.n_rel_pad;

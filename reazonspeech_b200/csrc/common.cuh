@@ -2,6 +2,7 @@
 // (inline PTX; no CUTLASS dependency), bf16 packing and warp reductions.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,6 +31,10 @@ __device__ __forceinline__ float warp_max(float v) {
 // ---------------------------------------------------------------- bf16 helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {

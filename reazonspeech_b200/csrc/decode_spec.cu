@@ -73,12 +73,28 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// fp32 pair -> three bf16 pairs with hi + mid + lo == x exactly (8 + 8 + 8 mantissa bits)
-__device__ __forceinline__ void split3(float2 x, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
-  hi = pack_bf16x2(x.x, x.y);
-  const float r0 = x.x - bf16_lo(hi), r1 = x.y - bf16_hi(hi);
-  mid = pack_bf16x2(r0, r1);
-  lo = pack_bf16x2(r0 - bf16_lo(mid), r1 - bf16_hi(mid));
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// fp32 pair -> two IEEE-half pairs with hi + lo == x to 22 mantissa bits (11 + 11): the residual x - hi is exact in
+// fp32 and is itself rounded to half.  The legacy tensor path issues one m16n8k16 per ~19 cycles and scheduler on
+// sm_100, so the number of terms is what the joint costs; three bf16 terms (24 bits) were 1.5x slower.
+__device__ __forceinline__ void split2(float2 x, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// bf16 weight pair -> half pair.  Exact for 2^-14 <= |w| < 65504 (bf16 carries 8 mantissa bits, half 11); smaller
+// magnitudes become half subnormals (absolute error < 2^-25), which is below the fp32 summation noise of a logit.
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) { return pack_f16x2(bf16_lo(v), bf16_hi(v)); }
+__device__ __forceinline__ uint4 bf16x8_to_f16x8(uint4 v) {
+  return make_uint4(bf16x2_to_f16x2(v.x), bf16x2_to_f16x2(v.y), bf16x2_to_f16x2(v.z), bf16x2_to_f16x2(v.w));
 }
 
 __device__ __forceinline__ float2 ldcg2(const float* p) { return __ldcg(reinterpret_cast<const float2*>(p)); }
@@ -142,20 +158,20 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
     for (int i = tid; i < p.rows_j * (HJ / 8); i += kSpThreads) {
       const int r = i / (HJ / 8), c = i % (HJ / 8);
       uint4 v = make_uint4(zero, zero, zero, zero);
-      if (r < nj) v = reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c];
+      if (r < nj) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c]);
       *reinterpret_cast<uint4*>(s_wout + static_cast<size_t>(r) * WS + c * 8) = v;
     }
     for (int i = tid; i < 4 * p.units * (2 * HP / 8); i += kSpThreads) {
       const int r = i / (2 * HP / 8), c = i % (2 * HP / 8);
       const int gate = r / p.units, u = r % p.units;
       uint4 v = make_uint4(zero, zero, zero, zero);
-      if (u < nu) v = reinterpret_cast<const uint4*>(p.w_lstm + (static_cast<size_t>(gate) * HP + u0 + u) * 2 * HP)[c];
+      if (u < nu) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_lstm + (static_cast<size_t>(gate) * HP + u0 + u) * 2 * HP)[c]);
       *reinterpret_cast<uint4*>(s_wlstm + static_cast<size_t>(r) * LS + c * 8) = v;
     }
     for (int i = tid; i < p.rows_p * (HP / 8); i += kSpThreads) {
       const int r = i / (HP / 8), c = i % (HP / 8);
       uint4 v = make_uint4(zero, zero, zero, zero);
-      if (r < np) v = reinterpret_cast<const uint4*>(p.w_pred + static_cast<size_t>(p0 + r) * HP)[c];
+      if (r < np) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_pred + static_cast<size_t>(p0 + r) * HP)[c]);
       *reinterpret_cast<uint4*>(s_wpred + static_cast<size_t>(r) * (HP + 8) + c * 8) = v;
     }
     for (int i = tid; i < n_tiles * 8; i += kSpThreads) s_bout[i] = i < nj ? p.b_out[j0 + i] : -INFINITY;
@@ -207,15 +223,15 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 #pragma unroll
         for (int i = 0; i < KSW_L; ++i) {
           const int ks = kw * KSW_L + i;
-          uint32_t ah[4], am[4], al[4];
-          split3(xa[i][0], ah[0], am[0], al[0]); split3(xb[i][0], ah[1], am[1], al[1]);
-          split3(xa[i][1], ah[2], am[2], al[2]); split3(xb[i][1], ah[3], am[3], al[3]);
+          uint32_t ah[4], al[4];
+          split2(xa[i][0], ah[0], al[0]); split2(xb[i][0], ah[1], al[1]);
+          split2(xa[i][1], ah[2], al[2]); split2(xb[i][1], ah[3], al[3]);
 #pragma unroll
           for (int n = 0; n < 3; ++n) {
             if (n * 8 < 4 * p.units) {                 // warp-uniform
               const __nv_bfloat16* wr = s_wlstm + static_cast<size_t>(n * 8 + gid) * LS + ks * 16 + tig * 2;
               const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-              mma_bf16_16816(acc[n], ah, b0, b1); mma_bf16_16816(acc[n], am, b0, b1); mma_bf16_16816(acc[n], al, b0, b1);
+              mma_f16_16816(acc[n], ah, b0, b1); mma_f16_16816(acc[n], al, b0, b1);
             }
           }
         }
@@ -272,12 +288,12 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 #pragma unroll
         for (int i = 0; i < KSW_P; ++i) {
           const int ks = kw * KSW_P + i;
-          uint32_t ah[4], am[4], al[4];
-          split3(xa[i][0], ah[0], am[0], al[0]); split3(xb[i][0], ah[1], am[1], al[1]);
-          split3(xa[i][1], ah[2], am[2], al[2]); split3(xb[i][1], ah[3], am[3], al[3]);
+          uint32_t ah[4], al[4];
+          split2(xa[i][0], ah[0], al[0]); split2(xb[i][0], ah[1], al[1]);
+          split2(xa[i][1], ah[2], al[2]); split2(xb[i][1], ah[3], al[3]);
           const __nv_bfloat16* wr = s_wpred + static_cast<size_t>(gid) * (HP + 8) + ks * 16 + tig * 2;
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-          mma_bf16_16816(acc, ah, b0, b1); mma_bf16_16816(acc, am, b0, b1); mma_bf16_16816(acc, al, b0, b1);
+          mma_f16_16816(acc, ah, b0, b1); mma_f16_16816(acc, al, b0, b1);
         }
         {
           float* r0 = red + (warp * 16 + gid) * 8 + tig * 2;
@@ -352,8 +368,8 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
         }
         const unsigned mask = __ballot_sync(0xffffffffu, row_b >= 0);
         if (mask == 0u) continue;                             // identical in every warp of the CTA
-        float4 gv[PER];
-        auto load_half = [&](int h) {
+        float4 gv0[PER], gv1[PER];
+        auto load_half = [&](int h, float4 (&gv)[PER]) {
 #pragma unroll
           for (int i = 0; i < PER; ++i) {
             const int idx = tid + kSpThreads * i;
@@ -370,13 +386,13 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
             }
           }
         };
-        auto store_half = [&]() {
+        auto store_half = [&](const float4 (&gv)[PER], float sc) {
 #pragma unroll
           for (int i = 0; i < PER; ++i) {
             const int idx = tid + kSpThreads * i;
             if (idx < kPassRows * V4_ROW) {
               const int r = idx / V4_ROW, c4 = idx % V4_ROW;
-              *reinterpret_cast<float4*>(s_g + r * GS + 4 * c4) = gv[i];
+              *reinterpret_cast<float4*>(s_g + r * GS + 4 * c4) = make_float4(gv[i].x * sc, gv[i].y * sc, gv[i].z * sc, gv[i].w * sc);
             }
           }
         };
@@ -393,16 +409,16 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
             const float2 x1 = *reinterpret_cast<const float2*>(ga + 8 * GS + ks * 16);
             const float2 x2 = *reinterpret_cast<const float2*>(ga + ks * 16 + 8);
             const float2 x3 = *reinterpret_cast<const float2*>(ga + 8 * GS + ks * 16 + 8);
-            uint32_t ah[4], am[4], al[4];
-            split3(x0, ah[0], am[0], al[0]); split3(x1, ah[1], am[1], al[1]);
-            split3(x2, ah[2], am[2], al[2]); split3(x3, ah[3], am[3], al[3]);
+            uint32_t ah[4], al[4];
+            split2(x0, ah[0], al[0]); split2(x1, ah[1], al[1]);
+            split2(x2, ah[2], al[2]); split2(x3, ah[3], al[3]);
 #pragma unroll
             for (int n = 0; n < kMaxTilesPerWarp; ++n) {
               const int nt = ng + 4 * n;
               if (nt < n_tiles) {                            // warp-uniform
                 const __nv_bfloat16* wr = s_wout + static_cast<size_t>(nt * 8 + gid) * WS + h * KH + ks * 16 + tig * 2;
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-                mma_bf16_16816(acc[n], ah, b0, b1); mma_bf16_16816(acc[n], am, b0, b1); mma_bf16_16816(acc[n], al, b0, b1);
+                mma_f16_16816(acc[n], ah, b0, b1); mma_f16_16816(acc[n], al, b0, b1);
               }
             }
           }
@@ -410,14 +426,22 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
         long long tj = 0;
         if (cta == 0 && tid == 0) tj = clock64();
         auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
-        load_half(0);
-        store_half();
+        load_half(0, gv0);
+        load_half(1, gv1);                                    // both k-halves in flight together
+        // IEEE half tops out at 65504: in the (absurd for a transducer joint) case that an activation of this pass
+        // exceeds 2^15, the whole pass is evaluated on activations scaled by 2^-10 and the logits scaled back
+        bool big = false;
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+          big |= fmaxf(fmaxf(fmaxf(gv0[i].x, gv0[i].y), fmaxf(gv0[i].z, gv0[i].w)), fmaxf(fmaxf(gv1[i].x, gv1[i].y), fmaxf(gv1[i].z, gv1[i].w))) > 32768.f;
+        const bool scaled = __syncthreads_or(big) != 0;
+        const float sc = scaled ? 0.0009765625f : 1.f, isc = scaled ? 1024.f : 1.f;
+        store_half(gv0, sc);
         __syncthreads();
         jtick(8);
-        load_half(1);                                         // in flight under the MMAs of half 0
         mma_half(0);
         __syncthreads();
-        store_half();
+        store_half(gv1, sc);
         __syncthreads();
         mma_half(1);
         jtick(9);
@@ -432,7 +456,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int col = nt * 8 + tig * 2 + (q & 1), hrow = q >> 1;
-                const float v = acc[n][q] + s_bout[col];
+                const float v = acc[n][q] * isc + s_bout[col];
                 if (col < nj && (v > bv[hrow] || (v == bv[hrow] && j0 + col < bi[hrow]))) { bv[hrow] = v; bi[hrow] = j0 + col; }
               }
             }

@@ -15,14 +15,19 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                  const float* __restrict__ g2, const float* __restrict__ b2, int rows, float eps) {
+  // Persistent: a warp walks rows (stride = warps in the grid) with the NEXT row's loads already in flight while
+  // the current one is reduced and stored -- short-lived one-row warps left HBM at ~40 % (profiles/r01_v2_other_ncu.md).
   constexpr int D = 128 * NV;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = lane_id();
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-  float4 v[NV];
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV], nx[NV];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  }
 
   auto normalize = [&](const float* __restrict__ g, const float* __restrict__ b) {
     float s = 0.f;
@@ -47,17 +52,27 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, cons
     }
   };
 
-  normalize(g1, b1);
-  if (out_f32 != nullptr) {
-    float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D);
+  for (; row < rows; row += wstride) {
+    const int nrow = row + wstride;
+    if (nrow < rows) {                                         // warp-uniform
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(nrow) * D);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) o[lane + 32 * i] = v[i];
-  }
-  if (g2 != nullptr) normalize(g2, b2);
-  if (out_bf16 != nullptr) {
-    uint2* o = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * D);
+      for (int i = 0; i < NV; ++i) nx[i] = xr[lane + 32 * i];
+    }
+    normalize(g1, b1);
+    if (out_f32 != nullptr) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) o[lane + 32 * i] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+      for (int i = 0; i < NV; ++i) o[lane + 32 * i] = v[i];
+    }
+    if (g2 != nullptr) normalize(g2, b2);
+    if (out_bf16 != nullptr) {
+      uint2* o = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * D);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) o[lane + 32 * i] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = nx[i];
   }
 }
 
@@ -65,7 +80,15 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
                              const float* gamma2, const float* beta2, int rows, int d, float eps, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   const int wpb = 8;
-  const dim3 grid((rows + wpb - 1) / wpb), block(32 * wpb);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const int need = (rows + wpb - 1) / wpb;
+  const int cap = num_sms * 2;                                 // 2 resident CTAs per SM (16 warps x 2 rows in flight)
+  const dim3 grid(need < cap ? need : cap), block(32 * wpb);
   auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
   switch (d) {
     case 256: layernorm_kernel<2><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;

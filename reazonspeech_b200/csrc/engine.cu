@@ -70,6 +70,11 @@ struct rs_engine {
   std::vector<cudaEvent_t> gemm_ev;     // pairs
   size_t gemm_ev_used = 0;
   double gemm_flops = 0.0;
+  // per-kernel timing inside the real pipeline (warm caches, back-to-back launches): event pair around every launch
+  bool ktiming = false;
+  cudaStream_t cur_stream = nullptr;
+  std::vector<cudaEvent_t> k_ev;
+  std::vector<std::string> k_tag;       // one per event pair
   // rs_transcribe_batch: host->device copies run on their own stream in utterance chunks so the frontend of
   // chunk i overlaps the copy of chunk i+1
   static constexpr int kCopyChunks = 8;
@@ -130,7 +135,7 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.abuf = take(static_cast<size_t>(p.M) * d * 2);
   p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
   p.n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32;
-  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * p.n_rel_pad * 4);
+  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * p.n_rel_pad * 2);    // IEEE half
   p.enc = take(static_cast<size_t>(p.M) * d * 4);
   p.encp = take(static_cast<size_t>(p.M) * c.joint_hidden * 4);
   p.tokens = take(static_cast<size_t>(B) * U_max * 4);
@@ -226,6 +231,21 @@ int gemm(rs_engine* e, const void* a, const void* w, const float* bias, const fl
   return gemm_args(e, g, s);
 }
 
+void ktime_begin(rs_engine* e, const char* tag) {
+  if (!e->ktiming) return;
+  const size_t i = 2 * e->k_tag.size();
+  while (e->k_ev.size() < i + 2) { cudaEvent_t ev; cudaEventCreate(&ev); e->k_ev.push_back(ev); }
+  std::string t(tag);
+  if (t.rfind("rs::", 0) == 0) t = t.substr(4);
+  const size_t par = t.find('(');
+  e->k_tag.push_back(par == std::string::npos ? t : t.substr(0, par));
+  cudaEventRecord(e->k_ev[i], e->cur_stream);
+}
+void ktime_end(rs_engine* e) {
+  if (!e->ktiming) return;
+  cudaEventRecord(e->k_ev[2 * e->k_tag.size() - 1], e->cur_stream);
+}
+
 int gemm_args(rs_engine* e, const rs::GemmArgs& g, cudaStream_t s) {
   const int M = g.M, N = g.N, K = g.K;
   char msg[256] = "";
@@ -239,7 +259,14 @@ int gemm_args(rs_engine* e, const rs::GemmArgs& g, cudaStream_t s) {
     cudaEventRecord(e->gemm_ev[e->gemm_ev_used], s);
     timed = true;
   }
+  if (e->ktiming) {
+    char tag[64];
+    snprintf(tag, sizeof tag, "gemm N=%d K=%d epi=%d%s", N, K, g.epilogue, g.n_batch > 1 ? " batched" : "");
+    e->cur_stream = s;
+    ktime_begin(e, tag);
+  }
   cudaError_t c = rs::launch_gemm(g, e->num_sms, s, msg);
+  ktime_end(e);
   if (c != cudaSuccess) return fail(e, RS_ERR_CUDA, "gemm: %s", msg);
   if (timed) {
     cudaEventRecord(e->gemm_ev[e->gemm_ev_used + 1], s);
@@ -253,7 +280,9 @@ int gemm_args(rs_engine* e, const rs::GemmArgs& g, cudaStream_t s) {
 #define RS_TRY(x) do { int _r = (x); if (_r != RS_OK) return _r; } while (0)
 #define RS_K(e, call, n)                                                                       \
   do {                                                                                         \
+    ktime_begin((e), #call);                                                                   \
     cudaError_t _c = (call);                                                                   \
+    ktime_end((e));                                                                            \
     if (_c != cudaSuccess) return fail((e), RS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_c)); \
     (e)->launches += (n);                                                                      \
   } while (0)
@@ -270,6 +299,7 @@ void mark(rs_engine* e, int i, cudaStream_t s) {
 }
 
 int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, cudaStream_t s) {
+  e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   RS_K(e, rs::launch_logmel(wav, len, B, L_max, mel, mel_len, nullptr, &e->fe, c.n_mels, c.n_window_stride, c.n_fft,
                            c.n_window_size, c.preemph, c.log_zero_guard, c.norm_eps, s), 2);
@@ -277,6 +307,7 @@ int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_m
 }
 
 int do_sub_conv0(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, int b0, int nb, cudaStream_t s) {
+  e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   const int C = c.sub_channels;
   rs::SubsampleArgs sa{mel + static_cast<size_t>(b0) * p.F_max * c.n_mels, mel_len + b0, nb, p.F_max, c.n_mels, C,
@@ -288,6 +319,7 @@ int do_sub_conv0(rs_engine* e, const Plan& p, const float* mel, const int32_t* m
 
 int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, float* enc, int32_t* enc_len,
               int n_layers, cudaStream_t s, bool conv0_done = false) {
+  e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   const int d = c.d_model, C = c.sub_channels, M = p.M, B = p.B;
   if (n_layers < 0 || n_layers > c.n_layers) n_layers = c.n_layers;
@@ -317,12 +349,12 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
     {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
-      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F32, 1.f};
+      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16, 1.f};
       g.lda = 3 * d; g.ldo = c.n_heads * p.n_rel_pad; g.n_batch = c.n_heads;
       g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad;
       RS_TRY(gemm_args(e, g, s));
     }
-    rs::AttnArgs aa{hb, at<float>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
+    rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
     RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
     RS_TRY(gemm(e, ab, L.wo, L.bo, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
     RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
@@ -346,6 +378,7 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
 
 int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_len, int T_max, int32_t* tokens,
               int32_t* frames, int32_t* ntok, int U_max, cudaStream_t s) {
+  e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   const int M = p.B * T_max;
   RS_K(e, rs::launch_f32_to_bf16(enc, at<void>(e, p.xn), static_cast<int64_t>(M) * c.d_model, s), 1);
@@ -409,6 +442,7 @@ void rs_engine_destroy(rs_engine* e) {
   for (auto& ev : e->copy_ev) if (ev) cudaEventDestroy(ev);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
+  for (auto& ev : e->k_ev) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -577,6 +611,35 @@ int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* o
   const size_t off = p.dec_ws + static_cast<size_t>(2) * B * e->cfg.pred_hidden * 4 + static_cast<size_t>(B) * e->cfg.joint_hidden * 4 +
                      static_cast<size_t>(3) * B * 8 + 64;
   RS_CUDA(e, cudaMemcpy(out8, static_cast<char*>(e->ws) + off, 96, cudaMemcpyDeviceToHost));
+  return RS_OK;
+}
+
+int rs_enable_kernel_timing(rs_engine* e, int on) {
+  if (!e) return RS_ERR_INVALID_ARG;
+  e->ktiming = on != 0;
+  e->k_tag.clear();
+  return RS_OK;
+}
+
+// Text summary "name\tcount\ttotal_ms\n..." of every launch since rs_enable_kernel_timing(e, 1); resets the log.
+int rs_kernel_timing(rs_engine* e, char* buf, int buf_bytes) {
+  if (!e || !buf || buf_bytes <= 0) return RS_ERR_INVALID_ARG;
+  RS_CUDA(e, cudaDeviceSynchronize());
+  std::map<std::string, std::pair<int, double>> agg;
+  for (size_t i = 0; i < e->k_tag.size(); ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e->k_ev[2 * i], e->k_ev[2 * i + 1]);
+    auto& a = agg[e->k_tag[i]];
+    a.first += 1; a.second += t;
+  }
+  std::string out;
+  char line[160];
+  for (const auto& kv : agg) {
+    snprintf(line, sizeof line, "%s\t%d\t%.4f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  snprintf(buf, static_cast<size_t>(buf_bytes), "%s", out.c_str());
+  e->k_tag.clear();
   return RS_OK;
 }
 

@@ -87,6 +87,23 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
   const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
   uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
   switch (p.epilogue) {
+    case RS_EPI_BIAS_F16: {                                    // same 16-bit store pattern as the bf16 epilogues
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stage_u + lane * 20 + 4 * j) =
+            make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = i * 8 + (lane >> 2), cw = (lane & 3) * 4;
+        const int row = tile_row0 + rl;
+        const uint4 a = *reinterpret_cast<const uint4*>(stage_u + rl * 20 + cw);
+        if (row < p.M)
+          *reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 + cw * 2) = a;
+      }
+      break;
+    }
     case RS_EPI_BIAS_BF16:
     case RS_EPI_BIAS_RELU_BF16:
     case RS_EPI_BIAS_SWISH_BF16: {

@@ -49,7 +49,7 @@ cudaError_t launch_conv_dw(const void* u, void* out, const float* w /*[k,d]*/, c
 
 struct AttnArgs {
   const void* qkv;       // bf16 [B*T_max, 3*d]: q | k | v
-  const float* bd;       // f32 [B*T_max, H, n_rel_pad]: (q + v_bias) . p[c], from the batched tcgen05 GEMM
+  const void* bd;        // f16 [B*T_max, H, n_rel_pad]: (q + v_bias) . p[c], from the batched tcgen05 GEMM
   int n_rel_pad;
   const float* bias_u;   // f32 [H, dk]
   void* out;             // bf16 [B*T_max, d]

@@ -21,7 +21,7 @@ from .weights import StateDict, hann_window, mel_filterbank, rel_pos_table
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librs_engine.so")
 MEL_MAX_W = 40
 
-EPI_BIAS_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_SWISH_BF16, EPI_BIAS_GLU_BF16, EPI_RESID_F32, EPI_BIAS_F32 = range(6)
+EPI_BIAS_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_SWISH_BF16, EPI_BIAS_GLU_BF16, EPI_RESID_F32, EPI_BIAS_F32, EPI_BIAS_F16 = range(7)
 
 
 class RsModelConfig(C.Structure):
@@ -49,6 +49,7 @@ EXPORTS = [
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
+    "rs_enable_kernel_timing", "rs_kernel_timing",
 ]
 
 
@@ -89,6 +90,10 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_stage_times_ms.argtypes = [vp, f32p]
     lib.rs_debug_decode_cycles.argtypes = [vp, ip, ip, ip, C.POINTER(C.c_int64)]
     lib.rs_debug_decode_cycles.restype = ip
+    lib.rs_enable_kernel_timing.argtypes = [vp, ip]
+    lib.rs_enable_kernel_timing.restype = ip
+    lib.rs_kernel_timing.argtypes = [vp, C.c_char_p, ip]
+    lib.rs_kernel_timing.restype = ip
     lib.rs_enable_gemm_timing.argtypes = [vp, ip]
     lib.rs_gemm_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode",
@@ -345,6 +350,8 @@ class Engine:
         if out is None:
             if epilogue in (EPI_RESID_F32, EPI_BIAS_F32):
                 out = torch.empty(M, N, dtype=torch.float32, device=self.device)
+            elif epilogue == EPI_BIAS_F16:
+                out = torch.empty(M, N, dtype=torch.float16, device=self.device)
             elif epilogue == EPI_BIAS_GLU_BF16:
                 out = torch.empty(M, N // 2, dtype=torch.bfloat16, device=self.device)
             else:
@@ -364,6 +371,19 @@ class Engine:
 
     def enable_stage_timing(self, on: bool = True):
         self._check(self.lib.rs_enable_stage_timing(self.h, int(on)), "rs_enable_stage_timing")
+
+    def kernel_timing(self, enable: Optional[bool] = None):
+        """enable=True/False switches per-launch event timing; with None returns {name: (launches, total_ms)} and resets."""
+        if enable is not None:
+            self._check(self.lib.rs_enable_kernel_timing(self.h, int(enable)), "rs_enable_kernel_timing")
+            return None
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self.lib.rs_kernel_timing(self.h, buf, len(buf)), "rs_kernel_timing")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split("\t")
+            out[name] = (int(n), float(ms))
+        return out
 
     def decode_cycles(self, B: int, L_max: int, U_max: int):
         out = (C.c_int64 * 12)()

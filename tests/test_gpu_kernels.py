@@ -51,7 +51,7 @@ def test_gemm_bias_f32(tiny_engine, M, N, K):
 
 
 @pytest.mark.parametrize("epi", [E.EPI_BIAS_BF16, E.EPI_BIAS_RELU_BF16, E.EPI_BIAS_SWISH_BF16, E.EPI_BIAS_GLU_BF16,
-                                 E.EPI_RESID_F32])
+                                 E.EPI_RESID_F32, E.EPI_BIAS_F16])
 def test_gemm_epilogues(tiny_engine, epi):
     eng = tiny_engine
     M, N, K = 517, 512, 256
@@ -74,8 +74,8 @@ def test_gemm_epilogues(tiny_engine, epi):
     else:
         out = eng.gemm(a, w, bias, epi).float()
         ref = {E.EPI_BIAS_BF16: acc, E.EPI_BIAS_RELU_BF16: torch.relu(acc),
-               E.EPI_BIAS_SWISH_BF16: torch.nn.functional.silu(acc)}[epi]
-        tol = 1.2e-2
+               E.EPI_BIAS_SWISH_BF16: torch.nn.functional.silu(acc), E.EPI_BIAS_F16: acc}[epi]
+        tol = 2e-3 if epi == E.EPI_BIAS_F16 else 1.2e-2       # half: 2^-11 relative output rounding
     torch.cuda.synchronize()
     err = ((out - ref).abs() / (ref.abs() + 1.0)).max().item()
     assert err < tol, f"epilogue {epi}: max scaled err {err}"
