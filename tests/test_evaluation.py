@@ -1,0 +1,63 @@
+"""CER utilities and the evaluator's host logic (no GPU: the model is a stub with the transcribe_batch seam)."""
+import json
+
+import pytest
+
+from reazonspeech_b200.evaluation import BaseEvaluator, calculate_cer, normalize
+from reazonspeech_b200.evaluation.utils import edit_distance, japanese_number
+
+
+def test_normalize_strips_punctuation_and_folds_fullwidth():
+    assert normalize("こんにちは、世界。") == "こんにちは世界"
+    assert normalize("「ＡＢＣ」ｘｙｚ！？") == "ABCxyz"            # utils.py:15-18
+    assert normalize("１２３") == "百二十三"                      # full-width digits fold, then read as a number
+
+
+@pytest.mark.parametrize("text,want", [("0", "零"), ("7", "七"), ("10", "十"), ("11", "十一"), ("20", "二十"), ("105", "百五"),
+                                       ("1000", "千"), ("2024", "二千二十四"), ("10000", "一万"), ("12345", "一万二千三百四十五"),
+                                       ("100000000", "一億"), ("3.14", "三点一四")])
+def test_japanese_number(text, want):
+    assert japanese_number(text) == want
+
+
+def test_edit_distance_known_values():
+    assert edit_distance("kitten", "sitting") == 3
+    assert edit_distance("", "abc") == 3 and edit_distance("abc", "abc") == 0
+    assert edit_distance("こんにちは", "こんばんは") == 2
+
+
+def test_calculate_cer():
+    r = calculate_cer("今日は、いい天気です。", "今日はいい天気でした")
+    assert r["length"] == 9 and r["distance"] == 2 and abs(r["cer"] - 2 / 9) < 1e-12
+
+
+class _Stub(BaseEvaluator):
+    calls = []
+
+    def _evaluate(self, example, **kw):
+        return {"prediction": example["audio"]["path"].upper()}
+
+    def _evaluate_batch(self, batch, **kw):
+        _Stub.calls.append(len(batch["audio"]))
+        return {"predictions": [a["path"].upper() for a in batch["audio"]]}
+
+
+def test_evaluate_single_and_batched_agree(tmp_path, capsys):
+    rows = [{"audio": {"path": p}, "transcription": t} for p, t in (("abc", "ABC"), ("de", "DX"), ("f", "F"), ("gh", "GH"), ("ijk", "IJK"))]
+    ev = _Stub(text_column="transcription")
+    one = ev.evaluate(dataset=rows)
+    out = tmp_path / "r.jsonl"
+    _Stub.calls.clear()
+    many = ev.evaluate(dataset=rows, batch_size=2, output_file=out)
+    assert _Stub.calls == [2, 2, 1]                              # really batched (the reference's map is not, base.py:205-212)
+    assert [r["prediction"] for r in one] == [r["prediction"] for r in many] == ["ABC", "DE", "F", "GH", "IJK"]
+    assert sum(r["distance"] for r in many) == 1 and sum(r["length"] for r in many) == 11
+    assert capsys.readouterr().out.count("CER: 9.09%") == 2       # base.py:223-225 report line
+    lines = [json.loads(l) for l in out.read_text().splitlines()]
+    assert len(lines) == 5 and lines[1]["prediction"] == "DE" and lines[1]["distance"] == 1
+    assert abs(ev.calculate_cer(many, text_column="transcription") - 1 / 11) < 1e-12
+
+
+def test_evaluate_without_dataset_raises():
+    with pytest.raises(ValueError):
+        _Stub().evaluate()
