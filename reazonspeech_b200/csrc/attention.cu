@@ -93,20 +93,12 @@ local_attention_kernel(const AttnDev p) {
     return;
   }
 
-  // ---- phase 0: Q tile -> (q+u) in bf16; global-key scores
+  // ---- phase 0: Q tile (already q + pos_bias_u: folded into the QKV projection's bias at pack time); global-key scores
   for (int id = threadIdx.x; id < QT * 16; id += blockDim.x) {
     const int r = id >> 4, c = (id & 15) * 8;
     uint4 raw = make_uint4(0, 0, 0, 0);
     if (q0 + r < p.T_max) raw = *reinterpret_cast<const uint4*>(qbase + static_cast<size_t>(q0 + r) * ld + c);
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-    uint32_t qu[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 q2 = unpack_bf16x2(w[i]);
-      const float2 u2 = *reinterpret_cast<const float2*>(p.bias_u + h * DK + c + 2 * i);
-      qu[i] = pack_bf16x2(q2.x + u2.x, q2.y + u2.y);
-    }
-    *reinterpret_cast<uint4*>(sQU + r * LDS + c) = make_uint4(qu[0], qu[1], qu[2], qu[3]);
+    *reinterpret_cast<uint4*>(sQU + r * LDS + c) = raw;
   }
   if (p.n_global > 0) {
     const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;     // 2 threads per row, 64 dims each
@@ -121,7 +113,8 @@ local_attention_kernel(const AttnDev p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 x = unpack_bf16x2(aw[j]), y = unpack_bf16x2(bw[j]);
-          acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+          const float2 u2 = __ldg(reinterpret_cast<const float2*>(p.bias_u + h * DK + hf * 64 + i * 8 + 2 * j));   // the global key is scored against q, not q + u
+          acc = fmaf(x.x - u2.x, y.x, acc); acc = fmaf(x.y - u2.y, y.y, acc);
         }
       }
     }
@@ -303,7 +296,7 @@ global_row_attention_kernel(const AttnDev p) {
   const int t_pad = ((p.T_max > 1024 ? p.T_max : 1024) + 3) & ~3;
   float* red = gs + t_pad;
   float* sq = red + 8;
-  if (tid < DK) sq[tid] = __bfloat162float(qrow[tid]) * scale;
+  if (tid < DK) sq[tid] = (__bfloat162float(qrow[tid]) - p.bias_u[h * DK + tid]) * scale;   // q columns hold q + pos_bias_u
   __syncthreads();
   float mx = -INFINITY;
   for (int j = tid; j < len; j += 256) {

@@ -82,10 +82,13 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
 // fp32 pair -> two IEEE-half pairs with hi + lo == x to 22 mantissa bits (11 + 11): the residual x - hi is exact in
 // fp32 and is itself rounded to half.  The legacy tensor path issues one m16n8k16 per ~19 cycles and scheduler on
 // sm_100, so the number of terms is what the joint costs; three bf16 terms (24 bits) were 1.5x slower.
+// Magnitudes are clamped to the largest finite half before each conversion, which extends the exactly covered
+// range to |x| <= 2 * 65504; a transducer joint / LSTM input beyond that is outside what NeMo itself runs in fp16 AMP.
 __device__ __forceinline__ void split2(float2 x, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x.x, x.y);
+  constexpr float kMax = 65504.f;
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(x.x, -kMax), kMax), fminf(fmaxf(x.y, -kMax), kMax));
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x.x - hf.x, x.y - hf.y);
+  const __half2 l = __floats2half2_rn(fminf(fmaxf(x.x - hf.x, -kMax), kMax), fminf(fmaxf(x.y - hf.y, -kMax), kMax));
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
@@ -117,7 +120,8 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   constexpr int KSW_L = (2 * HP / 16) / kSpWarps;   // k16 steps per warp, LSTM
   constexpr int KSW_P = (HP / 16) / kSpWarps;       // k16 steps per warp, joint.pred
   constexpr int V4_ROW = KH / 4;             // float4 per staged row
-  constexpr int PER = (kPassRows * V4_ROW + kSpThreads - 1) / kSpThreads;
+  constexpr int ITEMS = kPassUtts * V4_ROW;  // loader items per k-half: (utterance, float4 column)
+  constexpr int PERU = (ITEMS + kSpThreads - 1) / kSpThreads;
   constexpr int G_FLOATS = (kPassRows * GS > kSpWarps * 16 * 24) ? kPassRows * GS : kSpWarps * 16 * 24;   // s_g doubles as the L / P reduction buffer
   static_assert(HJ % 32 == 0 && (2 * HP / 16) % kSpWarps == 0 && (HP / 16) % kSpWarps == 0, "shape");
 
@@ -368,31 +372,46 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
         }
         const unsigned mask = __ballot_sync(0xffffffffu, row_b >= 0);
         if (mask == 0u) continue;                             // identical in every warp of the CTA
-        float4 gv0[PER], gv1[PER];
-        auto load_half = [&](int h, float4 (&gv)[PER]) {
+        // loader item = (utterance of the pass, float4 column): pred_proj is fetched once for the four frames of a window
+        // and the item order is rotated by the vocabulary-slice index so the 37 CTAs of a group, which all need the same
+        // rows, do not ask L2 for the same lines at the same instant
+        float4 gv[PERU][kFrames];
+        auto load_half = [&](int h) {
 #pragma unroll
-          for (int i = 0; i < PER; ++i) {
-            const int idx = tid + kSpThreads * i;
-            gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int r = min(idx / V4_ROW, kPassRows - 1), c4 = idx % V4_ROW;
-            const int b = __shfl_sync(0xffffffffu, row_b, r);       // every warp holds the row table, lane r = row r
-            const int t = __shfl_sync(0xffffffffu, row_t, r);
-            if (idx < kPassRows * V4_ROW) {
-              if (b >= 0) {
-                const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.enc_proj + (static_cast<size_t>(b) * p.T_max + t) * HJ + h * KH) + c4);
-                const float4 q4 = ldcg4s(p.ppbuf + static_cast<size_t>(b) * HJ + h * KH + 4 * c4);
-                gv[i] = make_float4(fmaxf(e4.x + q4.x, 0.f), fmaxf(e4.y + q4.y, 0.f), fmaxf(e4.z + q4.z, 0.f), fmaxf(e4.w + q4.w, 0.f));
+          for (int i = 0; i < PERU; ++i) {
+            int it = tid + kSpThreads * i;
+            const bool in_range = it < ITEMS;
+            it = (it + slice * 29) % ITEMS;
+            const int ul = it / V4_ROW, c4 = it % V4_ROW;
+            int rb[kFrames], rt[kFrames];
+#pragma unroll
+            for (int j = 0; j < kFrames; ++j) {
+              rb[j] = __shfl_sync(0xffffffffu, row_b, ul * kFrames + j);     // every warp holds the row table, lane r = row r
+              rt[j] = __shfl_sync(0xffffffffu, row_t, ul * kFrames + j);
+            }
+#pragma unroll
+            for (int j = 0; j < kFrames; ++j) gv[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (in_range && rb[0] >= 0) {
+              const float4 q4 = ldcg4s(p.ppbuf + static_cast<size_t>(rb[0]) * HJ + h * KH + 4 * c4);
+#pragma unroll
+              for (int j = 0; j < kFrames; ++j) {
+                if (rb[j] >= 0) {
+                  const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.enc_proj + (static_cast<size_t>(rb[j]) * p.T_max + rt[j]) * HJ + h * KH) + c4);
+                  gv[i][j] = make_float4(fmaxf(e4.x + q4.x, 0.f), fmaxf(e4.y + q4.y, 0.f), fmaxf(e4.z + q4.z, 0.f), fmaxf(e4.w + q4.w, 0.f));
+                }
               }
             }
           }
         };
-        auto store_half = [&](const float4 (&gv)[PER], float sc) {
+        auto store_half = [&]() {
 #pragma unroll
-          for (int i = 0; i < PER; ++i) {
-            const int idx = tid + kSpThreads * i;
-            if (idx < kPassRows * V4_ROW) {
-              const int r = idx / V4_ROW, c4 = idx % V4_ROW;
-              *reinterpret_cast<float4*>(s_g + r * GS + 4 * c4) = make_float4(gv[i].x * sc, gv[i].y * sc, gv[i].z * sc, gv[i].w * sc);
+          for (int i = 0; i < PERU; ++i) {
+            int it = tid + kSpThreads * i;
+            if (it < ITEMS) {
+              it = (it + slice * 29) % ITEMS;
+              const int ul = it / V4_ROW, c4 = it % V4_ROW;
+#pragma unroll
+              for (int j = 0; j < kFrames; ++j) *reinterpret_cast<float4*>(s_g + (ul * kFrames + j) * GS + 4 * c4) = gv[i][j];
             }
           }
         };
@@ -426,22 +445,14 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
         long long tj = 0;
         if (cta == 0 && tid == 0) tj = clock64();
         auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
-        load_half(0, gv0);
-        load_half(1, gv1);                                    // both k-halves in flight together
-        // IEEE half tops out at 65504: in the (absurd for a transducer joint) case that an activation of this pass
-        // exceeds 2^15, the whole pass is evaluated on activations scaled by 2^-10 and the logits scaled back
-        bool big = false;
-#pragma unroll
-        for (int i = 0; i < PER; ++i)
-          big |= fmaxf(fmaxf(fmaxf(gv0[i].x, gv0[i].y), fmaxf(gv0[i].z, gv0[i].w)), fmaxf(fmaxf(gv1[i].x, gv1[i].y), fmaxf(gv1[i].z, gv1[i].w))) > 32768.f;
-        const bool scaled = __syncthreads_or(big) != 0;
-        const float sc = scaled ? 0.0009765625f : 1.f, isc = scaled ? 1024.f : 1.f;
-        store_half(gv0, sc);
+        load_half(0);
+        store_half();
         __syncthreads();
         jtick(8);
+        load_half(1);                                         // in flight under the MMAs of half 0
         mma_half(0);
         __syncthreads();
-        store_half(gv1, sc);
+        store_half();
         __syncthreads();
         mma_half(1);
         jtick(9);
@@ -456,7 +467,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const int col = nt * 8 + tig * 2 + (q & 1), hrow = q >> 1;
-                const float v = acc[n][q] * isc + s_bout[col];
+                const float v = acc[n][q] + s_bout[col];
                 if (col < nj && (v > bv[hrow] || (v == bv[hrow] && j0 + col < bi[hrow]))) { bv[hrow] = v; bi[hrow] = j0 + col; }
               }
             }

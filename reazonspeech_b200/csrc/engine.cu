@@ -39,8 +39,8 @@ struct LayerW {
 
 struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   int B, L_max, F_max, T1, F1, T2, F2, T3, F3, M;
-  size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, enc, encp;
-  int n_rel_pad;
+  size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, vt, enc, encp;
+  int n_rel_pad, ld_vt;
   size_t tokens, frames, ntok, dec_ws, total;
 };
 
@@ -136,6 +136,8 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
   p.n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32;
   p.bd = take(static_cast<size_t>(p.M) * c.n_heads * p.n_rel_pad * 2);    // IEEE half
+  p.ld_vt = ((p.M + 255) / 256) * 256 + 64;                               // V^T row pitch: covers the GEMM's 256-row tile overhang
+  p.vt = take(static_cast<size_t>(d) * p.ld_vt * 2);
   p.enc = take(static_cast<size_t>(p.M) * d * 4);
   p.encp = take(static_cast<size_t>(p.M) * c.joint_hidden * 4);
   p.tokens = take(static_cast<size_t>(B) * U_max * 4);
@@ -347,15 +349,27 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
     RS_TRY(gemm(e, hb, L.ff1_w2, L.ff1_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
-    RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
+    rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
+    aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt;
+    // RS_ATTN_MODE=1 keeps the mma.sync kernels (also the path for windows wider than 128)
+    const char* attn_env = getenv("RS_ATTN_MODE");
+    const int attn_mode = attn_env ? atoi(attn_env) : 0;
+    const bool attn_tc = attn_mode != 1 && rs::attention_tc_supported(aa);
+    if (attn_tc) {     // q | k row-major, V transposed (keys contiguous) for the tensor-core kernel's P.V product
+      rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_QKV_VT, 1.f};
+      g.out2 = at<void>(e, p.vt); g.split = 2 * d; g.ld2 = p.ld_vt;
+      RS_TRY(gemm_args(e, g, s));
+    } else {
+      RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
+    }
     {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
       rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16, 1.f};
       g.lda = 3 * d; g.ldo = c.n_heads * p.n_rel_pad; g.n_batch = c.n_heads;
       g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad;
       RS_TRY(gemm_args(e, g, s));
     }
-    rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
-    RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
+    if (attn_tc) RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);
+    else RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
     RS_TRY(gemm(e, ab, L.wo, L.bo, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
     RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     RS_TRY(gemm(e, xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f, s));

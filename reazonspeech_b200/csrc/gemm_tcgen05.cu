@@ -39,6 +39,7 @@ struct GemmDev {
   // optional batching along columns (one launch for all attention heads): batch b reads A columns
   // [b*a_col_stride, +K), W rows [b*w_row_stride, +N), bias + b*bias_stride, writes columns + b*out_col_stride
   int n_batch, a_col_stride, w_row_stride, bias_stride, out_col_stride;
+  void* out2; int split, ld2;    // RS_EPI_QKV_VT
 };
 
 template <int BN>
@@ -86,7 +87,28 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
   }
   const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
   uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
-  switch (p.epilogue) {
+  int epi = p.epilogue;
+  if (epi == RS_EPI_QKV_VT) {
+    if (col0 < p.split) {
+      epi = RS_EPI_BIAS_BF16;                                  // q | k columns: plain row-major bf16
+    } else {
+      // V columns: out2[col - split][row] = bf16(v).  Staged so that one store instruction covers 8 rows of out2
+      // (= 8 head dims) x 64 B (= 32 consecutive frames).
+      uint16_t* st16 = reinterpret_cast<uint16_t*>(stage);     // [32 dims][40] halves
+#pragma unroll
+      for (int j = 0; j < 32; ++j) st16[j * 40 + lane] = __bfloat16_as_ushort(__float2bfloat16_rn(v[j]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int dim = i * 8 + (lane >> 2), f0 = (lane & 3) * 8;
+        const uint4 a = *reinterpret_cast<const uint4*>(st16 + dim * 40 + f0);
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(col0 - p.split + dim) * p.ld2 + tile_row0 + f0) = a;
+      }
+      __syncwarp();
+      return;
+    }
+  }
+  switch (epi) {
     case RS_EPI_BIAS_F16: {                                    // same 16-bit store pattern as the bf16 epilogues
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -107,10 +129,10 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
     case RS_EPI_BIAS_BF16:
     case RS_EPI_BIAS_RELU_BF16:
     case RS_EPI_BIAS_SWISH_BF16: {
-      if (p.epilogue == RS_EPI_BIAS_RELU_BF16) {
+      if (epi == RS_EPI_BIAS_RELU_BF16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-      } else if (p.epilogue == RS_EPI_BIAS_SWISH_BF16) {
+      } else if (epi == RS_EPI_BIAS_SWISH_BF16) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = swishf_fast(v[j]);
       }
@@ -495,7 +517,7 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, a_cols, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, w_rows, g.K, g.K, BN, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride};
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
   gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
@@ -518,7 +540,7 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0};
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
@@ -544,6 +566,10 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
+  if (g.epilogue == RS_EPI_QKV_VT && (g.out2 == nullptr || g.split % 32 || g.ld2 % 8 || g.ld2 < ((g.M + 255) / 256) * 256 || g.n_batch > 1)) {
+    snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, ld2 >= M rounded up to 256");
+    return cudaErrorInvalidValue;
+  }
   // kernel choice depends on N only (never on M): a row's result must not depend on the batch it sits in
   if (g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0)
     return launch_2cta<256>(g, num_sms, stream, err);

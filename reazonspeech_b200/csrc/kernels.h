@@ -17,6 +17,8 @@ struct GemmArgs {
   // optional: A row stride (elements, default K), output row stride (default N), column batching
   int lda = 0, ldo = 0;
   int n_batch = 1, a_col_stride = 0, w_row_stride = 0, bias_stride = 0, out_col_stride = 0;
+  // RS_EPI_QKV_VT: columns >= split go, transposed, to out2 (bf16 [N - split, ld2]; ld2 >= M rounded up to 256)
+  void* out2 = nullptr; int split = 0, ld2 = 0;
 };
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
@@ -55,8 +57,13 @@ struct AttnArgs {
   void* out;             // bf16 [B*T_max, d]
   const int32_t* enc_len;
   int B, T_max, H, dk, w_left, w_right, n_global;
+  // tensor-core path (attention_tc.cu): V^T bf16 [H*dk, ld_vt] written by the QKV GEMM (RS_EPI_QKV_VT); the q columns
+  // of `qkv` hold q + pos_bias_u in BOTH paths (folded into the projection bias when the weights are packed)
+  const void* vt = nullptr; int ld_vt = 0;
 };
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream);
+bool attention_tc_supported(const AttnArgs& a);
+cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream);
 
 struct DecodeArgs {
   const float* enc_proj;      // f32 [B*T_max, Hj]  (joint.enc applied to every frame)

@@ -174,14 +174,18 @@ def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
             out[o + dst + ".w2"] = bf(sd[p + src + ".linear2.weight"]); out[o + dst + ".b2"] = f32(sd[p + src + ".linear2.bias"])
         a = p + "self_attn."
         out[o + "att.wqkv"] = bf(torch.cat([sd[a + "linear_q.weight"], sd[a + "linear_k.weight"], sd[a + "linear_v.weight"]], 0))
-        out[o + "att.bqkv"] = f32(torch.cat([sd[a + "linear_q.bias"], sd[a + "linear_k.bias"], sd[a + "linear_v.bias"]], 0))
+        # the q columns of the projection carry q + pos_bias_u (the content term (q+u).k is then a plain Q'K^T for the
+        # tensor cores); the positional term and the global token, which want q + pos_bias_v resp. q, get u taken out again
+        # through their own bias / in their own kernel
+        u_flat = sd[a + "pos_bias_u"].reshape(-1)
+        out[o + "att.bqkv"] = f32(torch.cat([sd[a + "linear_q.bias"] + u_flat, sd[a + "linear_k.bias"], sd[a + "linear_v.bias"]], 0))
         pos = torch.nn.functional.linear(table, sd[a + "linear_pos.weight"])          # input independent: once at load
         n_rel_pad = (cfg.n_rel + 31) // 32 * 32
         pos_h = torch.zeros(H, n_rel_pad, dk)
         pos_h[:, : cfg.n_rel] = pos.view(cfg.n_rel, H, dk).permute(1, 0, 2)
         out[o + "att.pos"] = bf(pos_h)                                                 # B operand of the batched BD GEMM
-        # (q + v).p = q.p + v.p: the second term is input independent -> the GEMM's bias
-        out[o + "att.bdbias"] = f32((out[o + "att.pos"].float() * sd[a + "pos_bias_v"][:, None, :]).sum(-1).reshape(-1))
+        # (q + v).p = (q + u).p + (v - u).p: the second term is input independent -> the GEMM's bias
+        out[o + "att.bdbias"] = f32((out[o + "att.pos"].float() * (sd[a + "pos_bias_v"] - sd[a + "pos_bias_u"])[:, None, :]).sum(-1).reshape(-1))
         out[o + "att.u"] = f32(sd[a + "pos_bias_u"].reshape(-1))
         out[o + "att.wo"] = bf(sd[a + "linear_out.weight"]); out[o + "att.bo"] = f32(sd[a + "linear_out.bias"])
         c = p + "conv."

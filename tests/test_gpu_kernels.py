@@ -280,3 +280,24 @@ def test_host_entry_chunked_copies_equal_device_entry(tiny_engine, B):
         n = int(nh[b])
         assert torch.equal(th[b, :n], td[b, :n].cpu()) and torch.equal(fh[b, :n], fd[b, :n].cpu())
     assert int(nh.sum()) > 0
+
+
+def test_tensor_core_attention_matches_mma_sync_attention(tiny_engine, monkeypatch):
+    """The tcgen05 attention (default) against the mma.sync kernels (RS_ATTN_MODE=1) through the whole encoder, ragged
+    batch with an utterance spanning several 128-row query tiles: relative L2 <= 5e-3 (both are bf16-operand,
+    fp32-accumulate evaluations of the same scores; P is rounded to bf16 at different points)."""
+    eng = tiny_engine
+    waves = [padded(synth_clip(80, 13.0)), padded(synth_clip(81, 0.9)), padded(synth_clip(82, 5.5)), padded(synth_clip(83, 10.3))]
+    mel, mel_len = _mel_batch(eng, waves)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("RS_ATTN_MODE", mode)
+        enc, enc_len = eng.encode(mel, mel_len)
+        torch.cuda.synchronize()
+        outs[mode] = enc.clone()
+    for i in range(len(waves)):
+        T = int(enc_len[i])
+        r = _rel(outs["0"][i, :T].cpu(), outs["1"][i, :T].cpu())
+        print(f"utt{i} T={T}: tcgen05 vs mma.sync attention, encoder rel-L2 {r:.3e}")
+        assert r < 5e-3
+        assert outs["0"][i, T:].abs().max().item() == 0.0 if T < outs["0"].shape[1] else True
