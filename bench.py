@@ -257,6 +257,7 @@ def main():
     eng.transcribe_device(wav_dev, len_dev, U, out_dev)
     kernel_ms = {k: {"launches": n, "ms": round(ms, 4)} for k, (n, ms) in sorted(eng.kernel_timing().items(), key=lambda kv: -kv[1][1])}
     eng.kernel_timing(False)
+    attn_cycles = eng.attention_cycles() if os.environ.get("RS_ATTN_MODE", "0") != "1" else None
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     # DRAM bytes per launch of the dominant kernel: mean of dram__bytes_read.sum + dram__bytes_write.sum over the
     # eight consecutive launches of the `ncu --set full` capture in profiles/r01_v2_gemm_ncu.md (not re-measured here)
@@ -279,13 +280,13 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic 16 kHz AM/FM clips; seeded random weights (619 M architecture, no checkpoint offline)",
         "config": {"workload": f"nemo-asr FastConformer-RNNT 619M, batch={B}x{args.seconds:g} s clips per GPU",
-                   "samples_per_clip": L, "enc_frames": eng.enc_frames(L), "parallelism": f"utterance-sharded x{world}, no collective",
+                   "samples_per_clip": L, "enc_frames": eng.cfg.enc_frames(L), "parallelism": f"utterance-sharded x{world}, no collective",
                    "l2": "per-step working set (~2 GB activations) exceeds the 126 MB L2; no explicit flush",
                    "tokens_per_clip": float(n_tok.float().mean())},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
-        "roofline": roofline, "stage_ms": stages, "kernel_ms": kernel_ms, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
+        "roofline": roofline, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
     }), flush=True)
 
 

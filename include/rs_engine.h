@@ -70,6 +70,10 @@ typedef enum rs_epilogue {
   RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias)   */
   RS_EPI_BIAS_F32 = 5,        /* out_f32[M,N]    = alpha * (acc + bias)                        */
   RS_EPI_BIAS_F16 = 6,        /* out_f16[M,N]    = acc + bias  (IEEE half: attention positional scores) */
+  RS_EPI_BIAS_F16_SKEW = 8,   /* attention positional scores for the tensor-core attention kernel: out_f16[row, col + (t mod 128)]
+                                 = alpha * (acc + bias),
+                                 with t = row mod T_max (T_max passed as ld2), only columns < split are written: thread `row`
+                                 of a 128-row query tile then finds the score of key column jj at the SAME offset in every row */
   RS_EPI_QKV_VT = 7           /* fused QKV projection: columns [0, split) -> out_bf16[M, ldo] as RS_EPI_BIAS_BF16,
                                  columns [split, N) -> TRANSPOSED into out2_bf16[N - split, ld2] (V^T, keys contiguous:
                                  the K-major B operand of the attention kernel's P.V product)               */
@@ -89,7 +93,8 @@ int rs_set_workspace(rs_engine* e, void* dev_ptr, size_t bytes);
 
 /* ---- shape arithmetic --------------------------------------------------------------------
  * rs_mel_frames / rs_enc_frames: TENSOR time sizes for a buffer of n_samples (frames of the centred
- * STFT = n/hop + 1, and ConvSubsampling.calc_length applied to it three times): what callers allocate.
+ * STFT = n/hop + 1; ConvSubsampling.calc_length applied to it three times, rounded up to a multiple of 8):
+ * what callers allocate.
  * rs_mel_valid / rs_enc_valid: the VALID lengths of an utterance of n_samples
  * (FilterbankFeatures.get_seq_len = n/hop, then calc_length x3): what mel_len / enc_len will hold. */
 int rs_mel_frames(const rs_engine* e, int n_samples);
@@ -137,6 +142,7 @@ int rs_stage_times_ms(const rs_engine* e, float* ms /*[8]*/);
  * device time, the summed algorithmic FLOPs (2*M*N*K) and the launch count since it was enabled or
  * last read, and resets the accumulators. */
 int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* out8);   /* profiling aid, see engine.cu */
+int rs_debug_attention_cycles(rs_engine* e, int64_t* out16);   /* clock64 stamps of one CTA of the last attention launch */
 int rs_enable_gemm_timing(rs_engine* e, int on);
 int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches);
 /* Per-kernel CUDA-event timing of EVERY launch inside the real pipeline (warm caches, back-to-back launches, unlike

@@ -19,7 +19,10 @@
 //   UMMA  O[128 x 128] = P V               -> TMEM columns [384, 512)       (24 x tcgen05.mma 128x128x16)
 //   epilogue  O + p_global * v_0, divided by the row sum -> bf16, staged and stored in whole 128-byte lines
 //
-// BD[i][c] = (q_i + pos_bias_v) . p[c] comes from the batched tcgen05 GEMM as before (IEEE half).  Rows of the
+// BD[i][c] = (q_i + pos_bias_v) . p[c] comes from the batched tcgen05 GEMM (IEEE half), whose epilogue stores it
+// row-skewed (RS_EPI_BIAS_F16_SKEW: column c + (i mod 128)) so that the score of a key column is at the same offset in
+// every row of a tile: one thread = one row reads it with 16-byte loads (the unskewed gather cost 32 cache lines per
+// load instruction and bound the whole kernel).  Rows of the
 // global token itself are overwritten afterwards by global_row_attention_tc_kernel (full attention, no
 // positional term).  Shared memory: 32 KB Q' + 96 KB K/P + 96 KB V^T; tensor memory: all 512 columns.
 #include <cuda.h>
@@ -40,7 +43,7 @@ constexpr uint32_t kOffQ = 0;                       // 2 slabs
 constexpr uint32_t kOffK = 2 * kSlab;               // 2 k-slabs x 3 row blocks; later P: 6 key-slabs
 constexpr uint32_t kOffV = kOffK + 6 * kSlab;       // 6 key-slabs of V^T
 constexpr uint32_t kOffBar = kOffV + 6 * kSlab;     // 4 mbarriers + tmem slot
-constexpr uint32_t kAtcSmem = kOffBar + 512 + 1024; // barriers, k_0 row, alignment slack
+constexpr uint32_t kAtcSmem = kOffBar + 1024 + 1024; // barriers, k_0 row, global-key scores, alignment slack
 // small arrays that alias the Q' tile once the S product has retired
 constexpr uint32_t kOffMax = kOffQ;                 // float [2][128]
 constexpr uint32_t kOffSum = kOffQ + 1024;          // float [2][128]
@@ -52,12 +55,16 @@ constexpr int kStagePitch = 64 + 8;                 // bf16 per staged output ro
 struct AtcDev {
   const __nv_bfloat16* qk;      // [M, ld_qk]: q' at column h*128, k at column d + h*128
   const __nv_bfloat16* vt;      // [d, ld_vt]: V^T, column = global frame index
-  const __half* bd;             // [M, H, n_rel_pad]
+  const __half* bd;             // [M, H, bd_pitch], row-skewed: score of relative offset c of frame t at column c + (t mod 128)
   const float* bias_u;          // [H, 128]
   __nv_bfloat16* out;           // [M, d]
   const int32_t* enc_len;
-  int T_max, H, w_left, w_right, n_global, n_rel_pad, ld_qk, ld_vt;
+  int T_max, H, w_left, w_right, n_global, bd_pitch, ld_qk, ld_vt;
 };
+
+// cycle stamps of CTA (1, 0, 0): [0..7] control thread, [8..15] first softmax thread (profiling aid, rs_debug_attention_cycles)
+__device__ long long g_atc_prof[16];
+#define ATC_STAMP(cond, slot) do { if (prof_cta && (cond)) g_atc_prof[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -94,6 +101,9 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
   const size_t row0 = static_cast<size_t>(b) * p.T_max;
   __nv_bfloat16* obase = p.out + row0 * d + h * TDK;
 
+  const bool prof_cta = blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0;
+  ATC_STAMP(threadIdx.x == 0, 0);
+  ATC_STAMP(threadIdx.x == 32, 8);
   if (q0 >= len) {                                   // fully padded tile: defined zeros
     for (int id = threadIdx.x; id < TQ * 16; id += blockDim.x) {
       const int r = id >> 4, c = (id & 15) * 8;
@@ -109,12 +119,24 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
   int rb_lo = (key_lo - j_base) >> 7, rb_hi = (key_hi - j_base) >> 7;        // inclusive, within [0, 2]
   rb_lo = max(rb_lo, 0); rb_hi = min(rb_hi, 2);
 
+  const int n_rb = rb_hi - rb_lo + 1;
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qk);
       tma_prefetch_desc(&tm_vt);
       mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
       fence_barrier_init();
+      // ---- loads: issued before the tensor-memory allocation and the CTA-wide sync so they overlap both
+      ATC_STAMP(true, 1);
+      mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>((2 + 2 * n_rb) * kSlab));
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_2d(base + kOffQ + kb * kSlab, &tm_qk, h * TDK + kb * 64, static_cast<int>(row0) + q0, bar_qk);
+        for (int rb = rb_lo; rb <= rb_hi; ++rb)
+          tma_load_2d(base + kOffK + (kb * 3 + rb) * kSlab, &tm_qk, d + h * TDK + kb * 64, static_cast<int>(row0) + j_base + rb * 128, bar_qk);
+      }
+      mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(2 * n_rb * kSlab));
+      for (int ks = 2 * rb_lo; ks <= 2 * rb_hi + 1; ++ks)
+        tma_load_2d(base + kOffV + ks * kSlab, &tm_vt, static_cast<int>(row0) + j_base + ks * 64, h * TDK, bar_v);
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
@@ -127,20 +149,10 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- loads
-      const int n_rb = rb_hi - rb_lo + 1;
-      mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>((2 + 2 * n_rb) * kSlab));
-      for (int kb = 0; kb < 2; ++kb) {
-        tma_load_2d(base + kOffQ + kb * kSlab, &tm_qk, h * TDK + kb * 64, static_cast<int>(row0) + q0, bar_qk);
-        for (int rb = rb_lo; rb <= rb_hi; ++rb)
-          tma_load_2d(base + kOffK + (kb * 3 + rb) * kSlab, &tm_qk, d + h * TDK + kb * 64, static_cast<int>(row0) + j_base + rb * 128, bar_qk);
-      }
-      mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(2 * n_rb * kSlab));
-      for (int ks = 2 * rb_lo; ks <= 2 * rb_hi + 1; ++ks)
-        tma_load_2d(base + kOffV + ks * kSlab, &tm_vt, static_cast<int>(row0) + j_base + ks * 64, h * TDK, bar_v);
       // ---- S = Q' K^T
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
       mbar_wait(bar_qk, 0);
+      ATC_STAMP(true, 2);
       tcgen05_fence_after();
       for (int kb = 0; kb < 2; ++kb) {
         const uint64_t da = umma_desc_k_sw128(base + kOffQ + kb * kSlab);
@@ -153,6 +165,7 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
         }
       }
       umma_commit(bar_s);
+      ATC_STAMP(true, 3);
     }
     __syncwarp();
   } else {
@@ -167,63 +180,106 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     float* s_v0 = reinterpret_cast<float*>(gen + kOffV0);
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
 
-    // global token: score of its key against this row, without bias_u and without a positional term
-    float sg2 = -INFINITY, v0mine = 0.f;
+    // global token: score of its key against this row, without bias_u and without a positional term:
+    // (q' - u) . k_0 = q'.k_0 (per row, by the hf == 0 warps) - u.k_0 (one scalar per CTA, by warp 1)
+    float v0mine = 0.f;
+    float* s_sg = reinterpret_cast<float*>(gen + kOffBar + 512);                   // [128] raw q'.k_0
+    float* s_uk = reinterpret_cast<float*>(gen + kOffBar + 448);
     if (p.n_global > 0) {
       const int st = threadIdx.x - 32;                                             // 0..255
       if (st < 16) *reinterpret_cast<uint4*>(s_k0 + st * 8) = __ldg(reinterpret_cast<const uint4*>(p.qk + row0 * p.ld_qk + d + h * TDK) + st);
       if (st >= 128) v0mine = __bfloat162float(p.vt[static_cast<size_t>(h * TDK + (st - 128)) * p.ld_vt + row0]);   // V row of frame 0, one dim per thread
       softmax_bar();
-      mbar_wait(bar_qk, 0);                                                        // Q' has landed
-      float uk = 0.f, acc = 0.f;
+      if (warp == 1) {
+        float uk = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const uint4 qv = *reinterpret_cast<const uint4*>(gen + kOffQ + (c >> 3) * kSlab + sw128(r, c & 7));
-        const uint4 kv = *reinterpret_cast<const uint4*>(s_k0 + c * 8);
-        const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv.x, kv.y, kv.z, kv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 q2 = unpack_bf16x2(qw[e]), k2 = unpack_bf16x2(kw[e]);
-          const float2 u2 = __ldg(reinterpret_cast<const float2*>(p.bias_u + h * TDK + c * 8 + 2 * e));
-          acc = fmaf(q2.x, k2.x, acc); acc = fmaf(q2.y, k2.y, acc);
-          uk = fmaf(u2.x, k2.x, uk); uk = fmaf(u2.y, k2.y, uk);
-        }
+        for (int e = 0; e < 4; ++e) uk = fmaf(__ldg(p.bias_u + h * TDK + lane * 4 + e), __bfloat162float(s_k0[lane * 4 + e]), uk);
+        uk = warp_sum(uk);
+        if (lane == 0) *s_uk = uk;
       }
-      sg2 = (acc - uk) * scale2;
+      if (hf == 0) {
+        mbar_wait(bar_qk, 0);                                                      // Q' has landed
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(gen + kOffQ + (c >> 3) * kSlab + sw128(r, c & 7));
+          const uint4 kv = *reinterpret_cast<const uint4*>(s_k0 + c * 8);
+          const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w}, kw[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 q2 = unpack_bf16x2(qw[e]), k2 = unpack_bf16x2(kw[e]);
+            acc0 = fmaf(q2.x, k2.x, acc0); acc1 = fmaf(q2.y, k2.y, acc1);
+          }
+        }
+        s_sg[r] = acc0 + acc1;
+      }
     }
 
+    // Positional scores, row-skewed by the GEMM epilogue: the score of key column jj of the window sits at column
+    // jj - (128 - w_left) of EVERY row of the tile, so a thread fetches a chunk's 32 scores with four 16-byte loads.
+    const __half* bdrow = p.bd + ((row0 + min(i, p.T_max - 1)) * p.H + h) * static_cast<size_t>(p.bd_pitch) - (128 - p.w_left);
+    float mx = -INFINITY;
+    unsigned live = 0;                                   // chunks of this warp that intersect the band
+    // rel = j - i = 32m + e - 128 - r; warp rows r in [32qd, 32qd+31]: the chunk matters to this warp iff ... (warp-uniform)
+    auto chunk_live = [&](int m) {
+      const int rel_max = 32 * m + 31 - 128 - 32 * qd, rel_min = 32 * m - 128 - 32 * qd - 31;
+      const int jl = j_base + 32 * m;
+      return !(rel_max < -p.w_left || rel_min > p.w_right || jl + 31 < 0 || jl >= len || (m >> 2) < rb_lo || (m >> 2) > rb_hi);
+    };
+#pragma unroll
+    for (int k = 0; k < 6; ++k) live |= chunk_live(hf * 6 + k) ? (1u << k) : 0u;
+    // the positional scores of the NEXT live chunk are requested before the current one is processed: a chunk's four
+    // 16-byte loads touch 32 different lines and their L2 latency (not the arithmetic) was what pass 1 waited for
+    uint4 bnext[4];
+    auto fetch = [&](int m) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bnext[c] = __ldg(reinterpret_cast<const uint4*>(bdrow + 32 * m) + c);
+    };
+    unsigned todo = live;
+    if (todo) fetch(hf * 6 + __ffs(todo) - 1);
+    ATC_STAMP(threadIdx.x == 32, 9);
     mbar_wait(bar_s, 0);
+    ATC_STAMP(threadIdx.x == 32, 10);
     tcgen05_fence_after();
     softmax_bar();                                       // every warp is done reading Q' (global-key scores)
+    const float sg2 = p.n_global > 0 ? (s_sg[r] - *s_uk) * scale2 : -INFINITY;
     // the Q' tile is dead now: its memory holds the row statistics and v_0
     if (p.n_global > 0 && threadIdx.x - 32 >= 128) s_v0[threadIdx.x - 32 - 128] = v0mine;
 
-    const __half* bdrow = p.bd + ((row0 + min(i, p.T_max - 1)) * p.H + h) * static_cast<size_t>(p.n_rel_pad);
     // ---- pass 1: t = (S + BD) * scale2 (log2 domain), masked; row maximum; t written back to tensor memory
-    float mx = -INFINITY;
-    unsigned live = 0;                                   // chunks of this warp that intersect the band
 #pragma unroll 1
-    for (int m = hf * 6; m < hf * 6 + 6; ++m) {
-      // rel = j - i = 32m + e - 128 - r; warp rows r in [32qd, 32qd+31]
-      const int rel_max = 32 * m + 31 - 128 - 32 * qd, rel_min = 32 * m - 128 - 32 * qd - 31;
+    while (todo) {
+      const int k = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int m = hf * 6 + k;
       const int jlo = j_base + 32 * m;
-      if (rel_max < -p.w_left || rel_min > p.w_right || jlo + 31 < 0 || jlo >= len || (m >> 2) < rb_lo || (m >> 2) > rb_hi) continue;   // warp-uniform
-      live |= 1u << (m - hf * 6);
+      uint4 braw[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) braw[c] = bnext[c];
+      if (todo) fetch(hf * 6 + __ffs(todo) - 1);
+      // columns e of this chunk the row may attend to: band (-w_left <= j - i <= w_right) and 0 <= j < len
+      const int e_lo = max(max(128 + r - p.w_left - 32 * m, -jlo), 0);
+      const int e_hi = row_ok ? min(min(128 + r + p.w_right - 32 * m, len - 1 - jlo), 31) : -1;
+      const unsigned live_e = e_hi >= e_lo ? ((0xffffffffu >> (31 - e_hi)) & (0xffffffffu << e_lo)) : 0u;   // bit e: column e attended
       uint32_t v[32];
       tmem_ld_32x32(t_row + m * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int rel = 32 * m + e - 128 - r, j = jlo + e;
-        const bool ok = row_ok && rel >= -p.w_left && rel <= p.w_right && j >= 0 && j < len;
-        float t = -INFINITY;
-        if (ok) t = (__uint_as_float(v[e]) + __half2float(__ldg(bdrow + rel + p.w_left))) * scale2;
-        mx = fmaxf(mx, t);
-        v[e] = __float_as_uint(t);
+      for (int e = 0; e < 32; e += 2) {
+        const uint32_t pair = (e & 7) == 0 ? braw[e >> 3].x : (e & 7) == 2 ? braw[e >> 3].y : (e & 7) == 4 ? braw[e >> 3].z : braw[e >> 3].w;
+        const float2 bdv = __half22float2(*reinterpret_cast<const __half2*>(&pair));
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const bool ok = (live_e >> (e + q)) & 1u;
+          const float t = ok ? fmaf(__uint_as_float(v[e + q]), scale2, q == 0 ? bdv.x : bdv.y) : -INFINITY;   // BD arrives pre-scaled
+          mx = fmaxf(mx, t);
+          v[e + q] = __float_as_uint(t);
+        }
       }
       tmem_st_32x32(t_row + m * 32, v);
     }
     tmem_st_wait();
+    ATC_STAMP(threadIdx.x == 32, 11);
     s_max[hf * 128 + r] = mx;
     softmax_bar();
     float m_row = fmaxf(fmaxf(s_max[r], s_max[128 + r]), sg2);
@@ -257,6 +313,7 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
         *reinterpret_cast<uint4*>(slab + sw128(r, cc0 + c)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
     }
+    ATC_STAMP(threadIdx.x == 32, 12);
     s_sum[hf * 128 + r] = sum;
     if (hf == 0) s_pg[r] = (p.n_global > 0 && row_ok) ? ex2f(sg2 - m_row) : 0.f;
     fence_proxy_async();                                 // P was written through the generic proxy, UMMA reads it through the async proxy
@@ -268,6 +325,7 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     if (lane == 0) {
       // ---- O = P V
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+      ATC_STAMP(true, 4);
       mbar_wait(bar_v, 0);
       tcgen05_fence_after();
       bool first = true;
@@ -281,6 +339,7 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
         }
       }
       umma_commit(bar_o);
+      ATC_STAMP(true, 5);
     }
     __syncwarp();
   } else {
@@ -293,7 +352,9 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     const float pg = s_pg[r];
     const float l = s_sum[r] + s_sum[128 + r] + pg;
     const float inv = (i < len && l > 0.f) ? 1.0f / l : 0.f;
+    ATC_STAMP(threadIdx.x == 32, 13);
     mbar_wait(bar_o, 0);
+    ATC_STAMP(threadIdx.x == 32, 14);
     tcgen05_fence_after();
     // staging: the P region is dead once bar_o has completed
     __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(gen + kOffK) + static_cast<size_t>(warp - 1) * 32 * kStagePitch;
@@ -324,12 +385,14 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
       if (row < p.T_max) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(row) * d + hf * 64 + cc) = a;
     }
     tcgen05_fence_before();
+    ATC_STAMP(threadIdx.x == 32, 15);
   }
   __syncthreads();
   if (warp == 0) {
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem_base);
+    ATC_STAMP(lane == 0, 6);
   }
 }
 
@@ -434,19 +497,24 @@ bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uin
 
 }  // namespace
 
+cudaError_t attention_tc_debug_cycles(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_atc_prof, sizeof(long long) * 16);
+}
+
 bool attention_tc_supported(const AttnArgs& a) {
-  return a.dk == TDK && a.w_left <= 128 && a.w_right <= 128 && a.n_global >= 0 && a.n_global <= 1 && a.vt != nullptr;
+  return a.dk == TDK && a.w_left <= 128 && a.w_right <= 128 && (a.w_left & 7) == 0 && a.n_global >= 0 && a.n_global <= 1 &&
+         a.vt != nullptr && (a.T_max & 7) == 0;
 }
 
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
-  if (!attention_tc_supported(a) || a.n_rel_pad < a.w_left + a.w_right + 1 || (a.ld_vt & 7)) return cudaErrorInvalidValue;
+  if (!attention_tc_supported(a) || a.bd_pitch < a.w_left + a.w_right + 128 || (a.bd_pitch & 7) || (a.ld_vt & 7)) return cudaErrorInvalidValue;
   const int d = a.H * TDK;
   const int64_t M = static_cast<int64_t>(a.B) * a.T_max;
   AtcDev p;
   p.qk = static_cast<const __nv_bfloat16*>(a.qkv); p.vt = static_cast<const __nv_bfloat16*>(a.vt);
   p.bd = static_cast<const __half*>(a.bd); p.bias_u = a.bias_u; p.out = static_cast<__nv_bfloat16*>(a.out);
   p.enc_len = a.enc_len; p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right;
-  p.n_global = a.n_global; p.n_rel_pad = a.n_rel_pad; p.ld_qk = 3 * d; p.ld_vt = a.ld_vt;
+  p.n_global = a.n_global; p.bd_pitch = a.bd_pitch; p.ld_qk = 3 * d; p.ld_vt = a.ld_vt;
   CUtensorMap tm_qk, tm_vt;
   if (!make_map(&tm_qk, p.qk, static_cast<uint64_t>(M), static_cast<uint64_t>(2 * d), static_cast<uint64_t>(p.ld_qk))) return cudaErrorInvalidValue;
   if (!make_map(&tm_vt, p.vt, static_cast<uint64_t>(d), static_cast<uint64_t>(M), static_cast<uint64_t>(p.ld_vt))) return cudaErrorInvalidValue;

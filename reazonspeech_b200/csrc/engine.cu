@@ -3,6 +3,7 @@
 // operation is one of the sm_100a kernels declared in kernels.h.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -45,6 +46,11 @@ struct Plan {           // workspace offsets (bytes) for one (B, L_max)
 };
 
 inline int conv_len(int n) { return (n - 1) / 2 + 1; }
+// Encoder-frame capacity of the padded activation tensors: the subsampled length rounded up to a multiple of 8, so that
+// every utterance starts at a 16-byte-aligned column of the transposed V buffer (TMA wants the innermost coordinate
+// 16-byte aligned: an odd T_max raised "illegal instruction" on the V^T tile loads of the attention kernel).
+constexpr int kBdSkewPitch = 384;   // 2 * 128 + 1 relative offsets + 127 of skew, rounded up: columns of a 128-query tile's key window
+inline int enc_capacity(int mel_frames) { return (conv_len(conv_len(conv_len(mel_frames))) + 7) & ~7; }
 
 }  // namespace
 
@@ -114,7 +120,7 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.F_max = L_max / c.n_window_stride + 1;
   p.T1 = conv_len(p.F_max); p.F1 = conv_len(c.n_mels);
   p.T2 = conv_len(p.T1); p.F2 = conv_len(p.F1);
-  p.T3 = conv_len(p.T2); p.F3 = conv_len(p.F2);
+  p.T3 = enc_capacity(p.F_max); p.F3 = conv_len(p.F2);
   p.M = B * p.T3;
   const size_t C = c.sub_channels, d = c.d_model;
   const size_t wide = static_cast<size_t>(c.d_ff) > 3 * d ? c.d_ff : 3 * d;
@@ -135,7 +141,9 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.abuf = take(static_cast<size_t>(p.M) * d * 2);
   p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
   p.n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32;
-  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * p.n_rel_pad * 2);    // IEEE half
+  // IEEE half positional scores; the tensor-core attention reads them row-skewed with a pitch of kBdSkewPitch per head
+  // (256 B of slack in front: its 16-byte loads may start up to 128 - w_left columns before a row)
+  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * kBdSkewPitch * 2 + 512) + 256;
   p.ld_vt = ((p.M + 255) / 256) * 256 + 64;                               // V^T row pitch: covers the GEMM's 256-row tile overhang
   p.vt = take(static_cast<size_t>(d) * p.ld_vt * 2);
   p.enc = take(static_cast<size_t>(p.M) * d * 4);
@@ -350,7 +358,7 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     RS_TRY(gemm(e, hb, L.ff1_w2, L.ff1_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
-    aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt;
+    aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt; aa.bd_pitch = kBdSkewPitch;
     // RS_ATTN_MODE=1 keeps the mma.sync kernels (also the path for windows wider than 128)
     const char* attn_env = getenv("RS_ATTN_MODE");
     const int attn_mode = attn_env ? atoi(attn_env) : 0;
@@ -366,6 +374,11 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
       rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16, 1.f};
       g.lda = 3 * d; g.ldo = c.n_heads * p.n_rel_pad; g.n_batch = c.n_heads;
       g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad;
+      if (attn_tc) {   // row-skewed layout: column c + (t mod 128), see RS_EPI_BIAS_F16_SKEW
+        g.epilogue = RS_EPI_BIAS_F16_SKEW; g.ldo = c.n_heads * kBdSkewPitch; g.out_col_stride = kBdSkewPitch;
+        g.split = c.att_left + c.att_right + 1; g.ld2 = p.T3;
+        g.alpha = 1.4426950408889634f / sqrtf(static_cast<float>(d / c.n_heads));   // scores leave the GEMM in the softmax's log2 domain
+      }
       RS_TRY(gemm_args(e, g, s));
     }
     if (attn_tc) RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);
@@ -465,7 +478,7 @@ const char* rs_last_error(const rs_engine* e) { return e ? e->err : g_create_err
 int rs_workspace_bytes(const rs_engine* e, int B, int L_max, size_t* bytes) {
   if (e == nullptr || bytes == nullptr || B <= 0 || L_max <= 0) return fail(e, RS_ERR_INVALID_ARG, "bad arguments");
   // token capacity: max_symbols per encoder frame is the hard upper bound of the greedy loop
-  const int T = conv_len(conv_len(conv_len(L_max / e->cfg.n_window_stride + 1)));
+  const int T = enc_capacity(L_max / e->cfg.n_window_stride + 1);
   *bytes = make_plan(e, B, L_max, T * e->cfg.max_symbols).total;
   return RS_OK;
 }
@@ -478,7 +491,7 @@ int rs_set_workspace(rs_engine* e, void* dev_ptr, size_t bytes) {
 }
 
 int rs_mel_frames(const rs_engine* e, int n) { return n / e->cfg.n_window_stride + 1; }
-int rs_enc_frames(const rs_engine* e, int n) { return conv_len(conv_len(conv_len(rs_mel_frames(e, n)))); }
+int rs_enc_frames(const rs_engine* e, int n) { return enc_capacity(rs_mel_frames(e, n)); }
 int rs_mel_valid(const rs_engine* e, int n) { return (n + 2 * (e->cfg.n_fft / 2) - e->cfg.n_fft) / e->cfg.n_window_stride; }
 int rs_enc_valid(const rs_engine* e, int n) { return conv_len(conv_len(conv_len(rs_mel_valid(e, n)))); }
 
@@ -654,6 +667,13 @@ int rs_kernel_timing(rs_engine* e, char* buf, int buf_bytes) {
   }
   snprintf(buf, static_cast<size_t>(buf_bytes), "%s", out.c_str());
   e->k_tag.clear();
+  return RS_OK;
+}
+
+int rs_debug_attention_cycles(rs_engine* e, int64_t* out16) {
+  if (!e || !out16) return RS_ERR_INVALID_ARG;
+  RS_CUDA(e, cudaDeviceSynchronize());
+  RS_CUDA(e, rs::attention_tc_debug_cycles(reinterpret_cast<long long*>(out16)));
   return RS_OK;
 }
 

@@ -72,6 +72,9 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
   }
 }
 
+// EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT, 2: RS_EPI_BIAS_F16_SKEW.
+// (One kernel with every path spilled registers in the common ones: 166 -> 168 registers + a stack frame, GEMMs 10-20 % slower.)
+template <int EG>
 __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
                                                int col0, int bt, const float4 (&rr)[8]) {
   float v[32];
@@ -88,7 +91,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
   const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
   uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
   int epi = p.epilogue;
-  if (epi == RS_EPI_QKV_VT) {
+  if constexpr (EG == 1) {
     if (col0 < p.split) {
       epi = RS_EPI_BIAS_BF16;                                  // q | k columns: plain row-major bf16
     } else {
@@ -107,6 +110,28 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       __syncwarp();
       return;
     }
+  }
+  if constexpr (EG == 2) {
+    // row-skewed half output (2-byte stores: the skew breaks vector alignment; 64 contiguous bytes per instruction)
+    uint16_t* st16 = reinterpret_cast<uint16_t*>(stage);       // [32 rows][40] halves
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      *reinterpret_cast<uint32_t*>(st16 + lane * 40 + 2 * j) = pack_f16x2(p.alpha * v[2 * j], p.alpha * v[2 * j + 1]);
+    __syncwarp();
+    const int col = col0 + lane;
+    if (col < p.split) {
+      int t = tile_row0 % p.ld2;                               // frame index of the chunk's first row (one division per chunk)
+      uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(tile_row0) * p.ldo + static_cast<size_t>(bt) * p.out_col_stride + col;
+      const int n_rows = min(32, p.M - tile_row0);
+#pragma unroll 4
+      for (int rr = 0; rr < n_rows; ++rr) {
+        dst[t & 127] = st16[rr * 40 + lane];
+        dst += p.ldo;
+        if (++t == p.ld2) t = 0;
+      }
+    }
+    __syncwarp();
+    return;
   }
   switch (epi) {
     case RS_EPI_BIAS_F16: {                                    // same 16-bit store pattern as the bf16 epilogues
@@ -195,7 +220,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
   __syncwarp();                                                // staging buffer reusable; reconverged for the next tcgen05.ld
 }
 
-template <int BN>
+template <int BN, int EG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
@@ -306,7 +331,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store(p, r, stage, tile_row0, lane, col0, bt, cur);
+        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -339,7 +364,7 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 32 * 36 * 4 * 8 /*epilogue staging*/;
 };
 
-template <int BN>
+template <int BN, int EG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
   using Cfg = Gemm2Cfg<BN>;
@@ -450,7 +475,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store(p, r, stage, tile_row0, lane, col0, 0, cur);
+        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -500,12 +525,14 @@ static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint6
   return true;
 }
 
-template <int BN>
-static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+inline int epilogue_group(int epilogue) { return epilogue == RS_EPI_QKV_VT ? 1 : (epilogue == RS_EPI_BIAS_F16_SKEW ? 2 : 0); }
+
+template <int BN, int EG>
+static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
     attr_set = true;
   }
@@ -520,18 +547,27 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  gemm_bf16_tn_kernel<BN, EG><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
 }
 
 template <int BN>
-static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  switch (epilogue_group(g.epilogue)) {
+    case 1: return launch_bn_eg<BN, 1>(g, num_sms, stream, err);
+    case 2: return launch_bn_eg<BN, 2>(g, num_sms, stream, err);
+    default: return launch_bn_eg<BN, 0>(g, num_sms, stream, err);
+  }
+}
+
+template <int BN, int EG>
+static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
     attr_set = true;
   }
@@ -544,10 +580,19 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm_bf16_tn_2cta_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  gemm_bf16_tn_2cta_kernel<BN, EG><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm 2cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
+}
+
+template <int BN>
+static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  switch (epilogue_group(g.epilogue)) {
+    case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
+    case 2: return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
+    default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
+  }
 }
 
 static int g_gemm_mode = -1;   // RS_GEMM_MODE: 0 = 1-CTA kernels only, 1 (default) = 2-CTA pairs where the shape allows
@@ -566,6 +611,10 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
+  if (g.epilogue == RS_EPI_BIAS_F16_SKEW && (g.ld2 <= 0 || g.split <= 0)) {
+    snprintf(err, 256, "gemm: RS_EPI_BIAS_F16_SKEW needs ld2 = T_max and split = valid columns");
+    return cudaErrorInvalidValue;
+  }
   if (g.epilogue == RS_EPI_QKV_VT && (g.out2 == nullptr || g.split % 32 || g.ld2 % 8 || g.ld2 < ((g.M + 255) / 256) * 256 || g.n_batch > 1)) {
     snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, ld2 >= M rounded up to 256");
     return cudaErrorInvalidValue;

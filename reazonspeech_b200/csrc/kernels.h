@@ -60,10 +60,13 @@ struct AttnArgs {
   // tensor-core path (attention_tc.cu): V^T bf16 [H*dk, ld_vt] written by the QKV GEMM (RS_EPI_QKV_VT); the q columns
   // of `qkv` hold q + pos_bias_u in BOTH paths (folded into the projection bias when the weights are packed)
   const void* vt = nullptr; int ld_vt = 0;
+  // tensor-core path: `bd` is row-skewed (RS_EPI_BIAS_F16_SKEW), bd_pitch halves per (row, head)
+  int bd_pitch = 0;
 };
 cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream);
 bool attention_tc_supported(const AttnArgs& a);
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream);
+cudaError_t attention_tc_debug_cycles(long long* out16);   // clock64 stamps of CTA (1,0,0) of the last launch
 
 struct DecodeArgs {
   const float* enc_proj;      // f32 [B*T_max, Hj]  (joint.enc applied to every frame)

@@ -49,7 +49,7 @@ EXPORTS = [
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
-    "rs_enable_kernel_timing", "rs_kernel_timing",
+    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
 ]
 
 
@@ -299,7 +299,7 @@ class Engine:
         B, F, _ = mel.shape
         L = (F - 1) * self.cfg.n_window_stride
         self.ensure_workspace(B, L)
-        T = conv_out_len(conv_out_len(conv_out_len(F)))
+        T = self.enc_frames(L)                       # capacity of the padded encoder tensors (a multiple of 8)
         enc = torch.empty(B, T, self.cfg.d_model, dtype=torch.float32, device=self.device)
         enc_len = torch.empty(B, dtype=torch.int32, device=self.device)
         self._check(self.lib.rs_encode(self.h, mel.data_ptr(), mel_len.data_ptr(), B, F, enc.data_ptr(), enc_len.data_ptr(),
@@ -388,6 +388,16 @@ class Engine:
             name, n, ms = line.split("\t")
             out[name] = (int(n), float(ms))
         return out
+
+    def attention_cycles(self):
+        """clock64 stamps of CTA (1,0,0) of the last tensor-core attention launch, relative to its first stamp."""
+        out = (C.c_int64 * 16)()
+        self.lib.rs_debug_attention_cycles.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        self._check(self.lib.rs_debug_attention_cycles(self.h, out), "rs_debug_attention_cycles")
+        v = list(out)
+        names = ["start", "tma_issue", "qk_landed", "s_issued", "pv_wait", "pv_issued", "dealloc", "_",
+                 "sm_start", "sm_gscore_done", "sm_s_ready", "sm_pass1", "sm_pass2", "sm_o_wait", "sm_o_ready", "sm_end"]
+        return {n: int(x - v[0]) for n, x in zip(names, v) if n != "_"}
 
     def decode_cycles(self, B: int, L_max: int, U_max: int):
         out = (C.c_int64 * 12)()

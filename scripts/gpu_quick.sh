@@ -1,5 +1,6 @@
-#!/bin/bash
-cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
-mkdir -p gpurun_out
-echo "=== encoder/e2e tests"; timeout -k 10 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "encoder or end_to_end or teacher" -p no:cacheprovider 2>&1 | tail -4
-echo "=== bench"; timeout -k 10 1200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench.err | tee gpurun_out/bench.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['stage_ms'], d['config']['tokens_per_clip'], d['roofline']['achieved'], d['roofline']['gemm_ms_per_step'], d['decode_cycles_cta0'])"; tail -3 gpurun_out/bench.err
+cd "${GRAFT_REPO_ROOT:-.}"
+CAL=reazonspeech_b200/data/synth_calib_24x1024_v3000_p640_j640_seed0.json
+timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | grep -vE "^\s*$" | tail -12 | cut -c1-250 | tee gpurun_out/r1j_tests.log
+timeout 600 python scripts/calibrate_synthetic.py --config full --out gpurun_out/calib_full.json > gpurun_out/r1j_calib.log 2>&1 && cp gpurun_out/calib_full.json $CAL
+tail -1 gpurun_out/r1j_calib.log | cut -c1-400
+timeout -k 10 600 python bench.py --no-cpu-baseline --steps 10 > gpurun_out/r1j_bench.json 2> gpurun_out/r1j_bench.err; echo "bench exit $?"; tail -3 gpurun_out/r1j_bench.err
