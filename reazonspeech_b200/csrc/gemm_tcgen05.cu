@@ -493,6 +493,149 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------- 4-CTA variant: A multicast
+// Cluster of FOUR CTAs = two SM pairs that work on the SAME 256 rows of A and on two neighbouring 256-column tiles of W.
+// EXPERIMENT, not the default (see g_gemm_mode): measured slower than the 2-CTA kernel.
+// The 2-CTA kernel moves ~760 MB from L2 per FFN launch (~10 TB/s at 71 % tensor-pipe activity,
+// profiles/r01_v3_gemm_ncu.md): every pair pulls its own copy of the A rows.  Here each CTA loads 64 of the 128 A rows it
+// needs and TMA multicasts them to the CTA of the other pair that needs the same rows (ranks r and r+2), so a pair
+// receives 32 KB of A per k-block for 16 KB of L2 reads: 48 KB instead of 64 KB per pair and k-block.
+// Barriers: full[] per pair leader as before (every destination credits its own leader); empty[] now counts the commits of
+// BOTH pairs (a stage is rewritten in two pairs' shared memory at once), each commit multicast to all four CTAs.
+template <int BN, int EG>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_4cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+
+  const int warp = warp_id_uniform();
+  const int lane = lane_id();
+  const uint32_t rank = cluster_ctarank();                   // 0..3
+  const uint32_t pair = rank >> 1, r = rank & 1u;
+  const bool leader = r == 0;
+  const uint32_t lead_rank = rank & ~1u;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_n2 = p.N / (2 * BN);                         // pairs of column tiles
+  const int num_tiles = num_m * num_n2;
+  const int num_k = p.K / BK;
+  const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (all four CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint16_t a_mask = static_cast<uint16_t>((1u << r) | (1u << (r + 2)));      // the two CTAs that consume these A rows
+      for (int tile = cid; tile < num_tiles; tile += ncl) {
+        const int a_row = (tile / num_n2) * 2 * BM + static_cast<int>(r) * BM + static_cast<int>(pair) * (BM / 2);
+        const int n0 = ((tile % num_n2) * 2 + static_cast<int>(pair)) * BN + static_cast<int>(r) * (BN / 2);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);           // both pairs have consumed this stage
+          tma_load_2d_2sm_mc(smem_a(stage) + pair * (kABytes / 2), &tm_a, kb * BK, a_row, full_bar(stage), a_mask);
+          tma_load_2d_2sm(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(full_bar(stage), lead_rank);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (the leader of each pair)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_a(stage));
+          const uint64_t db = umma_desc_k_sw128(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm_mask(empty_bar(stage), 0xF);       // every CTA of the cluster writes into / is written by this stage
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm_mask(tfull_bar(acc), pair_mask);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (own TMEM half of own pair's tile)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * kStageBytesPerWarp);
+    int it = 0;
+    for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m0 = (tile / num_n2) * 2 * BM + static_cast<int>(r) * BM;
+      const int n0 = ((tile % num_n2) * 2 + static_cast<int>(pair)) * BN;
+      const int tile_row0 = m0 + q * 32;
+      const bool pre = p.epilogue == RS_EPI_RESID_F32;
+      float4 rr[8], cur[8];
+      resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+        const int col0 = n0 + chunk * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+        resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
+        uint32_t rg[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, rg);
+        tmem_ld_wait();
+        epilogue_store<EG>(p, rg, stage, tile_row0, lane, col0, 0, cur);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), lead_rank);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -595,7 +738,49 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   }
 }
 
-static int g_gemm_mode = -1;   // RS_GEMM_MODE: 0 = 1-CTA kernels only, 1 (default) = 2-CTA pairs where the shape allows
+template <int BN, int EG>
+static cudaError_t launch_4cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_4cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(4cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
+    attr_set = true;
+  }
+  CUtensorMap tm_a, tm_b;
+  const int lda = g.lda > 0 ? g.lda : g.K;
+  const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
+  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM / 2, err)) return cudaErrorInvalidValue;     // 64-row boxes: half of a CTA's A rows
+  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
+  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
+  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / (2 * BN));
+  int clusters = num_sms / 4;
+  if (tiles < clusters) clusters = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_4cta_kernel<BN, EG>, tm_a, tm_b, p);
+  if (e != cudaSuccess) snprintf(err, 256, "gemm 4cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
+  return e;
+}
+
+template <int BN>
+static cudaError_t launch_4cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  switch (epilogue_group(g.epilogue)) {
+    case 1: return launch_4cta_eg<BN, 1>(g, num_sms, stream, err);
+    case 2: return launch_4cta_eg<BN, 2>(g, num_sms, stream, err);
+    default: return launch_4cta_eg<BN, 0>(g, num_sms, stream, err);
+  }
+}
+
+// RS_GEMM_MODE: 0 = 1-CTA kernels only, 1 (default) = 2-CTA pairs, 2 = 4-CTA clusters with A multicast where N % 512 == 0.
+// Mode 2 is correct (all GEMM / model tests pass with it) but measured 1.3-1.7x SLOWER than mode 1 on every encoder shape
+// (FFN W1 139.6 vs 82.8 us): with a 5-stage ring of 32 KB per CTA the loop "MMA retires -> commit -> producer -> TMA -> full"
+// is latency-bound, and coupling two pairs through cluster-wide empty barriers and multicast lengthens exactly that loop.
+static int g_gemm_mode = -1;
 
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   if (g_gemm_mode < 0) {
@@ -620,7 +805,9 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   // kernel choice depends on N only (never on M): a row's result must not depend on the batch it sits in
-  if (g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0)
+  if (g_gemm_mode == 2 && g.n_batch <= 1 && g.N % 512 == 0)
+    return launch_4cta<256>(g, num_sms, stream, err);
+  if (g_gemm_mode >= 1 && g.n_batch <= 1 && g.N % 256 == 0)
     return launch_2cta<256>(g, num_sms, stream, err);
   // Widest tile that still yields at least ~one wave of tiles; narrow N uses a narrower tile.
   if (g.N >= 256 && g.N % 256 == 0) return launch_bn<256>(g, num_sms, stream, err);
