@@ -120,51 +120,87 @@ cudaError_t launch_sub_conv0_dw1(const SubsampleArgs& a, cudaStream_t stream) {
 
 // Depthwise 3x3 s2 p1 on channels-last bf16 [B, Tin, Fin, C] -> [B, Tout, Fout, C].
 // The valid input length of utterance b is conv_len applied `len_shift` times to mel_len[b].
-__global__ void __launch_bounds__(128)
+// One thread = eight channels of one output frame, ALL Fout frequency bins: the 72 tap weights are fetched once per
+// thread instead of once per output (the one-output-per-thread version issued as many weight loads as FMAs and ran at
+// a sixth of the HBM rate), and the input column shared by neighbouring bins (stride 2, kernel 3) is reused from registers.
+constexpr int kDwThreads = 128;
+__global__ void __launch_bounds__(kDwThreads)
 sub_dw_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ w,
               const float* __restrict__ bias, const int32_t* __restrict__ mel_len, int len_shift, int Tin, int Fin,
               int Tout, int Fout, int C) {
-  // eight channels per thread: one 16-byte load per tap
-  const int b = blockIdx.z, t = blockIdx.y;
+  const int b = blockIdx.z;
   int lin = mel_len[b];
   for (int i = 0; i < len_shift; ++i) lin = conv_len(lin);
   const int lout = conv_len(lin);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // over Fout * C/8
   const int c8 = C / 8;
-  if (idx >= Fout * c8) return;
-  const int f = idx / c8, c = (idx % c8) * 8;
-  uint4* o = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * Tout + t) * Fout + f) * C + c);
-  if (t >= lout) { *o = make_uint4(0u, 0u, 0u, 0u); return; }
-  float a[8];
+  const int t = blockIdx.y * (kDwThreads / c8) + threadIdx.x / c8;   // a block covers kDwThreads / c8 whole frames
+  const int c = (threadIdx.x % c8) * 8;
+  if (t >= Tout) return;
+  __nv_bfloat16* orow = out + ((static_cast<size_t>(b) * Tout + t) * Fout) * C + c;
+  if (t >= lout) {
+    for (int f = 0; f < Fout; ++f) *reinterpret_cast<uint4*>(orow + static_cast<size_t>(f) * C) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  float wt[9][8], bs[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = __ldg(bias + c + k);
+  for (int k = 0; k < 8; ++k) {
+    bs[k] = __ldg(bias + c + k);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) wt[q][k] = __ldg(w + (c + k) * 9 + q);
+  }
+  // input rows 2t-1, 2t, 2t+1 (absent rows read as zero)
+  const __nv_bfloat16* rowp[3];
+  bool rok[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     const int ti = 2 * t - 1 + i;
-    if (ti < 0 || ti >= lin || ti >= Tin) continue;
+    rok[i] = ti >= 0 && ti < lin && ti < Tin;
+    rowp[i] = in + ((static_cast<size_t>(b) * Tin + (rok[i] ? ti : 0)) * Fin) * C + c;
+  }
+  auto load_col = [&](int fi, float (&col)[3][8]) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int fi = 2 * f - 1 + j;
-      if (fi < 0 || fi >= Fin) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * Tin + ti) * Fin + fi) * C + c));
+    for (int i = 0; i < 3; ++i) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (rok[i] && fi >= 0 && fi < Fin) v = __ldg(reinterpret_cast<const uint4*>(rowp[i] + static_cast<size_t>(fi) * C));
       const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a[2 * k] = fmaf(bf16_lo(vw[k]), __ldg(w + (c + 2 * k) * 9 + i * 3 + j), a[2 * k]);
-        a[2 * k + 1] = fmaf(bf16_hi(vw[k]), __ldg(w + (c + 2 * k + 1) * 9 + i * 3 + j), a[2 * k + 1]);
-      }
+      for (int k = 0; k < 4; ++k) { col[i][2 * k] = bf16_lo(vw[k]); col[i][2 * k + 1] = bf16_hi(vw[k]); }
     }
+  };
+  float left[3][8], mid[3][8], right[3][8];
+  load_col(-1, left);
+  for (int f = 0; f < Fout; ++f) {
+    load_col(2 * f, mid);
+    load_col(2 * f + 1, right);
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s = bs[k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        s = fmaf(left[i][k], wt[i * 3 + 0][k], s);
+        s = fmaf(mid[i][k], wt[i * 3 + 1][k], s);
+        s = fmaf(right[i][k], wt[i * 3 + 2][k], s);
+      }
+      a[k] = s;
+    }
+    *reinterpret_cast<uint4*>(orow + static_cast<size_t>(f) * C) =
+        make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) left[i][k] = right[i][k];
   }
-  *o = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
 }
 
 cudaError_t launch_sub_dw(const void* in, void* out, const float* w, const float* b, const int32_t* mel_len, int len_shift,
                           int B, int Tin, int Fin, int Tout, int Fout, int C, cudaStream_t stream) {
-  if (C % 8) return cudaErrorInvalidValue;
-  const int work = Fout * (C / 8);
-  const dim3 grid((work + 127) / 128, Tout, B);
-  sub_dw_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), w, b,
-                                          mel_len, len_shift, Tin, Fin, Tout, Fout, C);
+  const int c8 = C / 8;
+  if (C % 8 || c8 > kDwThreads || kDwThreads % c8) return cudaErrorInvalidValue;
+  const int frames_per_block = kDwThreads / c8;
+  const dim3 grid(1, (Tout + frames_per_block - 1) / frames_per_block, B);
+  sub_dw_kernel<<<grid, kDwThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), w, b,
+                                                 mel_len, len_shift, Tin, Fin, Tout, Fout, C);
   return cudaGetLastError();
 }
 
