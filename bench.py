@@ -258,11 +258,14 @@ def main():
     kernel_ms = {k: {"launches": n, "ms": round(ms, 4)} for k, (n, ms) in sorted(eng.kernel_timing().items(), key=lambda kv: -kv[1][1])}
     eng.kernel_timing(False)
     attn_cycles = eng.attention_cycles() if os.environ.get("RS_ATTN_MODE", "0") != "1" else None
+    # ALGORITHMIC FLOPs: the engine counts 2*M*N*K with M = B x frame capacity (a multiple of 8: 392 for 388 valid
+    # frames); the roofline numerator keeps only the valid rows
+    g_flops *= eng.cfg.enc_frames(L) / max(eng.enc_frames(L), 1)
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     # DRAM bytes per launch of the dominant kernel: mean of dram__bytes_read.sum + dram__bytes_write.sum over the
-    # eight consecutive launches of the `ncu --set full` capture in profiles/r01_v2_gemm_ncu.md (not re-measured here)
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": 1.011e8,
-                "traffic_source": "profiles/r01_v2_gemm_ncu.md (mean over 8 launches, bytes)",
+    # six consecutive launches of the `ncu --set full` capture in profiles/r01_v4_gemm_ncu.md (not re-measured here)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": 1.176e8,
+                "traffic_source": "profiles/r01_v4_gemm_ncu.md (dram read + write, mean over 6 consecutive launches, bytes)",
                 "kernel": "gemm_bf16_tn_kernel (tcgen05.mma, all encoder/joint GEMMs)", "peak_source": f"{src} bf16_tflops_sustained",
                 "launches_per_step": g_n // max(args.steps, 1), "gemm_ms_per_step": g_ms / max(args.steps, 1),
                 "algorithmic_gflop_per_step": g_flops / max(args.steps, 1) / 1e9,

@@ -447,25 +447,37 @@ global_row_attention_tc_kernel(const AtcDev p) {
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   const float inv = 1.0f / (((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7])));
-  // out[dim] = sum_j p_j V^T[dim][j]: a warp takes 16 dims, its lanes stride over the keys eight at a time (the last,
-  // partial group of eight goes key by key: what follows the utterance in V^T is not this kernel's to read)
+  // out[dim] = sum_j p_j V^T[dim][j]: thread = (dim, one of two key segments); it walks its V^T row eight keys (16 bytes)
+  // at a time with four loads in flight (the last, partial group of eight goes key by key: what follows the utterance in
+  // V^T is not this kernel's to read).  A warp-per-dim version with shuffle reductions took 40 us per launch.
+  __syncthreads();
   const __nv_bfloat16* vt = p.vt + static_cast<size_t>(h * TDK) * p.ld_vt + row0;
   const int len8 = ((row0 & 7) == 0) ? (len & ~7) : 0;
-  for (int dd = warp * 16; dd < warp * 16 + 16; ++dd) {
-    const __nv_bfloat16* vr = vt + static_cast<size_t>(dd) * p.ld_vt;
-    float a = 0.f;
-    for (int j = lane * 8; j < len8; j += 256) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(vr + j));
-      const float4 p0 = *reinterpret_cast<const float4*>(gs + j), p1 = *reinterpret_cast<const float4*>(gs + j + 4);
-      a = fmaf(p0.x, bf16_lo(raw.x), a); a = fmaf(p0.y, bf16_hi(raw.x), a);
-      a = fmaf(p0.z, bf16_lo(raw.y), a); a = fmaf(p0.w, bf16_hi(raw.y), a);
-      a = fmaf(p1.x, bf16_lo(raw.z), a); a = fmaf(p1.y, bf16_hi(raw.z), a);
-      a = fmaf(p1.z, bf16_lo(raw.w), a); a = fmaf(p1.w, bf16_hi(raw.w), a);
-    }
-    for (int j = len8 + lane; j < len; j += 32) a = fmaf(gs[j], __bfloat162float(vr[j]), a);
-    a = warp_sum(a);
-    if (lane == 0) p.out[row0 * d + h * TDK + dd] = __float2bfloat16_rn(a * inv);
+  const int dim = tid & 127, seg = tid >> 7;
+  const int n8 = len8 >> 3;                                  // whole groups of eight keys
+  const int g_lo = seg == 0 ? 0 : (n8 + 1) / 2, g_hi = seg == 0 ? (n8 + 1) / 2 : n8;
+  const __nv_bfloat16* vr = vt + static_cast<size_t>(dim) * p.ld_vt;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  auto dot8 = [&](const uint4 raw, int j, float& acc) {
+    const float4 p0 = *reinterpret_cast<const float4*>(gs + j), p1 = *reinterpret_cast<const float4*>(gs + j + 4);
+    acc = fmaf(p0.x, bf16_lo(raw.x), acc); acc = fmaf(p0.y, bf16_hi(raw.x), acc);
+    acc = fmaf(p0.z, bf16_lo(raw.y), acc); acc = fmaf(p0.w, bf16_hi(raw.y), acc);
+    acc = fmaf(p1.x, bf16_lo(raw.z), acc); acc = fmaf(p1.y, bf16_hi(raw.z), acc);
+    acc = fmaf(p1.z, bf16_lo(raw.w), acc); acc = fmaf(p1.w, bf16_hi(raw.w), acc);
+  };
+  int g = g_lo;
+  for (; g + 4 <= g_hi; g += 4) {
+    const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(vr) + g), r1 = __ldg(reinterpret_cast<const uint4*>(vr) + g + 1);
+    const uint4 r2 = __ldg(reinterpret_cast<const uint4*>(vr) + g + 2), r3 = __ldg(reinterpret_cast<const uint4*>(vr) + g + 3);
+    dot8(r0, 8 * g, a0); dot8(r1, 8 * g + 8, a1); dot8(r2, 8 * g + 16, a2); dot8(r3, 8 * g + 24, a3);
   }
+  for (; g < g_hi; ++g) dot8(__ldg(reinterpret_cast<const uint4*>(vr) + g), 8 * g, a0);
+  if (seg == 1) for (int j = len8; j < len; ++j) a1 = fmaf(gs[j], __bfloat162float(vr[j]), a1);
+  const float part = (a0 + a1) + (a2 + a3);
+  __syncthreads();                                   // everyone is done reading the probabilities
+  if (seg == 1) gs[dim] = part;
+  __syncthreads();
+  if (seg == 0) p.out[row0 * d + h * TDK + dim] = __float2bfloat16_rn((part + gs[dim]) * inv);
 }
 
 typedef CUresult (*EncodeTiledFnA)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
