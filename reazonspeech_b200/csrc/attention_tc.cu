@@ -224,7 +224,8 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     auto chunk_live = [&](int m) {
       const int rel_max = 32 * m + 31 - 128 - 32 * qd, rel_min = 32 * m - 128 - 32 * qd - 31;
       const int jl = j_base + 32 * m;
-      return !(rel_max < -p.w_left || rel_min > p.w_right || jl + 31 < 0 || jl >= len || (m >> 2) < rb_lo || (m >> 2) > rb_hi);
+      return !(rel_max < -p.w_left || rel_min > p.w_right || jl + 31 < 0 || jl >= len || (m >> 2) < rb_lo || (m >> 2) > rb_hi ||
+               q0 + 32 * qd >= len);                     // every row of this warp lies beyond the utterance (last tile)
     };
 #pragma unroll
     for (int k = 0; k < 6; ++k) live |= chunk_live(hf * 6 + k) ? (1u << k) : 0u;

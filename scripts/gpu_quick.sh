@@ -1,7 +1,3 @@
 cd "${GRAFT_REPO_ROOT:-.}"
-CAL=reazonspeech_b200/data/synth_calib_24x1024_v3000_p640_j640_seed0.json
-timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | grep -vE "^\s*$" | tail -12 | cut -c1-250 | tee gpurun_out/r1m_tests.log
-timeout 600 python scripts/calibrate_synthetic.py --config full --out gpurun_out/calib_full.json > gpurun_out/r1m_calib.log 2>&1 && cp gpurun_out/calib_full.json $CAL
-tail -1 gpurun_out/r1m_calib.log | cut -c1-200
-timeout -k 10 600 python bench.py --steps 20 > gpurun_out/r1m_bench.json 2> gpurun_out/r1m_bench.err; echo "bench exit $?"; tail -3 gpurun_out/r1m_bench.err
-timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1250 -c 420 --csv --log-file gpurun_out/r01_v5_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "launch list exit $?"
+timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -p no:cacheprovider -k "long_form" -s 2>&1 | grep -E "utt|passed|failed|Error|error" | head -12 | cut -c1-250
+timeout -k 10 600 python bench.py --no-cpu-baseline --steps 5 --batch 128 > gpurun_out/r1n_bench_b128.json 2> gpurun_out/r1n_bench_b128.err; echo "bench b128 exit $?"; tail -3 gpurun_out/r1n_bench_b128.err | cut -c1-300

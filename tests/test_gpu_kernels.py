@@ -301,3 +301,29 @@ def test_tensor_core_attention_matches_mma_sync_attention(tiny_engine, monkeypat
         print(f"utt{i} T={T}: tcgen05 vs mma.sync attention, encoder rel-L2 {r:.3e}")
         assert r < 5e-3
         assert outs["0"][i, T:].abs().max().item() == 0.0 if T < outs["0"].shape[1] else True
+
+
+def test_long_form_clip_in_one_call(tiny_engine, tiny_cfg, tiny_sd):
+    """the reference feeds audio of any length to the model in one shot (transcribe.py:44-53,
+    relying on local attention).  A 150 s clip (1 882 encoder frames = 15 query tiles of the tensor-core attention,
+    ~470 decode windows) goes through the engine in one call, next to a short one: encoder within 2e-2 relative L2 of the
+    fp32 oracle, decisions equal to the oracle's up to the first near-tie."""
+    from oracle import nemo_restated as O
+    eng = tiny_engine
+    waves = [padded(synth_clip(90, 150.0)), padded(synth_clip(91, 2.0))]
+    x, lens = pad_batch(waves, "cuda")
+    mel, mel_len = eng.log_mel(x, lens)
+    enc, enc_len = eng.encode(mel, mel_len)
+    tokens, frames, ntok = eng.transcribe_device(x, lens)
+    torch.cuda.synchronize()
+    for i, w in enumerate(waves):
+        with torch.no_grad():
+            ref = O.encoder(O.log_mel(torch.from_numpy(w), tiny_cfg), tiny_sd, tiny_cfg)
+            emu = O.transcribe_tokens(torch.from_numpy(w), tiny_sd, tiny_cfg, emulate=True)
+        T = ref.shape[0]
+        assert int(enc_len[i]) == T == tiny_cfg.enc_frames(len(w))
+        r = _rel(enc[i, :T].cpu(), ref)
+        n = int(ntok[i])
+        print(f"utt{i}: T={T}, encoder rel-L2 {r:.3e}, {n} tokens (oracle {len(emu.tokens)})")
+        assert r < 2e-2
+        check_tokens_against_oracle(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), emu, T, tiny_cfg, 5e-2, f"utt{i}")
