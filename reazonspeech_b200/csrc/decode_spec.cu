@@ -13,9 +13,9 @@
 //  2. With kFrames x B rows per iteration the joint is a real (small) GEMM.  The CTAs form a 2-D grid,
 //     kGroups utterance groups x S vocabulary slices: a CTA keeps its ~82 rows of W_out in shared memory
 //     for the whole decode and multiplies them with the relu(enc_proj + pred_proj) rows of its group
-//     (32 rows per pass) on mma.sync m16n8k16.  Activations stay fp32-exact: every fp32 value is split into
-//     three bf16 terms (hi + mid + lo = 24 mantissa bits), the weights are bf16 already, accumulation is
-//     fp32 - the products are the same as an fp32 FMA's, only the summation order differs.
+//     (32 rows per pass) on mma.sync m16n8k16.  Activations keep 22 mantissa bits: every fp32 value is split into
+//     two IEEE-half terms (hi + lo), the bf16 weights are exact in half, accumulation is fp32 (a three-term bf16
+//     split gave 24 bits but cost 1.5x: the legacy tensor path issues one m16n8k16 per ~19 cycles and scheduler).
 //     The LSTM step and joint.pred of the utterances that emitted are the same kind of GEMM (rows =
 //     utterances, K split over the warps, A fragments loaded straight from L2).
 //
