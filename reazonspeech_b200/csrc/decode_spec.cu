@@ -109,7 +109,21 @@ __device__ __forceinline__ unsigned long long pack_best(float v, int row) {
   return (static_cast<unsigned long long>(fb) << 32) | (0xffffffffu - static_cast<unsigned int>(row));   // ties -> lower row
 }
 
-template <int HJ, int HP>
+// TCJ = true: the joint window runs on tcgen05 instead of mma.sync.  A = the CTA's W_out rows as IEEE half in
+// 128B-swizzled K-major slabs of 64 columns (88 rows stored per slab; the M = 128 instruction reads on into the next slab /
+// region, whose rows land in accumulator lanes nobody looks at), B = the 32 (utterance, frame) activation rows as two half
+// planes (hi, lo) staged one k-half at a time, D = [128 vocabulary rows x (32 hi | 32 lo)] fp32 in tensor memory.  40 UMMAs
+// of 128x64x16 per pass replace 1760 mma.sync per CTA, which were issue-bound on the legacy path (~19 cycles each).
+// The hi and lo planes of the activations sit side by side as ONE B tile of 64 rows (rows 0-31 hi, 32-63 lo), so a k16 step
+// is one 128x64x16 UMMA and the two halves of D are added in the epilogue: small-N UMMAs cost about the same per
+// instruction as wider ones, so 80 instructions of N=32 took twice as long as 40 of N=64.
+constexpr uint32_t kIdescF16_128x64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);   // D=f32, A=B=f16, K-major
+
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  umma_bf16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);      // same instruction (kind::f16); the operand formats live in idesc
+}
+
+template <int HJ, int HP, bool TCJ>
 __global__ void __launch_bounds__(kSpThreads, 1)
 rnnt_greedy_spec_kernel(const SpecDev p) {
   constexpr int KH = HJ / 2;                 // joint k-half staged in shared memory at a time
@@ -143,27 +157,57 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 
   // ---- shared memory carve-up.  B fragments of a partial last n8-tile read past the end of a weight array
   // into the next one; those columns are masked, and every array is followed by at least 8 more rows of bytes.
-  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(ssm);                      // [rows_j][WS]
-  __nv_bfloat16* s_wlstm = s_wout + static_cast<size_t>(p.rows_j) * WS;               // [4*units][LS] gate-major
+  // TCJ: [A slabs | B planes (also the L / P reduction buffer)] first, 1024-byte aligned, then the same arrays as before.
+  constexpr int KSLABS = HJ / 64;                                  // 64-column slabs of A
+  constexpr int NSLAB_H = KH / 64;                                 // slabs per staged k-half
+  const int rows_a8 = (p.rows_j + 7) & ~7;
+  const uint32_t a_slab = static_cast<uint32_t>(rows_a8) * 128u;   // bytes per A slab
+  constexpr uint32_t kBSlab = 8192u;                               // B slab: 64 rows x 128 B = hi plane (rows 0-31) | lo plane (rows 32-63)
+  constexpr uint32_t kBRegion = (NSLAB_H * kBSlab > 16384u) ? NSLAB_H * kBSlab : 16384u;   // >= what an M = 128 read of the last A slab overruns
+  uint8_t* sbase = ssm;
+  uint32_t tc_base = 0;
+  if constexpr (TCJ) {
+    tc_base = (smem_u32(ssm) + 1023u) & ~1023u;
+    sbase = ssm + (tc_base - smem_u32(ssm)) + KSLABS * a_slab + kBRegion;
+  }
+  uint8_t* gA = ssm + (tc_base - smem_u32(ssm));                   // TCJ: generic pointers to the A slabs / B planes
+  uint8_t* gB = gA + KSLABS * a_slab;
+  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(sbase);                    // [rows_j][WS]   (not TCJ)
+  __nv_bfloat16* s_wlstm = s_wout + (TCJ ? 0 : static_cast<size_t>(p.rows_j) * WS);   // [4*units][LS] gate-major
   __nv_bfloat16* s_wpred = s_wlstm + static_cast<size_t>(4 * p.units) * LS;           // [rows_p][WS']  (WS' = HP + 8)
-  float* s_g = reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8));   // [32][GS]; also the L / P reduction buffer
-  float* s_bout = s_g + G_FLOATS;                                                    // [n_tiles*8], -inf beyond nj
-  float* s_c = s_bout + n_tiles * 8;                                                 // [B][units]
+  float* s_g = TCJ ? reinterpret_cast<float*>(gB)
+                   : reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8));   // [32][GS]; also the L / P reduction buffer
+  float* s_bout = TCJ ? reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8)) : s_g + G_FLOATS;   // -inf beyond nj
+  const int n_bout = TCJ ? 128 : n_tiles * 8;
+  float* s_c = s_bout + n_bout;                                                      // [B][units]
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_c + ((static_cast<size_t>(B) * p.units + 1) & ~static_cast<size_t>(1)));   // [32][4]
   int* s_t = reinterpret_cast<int*>(s_best + kPassRows * 4);
   int* s_sym = s_t + B; int* s_n = s_sym + B; int* s_par = s_n + B; int* s_tok = s_par + B;
   int* s_emit = s_tok + B; int* s_len = s_emit + B;
   int* s_act = s_len + B;                                                            // ordered list of the utterances with frames left
   int* s_cnt = s_act + B;                                                            // [0] n_emit, [1] n_active, [2..2+8) warp counts x2
+  // TCJ: one mbarrier (MMA completion) + the tensor-memory slot, 8-byte aligned after s_cnt
+  const uint32_t tc_bar = (smem_u32(s_cnt + 2 + 2 * kSpWarps) + 7u) & ~7u;
+  const uint32_t tc_slot = tc_bar + 8;
 
   {
     const uint32_t zero = 0;
     // W_out slice (rows beyond nj zero-filled)
-    for (int i = tid; i < p.rows_j * (HJ / 8); i += kSpThreads) {
-      const int r = i / (HJ / 8), c = i % (HJ / 8);
-      uint4 v = make_uint4(zero, zero, zero, zero);
-      if (r < nj) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c]);
-      *reinterpret_cast<uint4*>(s_wout + static_cast<size_t>(r) * WS + c * 8) = v;
+    if constexpr (TCJ) {
+      for (int i = tid; i < rows_a8 * (HJ / 8); i += kSpThreads) {
+        const int r = i / (HJ / 8), c = i % (HJ / 8);          // c: 16-byte chunk (8 columns) of the row
+        uint4 v = make_uint4(zero, zero, zero, zero);
+        if (r < nj) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c]);
+        *reinterpret_cast<uint4*>(gA + (c >> 3) * a_slab + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
+      }
+      if (tid == 0) { mbar_init(tc_bar, 1); fence_barrier_init(); }
+    } else {
+      for (int i = tid; i < p.rows_j * (HJ / 8); i += kSpThreads) {
+        const int r = i / (HJ / 8), c = i % (HJ / 8);
+        uint4 v = make_uint4(zero, zero, zero, zero);
+        if (r < nj) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c]);
+        *reinterpret_cast<uint4*>(s_wout + static_cast<size_t>(r) * WS + c * 8) = v;
+      }
     }
     for (int i = tid; i < 4 * p.units * (2 * HP / 8); i += kSpThreads) {
       const int r = i / (2 * HP / 8), c = i % (2 * HP / 8);
@@ -178,14 +222,23 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
       if (r < np) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_pred + static_cast<size_t>(p0 + r) * HP)[c]);
       *reinterpret_cast<uint4*>(s_wpred + static_cast<size_t>(r) * (HP + 8) + c * 8) = v;
     }
-    for (int i = tid; i < n_tiles * 8; i += kSpThreads) s_bout[i] = i < nj ? p.b_out[j0 + i] : -INFINITY;
+    for (int i = tid; i < n_bout; i += kSpThreads) s_bout[i] = i < nj ? p.b_out[j0 + i] : -INFINITY;
     for (int i = tid; i < B * p.units; i += kSpThreads) s_c[i] = 0.f;
     for (int b = tid; b < B; b += kSpThreads) {
       s_t[b] = 0; s_sym[b] = 0; s_n[b] = 0; s_par[b] = 0; s_tok[b] = blank; s_emit[b] = b; s_len[b] = p.enc_len[b];
     }
     if (tid == 0) { s_cnt[0] = B; s_cnt[1] = 0; }
   }
+  uint32_t tmem_d = 0, mma_phase = 0;
+  if constexpr (TCJ) {
+    if (warp == 0) tmem_alloc<64>(tc_slot);
+    tcgen05_fence_before();
+  }
   __syncthreads();
+  if constexpr (TCJ) {
+    tcgen05_fence_after();
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_d) : "r"(tc_slot));
+  }
 
   unsigned int target = 0;
   int iter = 0;
@@ -445,42 +498,124 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
         long long tj = 0;
         if (cta == 0 && tid == 0) tj = clock64();
         auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
-        load_half(0);
-        store_half();
-        __syncthreads();
-        jtick(8);
-        load_half(1);                                         // in flight under the MMAs of half 0
-        mma_half(0);
-        __syncthreads();
-        store_half();
-        __syncthreads();
-        mma_half(1);
-        jtick(9);
-        // ---- argmax of this warp's columns per row, then across the 4 lanes of a row, then across the 4 warps of the tile
-        {
-          float bv[2] = {-INFINITY, -INFINITY};
-          int bi[2] = {0x7fffffff, 0x7fffffff};
+        if constexpr (TCJ) {
+          // ---- tcgen05 joint: D[vocabulary row, (utterance, frame) row] in tensor memory
+          auto write_planes = [&]() {                         // gv -> two IEEE-half planes, 128B-swizzled K-major, 32 rows per slab
 #pragma unroll
-          for (int n = 0; n < kMaxTilesPerWarp; ++n) {
-            const int nt = ng + 4 * n;
-            if (nt < n_tiles) {
+            for (int i = 0; i < PERU; ++i) {
+              int it = tid + kSpThreads * i;
+              if (it < ITEMS) {
+                it = (it + slice * 29) % ITEMS;
+                const int ul = it / V4_ROW, c4 = it % V4_ROW;
+                const int kcol = 4 * c4;                      // column inside the k-half
+                const uint32_t off_k = static_cast<uint32_t>(kcol >> 6) * kBSlab, chunk = (kcol & 63) >> 3, sub = (kcol & 7) * 2;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int col = nt * 8 + tig * 2 + (q & 1), hrow = q >> 1;
-                const float v = acc[n][q] + s_bout[col];
-                if (col < nj && (v > bv[hrow] || (v == bv[hrow] && j0 + col < bi[hrow]))) { bv[hrow] = v; bi[hrow] = j0 + col; }
+                for (int j = 0; j < kFrames; ++j) {
+                  const int row = ul * kFrames + j;
+                  uint32_t h0, l0, h1, l1;
+                  split2(make_float2(gv[i][j].x, gv[i][j].y), h0, l0);
+                  split2(make_float2(gv[i][j].z, gv[i][j].w), h1, l1);
+                  uint8_t* dst = gB + off_k + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4) + sub;
+                  *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                  *reinterpret_cast<uint2*>(dst + 4096) = make_uint2(l0, l1);       // row + 32 of the same slab
+                }
               }
             }
-          }
+          };
+          auto issue_half = [&](int h) {                      // one thread: NSLAB_H slabs x 4 k16 steps, N = 64 (hi | lo)
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int sl = 0; sl < NSLAB_H; ++sl) {
+              const uint64_t da = umma_desc_k_sw128(tc_base + static_cast<uint32_t>(h * NSLAB_H + sl) * a_slab);
+              const uint64_t db = umma_desc_k_sw128(tc_base + KSLABS * a_slab + sl * kBSlab);
 #pragma unroll
-          for (int hrow = 0; hrow < 2; ++hrow) {
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-              const float ov = __shfl_xor_sync(0xffffffffu, bv[hrow], o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi[hrow], o);
-              if (ov > bv[hrow] || (ov == bv[hrow] && oi < bi[hrow])) { bv[hrow] = ov; bi[hrow] = oi; }
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, kIdescF16_128x64, (h | sl | k) != 0 ? 1u : 0u);
             }
-            if (tig == 0) s_best[(mt * 16 + hrow * 8 + gid) * 4 + ng] = (bi[hrow] != 0x7fffffff) ? pack_best(bv[hrow], bi[hrow]) : 0ull;
+            umma_commit(tc_bar);
+          };
+          load_half(0);
+          write_planes();
+          fence_proxy_async();
+          tcgen05_fence_before();
+          __syncthreads();
+          jtick(8);
+          if (tid == 0) issue_half(0);
+          __syncwarp();
+          load_half(1);                                       // in flight under the MMAs of half 0
+          mbar_wait(tc_bar, mma_phase); mma_phase ^= 1u;      // half 0 consumed: the planes may be rewritten
+          write_planes();
+          fence_proxy_async();
+          tcgen05_fence_before();
+          __syncthreads();
+          if (tid == 0) issue_half(1);
+          __syncwarp();
+          mbar_wait(tc_bar, mma_phase); mma_phase ^= 1u;
+          tcgen05_fence_after();
+          jtick(9);
+          // ---- argmax over the vocabulary rows (= TMEM lanes) per (utterance, frame) column: warp w holds rows 32w..32w+31
+          if (warp < 4) {
+            uint32_t v[32], vlo[32];
+            tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16), v);          // A . hi
+            tmem_ld_32x32(tmem_d + (static_cast<uint32_t>(warp * 32) << 16) + 32, vlo);   // A . lo
+            tmem_ld_wait();
+            const int rr = warp * 32 + lane;
+            const bool rvalid = rr < nj;
+            const float bias = s_bout[rr];
+            unsigned my_key = 0; int my_row = 0x7fffffff;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              unsigned fb = __float_as_uint((__uint_as_float(v[c]) + __uint_as_float(vlo[c])) + bias);
+              fb = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);               // order-preserving
+              const unsigned key = rvalid ? fb : 0u;
+              const unsigned mk = __reduce_max_sync(0xffffffffu, key);
+              const unsigned cand = (key == mk && rvalid) ? static_cast<unsigned>(rr) : 0x7fffffffu;
+              const unsigned mr = __reduce_min_sync(0xffffffffu, cand);         // ties -> lower row
+              if (lane == c) { my_key = mk; my_row = static_cast<int>(mr); }
+            }
+            s_best[lane * 4 + warp] = (my_row != 0x7fffffff && my_key != 0u)
+                                          ? ((static_cast<unsigned long long>(my_key) << 32) | (0xffffffffu - static_cast<unsigned>(j0 + my_row)))
+                                          : 0ull;
+          }
+          tcgen05_fence_before();
+        } else {
+        load_half(0);
+          store_half();
+          __syncthreads();
+          jtick(8);
+          load_half(1);                                         // in flight under the MMAs of half 0
+          mma_half(0);
+          __syncthreads();
+          store_half();
+          __syncthreads();
+          mma_half(1);
+          jtick(9);
+          // ---- argmax of this warp's columns per row, then across the 4 lanes of a row, then across the 4 warps of the tile
+          {
+            float bv[2] = {-INFINITY, -INFINITY};
+            int bi[2] = {0x7fffffff, 0x7fffffff};
+#pragma unroll
+            for (int n = 0; n < kMaxTilesPerWarp; ++n) {
+              const int nt = ng + 4 * n;
+              if (nt < n_tiles) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int col = nt * 8 + tig * 2 + (q & 1), hrow = q >> 1;
+                  const float v = acc[n][q] + s_bout[col];
+                  if (col < nj && (v > bv[hrow] || (v == bv[hrow] && j0 + col < bi[hrow]))) { bv[hrow] = v; bi[hrow] = j0 + col; }
+                }
+              }
+            }
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+#pragma unroll
+              for (int o = 1; o <= 2; o <<= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv[hrow], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi[hrow], o);
+                if (ov > bv[hrow] || (ov == bv[hrow] && oi < bi[hrow])) { bv[hrow] = ov; bi[hrow] = oi; }
+              }
+              if (tig == 0) s_best[(mt * 16 + hrow * 8 + gid) * 4 + ng] = (bi[hrow] != 0x7fffffff) ? pack_best(bv[hrow], bi[hrow]) : 0ull;
+            }
           }
         }
         __syncthreads();
@@ -544,6 +679,11 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   }
   if (cta == 0) for (int b = tid; b < B; b += kSpThreads) p.n_tok[b] = s_n[b];
   if (cta == 0 && tid == 0) for (int i = 0; i < 12; ++i) p.prof[i] = prof[i];
+  if constexpr (TCJ) {
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem_d); }
+  }
 }
 
 // workspace: hbuf | ppbuf | (3*B*8 pad, keeps the counter/prof offset of decode_batched.cu) | counter + prof (256 B) | best
@@ -552,19 +692,19 @@ size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int /*num_sms*/) {
          static_cast<size_t>(3) * B * kFrames * 8;
 }
 
-template <int HJ, int HP>
+template <int HJ, int HP, bool TCJ>
 static cudaError_t launch_sp(SpecDev p, int grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(rnnt_greedy_spec_kernel<HJ, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(rnnt_greedy_spec_kernel<HJ, HP, TCJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_greedy_spec_kernel<HJ, HP>, kSpThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_greedy_spec_kernel<HJ, HP, TCJ>, kSpThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   void* args[] = {&p};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_spec_kernel<HJ, HP>), dim3(grid), dim3(kSpThreads), args, smem, stream);
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_spec_kernel<HJ, HP, TCJ>), dim3(grid), dim3(kSpThreads), args, smem, stream);
 }
 
-cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream) {
+cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream, bool tc_joint) {
   if (a.B <= 0 || num_sms < kGroups) return cudaErrorInvalidValue;
   const int G = num_sms;
   SpecDev p;
@@ -591,15 +731,26 @@ cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int nu
   if (n_tiles > 4 * kMaxTilesPerWarp || 4 * p.units > 24 || p.rows_p > 8 || 16 * p.units > kSpThreads) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(workspace, 0, rnnt_spec_workspace_bytes(a.B, a.Hj, a.Hp, num_sms), stream);
   if (e != cudaSuccess) return e;
+  const size_t state = ((static_cast<size_t>(a.B) * p.units + 1) & ~static_cast<size_t>(1)) * 4 + kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 8 * 4 +
+                       (2 + 2 * kSpWarps) * 4 + 64;
+  const size_t w_lp = (static_cast<size_t>(4 * p.units) * (2 * a.Hp + 8) + static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
+  if (tc_joint) {
+    if (p.rows_j > 128) return cudaErrorInvalidValue;
+    const size_t rows_a8 = (p.rows_j + 7) & ~7;
+    const size_t b_bytes = static_cast<size_t>(a.Hj / 2 / 64) * 8192;
+    const size_t b_region = b_bytes > 16384 ? b_bytes : 16384;
+    const size_t smem = 1024 + static_cast<size_t>(a.Hj / 64) * rows_a8 * 128 + b_region + w_lp + 128 * 4 + state + 16;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640, true>(p, G, smem, stream);
+    if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128, true>(p, G, smem, stream);
+    return cudaErrorInvalidValue;
+  }
   const size_t gs = a.Hj / 2 + 8;
   const size_t g_floats = kPassRows * gs > static_cast<size_t>(kSpWarps) * 16 * 24 ? kPassRows * gs : static_cast<size_t>(kSpWarps) * 16 * 24;
-  size_t smem = (static_cast<size_t>(p.rows_j) * (a.Hj + 8) + static_cast<size_t>(4 * p.units) * (2 * a.Hp + 8) +
-                 static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
-  smem += (g_floats + n_tiles * 8 + ((static_cast<size_t>(a.B) * p.units + 1) & ~static_cast<size_t>(1))) * 4;
-  smem += kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 8 * 4 + (2 + 2 * kSpWarps) * 4 + 64;
+  const size_t smem = static_cast<size_t>(p.rows_j) * (a.Hj + 8) * 2 + w_lp + (g_floats + n_tiles * 8) * 4 + state;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640>(p, G, smem, stream);
-  if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128>(p, G, smem, stream);
+  if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640, false>(p, G, smem, stream);
+  if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128, false>(p, G, smem, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -418,12 +418,13 @@ int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_
   // One decode kernel for every batch size (windowed, weights-stationary, decode_spec.cu): an utterance's logits
   // are accumulated in the same order whether it is decoded alone or inside a batch, so results do not depend on
   // batch composition.  RS_DECODE_MODE selects the earlier kernels for A/B measurements:
-  //   0/unset/3: windowed tensor-path kernel, 1: one cluster per utterance, 2: batched one-frame-per-iteration kernel
+  //   0/unset/4: windowed kernel, joint on tcgen05 (default); 3: windowed kernel, joint on mma.sync; 1: one cluster per
+  //   utterance; 2: batched one-frame-per-iteration kernel
   const char* m = getenv("RS_DECODE_MODE");
   const int mode = m ? atoi(m) : 0;
   if (mode == 1) RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
   else if (mode == 2) RS_K(e, rs::launch_rnnt_greedy_batched(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
-  else RS_K(e, rs::launch_rnnt_greedy_spec(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
+  else RS_K(e, rs::launch_rnnt_greedy_spec(da, at<void>(e, p.dec_ws), e->num_sms, s, mode != 3), 2);
   return RS_OK;
 }
 

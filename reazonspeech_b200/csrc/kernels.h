@@ -88,7 +88,7 @@ cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int
 
 // windowed (kFrames per iteration) tensor-path variant (decode_spec.cu); workspace from rnnt_spec_workspace_bytes()
 size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int num_sms);
-cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream);
+cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream, bool tc_joint = false);
 
 // small utility kernels
 cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);

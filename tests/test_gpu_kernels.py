@@ -161,10 +161,11 @@ def test_encoder_vs_oracle(tiny_engine, tiny_cfg, tiny_sd, n_layers):
 
 
 # ------------------------------------------------------------------------------------ decode
-@pytest.mark.parametrize("mode", ["1", "2", "3"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "4"])
 def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd, mode, monkeypatch):
     """Decode kernels alone (1: one cluster per utterance, 2: batched weights-stationary grid, 3: windowed
-    tensor-path grid = the default): fed the ORACLE's encoder output, tokens and frames must be identical."""
+    grid with the joint on mma.sync, 4: the same with the joint on tcgen05): fed the ORACLE's encoder output, tokens
+    and frames must be identical."""
     from oracle import nemo_restated as O
     monkeypatch.setenv("RS_DECODE_MODE", mode)
     eng = tiny_engine
@@ -205,17 +206,18 @@ def test_windowed_decode_equals_sequential_kernel(tiny_engine, tiny_cfg, B, monk
     if B > 2:
         enc_len[2] = 0
     outs = {}
-    for mode in ("2", "3"):
+    for mode in ("2", "3", "4"):
         monkeypatch.setenv("RS_DECODE_MODE", mode)
         t, f, n = eng.greedy(enc.cuda(), enc_len.cuda())
         torch.cuda.synchronize()
         outs[mode] = (t.cpu(), f.cpu(), n.cpu())
-    n2, n3 = outs["2"][2], outs["3"][2]
-    print("tokens per utterance:", n3.tolist()[:12], "lens", enc_len.tolist()[:12])
-    assert torch.equal(n2, n3)
-    for b in range(B):
-        n = int(n2[b])
-        assert torch.equal(outs["2"][0][b, :n], outs["3"][0][b, :n]) and torch.equal(outs["2"][1][b, :n], outs["3"][1][b, :n]), f"utt {b}"
+    n2 = outs["2"][2]
+    print("tokens per utterance:", n2.tolist()[:12], "lens", enc_len.tolist()[:12])
+    for other in ("3", "4"):
+        assert torch.equal(n2, outs[other][2]), f"mode {other}"
+        for b in range(B):
+            n = int(n2[b])
+            assert torch.equal(outs["2"][0][b, :n], outs[other][0][b, :n]) and torch.equal(outs["2"][1][b, :n], outs[other][1][b, :n]), f"mode {other} utt {b}"
 
 
 def decisions_from(tokens, frames, T, max_symbols, blank):
