@@ -164,20 +164,24 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   const uint32_t a_slab = static_cast<uint32_t>(rows_a8) * 128u;   // bytes per A slab
   constexpr uint32_t kBSlab = 8192u;                               // B slab: 64 rows x 128 B = hi plane (rows 0-31) | lo plane (rows 32-63)
   constexpr uint32_t kBRegion = (NSLAB_H * kBSlab > 16384u) ? NSLAB_H * kBSlab : 16384u;   // >= what an M = 128 read of the last A slab overruns
-  uint8_t* sbase = ssm;
-  uint32_t tc_base = 0;
+  // TCJ order: [A slabs | W_lstm | W_pred | pad to 1024 | B slabs | bias, state ...].  The mma.sync B fragments of the LSTM /
+  // joint.pred phases read up to 8 rows past the end of their (5- or 20-row) arrays: those reads must land inside the
+  // allocation, so the big B region follows the weight arrays (a 2-utterance batch otherwise read past the end of shared memory).
+  uint32_t tc_base = 0, b_off = 0;
+  const uint32_t wlp_bytes = static_cast<uint32_t>((static_cast<size_t>(4 * p.units) * LS + static_cast<size_t>(p.rows_p) * (HP + 8)) * 2);
   if constexpr (TCJ) {
     tc_base = (smem_u32(ssm) + 1023u) & ~1023u;
-    sbase = ssm + (tc_base - smem_u32(ssm)) + KSLABS * a_slab + kBRegion;
+    b_off = (KSLABS * a_slab + wlp_bytes + 1023u) & ~1023u;
   }
-  uint8_t* gA = ssm + (tc_base - smem_u32(ssm));                   // TCJ: generic pointers to the A slabs / B planes
-  uint8_t* gB = gA + KSLABS * a_slab;
-  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(sbase);                    // [rows_j][WS]   (not TCJ)
-  __nv_bfloat16* s_wlstm = s_wout + (TCJ ? 0 : static_cast<size_t>(p.rows_j) * WS);   // [4*units][LS] gate-major
+  uint8_t* gA = ssm + (tc_base - smem_u32(ssm));                   // TCJ: generic pointers to the A slabs / B slabs
+  uint8_t* gB = gA + b_off;
+  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(ssm);                      // [rows_j][WS]   (not TCJ)
+  __nv_bfloat16* s_wlstm = TCJ ? reinterpret_cast<__nv_bfloat16*>(gA + KSLABS * a_slab)
+                               : s_wout + static_cast<size_t>(p.rows_j) * WS;         // [4*units][LS] gate-major
   __nv_bfloat16* s_wpred = s_wlstm + static_cast<size_t>(4 * p.units) * LS;           // [rows_p][WS']  (WS' = HP + 8)
   float* s_g = TCJ ? reinterpret_cast<float*>(gB)
                    : reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8));   // [32][GS]; also the L / P reduction buffer
-  float* s_bout = TCJ ? reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8)) : s_g + G_FLOATS;   // -inf beyond nj
+  float* s_bout = TCJ ? reinterpret_cast<float*>(gB + kBRegion) : s_g + G_FLOATS;    // -inf beyond nj
   const int n_bout = TCJ ? 128 : n_tiles * 8;
   float* s_c = s_bout + n_bout;                                                      // [B][units]
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_c + ((static_cast<size_t>(B) * p.units + 1) & ~static_cast<size_t>(1)));   // [32][4]
@@ -527,7 +531,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 #pragma unroll 1
             for (int sl = 0; sl < NSLAB_H; ++sl) {
               const uint64_t da = umma_desc_k_sw128(tc_base + static_cast<uint32_t>(h * NSLAB_H + sl) * a_slab);
-              const uint64_t db = umma_desc_k_sw128(tc_base + KSLABS * a_slab + sl * kBSlab);
+              const uint64_t db = umma_desc_k_sw128(tc_base + b_off + sl * kBSlab);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, kIdescF16_128x64, (h | sl | k) != 0 ? 1u : 0u);
@@ -739,7 +743,8 @@ cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int nu
     const size_t rows_a8 = (p.rows_j + 7) & ~7;
     const size_t b_bytes = static_cast<size_t>(a.Hj / 2 / 64) * 8192;
     const size_t b_region = b_bytes > 16384 ? b_bytes : 16384;
-    const size_t smem = 1024 + static_cast<size_t>(a.Hj / 64) * rows_a8 * 128 + b_region + w_lp + 128 * 4 + state + 16;
+    const size_t ab = ((static_cast<size_t>(a.Hj / 64) * rows_a8 * 128 + w_lp + 1023) & ~static_cast<size_t>(1023));   // A slabs, W_lstm, W_pred, pad
+    const size_t smem = 1024 + ab + b_region + 128 * 4 + state + 16;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640, true>(p, G, smem, stream);
     if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128, true>(p, G, smem, stream);
