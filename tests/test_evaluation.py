@@ -61,3 +61,34 @@ def test_evaluate_single_and_batched_agree(tmp_path, capsys):
 def test_evaluate_without_dataset_raises():
     with pytest.raises(ValueError):
         _Stub().evaluate()
+
+
+def test_multi_gpu_worker_shards_and_merges_in_order():
+    """The per-GPU worker of evaluate(num_gpus > 1), run in-process with a plain queue: each rank transcribes only its
+    shard (dealt by length) on device index rank % num_gpus, the merge restores input order."""
+    import queue
+    from reazonspeech_b200.evaluation.base import _gpu_worker
+    from reazonspeech_b200.sharding import shard_indices
+
+    seen = {}
+
+    class Probe(_Stub):
+        def _evaluate(self, example, rank=None, num_gpus=None, **kw):
+            seen.setdefault(rank, []).append(example["audio"]["path"])
+            return {"prediction": f"{example['audio']['path']}@{rank % num_gpus}"}
+
+        def _length_of(self, example):
+            return len(example["audio"]["path"])
+
+    rows = [{"audio": {"path": p}} for p in ("aaaa", "b", "ccc", "dd", "eeeeee")]
+    ev = Probe()
+    shards = shard_indices([ev._length_of(r) for r in rows], 2)
+    q = queue.Queue()
+    for rank in range(2):
+        _gpu_worker(rank, ev, rows, shards, None, 2, q)
+    merged = {}
+    while not q.empty():
+        merged.update(q.get()[1])
+    out = [merged[i] for i in range(len(rows))]
+    assert [o.split("@")[0] for o in out] == [r["audio"]["path"] for r in rows]
+    assert sorted(len(v) for v in seen.values()) == sorted(len(s) for s in shards) and set(seen) == {0, 1}

@@ -1,0 +1,62 @@
+"""Host-side contracts between engine.py::pack_weights and the attention kernels, checked on CPU against the oracle's
+own formulas (oracle/nemo_restated.py::local_attention_core):
+
+* pos_bias_u is folded into the q bias of the fused QKV projection, and the positional GEMM's bias takes it out again:
+  q' k = (q + u) k  and  q' p[c] + bdbias[c] = (q + v) p[c];
+* the row-skewed layout of the positional scores (RS_EPI_BIAS_F16_SKEW): thread = query row of a 128-row tile finds the
+  score of window column jj at the SAME column jj - (128 - w_left) in every row."""
+import torch
+
+from reazonspeech_b200.config import ModelConfig
+from reazonspeech_b200.engine import pack_weights
+from reazonspeech_b200.weights import random_state_dict, rel_pos_table
+
+
+def test_pos_bias_u_fold_is_algebraically_neutral():
+    cfg = ModelConfig.tiny()
+    sd = random_state_dict(cfg, seed=1)
+    pk = pack_weights(sd, cfg)
+    H, dk, d = cfg.n_heads, cfg.d_head, cfg.d_model
+    a = "encoder.layers.0.self_attn."
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, d, generator=g)
+    w, b = pk["L0.att.wqkv"].float(), pk["L0.att.bqkv"]
+    qkv = x @ w.T + b
+    qp = qkv[:, :d].view(-1, H, dk)                                # what the engine's QKV buffer holds in its q columns
+    k = qkv[:, d:2 * d].view(-1, H, dk)
+    q = (x @ sd[a + "linear_q.weight"].T + sd[a + "linear_q.bias"]).view(-1, H, dk)
+    u, v = sd[a + "pos_bias_u"], sd[a + "pos_bias_v"]
+    # content term: (q + u) . k
+    ac_engine = torch.einsum("ihd,jhd->hij", qp, k)
+    ac_oracle = torch.einsum("ihd,jhd->hij", q + u, k)
+    assert (ac_engine - ac_oracle).abs().max() < 1e-3
+    # positional term: (q + v) . p[c], with p = linear_pos(table) as the oracle builds it
+    pos = torch.nn.functional.linear(rel_pos_table(cfg), sd[a + "linear_pos.weight"]).view(cfg.n_rel, H, dk)
+    bd_oracle = torch.einsum("ihd,chd->ihc", q + v, pos)
+    p_packed = pk["L0.att.pos"].float()[:, : cfg.n_rel]            # [H, n_rel, dk] (bf16-rounded table)
+    bias = pk["L0.att.bdbias"].view(H, -1)[:, : cfg.n_rel]
+    bd_engine = torch.einsum("ihd,hcd->ihc", qp, p_packed) + bias
+    assert (bd_engine - bd_oracle).abs().max() < 5e-2 * bd_oracle.abs().max()     # table rounded to bf16
+    # global token: scored against q, not q + u
+    assert ((qp - u) - q).abs().max() < 1e-4
+
+
+def test_skewed_positional_layout_index_contract():
+    """Writer (GEMM epilogue): score of relative offset c of frame t goes to column c + (t mod 128).
+    Reader (attention kernel): row r = t - q0 of the tile reads window column jj (key j = q0 - 128 + jj) at
+    jj - (128 - w_left).  Both must address the same cell for every in-band (t, j)."""
+    for w_left, w_right in ((128, 128), (16, 16), (64, 32)):
+        for q0 in (0, 128, 384):
+            for r in (0, 1, 77, 127):
+                t = q0 + r
+                for rel in range(-w_left, w_right + 1):
+                    j = t + rel
+                    if j < 0:
+                        continue
+                    c = rel + w_left                               # relative-position index, oracle's `idx`
+                    written_col = c + (t % 128)
+                    jj = j - (q0 - 128)
+                    assert 0 <= jj < 384
+                    read_col = jj - (128 - w_left)
+                    assert read_col == written_col
+                    assert 0 <= written_col < 384                  # pitch of the skewed buffer
