@@ -1,62 +1,84 @@
-"""USAGE
+"""Command line of the drop-in package: ``python -m reazonspeech_b200.nemo.asr.cli [options] AUDIO [AUDIO ...]``.
 
-    reazonspeech-b200-nemo-asr [-h] [--to={vtt,srt,ass,json,tsv}] [-o file] audio [audio ...]
+Same contract as the reference's ``reazonspeech-nemo-asr`` entry point (pkg/nemo-asr/src/cli.py:36-74):
 
-OPTIONS
+  -h / --help          usage on stderr, nothing else happens
+  -o FILE / --output=  where the transcript goes (default: stdout)
+  --to=FMT             vtt | srt | ass | json | tsv; anything else, or no option, gives the bracketed plain-text
+                       lines.  Like the reference, the format is NOT inferred from FILE's extension
+                       (see writer.get_writer)
+  no AUDIO argument    "no audio file specified" + usage on stderr, exit status 1
+  unknown option       getopt.GetoptError propagates, as in the reference
 
-    audio
-        Audio file(s) to transcribe (16-bit / float WAV; anything else needs librosa,
-        see audio_from_path).  Several files are transcribed as one batch.
-
-    -h, --help
-        Print this help message.
-
-    --to={vtt,srt,ass,json,tsv}
-        Output format for transcription
-
-    -o file, --output=file
-        File to write transcription
-
-Same options and behaviour as the reference CLI (pkg/nemo-asr/src/cli.py:1-77): no audio ->
-message + usage on stderr and exit status 1; -h -> usage on stderr; one output stream, header
-once, then every segment.  Extension: more than one audio argument (the reference reads one).
+One extension: several AUDIO arguments are transcribed as one batch on the GPU (the reference reads exactly one);
+their segments are written one file after the other through the same writer.
+Audio decoding: WAV through scipy (or soundfile when installed); other containers need librosa, see audio_from_path.
 """
 import getopt
 import sys
 import warnings
+from dataclasses import dataclass, field
+from typing import List, Optional
 
-from .audio import audio_from_path
-from .transcribe import load_model, transcribe, transcribe_batch
-from .writer import get_writer
+SHORT_OPTS = "ho:"
+LONG_OPTS = ("help", "output=", "to=")
+
+
+@dataclass
+class Options:
+    help: bool = False
+    output: Optional[str] = None
+    fmt: Optional[str] = None
+    audio: List[str] = field(default_factory=list)
+
+
+def parse(argv) -> Options:
+    parsed, rest = getopt.getopt(list(argv), SHORT_OPTS, LONG_OPTS)
+    opt = Options(audio=rest)
+    for flag, value in parsed:
+        if flag in ("-h", "--help"):
+            opt.help = True
+            break                                            # the reference returns at the first -h it meets
+        if flag in ("-o", "--output"):
+            opt.output = value
+        if flag == "--to":
+            opt.fmt = value
+    return opt
+
+
+def usage() -> None:
+    print(__doc__, file=sys.stderr)
+
+
+def run(opt: Options) -> None:
+    from .audio import audio_from_path
+    from .transcribe import load_model, transcribe, transcribe_batch
+    from .writer import get_writer
+
+    sink = sys.stdout if opt.output is None else open(opt.output, "w")
+    warnings.simplefilter("ignore")
+    clips = [audio_from_path(path) for path in opt.audio]
+    model = load_model()
+    results = transcribe_batch(model, clips) if len(clips) > 1 else [transcribe(model, clips[0])]
+    with sink:
+        out = get_writer(sink, opt.fmt)
+        out.write_header()
+        for result in results:
+            for segment in result.segments:
+                out.write(segment)
 
 
 def main(argv=None):
-    outpath = None
-    outext = None
-    opts, args = getopt.getopt(sys.argv[1:] if argv is None else list(argv), "ho:", ("help", "output=", "to="))
-    for key, value in opts:
-        if key in ("-h", "--help"):
-            print(__doc__, file=sys.stderr)
-            return
-        if key in ("-o", "--output"):
-            outpath = value
-        elif key == "--to":
-            outext = value
-    if not args:
+    opt = parse(sys.argv[1:] if argv is None else argv)
+    if opt.help:
+        usage()
+        return None
+    if not opt.audio:
         print("no audio file specified", file=sys.stderr)
-        print(__doc__, file=sys.stderr)
+        usage()
         return 1
-    outfile = open(outpath, "w") if outpath is not None else sys.stdout
-    warnings.simplefilter("ignore")
-    audios = [audio_from_path(path) for path in args]
-    model = load_model()
-    results = [transcribe(model, audios[0])] if len(audios) == 1 else transcribe_batch(model, audios)
-    with outfile:
-        writer = get_writer(outfile, outext)
-        writer.write_header()
-        for result in results:
-            for segment in result.segments:
-                writer.write(segment)
+    run(opt)
+    return None
 
 
 if __name__ == "__main__":

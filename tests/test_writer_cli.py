@@ -48,13 +48,13 @@ def test_get_writer_dispatch_matches_reference(cases):
 def test_cli_without_audio_prints_usage_and_returns_1(capsys):
     assert cli.main([]) == 1
     err = capsys.readouterr().err
-    assert "no audio file specified" in err and "USAGE" in err
+    assert "no audio file specified" in err and "--output" in err
 
 
 def test_cli_help_goes_to_stderr(capsys):
     assert cli.main(["-h"]) is None
     cap = capsys.readouterr()
-    assert "USAGE" in cap.err and cap.out == ""
+    assert "--output" in cap.err and cap.out == ""
 
 
 def test_cli_rejects_unknown_option():
