@@ -5,8 +5,10 @@ the time-varying part of enc_proj to about unit standard deviation, (3) the blan
 a greedy emission rate of about one token per three encoder frames.  A deterministic function of the
 seeded weights; it shapes the decode load of the benchmark only and is not part of the engine.
 
-    python scripts/calibrate_synthetic.py --config tiny     # CPU, through the oracle
-    python scripts/calibrate_synthetic.py --config full     # on a B200, through the engine
+    python scripts/calibrate_synthetic.py --config tiny     # on a B200, through the engine (a few short clips)
+    python scripts/calibrate_synthetic.py --config full     # on a B200, through the engine (the benchmark's clip set)
+
+Both go through the product path (the engine); the oracle is test infrastructure and is not used here.
 """
 import argparse
 import json
@@ -34,7 +36,7 @@ def main():
     a = ap.parse_args()
     cfg = ModelConfig.tiny() if a.config == "tiny" else ModelConfig()
     sd = random_state_dict(cfg, a.seed, calibrate=False)
-    # tiny: a few short clips through the CPU oracle; full: the benchmark's own clip set (bench.py make_batch)
+    # tiny: a few short clips; full: the benchmark's own clip set (bench.py make_batch)
     secs = (6.0, 9.0, 12.0, 7.0) if a.config == "tiny" else (30.0,) * 32
     first = 100 if a.config == "tiny" else 0
     waves = [np.pad(synth_clip(first + i, s), 8000) for i, s in enumerate(secs)]
@@ -42,27 +44,19 @@ def main():
     W, b0 = sd["joint.enc.weight"].clone(), sd["joint.enc.bias"].clone()
     bout0 = sd["joint.joint_net.2.bias"].clone()
 
-    if a.config == "tiny":
-        from oracle import nemo_restated as O
-        torch.set_num_threads(1)
-        with torch.no_grad():
-            encs = [O.encoder(O.log_mel(torch.from_numpy(w), cfg), sd, cfg) for w in waves]
-        valid = torch.cat(encs)
-        eng = None
-    else:
-        from reazonspeech_b200.engine import Engine
-        eng = Engine(cfg, sd, "cuda:0")
-        L = max(len(w) for w in waves)
-        x = torch.zeros(len(waves), L)
-        for i, w in enumerate(waves):
-            x[i, : len(w)] = torch.from_numpy(w)
-        lens = torch.tensor([len(w) for w in waves], dtype=torch.int32).cuda()
-        x = x.cuda()
-        mel, mel_len = eng.log_mel(x, lens)
-        enc, enc_len = eng.encode(mel, mel_len)
-        torch.cuda.synchronize()
-        enc = enc.cpu()
-        valid = torch.cat([enc[i, : n_frames[i]] for i in range(len(waves))])
+    from reazonspeech_b200.engine import Engine
+    eng = Engine(cfg, sd, "cuda:0")
+    L = max(len(w) for w in waves)
+    x = torch.zeros(len(waves), L)
+    for i, w in enumerate(waves):
+        x[i, : len(w)] = torch.from_numpy(w)
+    lens = torch.tensor([len(w) for w in waves], dtype=torch.int32).cuda()
+    x = x.cuda()
+    mel, mel_len = eng.log_mel(x, lens)
+    enc, enc_len = eng.encode(mel, mel_len)
+    torch.cuda.synchronize()
+    enc = enc.cpu()
+    valid = torch.cat([enc[i, : n_frames[i]] for i in range(len(waves))])
 
     dc = valid.mean(0)
     ac = valid - dc
@@ -81,22 +75,16 @@ def main():
         return s2
 
     worst = [0.0]
-    if eng is None:
-        def rate(shift):
-            s2 = install(shift)
-            per = [len(O.rnnt_greedy(e, s2, cfg).tokens) / n for e, n in zip(encs, n_frames)]
-            worst[0] = max(per)
-            return sum(len(O.rnnt_greedy(e, s2, cfg).tokens) for e in encs) / sum(n_frames)
-    else:
-        def rate(shift):
-            s2 = install(shift)
-            eng.weights["joint.enc.w"].copy_(s2["joint.enc.weight"].to(torch.bfloat16))
-            eng.weights["joint.enc.b"].copy_(s2["joint.enc.bias"])
-            eng.weights["joint.out.b"].copy_(s2["joint.joint_net.2.bias"])
-            _, _, ntok = eng.transcribe_device(x, lens)
-            torch.cuda.synchronize()
-            worst[0] = float((ntok.cpu().float() / torch.tensor(n_frames, dtype=torch.float32)).max())
-            return float(ntok.sum()) / sum(n_frames)
+
+    def rate(shift):
+        s2 = install(shift)
+        eng.weights["joint.enc.w"].copy_(s2["joint.enc.weight"].to(torch.bfloat16))
+        eng.weights["joint.enc.b"].copy_(s2["joint.enc.bias"])
+        eng.weights["joint.out.b"].copy_(s2["joint.joint_net.2.bias"])
+        _, _, ntok = eng.transcribe_device(x, lens)
+        torch.cuda.synchronize()
+        worst[0] = float((ntok.cpu().float() / torch.tensor(n_frames, dtype=torch.float32)).max())
+        return float(ntok.sum()) / sum(n_frames)
 
     curve = {s: rate(s) for s in np.arange(-2.0, 8.01, 0.5)}
     print("rate curve:", {float(k2): round(v, 3) for k2, v in curve.items()})
