@@ -4,7 +4,7 @@ Measured (4 s clip, seeded weights, relative L2 against the fp32 oracle; today =
     2 x 256: 3.6e-3 -> 3.8e-3     6 x 512: 2.8e-3 -> 3.9e-3     12 x 1024: 2.7e-3 -> 5.1e-3   (tolerance 2e-2)
 Usage: python tests/studies/ln_fold_study.py"""
 import sys, math, numpy as np, torch, torch.nn.functional as F
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import nemo_restated as O
 from reazonspeech_b200.config import ModelConfig
 from reazonspeech_b200.weights import random_state_dict
