@@ -74,7 +74,10 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
 
 // EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT, 2: RS_EPI_BIAS_F16_SKEW.
 // (One kernel with every path spilled registers in the common ones: 166 -> 168 registers + a stack frame, GEMMs 10-20 % slower.)
-template <int EG>
+// SWZ: the fp32 staging uses 32-float rows with the float4 index XOR-ed by (row & 7) instead of 36-float padded rows: both
+// are conflict-free for the row-per-lane writes and the 4-rows-per-instruction reads, the swizzled form fits 4 KB per warp,
+// which is what leaves room for a 6th pipeline stage (RS_GEMM_STAGES=6 experiment).
+template <int EG, bool SWZ = false>
 __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
                                                int col0, int bt, const float4 (&rr)[8]) {
   float v[32];
@@ -200,8 +203,9 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
     }
     default: {  // RS_EPI_RESID_F32 / RS_EPI_BIAS_F32
 #pragma unroll
+      constexpr int LD = SWZ ? 32 : kStageLd;
       for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(stage + lane * kStageLd + 4 * j) =
+        *reinterpret_cast<float4*>(stage + lane * LD + 4 * (SWZ ? (j ^ (lane & 7)) : j)) =
             make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
       __syncwarp();
       const bool add = p.epilogue == RS_EPI_RESID_F32;
@@ -209,7 +213,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       for (int i = 0; i < 8; ++i) {                            // 4 rows x 128 B per instruction
         const int rl = i * 4 + (lane >> 3), cw = (lane & 7) * 4;
         const int row = tile_row0 + rl;
-        float4 a = *reinterpret_cast<const float4*>(stage + rl * kStageLd + cw);
+        float4 a = *reinterpret_cast<const float4*>(stage + rl * LD + (SWZ ? 4 * ((cw >> 2) ^ (rl & 7)) : cw));
         if (add) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
         if (row < p.M)
           *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 + cw) = a;
@@ -355,19 +359,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // is bound by L2 bandwidth (87 FLOP/B against ~12 TB/s), not by the tensor pipe; it also leaves room
 // for a 6-deep ring.  Barriers: full[] on the leader (both producers arrive, both TMAs credit it),
 // empty[] / tmem_full[] per CTA (commit multicast to both), tmem_empty[] on the leader.
-template <int BN>
+template <int BN, int ST = 0>
 struct Gemm2Cfg {
   static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : 7;
+  static constexpr int kStages = ST > 0 ? ST : ((BN == 256) ? 5 : 7);
+  static constexpr bool kSwz = ST == 6;                                   // 6 stages need the 4 KB-per-warp staging
+  static constexpr int kStagingPerWarp = kSwz ? 32 * 32 * 4 : kStageBytesPerWarp;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 32 * 36 * 4 * 8 /*epilogue staging*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiWarps * kStagingPerWarp /*epilogue staging*/;
 };
 
-template <int BN, int EG>
+template <int BN, int EG, int ST = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -454,7 +460,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     // ------------------------------------------------------------------ epilogue warps (both CTAs, own TMEM half)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * kStageBytesPerWarp);
+    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * Cfg::kStagingPerWarp);
     int it = 0;
     for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
       const int acc = it & 1;
@@ -475,7 +481,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
+        epilogue_store<EG, Cfg::kSwz>(p, r, stage, tile_row0, lane, col0, 0, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -705,12 +711,12 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   }
 }
 
-template <int BN, int EG>
+template <int BN, int EG, int ST = 0>
 static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, ST>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
     attr_set = true;
   }
@@ -723,7 +729,7 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm_bf16_tn_2cta_kernel<BN, EG><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  gemm_bf16_tn_2cta_kernel<BN, EG, ST><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm 2cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
@@ -731,10 +737,13 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
 
 template <int BN>
 static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  // RS_GEMM_STAGES=6: EXPERIMENT (not yet measured) -- a 6-deep ring for the common epilogues, made possible by the 4 KB
+  // swizzled fp32 staging; the default is the 5-deep ring with padded staging
+  static const int stages = getenv("RS_GEMM_STAGES") ? atoi(getenv("RS_GEMM_STAGES")) : 0;
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
     case 2: return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
-    default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
+    default: return stages == 6 ? launch_2cta_eg<BN, 0, 6>(g, num_sms, stream, err) : launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
   }
 }
 
