@@ -258,6 +258,24 @@ def main():
     kernel_ms = {k: {"launches": n, "ms": round(ms, 4)} for k, (n, ms) in sorted(eng.kernel_timing().items(), key=lambda kv: -kv[1][1])}
     eng.kernel_timing(False)
     attn_cycles = eng.attention_cycles() if os.environ.get("RS_ATTN_MODE", "0") != "1" else None
+    # memory-bound kernels against the measured copy bandwidth: ALGORITHMIC bytes over the
+    # in-pipeline time of their launches (event pairs above, so warm-L2 effects are included: a fraction can exceed 1)
+    valid_T = eng.cfg.enc_frames(L)
+    dm = eng.cfg.d_model
+
+    def hbm_line(key, bytes_per_step, what):
+        if key not in kernel_ms or kernel_ms[key]["ms"] <= 0:
+            return None
+        gbs = bytes_per_step / (kernel_ms[key]["ms"] * 1e-3) / 1e9
+        return {"kernel": key, "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "bytes_per_step": bytes_per_step, "what": what}
+
+    n_ln = kernel_ms.get("launch_layernorm", {}).get("launches", 0)
+    n_dw = kernel_ms.get("launch_conv_dw", {}).get("launches", 0)
+    roofline_hbm = [r for r in (
+        hbm_line("launch_logmel", B * (L * 4 + eng.cfg.mel_valid(L) * eng.cfg.n_mels * 4), "log-mel frontend: fp32 samples in, fp32 normalised features out (2.98 MB per clip)"),
+        hbm_line("launch_layernorm", n_ln * B * valid_T * dm * 6, "LayerNorm: fp32 row in, bf16 row out, per launch"),
+        hbm_line("launch_conv_dw", n_dw * B * valid_T * dm * 4, "depthwise conv + BN + Swish: bf16 in, bf16 out, per launch"),
+    ) if r is not None]
     # ALGORITHMIC FLOPs: the engine counts 2*M*N*K with M = B x frame capacity (a multiple of 8: 392 for 388 valid
     # frames); the roofline numerator keeps only the valid rows
     g_flops *= eng.cfg.enc_frames(L) / max(eng.enc_frames(L), 1)
@@ -289,7 +307,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
-        "roofline": roofline, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
     }), flush=True)
 
 
