@@ -36,6 +36,9 @@ struct LayerW {
   const float *ln_ff2_g, *ln_ff2_b, *ff2_b1, *ff2_b2;
   const void *ff2_w1, *ff2_w2;
   const float *ln_out_g, *ln_out_b;
+  // RS_LN_FOLD experiment (engine.py ln_fold_tensors): gamma-scaled weights and the (c, d) vectors of the folded LayerNorms
+  const void *wqkv_f = nullptr, *pw1_wf = nullptr, *ff2_w1f = nullptr;
+  const float *qkv_c = nullptr, *qkv_d = nullptr, *pw1_c = nullptr, *pw1_d = nullptr, *ff2_c = nullptr, *ff2_d = nullptr;
 };
 
 struct Plan {           // workspace offsets (bytes) for one (B, L_max)
@@ -43,12 +46,15 @@ struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, vt, enc, encp;
   int n_rel_pad, ld_vt;
   size_t tokens, frames, ntok, dec_ws, total;
+  size_t stats;   // RS_LN_FOLD experiment: per-row partial (sum, sum of squares) of the residual stream, [M][fold_slots][2] f32
 };
 
 inline int conv_len(int n) { return (n - 1) / 2 + 1; }
 // Encoder-frame capacity of the padded activation tensors: the subsampled length rounded up to a multiple of 8, so that
 // every utterance starts at a 16-byte-aligned column of the transposed V buffer (TMA wants the innermost coordinate
 // 16-byte aligned: an odd T_max raised "illegal instruction" on the V^T tile loads of the attention kernel).
+// LayerNorm-fold experiment: one (sum, sum of squares) slot per 256-column tile of the producer GEMM and column half
+inline int fold_slots(int d_model) { return 2 * (d_model / 256); }
 constexpr int kBdSkewPitch = 384;   // 2 * 128 + 1 relative offsets + 127 of skew, rounded up: columns of a 128-query tile's key window
 inline int enc_capacity(int mel_frames) { return (conv_len(conv_len(conv_len(mel_frames))) + 7) & ~7; }
 
@@ -66,6 +72,7 @@ struct rs_engine {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int U_cap = 0;
+  bool ln_fold = false;   // RS_LN_FOLD=1 and the folded tensors are in the weight table (experiment, unmeasured)
   mutable char err[512] = "";
   int64_t launches = 0;
   bool timing = false;
@@ -152,6 +159,7 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.frames = take(static_cast<size_t>(B) * U_max * 4);
   p.ntok = take(static_cast<size_t>(B) * 4);
   p.dec_ws = take(dec_ws_bytes(e, B));
+  if (e->ln_fold) p.stats = take(static_cast<size_t>(p.M) * fold_slots(c.d_model) * 2 * 4);   // appended: the default layout is unchanged
   p.total = off;
   return p;
 }
@@ -215,6 +223,11 @@ int bind_weights(rs_engine* e) {
     NEED(L.ff2_w1, N("ff2.w1"), RS_BF16, ff * d); NEED(L.ff2_b1, N("ff2.b1"), RS_F32, ff);
     NEED(L.ff2_w2, N("ff2.w2"), RS_BF16, d * ff); NEED(L.ff2_b2, N("ff2.b2"), RS_F32, d);
     NEED(L.ln_out_g, N("ln_out.g"), RS_F32, d); NEED(L.ln_out_b, N("ln_out.b"), RS_F32, d);
+    if (e->ln_fold) {
+      NEED(L.wqkv_f, N("att.wqkv.fold"), RS_BF16, 3 * d * d); NEED(L.qkv_c, N("att.wqkv.fold_c"), RS_F32, 3 * d); NEED(L.qkv_d, N("att.wqkv.fold_d"), RS_F32, 3 * d);
+      NEED(L.pw1_wf, N("conv.pw1.w.fold"), RS_BF16, 2 * d * d); NEED(L.pw1_c, N("conv.pw1.w.fold_c"), RS_F32, 2 * d); NEED(L.pw1_d, N("conv.pw1.w.fold_d"), RS_F32, 2 * d);
+      NEED(L.ff2_w1f, N("ff2.w1.fold"), RS_BF16, ff * d); NEED(L.ff2_c, N("ff2.w1.fold_c"), RS_F32, ff); NEED(L.ff2_d, N("ff2.w1.fold_d"), RS_F32, ff);
+    }
   }
   const int64_t Hj = c.joint_hidden, Hp = c.pred_hidden, NC = c.vocab_size + 1;
   NEED(e->dec.enc_w, "joint.enc.w", RS_BF16, Hj * d); NEED(e->dec.enc_b, "joint.enc.b", RS_F32, Hj);
@@ -352,11 +365,23 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     const LayerW& L0 = e->layers[0];
     RS_K(e, rs::launch_layernorm(x, L0.ln_ff1_g, L0.ln_ff1_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
   }
+  // LayerNorm-fold experiment: the residual GEMM in front of a folded LayerNorm also leaves bf16(x) in xn and the row sums
+  // in `stats`; the GEMM behind it reads xn with gamma-scaled weights and finishes the normalisation in its epilogue.
+  const bool fold = e->ln_fold;
+  float* stats = fold ? at<float>(e, p.stats) : nullptr;
+  auto resid_gemm = [&](const void* a, const void* w, const float* bias, int K, float alpha, bool producer) -> int {
+    rs::GemmArgs g{a, w, bias, x, x, M, d, K, RS_EPI_RESID_F32, alpha};
+    if (producer) { g.stats_out = stats; g.xb = xn; g.stats_slots = fold_slots(d); }
+    return gemm_args(e, g, s);
+  };
+  auto consumer = [&](rs::GemmArgs& g, const void* wf, const float* fc, const float* fd) {
+    g.w = wf; g.bias = nullptr; g.fold_c = fc; g.fold_d = fd; g.stats_in = stats; g.stats_slots = fold_slots(d); g.fold_n = d; g.ln_eps = c.ln_eps;
+  };
   for (int i = 0; i < n_layers; ++i) {
     const LayerW& L = e->layers[i];
     RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
-    RS_TRY(gemm(e, hb, L.ff1_w2, L.ff1_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
-    RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(resid_gemm(hb, L.ff1_w2, L.ff1_b2, c.d_ff, 0.5f, fold));
+    if (!fold) RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
     aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt; aa.bd_pitch = kBdSkewPitch;
     // RS_ATTN_MODE=1 keeps the mma.sync kernels (also the path for windows wider than 128)
@@ -366,9 +391,12 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     if (attn_tc) {     // q | k row-major, V transposed (keys contiguous) for the tensor-core kernel's P.V product
       rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_QKV_VT, 1.f};
       g.out2 = at<void>(e, p.vt); g.split = 2 * d; g.ld2 = p.ld_vt;
+      if (fold) consumer(g, L.wqkv_f, L.qkv_c, L.qkv_d);
       RS_TRY(gemm_args(e, g, s));
     } else {
-      RS_TRY(gemm(e, xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f, s));
+      rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f};
+      if (fold) consumer(g, L.wqkv_f, L.qkv_c, L.qkv_d);
+      RS_TRY(gemm_args(e, g, s));
     }
     {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
       rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16, 1.f};
@@ -383,14 +411,22 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     }
     if (attn_tc) RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);
     else RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
-    RS_TRY(gemm(e, ab, L.wo, L.bo, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
-    RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
-    RS_TRY(gemm(e, xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f, s));
+    RS_TRY(resid_gemm(ab, L.wo, L.bo, d, 1.f, fold));
+    if (!fold) RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    {
+      rs::GemmArgs g{xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f};
+      if (fold) consumer(g, L.pw1_wf, L.pw1_c, L.pw1_d);
+      RS_TRY(gemm_args(e, g, s));
+    }
     RS_K(e, rs::launch_conv_dw(ab, cb, L.dw_w, L.dw_shift, enc_len, B, p.T3, d, c.conv_kernel, s), 1);
-    RS_TRY(gemm(e, cb, L.pw2_w, L.pw2_b, x, x, M, d, d, RS_EPI_RESID_F32, 1.f, s));
-    RS_K(e, rs::launch_layernorm(x, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
-    RS_TRY(gemm(e, xn, L.ff2_w1, L.ff2_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
-    RS_TRY(gemm(e, hb, L.ff2_w2, L.ff2_b2, x, x, M, d, c.d_ff, RS_EPI_RESID_F32, 0.5f, s));
+    RS_TRY(resid_gemm(cb, L.pw2_w, L.pw2_b, d, 1.f, fold));
+    if (!fold) RS_K(e, rs::launch_layernorm(x, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    {
+      rs::GemmArgs g{xn, L.ff2_w1, L.ff2_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f};
+      if (fold) consumer(g, L.ff2_w1f, L.ff2_c, L.ff2_d);
+      RS_TRY(gemm_args(e, g, s));
+    }
+    RS_TRY(resid_gemm(hb, L.ff2_w2, L.ff2_b2, c.d_ff, 0.5f, false));
     if (i + 1 < n_layers) {   // norm_out chained with the next layer's norm_feed_forward1
       const LayerW& Ln = e->layers[i + 1];
       RS_K(e, rs::launch_layernorm(x, L.ln_out_g, L.ln_out_b, x, xn, Ln.ln_ff1_g, Ln.ln_ff1_b, M, d, c.ln_eps, s), 1);
@@ -454,6 +490,10 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   rs_engine* e = new rs_engine();
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount;
   for (int i = 0; i < n_weights; ++i) e->w[weights[i].name] = Tensor{weights[i].dev_ptr, weights[i].dtype, weights[i].numel};
+  {   // RS_LN_FOLD=1: EXPERIMENT, unmeasured -- fold three of the five LayerNorms of a layer into their consumer GEMMs
+    const char* f = getenv("RS_LN_FOLD");
+    e->ln_fold = f != nullptr && atoi(f) == 1 && cfg->d_model % 256 == 0 && e->w.count("L0.att.wqkv.fold") != 0;
+  }
   int r = bind_weights(e);
   if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }
   e->ev_ok = true;

@@ -41,6 +41,20 @@ struct GemmDev {
   int n_batch, a_col_stride, w_row_stride, bias_stride, out_col_stride;
   void* out2; int split, ld2;    // RS_EPI_QKV_VT
 };
+// LayerNorm fold (RS_LN_FOLD experiment, see GemmArgs): the extra fields live in a derived struct that only the EG 3 / 4
+// instances take, so the kernel parameter block -- and with it the generated code -- of the default instances is untouched.
+struct GemmDevFold : GemmDev {
+  const float* fold_c; const float* fold_d; const float* stats_in; float* stats_out; void* xb; int stats_slots; float fold_inv_n; float ln_eps;
+};
+template <int EG> struct DevOf { using type = GemmDev; };
+template <> struct DevOf<3> { using type = GemmDevFold; };
+template <> struct DevOf<4> { using type = GemmDevFold; };
+
+// Per-thread state of the LayerNorm-fold epilogues: the row's (r, r * mu) for a consumer, running row sums for a producer.
+struct EpiRow {
+  float r = 1.f, rm = 0.f;
+  float rs[8], rss[8];
+};
 
 template <int BN>
 struct GemmCfg {
@@ -78,12 +92,21 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
 // are conflict-free for the row-per-lane writes and the 4-rows-per-instruction reads, the swizzled form fits 4 KB per warp,
 // which is what leaves room for a 6th pipeline stage (RS_GEMM_STAGES=6 experiment).
 template <int EG, bool SWZ = false>
-__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
-                                               int col0, int bt, const float4 (&rr)[8]) {
+__device__ __forceinline__ void epilogue_store(const typename DevOf<EG>::type& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
+                                               int col0, int bt, const float4 (&rr)[8], EpiRow& er) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias != nullptr) {
+  if constexpr (EG == 3) {                                     // folded LayerNorm: y = r * acc - r * mu * c[n] + d[n]
+    const float4* c4 = reinterpret_cast<const float4*>(p.fold_c + col0);
+    const float4* d4 = reinterpret_cast<const float4*>(p.fold_d + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 c = __ldg(c4 + j), dd = __ldg(d4 + j);
+      v[4 * j] = fmaf(er.r, v[4 * j], fmaf(-er.rm, c.x, dd.x)); v[4 * j + 1] = fmaf(er.r, v[4 * j + 1], fmaf(-er.rm, c.y, dd.y));
+      v[4 * j + 2] = fmaf(er.r, v[4 * j + 2], fmaf(-er.rm, c.z, dd.z)); v[4 * j + 3] = fmaf(er.r, v[4 * j + 3], fmaf(-er.rm, c.w, dd.w));
+    }
+  } else if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -94,7 +117,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
   const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
   uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
   int epi = p.epilogue;
-  if constexpr (EG == 1) {
+  if constexpr (EG == 1 || EG == 3) if (EG == 1 || p.epilogue == RS_EPI_QKV_VT) {
     if (col0 < p.split) {
       epi = RS_EPI_BIAS_BF16;                                  // q | k columns: plain row-major bf16
     } else {
@@ -138,6 +161,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
   }
   switch (epi) {
     case RS_EPI_BIAS_F16: {                                    // same 16-bit store pattern as the bf16 epilogues
+      if constexpr (EG == 3) break;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(stage_u + lane * 20 + 4 * j) =
@@ -202,9 +226,9 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       break;
     }
     default: {  // RS_EPI_RESID_F32 / RS_EPI_BIAS_F32
-#pragma unroll
+      if constexpr (EG == 3) break;                            // fold consumers write bf16 only (launcher-checked)
       constexpr int LD = SWZ ? 32 : kStageLd;
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j)                              // (fully unrolled by the compiler: constant trip count)
         *reinterpret_cast<float4*>(stage + lane * LD + 4 * (SWZ ? (j ^ (lane & 7)) : j)) =
             make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
       __syncwarp();
@@ -217,6 +241,15 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
         if (add) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
         if (row < p.M)
           *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 + cw) = a;
+        if constexpr (EG == 4) {                               // producer of a folded LayerNorm: bf16 copy + row sums
+          if (row < p.M)
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.xb) + static_cast<size_t>(row) * p.ldo + col0 + cw) =
+                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+          float s1 = (a.x + a.y) + (a.z + a.w), s2 = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+#pragma unroll
+          for (int o = 1; o <= 4; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+          er.rs[i] += s1; er.rss[i] += s2;                     // the 8 lanes of a row all hold its chunk sums
+        }
       }
       break;
     }
@@ -335,7 +368,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur);
+        EpiRow er_unused;
+        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur, er_unused);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -372,7 +406,7 @@ struct Gemm2Cfg {
 
 template <int BN, int EG, int ST = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const typename DevOf<EG>::type p) {
   using Cfg = Gemm2Cfg<BN, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -467,9 +501,25 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (tile % num_n) * BN;
       const int tile_row0 = m0 + q * 32;
-      const bool pre = p.epilogue == RS_EPI_RESID_F32;
+      const bool pre = EG != 3 && p.epilogue == RS_EPI_RESID_F32;   // a fold consumer never carries a residual
       float4 rr[8], cur[8];
       resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
+      EpiRow er;
+      if constexpr (EG == 3) {                                   // (mu, r) of this thread's row from the producer's partial sums
+        const int row = tile_row0 + lane;
+        float s1 = 0.f, s2 = 0.f;
+        if (row < p.M) {
+          const float2* st = reinterpret_cast<const float2*>(p.stats_in) + static_cast<size_t>(row) * p.stats_slots;
+          for (int k = 0; k < p.stats_slots; ++k) { const float2 t = __ldg(st + k); s1 += t.x; s2 += t.y; }
+        }
+        const float mu = s1 * p.fold_inv_n;
+        er.r = rsqrtf(fmaxf(s2 * p.fold_inv_n - mu * mu, 0.f) + p.ln_eps);
+        er.rm = er.r * mu;
+      }
+      if constexpr (EG == 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { er.rs[i] = 0.f; er.rss[i] = 0.f; }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -481,7 +531,17 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store<EG, Cfg::kSwz>(p, r, stage, tile_row0, lane, col0, 0, cur);
+        epilogue_store<EG, Cfg::kSwz>(p, r, stage, tile_row0, lane, col0, 0, cur, er);
+      }
+      if constexpr (EG == 4) {                                   // one (sum, sum of squares) per row and (column tile, half)
+        if ((lane & 7) == 0) {
+          const int slot = (n0 / BN) * 2 + half;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = tile_row0 + i * 4 + (lane >> 3);
+            if (row < p.M) reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(row) * p.stats_slots + slot] = make_float2(er.rs[i], er.rss[i]);
+          }
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -624,7 +684,8 @@ gemm_bf16_tn_4cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         uint32_t rg[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, rg);
         tmem_ld_wait();
-        epilogue_store<EG>(p, rg, stage, tile_row0, lane, col0, 0, cur);
+        EpiRow er_unused;
+        epilogue_store<EG>(p, rg, stage, tile_row0, lane, col0, 0, cur, er_unused);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -675,6 +736,7 @@ static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint6
 }
 
 inline int epilogue_group(int epilogue) { return epilogue == RS_EPI_QKV_VT ? 1 : (epilogue == RS_EPI_BIAS_F16_SKEW ? 2 : 0); }
+inline bool ln_fold_args(const GemmArgs& g) { return g.fold_c != nullptr || g.stats_out != nullptr; }
 
 template <int BN, int EG>
 static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
@@ -725,7 +787,26 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
+  typename DevOf<EG>::type p{};
+  static_cast<GemmDev&>(p) = GemmDev{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
+  if constexpr (EG == 3 || EG == 4) {
+    p.fold_c = g.fold_c; p.fold_d = g.fold_d; p.stats_in = g.stats_in; p.stats_out = g.stats_out; p.xb = g.xb;
+    p.stats_slots = g.stats_slots; p.fold_inv_n = g.fold_n > 0 ? 1.0f / static_cast<float>(g.fold_n) : 0.f; p.ln_eps = g.ln_eps;
+  }
+  if constexpr (EG == 4) {
+    if (g.epilogue != RS_EPI_RESID_F32 || g.xb == nullptr || g.stats_slots != 2 * (g.N / BN)) {
+      snprintf(err, 256, "LayerNorm-fold producer needs RS_EPI_RESID_F32, xb and stats_slots == 2 * N / %d (got %d)", BN, g.stats_slots);
+      return cudaErrorInvalidValue;
+    }
+  }
+  if constexpr (EG == 3) {
+    const bool bf16_out = g.epilogue == RS_EPI_BIAS_BF16 || g.epilogue == RS_EPI_BIAS_RELU_BF16 || g.epilogue == RS_EPI_BIAS_SWISH_BF16 ||
+                          g.epilogue == RS_EPI_BIAS_GLU_BF16 || g.epilogue == RS_EPI_QKV_VT;
+    if (g.fold_d == nullptr || g.stats_in == nullptr || g.stats_slots <= 0 || g.fold_n <= 0 || !bf16_out) {
+      snprintf(err, 256, "LayerNorm-fold consumer needs fold_c, fold_d, stats_in, stats_slots, fold_n and a bf16 epilogue");
+      return cudaErrorInvalidValue;
+    }
+  }
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
@@ -740,6 +821,8 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   // RS_GEMM_STAGES=6: EXPERIMENT (not yet measured) -- a 6-deep ring for the common epilogues, made possible by the 4 KB
   // swizzled fp32 staging; the default is the 5-deep ring with padded staging
   static const int stages = getenv("RS_GEMM_STAGES") ? atoi(getenv("RS_GEMM_STAGES")) : 0;
+  if (g.fold_c != nullptr) return launch_2cta_eg<BN, 3>(g, num_sms, stream, err);      // RS_LN_FOLD experiment (consumer)
+  if (g.stats_out != nullptr) return launch_2cta_eg<BN, 4>(g, num_sms, stream, err);   // RS_LN_FOLD experiment (producer)
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
     case 2: return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
@@ -811,6 +894,10 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
   }
   if (g.epilogue == RS_EPI_QKV_VT && (g.out2 == nullptr || g.split % 32 || g.ld2 % 8 || g.ld2 < ((g.M + 255) / 256) * 256 || g.n_batch > 1)) {
     snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, ld2 >= M rounded up to 256");
+    return cudaErrorInvalidValue;
+  }
+  if (ln_fold_args(g) && !(g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0)) {
+    snprintf(err, 256, "gemm: the LayerNorm-fold epilogues exist in the 2-CTA kernel only (RS_GEMM_MODE=1, N %% 256 == 0)");
     return cudaErrorInvalidValue;
   }
   // kernel choice depends on N only (never on M): a row's result must not depend on the batch it sits in

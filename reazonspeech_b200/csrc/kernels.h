@@ -19,6 +19,13 @@ struct GemmArgs {
   int n_batch = 1, a_col_stride = 0, w_row_stride = 0, bias_stride = 0, out_col_stride = 0;
   // RS_EPI_QKV_VT: columns >= split go, transposed, to out2 (bf16 [N - split, ld2]; ld2 >= M rounded up to 256)
   void* out2 = nullptr; int split = 0, ld2 = 0;
+  // EXPERIMENT (RS_LN_FOLD=1): LayerNorm folded into its consumer GEMM.
+  //   producer (RS_EPI_RESID_F32 with stats_out): also writes bf16(x) to xb and, per row and per (column tile, column half),
+  //     the partial sums (sum x, sum x^2) of its 128 columns to stats_out[row][stats_slots][2];
+  //   consumer (fold_c != nullptr): A = bf16(x), W = bf16(W * gamma); the epilogue applies
+  //     y = r * acc - r * mu * fold_c[n] + fold_d[n] with (mu, r) of the row from stats_in, then its usual activation.
+  const float* fold_c = nullptr; const float* fold_d = nullptr; const float* stats_in = nullptr;
+  float* stats_out = nullptr; void* xb = nullptr; int stats_slots = 0; int fold_n = 0; float ln_eps = 1e-5f;
 };
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
