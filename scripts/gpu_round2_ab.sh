@@ -1,0 +1,35 @@
+#!/bin/bash
+# First GPU call of round 2: validate and A/B the experiments that round 1 left unmeasured.
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_round2_ab.sh'
+# Writes gpurun_out/ab_<variant>.json (one bench line each) and gpurun_out/ab_summary.txt.
+# An experiment changes the numerics slightly, which moves the synthetic checkpoint's token count:
+# compare ms of the ENCODER stages and the per-kernel table, not only the headline.
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+mkdir -p gpurun_out
+echo "=== default suite"; timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
+echo "=== experiments (parity)"; RS_RUN_EXPERIMENTS=1 timeout -k 10 600 python -m pytest tests/experiments -m gpu -q -s -p no:cacheprovider 2>&1 | grep -E "utt|passed|failed|Error" | cut -c1-200
+run() {   # name, env assignments...
+  local name=$1; shift
+  echo "=== bench $name"
+  env "$@" timeout -k 10 600 python bench.py --steps 10 --warmup 3 > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err || tail -n 5 gpurun_out/ab_$name.err
+}
+run default RS_NONE=1
+run stages6 RS_GEMM_STAGES=6
+run lnfold RS_LN_FOLD=1
+run lnfold_stages6 RS_LN_FOLD=1 RS_GEMM_STAGES=6
+python - <<'PY' | tee gpurun_out/ab_summary.txt
+import json, glob, os
+rows = []
+for f in sorted(glob.glob("gpurun_out/ab_*.json")):
+    try:
+        j = json.loads(open(f).read().strip().splitlines()[-1])
+    except Exception as e:
+        print(os.path.basename(f), "unreadable:", e); continue
+    k = j.get("kernel_ms", {})
+    gem = sum(v["ms"] for n, v in k.items() if n.startswith("gemm"))
+    ln = sum(v["ms"] for n, v in k.items() if "layernorm" in n)
+    rows.append((os.path.basename(f)[3:-5], j["value"], j["e2e"]["value"], j["ms_per_step"], gem, ln, j.get("roofline", {}).get("frac")))
+print(f"{'variant':18s} {'RTFx':>9s} {'e2e':>9s} {'ms/step':>8s} {'gemm ms':>8s} {'LN ms':>7s} {'gemm frac':>9s}")
+for r in rows:
+    print(f"{r[0]:18s} {r[1]:9.0f} {r[2]:9.0f} {r[3]:8.2f} {r[4]:8.2f} {r[5]:7.2f} {r[6] if r[6] is None else round(r[6], 3)!s:>9s}")
+PY
