@@ -18,7 +18,10 @@ LayerNorm order: encoder output relative L2 1e-5).  Parakeet has full relative-p
 so the pin covers the local-attention code path with T <= w + 1 and no global token.  NOT covered, and
 still recalled (R) rather than verified: the global-token wiring of
 RelPositionMultiHeadAttentionLongformer, and the RNN-T prediction network / joint / greedy loop
-(``max_symbols``) -- standard LSTM-transducer arithmetic restated from NeMo's modules/rnnt.py.
+(``max_symbols``) -- standard LSTM-transducer arithmetic restated from NeMo's modules/rnnt.py.  For the
+latter, tests/test_oracle_cpu.py::test_greedy_matches_stock_module_implementation at least ties the hand-written
+LSTM cell, gate order, bias handling and joint to stock torch.nn modules (nn.LSTM is the module NeMo wraps) built
+under the checkpoint's parameter names and loaded with strict=True; the loop's control flow stays recalled (R).
 The reference-owned ``decode_hypothesis`` is pinned separately by importing the reference's decode.py
 (tests/golden/make_decode_golden.py).
 

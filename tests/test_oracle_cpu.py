@@ -124,3 +124,45 @@ def test_pack_weights_layouts(tiny_cfg, tiny_sd):
     y2 = torch.nn.functional.conv1d(x, w.T.unsqueeze(1).contiguous(), p["L0.conv.dw.shift"], padding=4, groups=d)
     assert (y - y2).abs().max() < 1e-4
     assert p["pred.lstm.w"].shape == (4 * tiny_cfg.pred_hidden, 2 * tiny_cfg.pred_hidden)
+
+
+class _ModuleRnnt(torch.nn.Module):
+    """The prediction and joint networks built from stock torch.nn modules under the CHECKPOINT's parameter names
+    (decoder.prediction.embed / .dec_rnn.lstm, joint.enc / .pred / .joint_net = [ReLU, Dropout, Linear]),
+    so that the state dict loads with strict=True.  torch.nn.LSTM is the very module NeMo wraps; this pins the oracle's
+    hand-written cell, gate order and bias handling to the library implementation and its key layout."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        pred = torch.nn.Module()
+        pred.embed = torch.nn.Embedding(cfg.n_classes, cfg.pred_hidden, padding_idx=cfg.blank)
+        rnn = torch.nn.Module()
+        rnn.lstm = torch.nn.LSTM(cfg.pred_hidden, cfg.pred_hidden, num_layers=1)
+        pred.dec_rnn = rnn
+        self.decoder = torch.nn.Module()
+        self.decoder.prediction = pred
+        self.joint = torch.nn.Module()
+        self.joint.enc = torch.nn.Linear(cfg.d_model, cfg.joint_hidden)
+        self.joint.pred = torch.nn.Linear(cfg.pred_hidden, cfg.joint_hidden)
+        self.joint.joint_net = torch.nn.Sequential(torch.nn.ReLU(), torch.nn.Dropout(0.2), torch.nn.Linear(cfg.joint_hidden, cfg.n_classes))
+
+
+def test_greedy_matches_stock_module_implementation(tiny_cfg, tiny_sd):
+    cfg = tiny_cfg
+    m = _ModuleRnnt(cfg).eval()
+    m.load_state_dict({k: v for k, v in tiny_sd.items() if k.startswith(("decoder.", "joint."))}, strict=True)
+    enc = 2.0 * torch.randn(60, cfg.d_model, generator=torch.Generator().manual_seed(5))
+    ref = O.rnnt_greedy(enc, tiny_sd, cfg)
+    assert 0 < len(ref.tokens) < 60 * cfg.max_symbols
+    with torch.no_grad():
+        f = m.joint.enc(enc)
+        tokens, frames, state, last = [], [], None, cfg.blank            # SOS = blank, whose embedding row is zero
+        for t in range(enc.shape[0]):
+            for _ in range(cfg.max_symbols):
+                g, new_state = m.decoder.prediction.dec_rnn.lstm(m.decoder.prediction.embed(torch.tensor([[last]])), state)
+                logits = m.joint.joint_net(f[t] + m.joint.pred(g[0, 0]))
+                k = int(logits.argmax())
+                if k == cfg.blank:
+                    break
+                tokens.append(k); frames.append(t); state, last = new_state, k
+    assert tokens == ref.tokens and frames == ref.frames
