@@ -72,6 +72,9 @@ struct rs_engine {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int U_cap = 0;
+  // RS_GEMM_SPLITK=1 (experiment, unmeasured): engine-owned workspace of the split-K tail of the 2-CTA GEMM
+  float* sk_partials = nullptr;
+  unsigned int* sk_flags = nullptr;
   bool ln_fold = false;   // RS_LN_FOLD=1 and the folded tensors are in the weight table (experiment, unmeasured)
   mutable char err[512] = "";
   int64_t launches = 0;
@@ -269,7 +272,9 @@ void ktime_end(rs_engine* e) {
   cudaEventRecord(e->k_ev[2 * e->k_tag.size() - 1], e->cur_stream);
 }
 
-int gemm_args(rs_engine* e, const rs::GemmArgs& g, cudaStream_t s) {
+int gemm_args(rs_engine* e, const rs::GemmArgs& g_in, cudaStream_t s) {
+  rs::GemmArgs g = g_in;
+  g.sk_partials = e->sk_partials; g.sk_flags = e->sk_flags;      // nullptr unless RS_GEMM_SPLITK=1
   const int M = g.M, N = g.N, K = g.K;
   char msg[256] = "";
   bool timed = false;
@@ -496,6 +501,17 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   }
   int r = bind_weights(e);
   if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }
+  if (const char* sk = getenv("RS_GEMM_SPLITK"); sk != nullptr && atoi(sk) == 1) {
+    const int ncl = e->num_sms / 2;
+    if (cudaMalloc(&e->sk_partials, rs::splitk_partial_bytes(ncl)) != cudaSuccess ||
+        cudaMalloc(&e->sk_flags, rs::splitk_flag_bytes(ncl)) != cudaSuccess ||
+        cudaMemset(e->sk_flags, 0, rs::splitk_flag_bytes(ncl)) != cudaSuccess) {
+      snprintf(g_create_error, sizeof g_create_error, "RS_GEMM_SPLITK: cannot allocate the split-K workspace (%s)", cudaGetErrorString(cudaGetLastError()));
+      cudaFree(e->sk_partials); cudaFree(e->sk_flags);
+      delete e;
+      return RS_ERR_CUDA;
+    }
+  }
   e->ev_ok = true;
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) e->ev_ok = false;
   e->copy_ok = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -511,6 +527,8 @@ void rs_engine_destroy(rs_engine* e) {
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
   for (auto& ev : e->k_ev) cudaEventDestroy(ev);
+  cudaFree(e->sk_partials);
+  cudaFree(e->sk_flags);
   delete e;
 }
 
@@ -690,6 +708,25 @@ int rs_enable_kernel_timing(rs_engine* e, int on) {
 }
 
 // Text summary "name\tcount\ttotal_ms\n..." of every launch since rs_enable_kernel_timing(e, 1); resets the log.
+// Host-only: the work list of the split-K tail experiment (kernels.h) for `num_tiles` tiles on `ncl` clusters, as rows
+// (cluster, position, tile, k0, k1, kind, part).  Returns the number of rows (also when it exceeds max_rows).
+int rs_debug_splitk_schedule(int num_tiles, int ncl, int num_k, int32_t* rows7, int max_rows, int* split) {
+  if (num_tiles <= 0 || ncl <= 0 || num_k <= 0) return -1;
+  const rs::SplitKPlan plan = rs::splitk_plan(num_tiles, ncl, num_k);
+  if (split) *split = plan.S;
+  int n = 0;
+  for (int cid = 0; cid < ncl; ++cid) {
+    rs::SplitKItem w;
+    for (int it = 0; rs::splitk_item(plan, it, cid, ncl, num_k, w); ++it, ++n) {
+      if (rows7 != nullptr && n < max_rows) {
+        int32_t* r = rows7 + 7 * n;
+        r[0] = cid; r[1] = it; r[2] = w.tile; r[3] = w.k0; r[4] = w.k1; r[5] = w.kind; r[6] = w.part;
+      }
+    }
+  }
+  return n;
+}
+
 int rs_kernel_timing(rs_engine* e, char* buf, int buf_bytes) {
   if (!e || !buf || buf_bytes <= 0) return RS_ERR_INVALID_ARG;
   RS_CUDA(e, cudaDeviceSynchronize());

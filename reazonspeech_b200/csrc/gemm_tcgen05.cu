@@ -568,6 +568,179 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 // receives 32 KB of A per k-block for 16 KB of L2 reads: 48 KB instead of 64 KB per pair and k-block.
 // Barriers: full[] per pair leader as before (every destination credits its own leader); empty[] now counts the commits of
 // BOTH pairs (a stage is rewritten in two pairs' shared memory at once), each commit multicast to all four CTAs.
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (RS_GEMM_SPLITK=1, unmeasured): the 2-CTA kernel with the last, partial wave of tiles split along K
+// (kernels.h: SplitKPlan / splitk_item).  A separate kernel so that the default instances stay untouched; common
+// epilogues only (EG 0).  A work item is a (tile, k range): the three roles walk the same item list.
+struct GemmDevSk : GemmDev {
+  float* sk_partials; unsigned int* sk_flags; SplitKPlan plan;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_2cta_sk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDevSk p) {
+  using Cfg = Gemm2Cfg<BN, 0>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
+  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
+
+  const int warp = warp_id_uniform();
+  const int lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_n = p.N / BN;
+  const int num_k = p.K / BK;
+  const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
+  const SplitKPlan plan = p.plan;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      SplitKItem w;
+      for (int it = 0; splitk_item(plan, it, cid, ncl, num_k, w); ++it) {
+        const int m0 = (w.tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
+        const int n0 = (w.tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = w.k0; kb < w.k1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          tma_load_2d_2sm(smem_a(stage), &tm_a, kb * BK, m0, full_bar(stage));
+          tma_load_2d_2sm(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          else mbar_arrive_remote(full_bar(stage), 0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      SplitKItem w;
+      for (int it = 0; splitk_item(plan, it, cid, ncl, num_k, w); ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = w.k0; kb < w.k1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_a(stage));
+          const uint64_t db = umma_desc_k_sw128(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb != w.k0 || k != 0) ? 1u : 0u);
+          umma_commit_2sm(empty_bar(stage));
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own TMEM half)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * Cfg::kStagingPerWarp);
+    SplitKItem w;
+    for (int it = 0; splitk_item(plan, it, cid, ncl, num_k, w); ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m0 = (w.tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (w.tile % num_n) * BN;
+      const int tile_row0 = m0 + q * 32;
+      const bool pre = w.kind != 1 && p.epilogue == RS_EPI_RESID_F32;
+      float4 rr[8], cur[8];
+      resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);
+      // this warp's slice of a tail tile's partial accumulators: [tail tile][part - 1][rank][warp][chunk][j][lane]
+      auto partial = [&](int part, int ci) {
+        return p.sk_partials + ((((static_cast<size_t>(w.tail_idx) * (plan.S - 1) + (part - 1)) * 2 + rank) * kEpiWarps + (warp - 2)) * (BN / 64) + ci) * 1024 + lane;
+      };
+      unsigned int* flag = p.sk_flags + (static_cast<size_t>(w.tail_idx) * 2 + rank) * kEpiWarps + (warp - 2);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      if (w.kind == 2) {                                         // owner: every contributor of this warp's slice has published
+        if (lane == 0) {
+          unsigned int v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          } while (v < static_cast<unsigned int>(plan.S - 1));
+        }
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int chunk = half, ci = 0; chunk < BN / 32; chunk += 2, ++ci) {
+        const int col0 = n0 + chunk * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+        resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+        tmem_ld_wait();
+        if (w.kind == 1) {                                       // contributor: raw accumulators, coalesced over the lanes
+          float* dst = partial(w.part, ci);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dst + j * 32, __uint_as_float(r[j]));
+          continue;
+        }
+        if (w.kind == 2) {
+          for (int part = 1; part < plan.S; ++part) {            // fixed order: the sum does not depend on timing
+            const float* src = partial(part, ci);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(src + j * 32));
+          }
+        }
+        EpiRow er_unused;
+        epilogue_store<0, Cfg::kSwz>(p, r, stage, tile_row0, lane, col0, 0, cur, er_unused);
+      }
+      if (w.kind == 1) {                                         // publish: data first, then the flag
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+      } else if (w.kind == 2) {
+        __syncwarp();
+        if (lane == 0) *flag = 0u;                               // ready for the next launch (launches are stream-ordered)
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
 template <int BN, int EG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_4cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
@@ -816,11 +989,44 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
   return e;
 }
 
+// RS_GEMM_SPLITK experiment: true when the split-K kernel took the launch (rc then holds its result)
+template <int BN>
+static bool try_launch_2cta_sk(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err, cudaError_t* rc) {
+  using Cfg = Gemm2Cfg<BN, 0>;
+  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
+  const int clusters = num_sms / 2;                                // all of them: fewer tiles than clusters is a tail, too
+  const SplitKPlan plan = splitk_plan(tiles, clusters, g.K / BK);
+  if (plan.S <= 1 || g.K / BK < 32) return false;                  // nothing to gain, or k ranges too short to pay for the fix-up
+  static bool attr_set = false;
+  if (!attr_set) {
+    *rc = cudaFuncSetAttribute(gemm_bf16_tn_2cta_sk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (*rc != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta split-K smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(*rc)); return true; }
+    attr_set = true;
+  }
+  CUtensorMap tm_a, tm_b;
+  const int lda = g.lda > 0 ? g.lda : g.K;
+  const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
+  *rc = cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return true;
+  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return true;
+  GemmDevSk p{};
+  static_cast<GemmDev&>(p) = GemmDev{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
+  p.sk_partials = g.sk_partials; p.sk_flags = g.sk_flags; p.plan = plan;
+  gemm_bf16_tn_2cta_sk_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  *rc = cudaGetLastError();
+  if (*rc != cudaSuccess) snprintf(err, 256, "gemm 2cta split-K launch (M=%d N=%d K=%d S=%d): %s", g.M, g.N, g.K, plan.S, cudaGetErrorString(*rc));
+  return true;
+}
+
 template <int BN>
 static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   // RS_GEMM_STAGES=6: EXPERIMENT (not yet measured) -- a 6-deep ring for the common epilogues, made possible by the 4 KB
   // swizzled fp32 staging; the default is the 5-deep ring with padded staging
   static const int stages = getenv("RS_GEMM_STAGES") ? atoi(getenv("RS_GEMM_STAGES")) : 0;
+  if (g.sk_partials != nullptr && g.sk_flags != nullptr && !ln_fold_args(g) && epilogue_group(g.epilogue) == 0 && stages != 6) {
+    cudaError_t rc;                                                                       // RS_GEMM_SPLITK experiment
+    if (try_launch_2cta_sk<BN>(g, num_sms, stream, err, &rc)) return rc;
+  }
   if (g.fold_c != nullptr) return launch_2cta_eg<BN, 3>(g, num_sms, stream, err);      // RS_LN_FOLD experiment (consumer)
   if (g.stats_out != nullptr) return launch_2cta_eg<BN, 4>(g, num_sms, stream, err);   // RS_LN_FOLD experiment (producer)
   switch (epilogue_group(g.epilogue)) {

@@ -26,7 +26,50 @@ struct GemmArgs {
   //     y = r * acc - r * mu * fold_c[n] + fold_d[n] with (mu, r) of the row from stats_in, then its usual activation.
   const float* fold_c = nullptr; const float* fold_d = nullptr; const float* stats_in = nullptr;
   float* stats_out = nullptr; void* xb = nullptr; int stats_slots = 0; int fold_n = 0; float ln_eps = 1e-5f;
+  // EXPERIMENT (RS_GEMM_SPLITK=1): workspace of the split-K tail (see SplitKPlan below); nullptr = off
+  float* sk_partials = nullptr; unsigned int* sk_flags = nullptr;
 };
+// EXPERIMENT (RS_GEMM_SPLITK=1): split-K of the LAST, partial wave of a persistent GEMM.
+// With T tiles on C clusters the last wave runs T mod C tiles while the other clusters idle (N = 1024 at 32 clips:
+// 196 tiles on 74 clusters = 2.65 waves, paid as 3).  The tail tiles are cut into S parts along K; parts 1..S-1
+// ("contributors") dump their fp32 accumulators to a workspace and raise a flag, part 0 (the "owner") adds them in a
+// fixed order and runs the normal epilogue: deterministic, no atomics on data.  Contributors are scheduled before
+// owners and never wait, so an owner only ever waits for clusters that are making progress.
+struct SplitKItem { int tile, k0, k1, kind, tail_idx, part; };   // kind: 0 full tile, 1 contributor, 2 owner
+struct SplitKPlan { int full_rounds, tail, S; };
+#if defined(__CUDACC__)
+#define RS_HD __host__ __device__
+#else
+#define RS_HD
+#endif
+// S in 1..4 minimising ceil(tail * S / C) / S, the duration of the tail in tile times (ties: the smaller S).
+RS_HD inline SplitKPlan splitk_plan(int num_tiles, int ncl, int num_k) {
+  SplitKPlan pl{num_tiles / ncl, num_tiles % ncl, 1};
+  if (pl.tail == 0) return pl;
+  int best_num = 1, best_den = 1;                                 // cost of S = 1 is 1 tile time
+  for (int s = 2; s <= 4 && s * 8 <= num_k; ++s) {
+    const int rounds = (pl.tail * s + ncl - 1) / ncl;             // cost = rounds / s
+    if (rounds * best_den < best_num * s) { best_num = rounds; best_den = s; pl.S = s; }
+  }
+  return pl;
+}
+// it-th work item of cluster cid; false when the cluster is done.
+RS_HD inline bool splitk_item(const SplitKPlan& pl, int it, int cid, int ncl, int num_k, SplitKItem& w) {
+  if (it < pl.full_rounds) { w = SplitKItem{cid + it * ncl, 0, num_k, 0, 0, 0}; return true; }
+  const int g = cid + (it - pl.full_rounds) * ncl;
+  if (g >= pl.tail * pl.S) return false;
+  const int n_contrib = pl.tail * (pl.S - 1);
+  if (g < n_contrib) { w.kind = 1; w.tail_idx = g % pl.tail; w.part = 1 + g / pl.tail; }
+  else { w.kind = pl.S > 1 ? 2 : 0; w.tail_idx = g - n_contrib; w.part = 0; }
+  w.tile = pl.full_rounds * ncl + w.tail_idx;
+  w.k0 = static_cast<int>(static_cast<long long>(w.part) * num_k / pl.S);
+  w.k1 = static_cast<int>(static_cast<long long>(w.part + 1) * num_k / pl.S);
+  return true;
+}
+// Workspace of the split-K experiment: partial accumulators [tail < C][S - 1 <= 3][256 x 256] f32, then the flags.
+inline size_t splitk_partial_bytes(int ncl) { return static_cast<size_t>(ncl) * 3 * 256 * 256 * 4; }
+inline size_t splitk_flag_bytes(int ncl) { return static_cast<size_t>(ncl) * 2 * 8 * 4; }
+
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
 

@@ -49,7 +49,7 @@ EXPORTS = [
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
-    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
+    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles", "rs_debug_splitk_schedule",
 ]
 
 
@@ -92,6 +92,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_debug_decode_cycles.restype = ip
     lib.rs_enable_kernel_timing.argtypes = [vp, ip]
     lib.rs_enable_kernel_timing.restype = ip
+    lib.rs_debug_splitk_schedule.argtypes = [ip, ip, ip, vp, ip, C.POINTER(C.c_int)]
+    lib.rs_debug_splitk_schedule.restype = ip
     lib.rs_kernel_timing.argtypes = [vp, C.c_char_p, ip]
     lib.rs_kernel_timing.restype = ip
     lib.rs_enable_gemm_timing.argtypes = [vp, ip]

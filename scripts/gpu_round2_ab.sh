@@ -7,7 +7,9 @@
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
 echo "=== default suite"; timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-echo "=== experiments (parity)"; RS_RUN_EXPERIMENTS=1 timeout -k 10 600 python -m pytest tests/experiments -m gpu -q -s -p no:cacheprovider 2>&1 | grep -E "utt|passed|failed|Error" | cut -c1-200
+for t in test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
+  echo "=== experiment $t"; RS_RUN_EXPERIMENTS=1 timeout -k 10 300 python -m pytest tests/experiments/$t.py -m gpu -q -s -x -p no:cacheprovider 2>&1 | grep -E "utt|rep=|passed|failed|Error|error" | cut -c1-200
+done
 run() {   # name, env assignments...
   local name=$1; shift
   echo "=== bench $name"
@@ -16,7 +18,8 @@ run() {   # name, env assignments...
 run default RS_NONE=1
 run stages6 RS_GEMM_STAGES=6
 run lnfold RS_LN_FOLD=1
-run lnfold_stages6 RS_LN_FOLD=1 RS_GEMM_STAGES=6
+run splitk RS_GEMM_SPLITK=1
+run lnfold_splitk RS_LN_FOLD=1 RS_GEMM_SPLITK=1
 python - <<'PY' | tee gpurun_out/ab_summary.txt
 import json, glob, os
 rows = []
