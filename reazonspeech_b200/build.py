@@ -33,20 +33,30 @@ def _headers_mtime() -> float:
     return max(os.path.getmtime(h) for h in hs)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ, exist_ok=True)
+# Compile-time variants of the library (EXPERIMENTS; the default library is what every test and the bench load unless
+# RS_ENGINE_VARIANT names one).  "pdl": programmatic dependent launch in the encoder's kernels, see csrc/common.cuh.
+VARIANTS = {"pdl": ["-DRS_PDL=1"]}
+
+
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    if variant and variant not in VARIANTS:
+        raise ValueError(f"unknown variant {variant!r} (known: {sorted(VARIANTS)})")
+    obj_dir = OBJ + ("_" + variant if variant else "")
+    lib = LIB.replace(".so", f"_{variant}.so") if variant else LIB
+    defines = VARIANTS.get(variant, [])
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     hm = _headers_mtime()
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hm):
             jobs.append((s, o))
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc, *ARCH, *FLAGS, "-c", s, "-o", o]
+        cmd = [nvcc, *ARCH, *FLAGS, *defines, "-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,14 +67,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             list(ex.map(compile_one, jobs))
-    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
-    if jobs or not os.path.exists(LIB):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs]
+    objs = [os.path.join(obj_dir, s.replace(".cu", ".o")) for s in SOURCES]
+    if jobs or not os.path.exists(lib):
+        cmd = [nvcc, *ARCH, "-shared", "-o", lib, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    _variant = ""
+    if "--variant" in sys.argv:
+        _variant = sys.argv[sys.argv.index("--variant") + 1]
+    print(build(force="--force" in sys.argv, verbose=True, variant=_variant))

@@ -20,6 +20,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, cons
   // Persistent: a warp walks rows (stride = warps in the grid) with the NEXT row's loads already in flight while
   // the current one is reduced and stored -- short-lived one-row warps left HBM at ~40 % (profiles/r01_v2_other_ncu.md).
   constexpr int D = 128 * NV;
+  RS_PDL_TRIGGER(); RS_PDL_WAIT();                       // (-DRS_PDL variant only) x is the previous kernel's output
   const int lane = lane_id();
   const int wstride = gridDim.x * (blockDim.x >> 5);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -87,6 +88,7 @@ layernorm_rowwarp_kernel(const float* __restrict__ x, const float* __restrict__ 
                          float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                          const float* __restrict__ g2, const float* __restrict__ b2, int rows, float eps) {
   constexpr int D = 128 * NV;
+  RS_PDL_TRIGGER(); RS_PDL_WAIT();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
@@ -147,18 +149,18 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
   if (variant != nullptr && variant[0] == 'B') {                // measured within 1 us of each other (scripts/probes/ln_probe.py)
     const dim3 gridb(need), blockb(32 * wpb);
     switch (d) {
-      case 256: layernorm_rowwarp_kernel<2><<<gridb, blockb, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-      case 512: layernorm_rowwarp_kernel<4><<<gridb, blockb, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-      case 1024: layernorm_rowwarp_kernel<8><<<gridb, blockb, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+      case 256: RS_LAUNCH(layernorm_rowwarp_kernel<2>, gridb, blockb, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+      case 512: RS_LAUNCH(layernorm_rowwarp_kernel<4>, gridb, blockb, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+      case 1024: RS_LAUNCH(layernorm_rowwarp_kernel<8>, gridb, blockb, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
       default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
   }
   const dim3 grid(need < cap ? need : cap), block(32 * wpb);
   switch (d) {
-    case 256: layernorm_kernel<2><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-    case 512: layernorm_kernel<4><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-    case 1024: layernorm_kernel<8><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 256: RS_LAUNCH(layernorm_kernel<2>, grid, block, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 512: RS_LAUNCH(layernorm_kernel<4>, grid, block, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 1024: RS_LAUNCH(layernorm_kernel<8>, grid, block, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -178,6 +180,7 @@ conv_dw_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ 
   // unpacked into the KW-row sliding window as it advances.
   constexpr int PAD = (KW - 1) / 2;
   constexpr int ROWS = TT + KW - 1;
+  RS_PDL_TRIGGER(); RS_PDL_WAIT();
   const int b = blockIdx.z;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= d) return;
@@ -221,8 +224,8 @@ cudaError_t launch_conv_dw(const void* u, void* out, const float* w, const float
   constexpr int TT = 8;
   const int threads = d / 4 < 256 ? d / 4 : 256;
   const dim3 block(threads), grid((d / 4 + threads - 1) / threads, (T_max + TT - 1) / TT, B);
-  conv_dw_kernel<9, TT><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
-                                                    w, shift, enc_len, T_max, d);
+  RS_LAUNCH((conv_dw_kernel<9, TT>), grid, block, 0, stream, static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
+            w, shift, enc_len, T_max, d);
   return cudaGetLastError();
 }
 

@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
+  RS_PDL_TRIGGER();
   // 128B-swizzled operand tiles need 1024 B alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -295,6 +296,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  RS_PDL_WAIT();                                             // (-DRS_PDL variant only) operands come from the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -409,6 +411,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const typename DevOf<EG>::type p) {
   using Cfg = Gemm2Cfg<BN, ST>;
   extern __shared__ uint8_t smem_raw[];
+  RS_PDL_TRIGGER();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -444,6 +447,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  RS_PDL_WAIT();                                             // (-DRS_PDL variant only) operands come from the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -581,6 +585,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_2cta_sk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDevSk p) {
   using Cfg = Gemm2Cfg<BN, 0>;
   extern __shared__ uint8_t smem_raw[];
+  RS_PDL_TRIGGER();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -615,6 +620,7 @@ gemm_bf16_tn_2cta_sk_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  RS_PDL_WAIT();                                             // (-DRS_PDL variant only) operands come from the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -931,7 +937,7 @@ static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t str
   GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tn_kernel<BN, EG><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  RS_LAUNCH((gemm_bf16_tn_kernel<BN, EG>), grid, kGemmThreads, Cfg::kSmemBytes, stream, tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
@@ -983,7 +989,7 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm_bf16_tn_2cta_kernel<BN, EG, ST><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  RS_LAUNCH((gemm_bf16_tn_2cta_kernel<BN, EG, ST>), 2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream, tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm 2cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
@@ -1012,7 +1018,7 @@ static bool try_launch_2cta_sk(const GemmArgs& g, int num_sms, cudaStream_t stre
   GemmDevSk p{};
   static_cast<GemmDev&>(p) = GemmDev{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
   p.sk_partials = g.sk_partials; p.sk_flags = g.sk_flags; p.plan = plan;
-  gemm_bf16_tn_2cta_sk_kernel<BN><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  RS_LAUNCH(gemm_bf16_tn_2cta_sk_kernel<BN>, 2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream, tm_a, tm_b, p);
   *rc = cudaGetLastError();
   if (*rc != cudaSuccess) snprintf(err, 256, "gemm 2cta split-K launch (M=%d N=%d K=%d S=%d): %s", g.M, g.N, g.K, plan.S, cudaGetErrorString(*rc));
   return true;

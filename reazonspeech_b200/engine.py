@@ -58,12 +58,18 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
+    path = _LIB_PATH
+    variant = os.environ.get("RS_ENGINE_VARIANT", "")      # experiments only: a compile-time variant, e.g. "pdl" (build.py)
+    if variant:
+        path = _LIB_PATH.replace(".so", f"_{variant}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path}: build it first with `python -m reazonspeech_b200.build --variant {variant}`")
+    elif not os.path.exists(_LIB_PATH):
         if not build_if_missing:
             raise FileNotFoundError(_LIB_PATH)
         from .build import build
         build()
-    lib = C.CDLL(_LIB_PATH)
+    lib = C.CDLL(path)
     vp, ip, i32p, f32p = C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float)
     lib.rs_engine_create.argtypes = [C.POINTER(RsModelConfig), C.POINTER(RsTensor), ip, ip, C.POINTER(vp)]
     lib.rs_engine_create.restype = ip

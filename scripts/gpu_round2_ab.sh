@@ -10,6 +10,10 @@ echo "=== default suite"; timeout -k 10 900 python -m pytest tests -m gpu -q -x 
 for t in test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
   echo "=== experiment $t"; RS_RUN_EXPERIMENTS=1 timeout -k 10 300 python -m pytest tests/experiments/$t.py -m gpu -q -s -x -p no:cacheprovider 2>&1 | grep -E "utt|rep=|passed|failed|Error|error" | cut -c1-200
 done
+# compile-time variant with programmatic dependent launch (csrc/common.cuh RS_PDL): build it here BEFORE the gpurun call
+# (`python -m reazonspeech_b200.build --variant pdl`, the .so travels); built on the box only if that was forgotten
+[ -f reazonspeech_b200/librs_engine_pdl.so ] || python -m reazonspeech_b200.build --variant pdl | tail -1
+echo "=== whole -m gpu suite on the PDL variant"; RS_ENGINE_VARIANT=pdl timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
 run() {   # name, env assignments...
   local name=$1; shift
   echo "=== bench $name"
@@ -20,6 +24,8 @@ run stages6 RS_GEMM_STAGES=6
 run lnfold RS_LN_FOLD=1
 run splitk RS_GEMM_SPLITK=1
 run lnfold_splitk RS_LN_FOLD=1 RS_GEMM_SPLITK=1
+run pdl RS_ENGINE_VARIANT=pdl
+run pdl_lnfold_splitk RS_ENGINE_VARIANT=pdl RS_LN_FOLD=1 RS_GEMM_SPLITK=1
 python - <<'PY' | tee gpurun_out/ab_summary.txt
 import json, glob, os
 rows = []
