@@ -79,6 +79,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def python_api_rtfx(eng, n_clips: int, seconds: float, rank: int, batches: int = 4):
+    """RTFx of the call a user of the drop-in makes: ``transcribe_batch(model, audios)`` from numpy clips to
+    TranscribeResult objects (norm_audio, in-place padding into reused pinned staging, rs_transcribe_batch on a
+    worker thread, decode_hypothesis of batch k while batch k+1 runs) -- SURVEY.md section 8d item (ii)."""
+    from reazonspeech_b200.nemo.asr import TranscribeConfig, audio_from_numpy, transcribe_batch
+    from reazonspeech_b200.nemo.asr.transcribe import B200RnntModel
+    from reazonspeech_b200.synth import synth_clip
+    from reazonspeech_b200.tokenizer import PieceTableTokenizer, synthetic_pieces
+    model = B200RnntModel(eng, PieceTableTokenizer(synthetic_pieces(eng.cfg.vocab_size)), max_batch=n_clips)
+    audios = [audio_from_numpy(synth_clip(rank * n_clips + i, seconds), 16000) for i in range(n_clips)] * batches
+    cfg = TranscribeConfig(verbose=False)
+    transcribe_batch(model, audios[: 2 * n_clips], cfg)          # warm-up: sizes both staging sets
+    t0 = time.perf_counter()
+    res = transcribe_batch(model, audios, cfg)
+    dt = time.perf_counter() - t0
+    return {"value": len(audios) * seconds / dt, "unit": UNIT, "clips": len(audios), "ms_per_batch": 1e3 * dt / batches,
+            "subwords_per_clip": sum(len(r.subwords) for r in res) / len(res),
+            "what": "transcribe_batch(model, audios): numpy clips in, TranscribeResult out, one GPU"}
+
+
 def make_batch(n_clips: int, seconds: float, rank: int):
     from reazonspeech_b200.synth import synth_clip
     L = int(seconds * 16000) + 2 * PAD
@@ -296,6 +316,12 @@ def main():
         v, cores, secs = cpu_oracle_rtfx(args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"one {args.cpu_seconds:g} s clip, batch=1 fp32 greedy through the oracle port ({secs:.1f} s of CPU work)"}
+    api = None
+    if rank == 0:
+        try:
+            api = python_api_rtfx(eng, B, args.seconds, rank)
+        except Exception as exc:      # an extra: reported, never fatal to the contract keys
+            api = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -307,7 +333,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
-        "roofline": roofline, "roofline_hbm": roofline_hbm, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu,
+        "roofline": roofline, "roofline_hbm": roofline_hbm, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu, "python_api": api,
     }), flush=True)
 
 

@@ -21,7 +21,7 @@ from ...config import ModelConfig
 from ...engine import Engine
 from ...tokenizer import PieceTableTokenizer, SentencePieceTokenizer, synthetic_pieces
 from ...weights import load_nemo_archive, random_state_dict
-from .audio import norm_audio, pad_audio
+from .audio import SAMPLERATE, norm_audio, pad_audio
 from .decode import PAD_SECONDS, build_result, decode_hypothesis
 from .interface import AudioData, TranscribeConfig, TranscribeResult
 
@@ -45,6 +45,44 @@ class Hypothesis:
         return Hypothesis(y, [int(f) + i + 1 for i, f in enumerate(frames)])
 
 
+class HostStaging:
+    """Grow-only host buffers of one in-flight batch, reused across calls and pinned when a CUDA device is there:
+    allocating (cudaHostAlloc) and zero-filling a fresh 64 MB pinned batch costs more than the batch's GPU time."""
+
+    def __init__(self, pin: bool):
+        self.pin = pin
+        self._wav = self._lens = self._tok = self._frm = self._ntok = None
+
+    def _grown(self, buf, numel: int, dtype):
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(int(numel * 1.25) + 16, dtype=dtype)
+            if self.pin:
+                buf = buf.pin_memory()
+        return buf
+
+    def stage(self, waves: Sequence[np.ndarray], pad: int):
+        """Rows ``[zeros(pad) | wave | zeros(pad) | zeros to L]`` (pad_audio, audio.py:70-83, written in place) -> (wav [B, L], lens [B])."""
+        B = len(waves)
+        L = max(len(w) for w in waves) + 2 * pad
+        self._wav = self._grown(self._wav, B * L, torch.float32)
+        self._lens = self._grown(self._lens, B, torch.int32)
+        wav, lens = self._wav[: B * L].view(B, L), self._lens[:B]
+        rows = wav.numpy()
+        for r, w in enumerate(waves):
+            n = len(w)
+            rows[r, :pad] = 0.0
+            rows[r, pad:pad + n] = w                    # casts to float32 on the way in
+            rows[r, pad + n:] = 0.0
+            lens[r] = n + 2 * pad
+        return wav, lens
+
+    def outputs(self, B: int, U: int):
+        self._tok = self._grown(self._tok, B * U, torch.int32)
+        self._frm = self._grown(self._frm, B * U, torch.int32)
+        self._ntok = self._grown(self._ntok, B, torch.int32)
+        return self._tok[: B * U].view(B, U), self._frm[: B * U].view(B, U), self._ntok[:B]
+
+
 class B200RnntModel:
     """Engine + tokenizer behind NeMo's model surface."""
 
@@ -53,29 +91,55 @@ class B200RnntModel:
         self.cfg = engine.cfg
         self.tokenizer = tokenizer
         self.max_batch = max_batch
+        pin = torch.cuda.is_available()
+        self._staging = (HostStaging(pin), HostStaging(pin))      # double buffer: stage batch k+1 while batch k runs
 
     # -- token-level batched path
-    def transcribe_tokens(self, waveforms: Sequence[np.ndarray]):
-        """Padded 16 kHz mono float32 waveforms -> [(tokens, frames)] in input order.
+    def iter_token_batches(self, waveforms: Sequence[np.ndarray], pad: int = 0):
+        """16 kHz mono waveforms (each gets ``pad`` zero samples on both sides) -> yields ``(indices, [(tokens, frames)])``
+        batch by batch.
 
-        Utterances are sorted by length and cut into batches of at most ``max_batch`` so padding
-        waste stays small; results are scattered back to the caller's order."""
+        Utterances are sorted by length and cut into batches of at most ``max_batch`` so padding waste stays small.
+        The engine call of batch k runs on a worker thread (ctypes drops the GIL) while this thread stages batch k+1
+        into the other staging set and the caller post-processes batch k-1: on a long list the host work hides behind
+        the GPU.  One engine call is in flight at a time (an engine is not re-entrant)."""
+        from concurrent.futures import ThreadPoolExecutor
+        if len(waveforms) == 0:
+            return
         order = sorted(range(len(waveforms)), key=lambda i: len(waveforms[i]))
+        batches = [order[lo:lo + self.max_batch] for lo in range(0, len(order), self.max_batch)]
+        eng = self.engine
+        eng.ensure_workspace(len(batches[0]), len(waveforms[order[-1]]) + 2 * pad)        # once, on this thread
+
+        def run(staging, idx):
+            wav, lens = staging.stage([waveforms[i] for i in idx], pad)
+            out = staging.outputs(len(idx), eng.u_max(wav.shape[1]))
+            return wav, lens, out
+
+        def collect(done, idx):
+            tokens, frames, ntok = done
+            counts = ntok.tolist()
+            return idx, [(tokens[r, :n].tolist(), frames[r, :n].tolist()) for r, n in enumerate(counts[: len(idx)])]
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            in_flight = None
+            for k, idx in enumerate(batches):
+                wav, lens, out = run(self._staging[k & 1], idx)
+                nxt = (pool.submit(eng.transcribe_host, wav, lens, out[0].shape[1], out), idx)
+                if in_flight is not None:
+                    yield collect(in_flight[0].result(), in_flight[1])
+                in_flight = nxt
+            yield collect(in_flight[0].result(), in_flight[1])
+
+    def transcribe_tokens(self, waveforms: Sequence[np.ndarray], pad: int = 0):
+        """-> [(tokens, frames)] in input order."""
         results = [None] * len(waveforms)
-        for lo in range(0, len(order), self.max_batch):
-            idx = order[lo:lo + self.max_batch]
-            L = max(len(waveforms[i]) for i in idx)
-            host = torch.zeros(len(idx), L, dtype=torch.float32).pin_memory()
-            for r, i in enumerate(idx):
-                host[r, : len(waveforms[i])] = torch.from_numpy(np.ascontiguousarray(waveforms[i], dtype=np.float32))
-            lens = torch.tensor([len(waveforms[i]) for i in idx], dtype=torch.int32)
-            tokens, frames, ntok = self.engine.transcribe_host(host, lens)
-            for r, i in enumerate(idx):
-                n = int(ntok[r])
-                results[i] = (tokens[r, :n].tolist(), frames[r, :n].tolist())
+        for idx, items in self.iter_token_batches(waveforms, pad):
+            for i, item in zip(idx, items):
+                results[i] = item
         return results
 
-    # -- NeMo's call shape (transcribe.py:48-53)
+    # -- NeMo's call shape (transcribe.py:48-53): already padded tensors
     def transcribe(self, audio, batch_size: int = 1, return_hypotheses: bool = True, verbose: bool = True, **_):
         waves = [a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a) for a in audio]
         out = [Hypothesis.from_greedy(t, f, self.cfg.blank) for t, f in self.transcribe_tokens(waves)]
@@ -140,15 +204,31 @@ def transcribe(model, audio: AudioData, config: Optional[TranscribeConfig] = Non
 
 
 def transcribe_batch(model, audios: Sequence[AudioData], config: Optional[TranscribeConfig] = None) -> List[TranscribeResult]:
-    """Many utterances through one or a few engine launches; results in input order."""
+    """Many utterances through one or a few engine launches; results in input order.
+
+    Same per-utterance semantics as ``transcribe`` (norm_audio, 0.5 s of silence on both sides, greedy decode,
+    decode_hypothesis); the padding is written straight into the staging buffer and the post-processing of one batch
+    overlaps the engine call of the next.  A model object without ``iter_token_batches`` (e.g. a real NeMo model)
+    is driven through its ``transcribe`` method instead."""
     if config is None:
         config = TranscribeConfig()
-    waves = [torch.from_numpy(_prepare(a)) for a in audios]
-    hyps = model.transcribe(waves, batch_size=len(waves), return_hypotheses=True, verbose=config.verbose)
-    out = []
-    for hyp in hyps:
+    out: List[Optional[TranscribeResult]] = [None] * len(audios)
+
+    def finish(i, hyp):
         r = decode_hypothesis(model, hyp)
         if config.raw_hypothesis:
             r.hypothesis = hyp
-        out.append(r)
+        out[i] = r
+
+    if hasattr(model, "iter_token_batches"):
+        waves = [np.asarray(norm_audio(a).waveform) for a in audios]
+        blank = model.cfg.blank
+        for idx, items in model.iter_token_batches(waves, pad=int(PAD_SECONDS * SAMPLERATE)):
+            for i, (tokens, frames) in zip(idx, items):
+                finish(i, Hypothesis.from_greedy(tokens, frames, blank))
+    else:
+        tensors = [torch.from_numpy(_prepare(a)) for a in audios]
+        hyps = model.transcribe(tensors, batch_size=max(len(tensors), 1), return_hypotheses=True, verbose=config.verbose)
+        for i, hyp in enumerate(hyps):
+            finish(i, hyp)
     return out
