@@ -10,6 +10,7 @@ echo "=== default suite"; timeout -k 10 900 python -m pytest tests -m gpu -q -x 
 for t in test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
   echo "=== experiment $t"; RS_RUN_EXPERIMENTS=1 timeout -k 10 300 python -m pytest tests/experiments/$t.py -m gpu -q -s -x -p no:cacheprovider 2>&1 | grep -E "utt|rep=|passed|failed|Error|error" | cut -c1-200
 done
+echo "=== GEMM and encoder tests on the 6-stage ring"; RS_GEMM_STAGES=6 timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm or encoder" -p no:cacheprovider 2>&1 | tail -2
 # compile-time variant with programmatic dependent launch (csrc/common.cuh RS_PDL): build it here BEFORE the gpurun call
 # (`python -m reazonspeech_b200.build --variant pdl`, the .so travels); built on the box only if that was forgotten
 [ -f reazonspeech_b200/librs_engine_pdl.so ] || python -m reazonspeech_b200.build --variant pdl | tail -1
