@@ -117,24 +117,75 @@ class ModelConfig:
 
     @staticmethod
     def from_nemo_yaml(cfg: dict) -> "ModelConfig":
-        """Map a parsed ``model_config.yaml`` (dict) onto ModelConfig."""
+        """Map a parsed ``model_config.yaml`` (dict) onto ModelConfig.
+
+        Every setting that changes the arithmetic and that the kernels do not implement raises ValueError: a
+        checkpoint trained with another frontend normalisation, attention type, norm layer or prediction network must
+        not load and quietly transcribe garbage.  Training-only keys (dither, pad_to, dropout, spec-augment, optimiser)
+        are ignored, as ``model.transcribe`` ignores or zeroes them."""
         pre, enc = cfg["preprocessor"], cfg["encoder"]
         dec, joint = cfg["decoder"], cfg["joint"]
         sr = int(pre.get("sample_rate", 16000))
+
+        def require(block: str, d: dict, key: str, allowed, default):
+            v = d.get(key, default)
+            ok = any((v is None and a is None) or (v is not None and a is not None and (
+                (isinstance(a, float) and abs(float(v) - a) <= 1e-9 * max(1.0, abs(a))) or (not isinstance(a, float) and v == a))) for a in allowed)
+            if not ok:
+                raise ValueError(f"model_config.yaml: {block}.{key}={v!r} is not implemented by the engine (supported: {list(allowed)})")
+            return v
+
+        require("preprocessor", pre, "window", ("hann",), "hann")
+        require("preprocessor", pre, "normalize", ("per_feature",), "per_feature")
+        require("preprocessor", pre, "log", (True,), True)
+        require("preprocessor", pre, "log_zero_guard_type", ("add",), "add")
+        require("preprocessor", pre, "mag_power", (2.0,), 2.0)
+        require("preprocessor", pre, "lowfreq", (0, 0.0), 0)
+        require("preprocessor", pre, "highfreq", (None, sr / 2.0, sr // 2), None)
+        require("preprocessor", pre, "mel_norm", ("slaney",), "slaney")
+        require("preprocessor", pre, "frame_splicing", (1,), 1)
+        guard = pre.get("log_zero_guard_value", 2.0 ** -24)
+        if isinstance(guard, str):                                   # NeMo also accepts "tiny" / "eps" of float32
+            import numpy as np
+            guard = {"tiny": float(np.finfo(np.float32).tiny), "eps": float(np.finfo(np.float32).eps)}.get(guard)
+            if guard is None:
+                raise ValueError(f"model_config.yaml: preprocessor.log_zero_guard_value={pre['log_zero_guard_value']!r} not understood")
         ctx = enc.get("att_context_size", [128, 128]) or [128, 128]
-        if enc.get("self_attention_model", "rel_pos_local_attn") != "rel_pos_local_attn":
-            raise ValueError("engine implements self_attention_model=rel_pos_local_attn only")
-        if enc.get("subsampling", "dw_striding") != "dw_striding":
-            raise ValueError("engine implements subsampling=dw_striding only")
+        if ctx and isinstance(ctx[0], (list, tuple)):               # multi-lookahead configs list several contexts: the first is the default
+            ctx = ctx[0]
+        require("encoder", enc, "self_attention_model", ("rel_pos_local_attn",), "rel_pos_local_attn")
+        require("encoder", enc, "subsampling", ("dw_striding",), "dw_striding")
+        require("encoder", enc, "subsampling_factor", (8,), 8)
+        require("encoder", enc, "conv_norm_type", ("batch_norm",), "batch_norm")
+        require("encoder", enc, "untie_biases", (True,), True)
+        require("encoder", enc, "global_tokens_spacing", (1,), 1)
+        require("encoder", enc, "global_attn_separate", (False,), False)
+        require("encoder", enc, "conv_context_size", (None,), None)
+        n_mels = int(pre.get("features", 80))
+        if int(enc.get("feat_in", n_mels)) != n_mels:
+            raise ValueError(f"model_config.yaml: encoder.feat_in={enc.get('feat_in')} != preprocessor.features={n_mels}")
+        if int(ctx[0]) < 0 or int(ctx[1]) < 0:
+            raise ValueError(f"model_config.yaml: encoder.att_context_size={ctx} (unlimited context) is not implemented")
+        prednet, jointnet = dec["prednet"], joint["jointnet"]
+        require("decoder.prednet", prednet, "pred_rnn_layers", (1,), 1)
+        require("decoder", dec, "blank_as_pad", (True,), True)
+        require("joint.jointnet", jointnet, "activation", ("relu",), "relu")
+        vocab = int(dec.get("vocab_size", joint.get("num_classes", 3000)))
+        if "num_classes" in joint and int(joint["num_classes"]) != vocab:
+            raise ValueError(f"model_config.yaml: joint.num_classes={joint['num_classes']} != decoder.vocab_size={vocab}")
+        pred_hidden, d_model = int(prednet["pred_hidden"]), int(enc["d_model"])
+        if int(jointnet.get("pred_hidden", pred_hidden)) != pred_hidden or int(jointnet.get("encoder_hidden", d_model)) != d_model:
+            raise ValueError("model_config.yaml: joint.jointnet.{pred_hidden, encoder_hidden} disagree with decoder / encoder")
         return ModelConfig(
             sample_rate=sr,
             n_window_size=int(round(float(pre.get("window_size", 0.025)) * sr)),
             n_window_stride=int(round(float(pre.get("window_stride", 0.01)) * sr)),
-            n_fft=int(pre.get("n_fft", 512)),
-            n_mels=int(pre.get("features", 80)),
+            n_fft=int(pre.get("n_fft") or 512),
+            n_mels=n_mels,
             preemph=float(pre.get("preemph", 0.97) or 0.0),
+            log_zero_guard=float(guard),
             n_layers=int(enc["n_layers"]),
-            d_model=int(enc["d_model"]),
+            d_model=d_model,
             n_heads=int(enc.get("n_heads", 8)),
             ff_expansion=int(enc.get("ff_expansion_factor", 4)),
             conv_kernel=int(enc.get("conv_kernel_size", 9)),
@@ -143,9 +194,9 @@ class ModelConfig:
             att_left=int(ctx[0]), att_right=int(ctx[1]),
             global_tokens=int(enc.get("global_tokens", 1)),
             xscaling=bool(enc.get("xscaling", True)),
-            vocab_size=int(dec.get("vocab_size", joint.get("num_classes", 3000))),
-            pred_hidden=int(dec["prednet"]["pred_hidden"]),
-            joint_hidden=int(joint["jointnet"]["joint_hidden"]),
+            vocab_size=vocab,
+            pred_hidden=pred_hidden,
+            joint_hidden=int(jointnet["joint_hidden"]),
             max_symbols=int(cfg.get("decoding", {}).get("greedy", {}).get("max_symbols", 10) or 10),
         )
 
