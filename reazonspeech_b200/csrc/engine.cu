@@ -482,6 +482,10 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   if (cfg->d_model != 256 && cfg->d_model != 512 && cfg->d_model != 1024)
     return fail(nullptr, RS_ERR_UNSUPPORTED, "d_model=%d unsupported (256/512/1024)", cfg->d_model);
   if (cfg->conv_kernel != 9) return fail(nullptr, RS_ERR_UNSUPPORTED, "conv_kernel=%d unsupported (9)", cfg->conv_kernel);
+  if (cfg->global_tokens < 0 || cfg->global_tokens > 1)
+    return fail(nullptr, RS_ERR_UNSUPPORTED, "global_tokens=%d unsupported (the attention kernels implement 0 or 1)", cfg->global_tokens);
+  if (cfg->att_left < 0 || cfg->att_right < 0)
+    return fail(nullptr, RS_ERR_UNSUPPORTED, "att context (%d, %d) unsupported (limited local context only)", cfg->att_left, cfg->att_right);
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)

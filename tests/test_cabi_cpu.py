@@ -68,3 +68,17 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "import_module(\"oracle" not in src and "__import__(\"oracle" not in src, f
+
+
+def test_create_rejects_unsupported_configs_before_touching_a_device():
+    """Configuration checks come first in rs_engine_create, so they are observable without a GPU."""
+    lib = E.load_library()
+    arr = (E.RsTensor * 1)()
+    for field, value, needle in (("global_tokens", 2, b"global_tokens=2"), ("conv_kernel", 31, b"conv_kernel=31"),
+                                 ("n_fft", 1024, b"n_fft=1024"), ("att_left", -1, b"att context")):
+        cfg = E.to_rs_config(ModelConfig.tiny())
+        setattr(cfg, field, value)
+        h = C.c_void_p()
+        rc = lib.rs_engine_create(C.byref(cfg), arr, 0, 0, C.byref(h))
+        assert rc == -5 and not h, field                             # RS_ERR_UNSUPPORTED
+        assert needle in lib.rs_last_error(None), lib.rs_last_error(None)
