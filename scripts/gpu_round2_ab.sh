@@ -12,8 +12,8 @@ for t in test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeou
 done
 echo "=== GEMM and encoder tests on the 6-stage ring"; RS_GEMM_STAGES=6 timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm or encoder" -p no:cacheprovider 2>&1 | tail -2
 # compile-time variant with programmatic dependent launch (csrc/common.cuh RS_PDL): build it here BEFORE the gpurun call
-# (`python -m reazonspeech_b200.build --variant pdl`, the .so travels); built on the box only if that was forgotten
-[ -f reazonspeech_b200/librs_engine_pdl.so ] || python -m reazonspeech_b200.build --variant pdl | tail -1
+# (`python -m reazonspeech_b200.build --variant pdl`, the .so travels); rebuilt on the box only if it is stale
+python -m reazonspeech_b200.build --variant pdl | tail -1        # mtime-based: a no-op when it was built after the last source change
 echo "=== whole -m gpu suite on the PDL variant"; RS_ENGINE_VARIANT=pdl timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
 run() {   # name, env assignments...
   local name=$1; shift
