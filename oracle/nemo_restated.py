@@ -6,7 +6,7 @@ THIS IS TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and t
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  The product
 package ``reazonspeech_b200`` never does.
 
-PARITY: PINNED FOR N1-N7 AGAINST A THIRD-PARTY PORT OF NeMo, UNPINNED FOR THE REST.  The arithmetic
+PARITY: PINNED FOR N1-N7 AGAINST TWO THIRD-PARTY PORTS OF NeMo, UNPINNED FOR THE GLOBAL TOKEN AND THE GREEDY LOOP.  The arithmetic
 of this path lives in ``nemo_toolkit[asr] >= 2.6.1`` (pkg/nemo-asr/pyproject.toml:13), which is absent
 from /root/reference and cannot be imported offline, and the reference ships no tests, golden vectors
 or fixtures for it.  What the image does ship is ``transformers.models.parakeet``,
@@ -15,7 +15,14 @@ runs it on seeded weights/clips and tests/test_oracle_parakeet.py holds this fil
 (log-mel incl. the get_seq_len = L // hop length convention and the masked final frame, dw_striding
 subsampling, xscale, relative positional encoding + rel_shift, MHSA, convolution module, macaron FFN,
 LayerNorm order: encoder output relative L2 1e-5).  Parakeet has full relative-position attention only,
-so the pin covers the local-attention code path with T <= w + 1 and no global token.  NOT covered, and
+so that pin covers the local-attention code path with T <= w + 1 and no global token.  A SECOND third-party
+implementation closes the window gap: vLLM's Cohere-ASR model carries a near-verbatim port of NeMo's
+ConformerEncoder under NeMo's own parameter names (``vllm.model_executor.models.cohere_asr``);
+tests/golden/make_nemo_port_golden.py loads this file's seeded NeMo-named state dict into it with strict=True and runs
+it with LIMITED attention context (band mask, symmetric and asymmetric windows) on ragged zero-padded batches whose
+utterances are several windows long; tests/test_oracle_nemo_port.py holds this file to those outputs (relative L2
+3e-7): windowing, pad masks, the masking between the subsampling convolutions and the key names / tensor layouts of
+the checkpoint are therefore verified, not recalled.  NOT covered by any implementation in the image, and
 still recalled (R) rather than verified: the global-token wiring of
 RelPositionMultiHeadAttentionLongformer, and the RNN-T prediction network / joint / greedy loop
 (``max_symbols``) -- standard LSTM-transducer arithmetic restated from NeMo's modules/rnnt.py.  For the
