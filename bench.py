@@ -312,12 +312,12 @@ def main():
     if rank != 0:
         return
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU arm is timed at N=1 only (it is the same host either way)
         v, cores, secs = cpu_oracle_rtfx(args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"one {args.cpu_seconds:g} s clip, batch=1 fp32 greedy through the oracle port ({secs:.1f} s of CPU work)"}
     api = None
-    if rank == 0:
+    if world == 1:
         try:
             api = python_api_rtfx(eng, B, args.seconds, rank)
         except Exception as exc:      # an extra: reported, never fatal to the contract keys
