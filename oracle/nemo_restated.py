@@ -22,7 +22,9 @@ tests/golden/make_nemo_port_golden.py loads this file's seeded NeMo-named state 
 it with LIMITED attention context (band mask, symmetric and asymmetric windows) on ragged zero-padded batches whose
 utterances are several windows long; tests/test_oracle_nemo_port.py holds this file to those outputs (relative L2
 3e-7): windowing, pad masks, the masking between the subsampling convolutions and the key names / tensor layouts of
-the checkpoint are therefore verified, not recalled.  NOT covered by any implementation in the image, and
+the checkpoint are therefore verified, not recalled.  The same package also carries a copy of NeMo's
+``FilterbankFeatures`` class; a ragged batch goes through it (fp32 buffers, dither 0, pad_to 0) and on into the encoder
+port: ``log_mel`` here matches its valid frames to 2.6e-4 and the whole N1-N7 path matches end to end at 1.2e-5.  NOT covered by any implementation in the image, and
 still recalled (R) rather than verified: the global-token wiring of
 RelPositionMultiHeadAttentionLongformer, and the RNN-T prediction network / joint / greedy loop
 (``max_symbols``) -- standard LSTM-transducer arithmetic restated from NeMo's modules/rnnt.py.  For the

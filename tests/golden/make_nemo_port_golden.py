@@ -15,6 +15,11 @@ What this adds to the Parakeet pin (make_parakeet_golden.py):
     masking between the subsampling convolutions, masked_fill before the depthwise convolution), and every utterance's
     valid frames must equal the oracle's batch-of-one result -- the padding-invariance contract the engine is built on.
 
+  * the FRONTEND as well: the same vLLM package carries a copy of NeMo's ``FilterbankFeatures`` class
+    (``vllm.transformers_utils.processors.cohere_asr``: get_seq_len, preemphasis with the time mask, constant-padded centred
+    STFT, Slaney mel, log(x + 2^-24), per-feature normalisation with N-1, masking); a ragged batch goes through it and on
+    into the encoder port, so one case is NeMo's own classes end to end against the oracle's batch-of-one path.
+
 Still not covered by any third-party implementation in the image: the global token of
 RelPositionMultiHeadAttentionLongformer and the RNN-T greedy loop.
 
@@ -78,6 +83,42 @@ def port_encoder(cfg: ModelConfig, sd: dict):
     return enc
 
 
+def port_frontend(cfg: ModelConfig):
+    """vLLM's copy of NeMo's FilterbankFeatures, configured as model.transcribe runs it (dither 0, pad_to 0)."""
+    from vllm.transformers_utils.processors.cohere_asr import FilterbankFeatures
+    import torch._dynamo
+    torch._dynamo.config.disable = True          # the port's forward is decorated with torch.compile; run it eagerly (same arithmetic)
+    fe = FilterbankFeatures(sample_rate=cfg.sample_rate, n_window_size=cfg.n_window_size, n_window_stride=cfg.n_window_stride,
+                            window="hann", normalize="per_feature", n_fft=cfg.n_fft, preemph=cfg.preemph, nfilt=cfg.n_mels,
+                            lowfreq=0, highfreq=None, log=True, log_zero_guard_type="add", log_zero_guard_value=cfg.log_zero_guard,
+                            dither=0.0, pad_to=0, frame_splicing=1, mag_power=2.0, mel_norm="slaney").eval()
+    # The vLLM copy ends its constructor by rounding its two buffers to bfloat16 (a choice tied to Cohere's checkpoint);
+    # NeMo keeps them in fp32.  Re-create both with the class's own expressions, minus that cast.
+    from torchaudio.functional import melscale_fbanks
+    assert fe.window.dtype == torch.bfloat16 and fe.fb.dtype == torch.bfloat16, "the port changed: re-read its constructor"
+    fe.window = torch.hann_window(fe.win_length, periodic=False)
+    fe.fb = melscale_fbanks(n_freqs=fe.n_fft // 2 + 1, f_min=0, f_max=cfg.sample_rate / 2, n_mels=cfg.n_mels,
+                            sample_rate=cfg.sample_rate, norm="slaney", mel_scale="slaney").T.unsqueeze(0)
+    return fe
+
+
+FRONTEND_CLIPS = [(70, 1.3), (71, 3.9), (72, 0.6)]        # one ragged batch through the frontend port (and on into the encoder port)
+
+
+def run_frontend(cfg: ModelConfig, sd: dict):
+    """Ragged zero-padded batch -> FilterbankFeatures port -> ConformerEncoder port: NeMo's own classes end to end."""
+    waves = [padded_clip(s, sec) for s, sec in FRONTEND_CLIPS]
+    L = max(len(w) for w in waves)
+    x = torch.zeros(len(waves), L)
+    for i, w in enumerate(waves):
+        x[i, : len(w)] = torch.from_numpy(w)
+    lens = torch.tensor([len(w) for w in waves], dtype=torch.float)
+    with torch.no_grad():
+        feats, flen = port_frontend(cfg)(x, lens)                                      # [B, n_mels, F_max], [B]
+        enc, elen = port_encoder(cfg, sd)(audio_signal=feats, length=flen)
+    return waves, feats, flen.tolist(), [enc[i, :, : int(elen[i])].T.contiguous().numpy() for i in range(len(waves))]
+
+
 def run_case(kw: dict, wseed: int, clips):
     cfg = case_config(kw)
     sd = random_state_dict(cfg, seed=wseed, calibrate=False)
@@ -105,6 +146,23 @@ def main():
                 ref = O.encoder(O.log_mel(torch.from_numpy(waves[i]), cfg), sd, cfg)
             rel = float((torch.from_numpy(o).double() - ref.double()).norm() / ref.double().norm())
             print(f"{name} utt{i}: T={o.shape[0]} (window {cfg.att_left}+{cfg.att_right}+1), oracle vs port rel-L2 {rel:.3e}")
+    # frontend port (+ encoder port on its features), first case's config and weights
+    name, kw, wseed, _ = CASES[0]
+    cfg = case_config(kw)
+    sd = random_state_dict(cfg, seed=wseed, calibrate=False)
+    waves, feats, flen, encs = run_frontend(cfg, sd)
+    for i, w in enumerate(waves):
+        n = int(flen[i])
+        assert float(feats[i, :, n:].abs().max()) == 0.0 if n < feats.shape[2] else True
+        store[f"frontend/mel{i}"] = feats[i, :, :n].T.contiguous().numpy().astype(np.float32)      # [F_valid, n_mels]
+        store[f"frontend/enc{i}"] = encs[i].astype(np.float32)
+        with torch.no_grad():
+            mel = O.log_mel(torch.from_numpy(w), cfg)
+            ref = O.encoder(mel, sd, cfg)
+        err = float((mel.T - feats[i, :, :n].T).abs().max())
+        rel = float((torch.from_numpy(encs[i]).double() - ref.double()).norm() / ref.double().norm())
+        print(f"frontend utt{i}: {n} frames (oracle {mel.shape[1]}), log-mel max-abs {err:.3e}; encoder on port features vs oracle end to end rel-L2 {rel:.3e}")
+    store["frontend/n"] = np.int64(len(waves))
     np.savez_compressed(OUT, **store)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB")
 

@@ -54,3 +54,23 @@ def test_nemo_named_state_dict_loads_strictly_and_vectors_reproduce_live(golden)
         ref = golden[f"{name}/enc{i}"]
         assert out_len[i] == ref.shape[0]
         assert np.linalg.norm(o - ref) / np.linalg.norm(ref) < 1e-6
+
+
+def test_oracle_matches_filterbank_port_and_end_to_end(golden):
+    """NeMo's FilterbankFeatures (vLLM's copy, fp32 buffers) on a ragged batch, then the encoder port on ITS features:
+    the oracle's batch-of-one frontend must give the same valid frames (max-abs 2e-3: fp32 log of near-silent bins;
+    measured 2.6e-4) and the oracle's whole N1-N7 path the same encoder output (relative L2 1e-4; measured 1.2e-5)."""
+    name, kw, wseed, _ = G.CASES[0]
+    cfg = G.case_config(kw)
+    sd = random_state_dict(cfg, seed=wseed, calibrate=False)
+    assert int(golden["frontend/n"]) == len(G.FRONTEND_CLIPS)
+    for i, (cseed, secs) in enumerate(G.FRONTEND_CLIPS):
+        wave = torch.from_numpy(G.padded_clip(cseed, secs))
+        with torch.no_grad():
+            mel = O.log_mel(wave, cfg)
+            enc = O.encoder(mel, sd, cfg).numpy()
+        ref_mel, ref_enc = golden[f"frontend/mel{i}"], golden[f"frontend/enc{i}"]
+        assert ref_mel.shape == (cfg.mel_valid(wave.numel()), cfg.n_mels) == tuple(mel.T.shape)      # get_seq_len = L // hop
+        assert np.abs(mel.T.numpy() - ref_mel).max() < 2e-3
+        assert ref_enc.shape == enc.shape
+        assert np.linalg.norm(enc - ref_enc) / np.linalg.norm(ref_enc) < 1e-4
