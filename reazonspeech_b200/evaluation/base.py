@@ -154,7 +154,11 @@ def _predict_multi_gpu(evaluator: "BaseEvaluator", rows: List[dict], batch_size,
 class NemoB200Evaluator(BaseEvaluator):
     """The reference's RSNemoEvaluator (examples/rs-nemo/eval.py:15-32) on the B200 engine, with the batch hook
     implemented.  Rows carry ``{"audio": {"path": ...}}`` (datasets' undecoded Audio feature, eval.py:29) or
-    ``{"audio": {"array": ..., "sampling_rate": ...}}``."""
+    ``{"audio": {"array": ..., "sampling_rate": ...}}``.
+
+    ``evaluate(..., batch_size=N)`` hands N rows at a time to ``transcribe_batch``, which cuts them into engine batches
+    of at most ``max_batch`` (64) and overlaps staging, the engine call and the post-processing of consecutive engine
+    batches: a ``batch_size`` of a few hundred keeps the GPU busy, a ``batch_size`` <= 64 runs one engine call at a time."""
 
     def __init__(self, load_model_kwargs: Optional[dict] = None, **kwargs):
         super().__init__(**kwargs)
