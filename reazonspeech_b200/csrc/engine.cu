@@ -66,6 +66,8 @@ struct rs_engine {
   int num_sms = 148;
   std::map<std::string, Tensor> w;
   FeTablesHost fe;
+  rs::FeTablesB fe_b{};       // RS_LOGMEL_VARIANT=B (experiment, unmeasured): tables of logmel_b_kernel
+  bool logmel_b = false;
   struct { const float *c0w, *c0b, *d1w, *d1b, *p1b, *d2w, *d2b, *p2b, *ob; const void *p1w, *p2w, *ow; } sub;
   std::vector<LayerW> layers;
   struct { const void *enc_w, *out_w, *lstm_w, *pred_w; const float *enc_b, *out_b, *embed, *lstm_b, *pred_b; } dec;
@@ -199,6 +201,11 @@ int bind_weights(rs_engine* e) {
   NEED(e->fe.mel_start, "fe.mel_start", RS_I32, c.n_mels);
   NEED(e->fe.mel_count, "fe.mel_count", RS_I32, c.n_mels);
   NEED(e->fe.mel_w, "fe.mel_w", RS_F32, static_cast<int64_t>(c.n_mels) * 40);
+  if (e->logmel_b) {
+    NEED(e->fe_b.tw_b, "fe.b.tw_b", RS_F32, 512); NEED(e->fe_b.tw_x, "fe.b.tw_x", RS_F32, 512);
+    NEED(e->fe_b.lane_w, "fe.b.lane_w", RS_F32, 16 * 47); NEED(e->fe_b.lane_bins, "fe.b.lane_bins", RS_I32, 16 * 8);
+    NEED(e->fe_b.lane_nb, "fe.b.lane_nb", RS_I32, 16);
+  }
   NEED(e->sub.c0w, "sub.conv0.w", RS_F32, C * 9); NEED(e->sub.c0b, "sub.conv0.b", RS_F32, C);
   NEED(e->sub.d1w, "sub.dw1.w", RS_F32, C * 9); NEED(e->sub.d1b, "sub.dw1.b", RS_F32, C);
   NEED(e->sub.p1w, "sub.pw1.w", RS_BF16, C * C); NEED(e->sub.p1b, "sub.pw1.b", RS_F32, C);
@@ -329,6 +336,11 @@ void mark(rs_engine* e, int i, cudaStream_t s) {
 int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, cudaStream_t s) {
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
+  if (e->logmel_b) {
+    RS_K(e, rs::launch_logmel_b(wav, len, B, L_max, mel, mel_len, &e->fe, e->fe_b, c.n_mels, c.n_window_stride, c.n_fft,
+                                c.n_window_size, c.preemph, c.log_zero_guard, c.norm_eps, s), 2);
+    return RS_OK;
+  }
   RS_K(e, rs::launch_logmel(wav, len, B, L_max, mel, mel_len, nullptr, &e->fe, c.n_mels, c.n_window_stride, c.n_fft,
                            c.n_window_size, c.preemph, c.log_zero_guard, c.norm_eps, s), 2);
   return RS_OK;
@@ -502,6 +514,8 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   {   // RS_LN_FOLD=1: EXPERIMENT, unmeasured -- fold three of the five LayerNorms of a layer into their consumer GEMMs
     const char* f = getenv("RS_LN_FOLD");
     e->ln_fold = f != nullptr && atoi(f) == 1 && cfg->d_model % 256 == 0 && e->w.count("L0.att.wqkv.fold") != 0;
+    const char* lv = getenv("RS_LOGMEL_VARIANT");
+    e->logmel_b = lv != nullptr && lv[0] == 'B' && e->w.count("fe.b.tw_b") != 0;
   }
   int r = bind_weights(e);
   if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }

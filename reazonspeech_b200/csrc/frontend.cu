@@ -10,6 +10,7 @@
 // 256-pt complex radix-4 Stockham FFT in shared memory plus the even/odd split.
 // Output is time-major [B, F_max, n_mels] so the subsampling convs read channels-last.
 #include "common.cuh"
+#include "fft16.cuh"
 #include "kernels.h"
 
 namespace rs {
@@ -183,6 +184,159 @@ mel_normalize_kernel(float* __restrict__ mel, const int32_t* __restrict__ mel_le
     for (int f = tl; f < nf; f += 32) { float* p = base + static_cast<size_t>(f) * n_mels; *p = (*p - mean) * inv; }
     for (int f = nf + tl; f < F_max; f += 32) base[static_cast<size_t>(f) * n_mels] = 0.0f;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (RS_LOGMEL_VARIANT=B, unmeasured).  Same arithmetic as logmel_kernel up to the order of the FFT's additions,
+// organised to issue about half the instructions per frame and to keep two independent frames in flight per warp:
+//   * sixteen lanes per frame; the 256-point complex FFT is 16 x 16: lane t transforms the stride-16 samples t + 16 n1 in
+//     registers (fft16.cuh), multiplies by W256^(t k1), the sixteen lanes transpose through shared memory (row pitch 17),
+//     and a second register FFT over n2 leaves lane t with Z[t + 16 k2];
+//   * the real-FFT split needs Z[256 - k]: that is lane (16 - t) & 15, register 15 - k2 (lane 0: itself, (16 - k2) & 15)
+//     -- one pair of width-16 shuffles per bin;
+//   * every lane owns about 31 mel taps (filters dealt longest first at pack time, never split across lanes);
+//   * 64 frames per CTA, so the tables are staged once per 4x more frames than in logmel_kernel.
+// The per-frame arithmetic is replayed on the CPU from this description by tests/test_logmel_b_host.py.
+constexpr int kBFrames = 64;
+constexpr int kBLaneBins = 8;
+constexpr int kBLaneTaps = 47;
+constexpr int kBTrPitch = 17;
+
+__global__ void __launch_bounds__(32 * kFeWarps)
+logmel_b_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, int L_max, float* __restrict__ mel,
+                int32_t* __restrict__ mel_len, FeTables tb, FeTablesB tbb, int F_max, int n_mels, int hop, float preemph, float guard) {
+  extern __shared__ __align__(16) uint8_t fe_smem[];
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * kBFrames;
+  const int n = len[b];
+  const int n_frames = n / hop;                                      // FilterbankFeatures.get_seq_len, as in logmel_kernel
+  if (blockIdx.x == 0 && threadIdx.x == 0) mel_len[b] = n_frames;
+  if (f0 >= n_frames) return;
+
+  const int n_stage = (kBFrames - 1) * hop + kNfft + 1;
+  float* s_x = reinterpret_cast<float*>(fe_smem);                    // [n_stage]
+  float* s_win = s_x + ((n_stage + 3) & ~3);                         // [512]
+  float2* s_twb = reinterpret_cast<float2*>(s_win + kNfft);          // [16][16]  W256^(t k1) at [k1][t]
+  float2* s_twx = s_twb + 256;                                       // [16][16]  W512^(t + 16 k2) at [k2][t]
+  float* s_lw = reinterpret_cast<float*>(s_twx + 256);               // [16][kBLaneTaps]
+  int* s_lb = reinterpret_cast<int*>(s_lw + 16 * kBLaneTaps);        // [16][kBLaneBins]
+  int* s_lnb = s_lb + 16 * kBLaneBins;                               // [16]
+  float2* s_tr_all = reinterpret_cast<float2*>(s_lnb + 16);          // [16 half-warps][16 * 17]; later the frame's mel row
+  float* s_pw_all = reinterpret_cast<float*>(s_tr_all + 16 * 16 * kBTrPitch);   // [16 half-warps][260]
+
+  const int start = f0 * hop - kHalf - 1;
+  const float* xw = wav + static_cast<size_t>(b) * L_max;
+  for (int i = threadIdx.x; i < n_stage; i += blockDim.x) {
+    const int idx = start + i;
+    s_x[i] = (idx >= 0 && idx < n) ? __ldg(xw + idx) : 0.0f;
+  }
+  for (int i = threadIdx.x; i < kNfft; i += blockDim.x) s_win[i] = tb.window[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_twb[i] = reinterpret_cast<const float2*>(tbb.tw_b)[i];
+    s_twx[i] = reinterpret_cast<const float2*>(tbb.tw_x)[i];
+  }
+  for (int i = threadIdx.x; i < 16 * kBLaneTaps; i += blockDim.x) s_lw[i] = tbb.lane_w[i];
+  for (int i = threadIdx.x; i < 16 * kBLaneBins; i += blockDim.x) s_lb[i] = tbb.lane_bins[i];
+  if (threadIdx.x < 16) s_lnb[threadIdx.x] = tbb.lane_nb[threadIdx.x];
+  __syncthreads();
+
+  const int hw = threadIdx.x >> 4, t = threadIdx.x & 15;            // half-warp = frame slot, lane within the frame
+  float2* s_tr = s_tr_all + hw * 16 * kBTrPitch;
+  float* s_pw = s_pw_all + hw * 260;
+  float* s_o = reinterpret_cast<float*>(s_tr);                       // the transpose buffer is free again when the mel row is built
+  const int partner = (16 - t) & 15;
+
+  for (int it = 0; it < kBFrames / 16; ++it) {                       // both half-warps of a warp always run the whole body
+    const int fi = it * 16 + hw;
+    const int f = f0 + fi;
+    const bool live = f < n_frames;
+    // ---- windowed, pre-emphasised samples of this lane: complex z[16 n1 + t] = (s[32 n1 + 2t], s[32 n1 + 2t + 1])
+    const int off = fi * hop + 1;
+    const int g0 = f * hop - kHalf;
+    float2 v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int j = 32 * n1 + 2 * t;
+      const int gi = g0 + j;
+      const float xm = s_x[off + j - 1], x0 = s_x[off + j], x1 = s_x[off + j + 1];
+      const float y0 = (gi >= 0 && gi < n) ? x0 - preemph * xm : 0.0f;
+      const float y1 = (gi + 1 >= 0 && gi + 1 < n) ? x1 - preemph * x0 : 0.0f;
+      v[n1] = make_float2(y0 * s_win[j], y1 * s_win[j + 1]);
+    }
+    fft16(v);                                                        // over n1: v[k1] = A[t][k1]
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) s_tr[k1 * kBTrPitch + t] = cmul(v[k1], s_twb[k1 * 16 + t]);
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = s_tr[t * kBTrPitch + n2];
+    __syncwarp();
+    fft16(v);                                                        // over n2: v[k2] = Z[t + 16 k2]
+    // ---- real-FFT split and power spectrum
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      float2 zc;
+      zc.x = __shfl_sync(0xffffffffu, v[15 - k2].x, partner, 16);
+      zc.y = __shfl_sync(0xffffffffu, v[15 - k2].y, partner, 16);
+      if (t == 0) zc = v[(16 - k2) & 15];
+      const float2 zk = v[k2];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 o = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+      const float2 wo = cmul(s_twx[k2 * 16 + t], o);
+      const float re = e.x + wo.x, im = e.y + wo.y;
+      s_pw[t + 16 * k2] = re * re + im * im;
+    }
+    if (t == 0) { const float d = v[0].x - v[0].y; s_pw[256] = d * d; }
+    __syncwarp();
+    // ---- this lane's mel filters
+    {
+      const int nb = s_lnb[t];
+      const float* lw = s_lw + t * kBLaneTaps;
+      int pos = 0;
+      for (int bi = 0; bi < nb; ++bi) {
+        const int e = s_lb[t * kBLaneBins + bi];
+        const int m = e & 255, s0 = (e >> 8) & 1023, c = e >> 18;
+        float acc = 0.f;
+        for (int j = 0; j < c; ++j) acc = fmaf(lw[pos + j], s_pw[s0 + j], acc);
+        pos += c;
+        s_o[m] = logf(acc + guard);
+      }
+    }
+    __syncwarp();
+    if (live) {
+      float* orow = mel + (static_cast<size_t>(b) * F_max + f) * n_mels;
+      for (int m = t; m < n_mels; m += 16) orow[m] = s_o[m];
+    }
+    __syncwarp();
+  }
+}
+
+static size_t logmel_b_smem_bytes(int hop) {
+  const int n_stage = (kBFrames - 1) * hop + kNfft + 1;
+  size_t bytes = static_cast<size_t>(((n_stage + 3) & ~3) + kNfft) * 4 + 2 * 256 * 8 + 16 * kBLaneTaps * 4 + 16 * kBLaneBins * 4 + 16 * 4;
+  bytes += static_cast<size_t>(16) * 16 * kBTrPitch * 8 + static_cast<size_t>(16) * 260 * 4;
+  return bytes + 16;
+}
+
+cudaError_t launch_logmel_b(const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len,
+                            const void* tables, const FeTablesB& tbb, int n_mels, int hop, int n_fft, int win,
+                            float preemph, float guard, float eps, cudaStream_t stream) {
+  if (n_fft != kNfft || win > kNfft || n_mels > 128 || n_mels * 4 > 16 * kBTrPitch * 8 || hop <= 0) return cudaErrorInvalidValue;
+  const FeTables tb = *static_cast<const FeTables*>(tables);
+  const int F_max = L_max / hop + 1;
+  const size_t smem = logmel_b_smem_bytes(hop);
+  if (smem > 112 * 1024) return cudaErrorInvalidValue;               // two CTAs per SM
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(logmel_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const dim3 grid((F_max + kBFrames - 1) / kBFrames, B);
+  logmel_b_kernel<<<grid, 32 * kFeWarps, smem, stream>>>(wav, len, L_max, mel, mel_len, tb, tbb, F_max, n_mels, hop, preemph, guard);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  mel_normalize_kernel<<<dim3(B, (n_mels + 15) / 16), 512, 0, stream>>>(mel, mel_len, F_max, n_mels, eps);
+  return cudaGetLastError();
 }
 
 static size_t logmel_smem_bytes(int n_mels, int hop) {

@@ -79,6 +79,13 @@ cudaError_t launch_logmel(const float* wav, const int32_t* len, int B, int L_max
                           int hop, int n_fft, int win, float preemph, float guard, float eps,
                           cudaStream_t stream);
 
+// EXPERIMENT (RS_LOGMEL_VARIANT=B, unmeasured): the log-mel kernel with a register-resident 16 x 16 FFT, sixteen lanes per
+// frame and two frames per warp (frontend.cu logmel_b_kernel); tables from engine.py::frontend_tables_b.
+struct FeTablesB { const float* tw_b; const float* tw_x; const float* lane_w; const int32_t* lane_bins; const int32_t* lane_nb; };
+cudaError_t launch_logmel_b(const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len,
+                            const void* tables, const FeTablesB& tb, int n_mels, int hop, int n_fft, int win,
+                            float preemph, float guard, float eps, cudaStream_t stream);
+
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out_f32,
                              void* out_bf16, const float* gamma2, const float* beta2, int rows, int d,
                              float eps, cudaStream_t stream);

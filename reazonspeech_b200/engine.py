@@ -154,6 +154,47 @@ def frontend_tables(cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     }
 
 
+# Tables of the log-mel EXPERIMENT (RS_LOGMEL_VARIANT=B, frontend.cu logmel_b_kernel; unmeasured): 256-point FFT as 16 x 16
+# with sixteen lanes per frame.  Lane t of a frame holds the inter-pass twiddles W256^(t k1) and the real-split twiddles
+# W512^(t + 16 k2) in [k][t] order (conflict-free rows), and owns a fixed set of mel filters chosen so that every lane sums
+# about the same number of taps (longest-filter-first dealing); a filter is never split across lanes, so the order of
+# its sum is fixed.
+LOGMEL_B_LANES, LOGMEL_B_LANE_BINS, LOGMEL_B_LANE_TAPS = 16, 8, 47
+
+
+def frontend_tables_b(cfg: ModelConfig, base: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    t = np.arange(16, dtype=np.float64)[None, :]
+    k = np.arange(16, dtype=np.float64)[:, None]
+    ang_b = 2 * np.pi * (t * k) / 256.0
+    ang_x = 2 * np.pi * (t + 16 * k) / 512.0
+    tw_b = np.stack([np.cos(ang_b), -np.sin(ang_b)], axis=-1).astype(np.float32)           # [k1][t][2]
+    tw_x = np.stack([np.cos(ang_x), -np.sin(ang_x)], axis=-1).astype(np.float32)           # [k2][t][2]
+    start, count = base["fe.mel_start"].numpy(), base["fe.mel_count"].numpy()
+    w = base["fe.mel_w"].numpy().reshape(cfg.n_mels, MEL_MAX_W)
+    lanes = [[] for _ in range(LOGMEL_B_LANES)]
+    load = [0] * LOGMEL_B_LANES
+    for m in sorted(range(cfg.n_mels), key=lambda m: (-int(count[m]), m)):
+        i = min(range(LOGMEL_B_LANES), key=lambda i: (load[i], i))
+        lanes[i].append(m)
+        load[i] += int(count[m])
+    if max(len(l) for l in lanes) > LOGMEL_B_LANE_BINS or max(load) > LOGMEL_B_LANE_TAPS:
+        raise ValueError(f"log-mel variant B: {max(len(l) for l in lanes)} filters / {max(load)} taps on one lane exceed the kernel's limits")
+    lane_w = np.zeros((LOGMEL_B_LANES, LOGMEL_B_LANE_TAPS), dtype=np.float32)
+    lane_bins = np.zeros((LOGMEL_B_LANES, LOGMEL_B_LANE_BINS), dtype=np.int32)
+    lane_nb = np.zeros(LOGMEL_B_LANES, dtype=np.int32)
+    for i, ms in enumerate(lanes):
+        pos = 0
+        for j, m in enumerate(sorted(ms)):
+            c = int(count[m])
+            lane_w[i, pos:pos + c] = w[m, :c]
+            lane_bins[i, j] = m | (int(start[m]) << 8) | (c << 18)
+            pos += c
+        lane_nb[i] = len(ms)
+    return {"fe.b.tw_b": torch.from_numpy(tw_b).reshape(-1), "fe.b.tw_x": torch.from_numpy(tw_x).reshape(-1),
+            "fe.b.lane_w": torch.from_numpy(lane_w).reshape(-1), "fe.b.lane_bins": torch.from_numpy(lane_bins).reshape(-1),
+            "fe.b.lane_nb": torch.from_numpy(lane_nb)}
+
+
 def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     """NeMo-named fp32 state dict -> packed host tensors (bf16 GEMM weights, folded BN, ...)."""
     bf = lambda t: t.to(torch.bfloat16).contiguous()
@@ -264,6 +305,8 @@ class Engine:
         packed = pack_weights(state_dict, cfg)
         if os.environ.get("RS_LN_FOLD", "0") == "1":        # experiment, off by default: see ln_fold_tensors
             packed.update(ln_fold_tensors(packed, cfg))
+        if os.environ.get("RS_LOGMEL_VARIANT", "") == "B":  # experiment, off by default: see frontend_tables_b
+            packed.update(frontend_tables_b(cfg, packed))
         self.weights = {k: v.to(self.device) for k, v in packed.items()}
         self._names = [k.encode() for k in self.weights]
         arr = (RsTensor * len(self.weights))()

@@ -7,9 +7,10 @@
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
 echo "=== default suite"; timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-for t in test_gpu_asymmetric_window test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
+for t in test_gpu_asymmetric_window test_gpu_logmel_b test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
   echo "=== experiment $t"; RS_RUN_EXPERIMENTS=1 timeout -k 10 300 python -m pytest tests/experiments/$t.py -m gpu -q -s -x -p no:cacheprovider 2>&1 | grep -E "utt|rep=|passed|failed|Error|error" | cut -c1-200
 done
+echo "=== frontend tests on the log-mel variant B"; RS_LOGMEL_VARIANT=B timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parakeet.py tests/test_gpu_nemo_port.py -m gpu -q -x -k "logmel or parakeet or nemo_port or end_to_end" -p no:cacheprovider 2>&1 | tail -2
 echo "=== GEMM and encoder tests on the 6-stage ring"; RS_GEMM_STAGES=6 timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "gemm or encoder" -p no:cacheprovider 2>&1 | tail -2
 # compile-time variant with programmatic dependent launch (csrc/common.cuh RS_PDL): build it here BEFORE the gpurun call
 # (`python -m reazonspeech_b200.build --variant pdl`, the .so travels); rebuilt on the box only if it is stale
@@ -23,6 +24,7 @@ run() {   # name, env assignments...
 run default RS_NONE=1
 run stages6 RS_GEMM_STAGES=6
 run lnfold RS_LN_FOLD=1
+run logmelb RS_LOGMEL_VARIANT=B
 run splitk RS_GEMM_SPLITK=1
 run lnfold_splitk RS_LN_FOLD=1 RS_GEMM_SPLITK=1
 run pdl RS_ENGINE_VARIANT=pdl
@@ -38,8 +40,9 @@ for f in sorted(glob.glob("gpurun_out/ab_*.json")):
     k = j.get("kernel_ms", {})
     gem = sum(v["ms"] for n, v in k.items() if n.startswith("gemm"))
     ln = sum(v["ms"] for n, v in k.items() if "layernorm" in n)
-    rows.append((os.path.basename(f)[3:-5], j["value"], j["e2e"]["value"], j["ms_per_step"], gem, ln, j.get("roofline", {}).get("frac")))
-print(f"{'variant':18s} {'RTFx':>9s} {'e2e':>9s} {'ms/step':>8s} {'gemm ms':>8s} {'LN ms':>7s} {'gemm frac':>9s}")
+    lm = sum(v["ms"] for n, v in k.items() if "logmel" in n)
+    rows.append((os.path.basename(f)[3:-5], j["value"], j["e2e"]["value"], j["ms_per_step"], gem, ln, j.get("roofline", {}).get("frac"), lm))
+print(f"{'variant':18s} {'RTFx':>9s} {'e2e':>9s} {'ms/step':>8s} {'gemm ms':>8s} {'LN ms':>7s} {'gemm frac':>9s} {'logmel ms':>9s}")
 for r in rows:
-    print(f"{r[0]:18s} {r[1]:9.0f} {r[2]:9.0f} {r[3]:8.2f} {r[4]:8.2f} {r[5]:7.2f} {r[6] if r[6] is None else round(r[6], 3)!s:>9s}")
+    print(f"{r[0]:18s} {r[1]:9.0f} {r[2]:9.0f} {r[3]:8.2f} {r[4]:8.2f} {r[5]:7.2f} {r[6] if r[6] is None else round(r[6], 3)!s:>9s} {r[7]:9.3f}")
 PY
