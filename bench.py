@@ -94,7 +94,15 @@ def python_api_rtfx(eng, n_clips: int, seconds: float, rank: int, batches: int =
     t0 = time.perf_counter()
     res = transcribe_batch(model, audios, cfg)
     dt = time.perf_counter() - t0
+    from reazonspeech_b200.nemo.asr import transcribe
+    single = []
+    for a in audios[:6]:                                          # the reference's own call shape: one clip per call
+        t1 = time.perf_counter()
+        transcribe(model, a, cfg)
+        single.append(time.perf_counter() - t1)
+    single_ms = 1e3 * float(np.median(single[1:]))
     return {"value": len(audios) * seconds / dt, "unit": UNIT, "clips": len(audios), "ms_per_batch": 1e3 * dt / batches,
+            "single_clip_ms": single_ms, "single_clip_rtfx": seconds / (single_ms * 1e-3),
             "subwords_per_clip": sum(len(r.subwords) for r in res) / len(res),
             "what": "transcribe_batch(model, audios): numpy clips in, TranscribeResult out, one GPU"}
 
