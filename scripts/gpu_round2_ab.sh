@@ -7,7 +7,7 @@
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
 echo "=== default suite"; timeout -k 10 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-for t in test_gpu_asymmetric_window test_gpu_logmel_b test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
+for t in test_gpu_decode_edge_cases test_gpu_asymmetric_window test_gpu_logmel_b test_gpu_ln_fold test_gpu_splitk; do   # one process each, under timeout: a scheduling bug in an experiment would hang
   echo "=== experiment $t"; RS_RUN_EXPERIMENTS=1 timeout -k 10 300 python -m pytest tests/experiments/$t.py -m gpu -q -s -x -p no:cacheprovider 2>&1 | grep -E "utt|rep=|passed|failed|Error|error" | cut -c1-200
 done
 echo "=== frontend tests on the log-mel variant B"; RS_LOGMEL_VARIANT=B timeout -k 10 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_parakeet.py tests/test_gpu_nemo_port.py -m gpu -q -x -k "logmel or parakeet or nemo_port or end_to_end" -p no:cacheprovider 2>&1 | tail -2
