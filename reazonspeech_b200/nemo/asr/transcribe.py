@@ -121,6 +121,10 @@ class B200RnntModel:
             counts = ntok.tolist()
             return idx, [(tokens[r, :n].tolist(), frames[r, :n].tolist()) for r, n in enumerate(counts[: len(idx)])]
 
+        if len(batches) == 1:                                         # nothing to overlap: skip the thread hand-off (one-clip calls)
+            wav, lens, out = run(self._staging[0], batches[0])
+            yield collect(eng.transcribe_host(wav, lens, out[0].shape[1], out), batches[0])
+            return
         with ThreadPoolExecutor(max_workers=1) as pool:
             in_flight = None
             for k, idx in enumerate(batches):

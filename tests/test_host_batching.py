@@ -117,6 +117,10 @@ def test_pipeline_overlaps_staging_with_the_engine_call():
     assert [calls for _, calls in seen] == [2, 3, 4, 4]
     assert sorted(i for idx, _ in seen for i in idx) == list(range(8))
     assert all(name != threading.main_thread().name for _, _, name in eng.calls)
+    # a single batch has nothing to overlap with and stays on the caller's thread
+    eng.calls.clear()
+    assert model.transcribe_tokens(clips[:2]) == [_alone(w, 0) for w in clips[:2]]
+    assert [name for _, _, name in eng.calls] == [threading.main_thread().name]
 
 
 def test_transcribe_batch_matches_transcribe_per_clip():
