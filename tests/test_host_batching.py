@@ -148,3 +148,21 @@ def test_models_without_the_batch_iterator_go_through_their_transcribe_method():
     audios = [AudioData(w, 16000) for w in _clips(3, seed=5)]
     res = T.transcribe_batch(NemoLike(), audios)
     assert [r.text for r in res] == [_Tok().ids_to_text([(len(a.waveform) + 16000) % 50]) for a in audios]
+
+
+def test_random_batches_property():
+    """Property check over random clip counts, lengths, batch limits and paddings (hypothesis, bounded examples)."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=40, deadline=None)
+    @hyp.given(st.lists(st.integers(min_value=1, max_value=3000), min_size=1, max_size=12), st.integers(min_value=1, max_value=5),
+               st.sampled_from([0, 1, 160, 8000]), st.integers(min_value=0, max_value=2 ** 31 - 1))
+    def check(lengths, max_batch, pad, seed):
+        g = np.random.default_rng(seed)
+        clips = [g.standard_normal(n).astype(np.float32) for n in lengths]
+        model = T.B200RnntModel(FakeEngine(), _Tok(), max_batch=max_batch)
+        assert model.transcribe_tokens(clips, pad=pad) == [_alone(w, pad) for w in clips]
+        assert model.transcribe_tokens(clips[::-1], pad=pad) == [_alone(w, pad) for w in clips[::-1]]     # reused staging
+
+    check()
