@@ -69,3 +69,29 @@ def test_splitk_schedule_covers_every_k_step_once(num_tiles, ncl, num_k):
 def test_splitk_choice_for_the_ffn_shape():
     _, S = schedule(196, 74, 64)
     assert S == 3          # 48 tail tiles x 3 parts = 144 items on 74 clusters: 2 rounds of a third -> 2.67 waves instead of 3
+
+
+def test_splitk_schedule_random_shapes():
+    """Coverage and ordering invariants over random (tiles, clusters, k-steps): every k-step once, contributors scheduled
+    no later than their owner, never on a position behind it in the same cluster."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=150, deadline=None)
+    @hyp.given(st.integers(1, 900), st.integers(1, 80), st.integers(1, 130))
+    def check(num_tiles, ncl, num_k):
+        rows, S = schedule(num_tiles, ncl, num_k)
+        cover = np.zeros((num_tiles, num_k), np.int32)
+        for cid, it, tile, k0, k1, kind, part in rows:
+            assert 0 <= cid < ncl and 0 <= k0 < k1 <= num_k
+            cover[tile, k0:k1] += 1
+        assert (cover == 1).all()
+        assert 1 <= S <= 4 and (S == 1 or S * 8 <= num_k)
+        owners = {int(r[2]): r for r in rows if r[5] == 2}
+        for r in rows[rows[:, 5] == 1]:
+            o = owners[int(r[2])]
+            assert r[1] <= o[1] and (r[0] != o[0] or r[1] < o[1])
+        if S == 1:
+            assert (rows[:, 5] == 0).all()
+
+    check()
