@@ -283,6 +283,58 @@ def _greedy_loop(ep, sd, cfg, res):
     return res
 
 
+@dataclass
+class FollowResult:
+    """Outcome of walking a GIVEN decision sequence through the oracle's predictor + joint."""
+    n_decisions: int = 0
+    complete: bool = True                                  # the sequence accounts for every frame, no more, no less
+    gaps: List[tuple] = field(default_factory=list)        # (decision index, frame, given, oracle argmax, logit gap) where they differ
+    min_margin: float = float("inf")                       # smallest oracle top-2 margin met on the way
+
+
+def greedy_follow(enc: torch.Tensor, sd: StateDict, cfg: ModelConfig, decisions: List[int], emulate: bool = False) -> FollowResult:
+    """Re-synchronising comparison with a greedy decode produced elsewhere (the sm_100a engine).
+
+    Walks ``decisions`` (the argmax of EVERY joint evaluation, blanks included, as rebuilt from tokens + frames) through
+    the same control flow as ``rnnt_greedy`` but TEACHER-FORCED: the predictor state always follows the given decision.
+    Wherever the oracle's own argmax differs, the entry records ``logit[oracle argmax] - logit[given]`` -- the amount by
+    which the given decision loses under the oracle's arithmetic -- and the walk goes on, so one near-tie cannot hide the
+    rest of the sequence.  A decode is greedy-identical to the oracle iff ``gaps`` is empty and ``complete`` is true."""
+    res = FollowResult()
+    ep = joint_enc_proj(_q(enc, emulate), sd)
+    n_threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        hp = cfg.pred_hidden
+        emb = sd["decoder.prediction.embed.weight"]
+        h = torch.zeros(hp); c = torch.zeros(hp)
+        h_new, c_new = lstm_step(torch.zeros(hp), h, c, sd)
+        pp = F.linear(h_new, sd["joint.pred.weight"], sd["joint.pred.bias"])
+        W, b = sd["joint.joint_net.2.weight"], sd["joint.joint_net.2.bias"]
+        i = 0
+        for t in range(ep.shape[0]):
+            for _ in range(cfg.max_symbols):
+                if i >= len(decisions):
+                    res.complete = False
+                    return res
+                logits = F.linear(torch.relu(ep[t] + pp), W, b)
+                top2 = torch.topk(logits, 2)
+                res.min_margin = min(res.min_margin, float(top2.values[0] - top2.values[1]))
+                k = int(decisions[i]); i += 1
+                if k != int(top2.indices[0]):
+                    res.gaps.append((i - 1, t, k, int(top2.indices[0]), float(top2.values[0] - logits[k])))
+                if k == cfg.blank:
+                    break
+                h, c = h_new, c_new
+                h_new, c_new = lstm_step(emb[k], h, c, sd)
+                pp = F.linear(h_new, sd["joint.pred.weight"], sd["joint.pred.bias"])
+        res.n_decisions = i
+        res.complete = i == len(decisions)
+        return res
+    finally:
+        torch.set_num_threads(n_threads)
+
+
 # --------------------------------------------------------------------------------------
 # Whole path at the model.transcribe seam
 # --------------------------------------------------------------------------------------

@@ -362,13 +362,13 @@ cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.n_rel_pad = a.n_rel_pad;
   if (a.n_rel_pad < a.w_left + a.w_right + 1) return cudaErrorInvalidValue;
   const size_t smem = static_cast<size_t>(1 + 2 * kKvStages) * QT * LDS * 2 + QT * 4;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(local_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(global_row_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_once.set();
   }
   const dim3 grid((a.T_max + QT - 1) / QT, a.H, a.B);
   local_attention_kernel<<<grid, 128, smem, stream>>>(p);

@@ -533,13 +533,13 @@ cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   CUtensorMap tm_qk, tm_vt;
   if (!make_map(&tm_qk, p.qk, static_cast<uint64_t>(M), static_cast<uint64_t>(2 * d), static_cast<uint64_t>(p.ld_qk))) return cudaErrorInvalidValue;
   if (!make_map(&tm_vt, p.vt, static_cast<uint64_t>(d), static_cast<uint64_t>(M), static_cast<uint64_t>(p.ld_vt))) return cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(local_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kAtcSmem));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(global_row_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_once.set();
   }
   const dim3 grid((a.T_max + TQ - 1) / TQ, a.H, a.B);
   RS_LAUNCH(local_attention_tc_kernel, grid, kAtcThreads, kAtcSmem, stream, tm_qk, tm_vt, p);

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 // EXPERIMENT (variant library built with -DRS_PDL=1, see build.py --variant pdl): programmatic
 // dependent launch.  A kernel launched with the programmatic-stream-serialization attribute may start while its
 // predecessor in the stream is still running; RS_PDL_WAIT() is where it blocks until that predecessor has completed
@@ -38,6 +40,15 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 #else
 #define RS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a second engine on another GPU of the same process
+// (load_model("cuda:1") after "cuda:0", or the one-process multi-GPU model) must opt in again.  One bit per device
+// ordinal; two threads racing on the same device both set the attribute, which is harmless.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool pending() const { int d = 0; cudaGetDevice(&d); return ((done.load(std::memory_order_acquire) >> (d & 63)) & 1ull) == 0; }
+  void set() { int d = 0; cudaGetDevice(&d); done.fetch_or(1ull << (d & 63), std::memory_order_release); }
+};
 
 constexpr int kWarp = 32;
 

@@ -49,7 +49,7 @@ struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   size_t stats;   // RS_LN_FOLD experiment: per-row partial (sum, sum of squares) of the residual stream, [M][fold_slots][2] f32
 };
 
-inline int conv_len(int n) { return (n - 1) / 2 + 1; }
+inline int conv_len(int n) { return n > 0 ? (n - 1) / 2 + 1 : 0; }   // floor division as in NeMo's calc_length: 0 stays 0
 // Encoder-frame capacity of the padded activation tensors: the subsampled length rounded up to a multiple of 8, so that
 // every utterance starts at a 16-byte-aligned column of the transposed V buffer (TMA wants the innermost coordinate
 // 16-byte aligned: an odd T_max raised "illegal instruction" on the V^T tile loads of the attention kernel).
@@ -252,7 +252,7 @@ __global__ void enc_len_kernel(const int32_t* __restrict__ mel_len, int32_t* __r
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   int n = mel_len[b];
-  for (int i = 0; i < 3; ++i) n = (n - 1) / 2 + 1;
+  for (int i = 0; i < 3; ++i) n = n > 0 ? (n - 1) / 2 + 1 : 0;
   enc_len[b] = n;
 }
 

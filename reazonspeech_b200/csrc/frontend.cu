@@ -325,11 +325,11 @@ cudaError_t launch_logmel_b(const float* wav, const int32_t* len, int B, int L_m
   const int F_max = L_max / hop + 1;
   const size_t smem = logmel_b_smem_bytes(hop);
   if (smem > 112 * 1024) return cudaErrorInvalidValue;               // two CTAs per SM
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(logmel_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_once.set();
   }
   const dim3 grid((F_max + kBFrames - 1) / kBFrames, B);
   logmel_b_kernel<<<grid, 32 * kFeWarps, smem, stream>>>(wav, len, L_max, mel, mel_len, tb, tbb, F_max, n_mels, hop, preemph, guard);
@@ -352,11 +352,11 @@ cudaError_t launch_logmel(const float* wav, const int32_t* len, int B, int L_max
   const FeTables tb = *static_cast<const FeTables*>(tables);
   const int F_max = L_max / hop + 1;
   const size_t smem = logmel_smem_bytes(n_mels, hop);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
+    attr_once.set();
   }
   if (smem > 160 * 1024) return cudaErrorInvalidValue;
   const dim3 grid((F_max + kFramesPerBlock - 1) / kFramesPerBlock, B);

@@ -920,11 +920,11 @@ inline bool ln_fold_args(const GemmArgs& g) { return g.fold_c != nullptr || g.st
 template <int BN, int EG>
 static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
-    attr_set = true;
+    attr_once.set();
   }
   CUtensorMap tm_a, tm_b;
   const int nb = g.n_batch > 0 ? g.n_batch : 1;
@@ -955,11 +955,11 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
 template <int BN, int EG, int ST = 0>
 static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   using Cfg = Gemm2Cfg<BN, ST>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
-    attr_set = true;
+    attr_once.set();
   }
   CUtensorMap tm_a, tm_b;
   const int lda = g.lda > 0 ? g.lda : g.K;
@@ -1003,11 +1003,11 @@ static bool try_launch_2cta_sk(const GemmArgs& g, int num_sms, cudaStream_t stre
   const int clusters = num_sms / 2;                                // all of them: fewer tiles than clusters is a tail, too
   const SplitKPlan plan = splitk_plan(tiles, clusters, g.K / BK);
   if (plan.S <= 1 || g.K / BK < 32) return false;                  // nothing to gain, or k ranges too short to pay for the fix-up
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     *rc = cudaFuncSetAttribute(gemm_bf16_tn_2cta_sk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (*rc != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta split-K smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(*rc)); return true; }
-    attr_set = true;
+    attr_once.set();
   }
   CUtensorMap tm_a, tm_b;
   const int lda = g.lda > 0 ? g.lda : g.K;
@@ -1045,11 +1045,11 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
 template <int BN, int EG>
 static cudaError_t launch_4cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_4cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(4cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
-    attr_set = true;
+    attr_once.set();
   }
   CUtensorMap tm_a, tm_b;
   const int lda = g.lda > 0 ? g.lda : g.K;

@@ -13,7 +13,8 @@
 
 namespace rs {
 
-__host__ __device__ __forceinline__ int conv_len(int n) { return (n - 1) / 2 + 1; }
+// floor((n - 1) / 2) + 1 as NeMo's calc_length computes it: 0 frames stay 0 (C division would truncate -1/2 to 0 and give 1)
+__host__ __device__ __forceinline__ int conv_len(int n) { return n > 0 ? (n - 1) / 2 + 1 : 0; }
 
 constexpr int kSubTT = 4;     // t2 rows per CTA
 constexpr int kMelOff = 4;    // smem column of mel bin 0 (bin -1 sits at column 3) so bins 4k..4k+3 are one aligned LDS.128

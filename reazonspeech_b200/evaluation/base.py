@@ -124,30 +124,60 @@ def _jsonable(v) -> bool:
 
 
 def _gpu_worker(rank: int, evaluator: "BaseEvaluator", rows: List[dict], shards: List[List[int]], batch_size, num_gpus: int, queue):
-    mine = shards[rank]
-    preds = evaluator._predict([rows[i] for i in mine], batch_size, rank, num_gpus)
-    queue.put((rank, dict(zip(mine, preds))))
+    try:
+        mine = shards[rank]
+        preds = evaluator._predict([rows[i] for i in mine], batch_size, rank, num_gpus)
+        queue.put((rank, dict(zip(mine, preds)), None))
+    except BaseException as exc:                          # the parent re-raises: a dead worker must not look like a slow one
+        import traceback
+        queue.put((rank, None, f"{type(exc).__name__}: {exc}\n{traceback.format_exc()}"))
 
 
-def _predict_multi_gpu(evaluator: "BaseEvaluator", rows: List[dict], batch_size, num_gpus: int) -> List[str]:
+def _predict_multi_gpu(evaluator: "BaseEvaluator", rows: List[dict], batch_size, num_gpus: int, poll_s: float = 1.0) -> List[str]:
     """One spawned process per GPU, utterances dealt by length (reazonspeech_b200.sharding); results return through
-    a queue and are put back in input order."""
+    a queue and are put back in input order.  A worker that raises (missing checkpoint, out of memory, unreadable audio)
+    or dies without a word makes the call raise -- like ``datasets.map(num_proc=...)`` in the reference (base.py:198-204)
+    -- and the remaining workers are terminated.  The caller's ``evaluator.model`` is left as it was."""
+    import copy
+    import queue as queue_mod
     import torch.multiprocessing as mp
     from ..sharding import shard_indices
     lengths = [evaluator._length_of(r) for r in rows]
     shards = shard_indices(lengths, num_gpus)
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
-    evaluator.model = None                               # each worker loads its own replica on its own device
-    procs = [ctx.Process(target=_gpu_worker, args=(r, evaluator, rows, shards, batch_size, num_gpus, queue)) for r in range(num_gpus)]
+    worker_eval = copy.copy(evaluator)                    # shallow: each worker loads its own replica on its own device,
+    worker_eval.model = None                              # the caller keeps the model it passed in
+    procs = [ctx.Process(target=_gpu_worker, args=(r, worker_eval, rows, shards, batch_size, num_gpus, queue)) for r in range(num_gpus)]
     for p in procs:
         p.start()
-    merged = {}
-    for _ in procs:
-        _, part = queue.get()
-        merged.update(part)
-    for p in procs:
-        p.join()
+    merged, done, error = {}, set(), None
+    try:
+        while len(done) < len(procs) and error is None:
+            try:
+                rank, part, err = queue.get(timeout=poll_s)
+            except queue_mod.Empty:
+                dead = [r for r, p in enumerate(procs) if r not in done and p.exitcode is not None]
+                if dead:                                  # exited without reporting (killed, segfault, CUDA abort)
+                    try:                                  # its message may still be in flight
+                        rank, part, err = queue.get(timeout=poll_s)
+                    except queue_mod.Empty:
+                        error = f"evaluation worker {dead[0]} exited with code {procs[dead[0]].exitcode} without a result"
+                        break
+                else:
+                    continue
+            if err is not None:
+                error = f"evaluation worker {rank} failed: {err}"
+                break
+            merged.update(part)
+            done.add(rank)
+    finally:
+        for p in procs:
+            if error is not None and p.is_alive():
+                p.terminate()
+            p.join()
+    if error is not None:
+        raise RuntimeError(error)
     return [merged[i] for i in range(len(rows))]
 
 

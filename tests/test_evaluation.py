@@ -92,3 +92,31 @@ def test_multi_gpu_worker_shards_and_merges_in_order():
     out = [merged[i] for i in range(len(rows))]
     assert [o.split("@")[0] for o in out] == [r["audio"]["path"] for r in rows]
     assert sorted(len(v) for v in seen.values()) == sorted(len(s) for s in shards) and set(seen) == {0, 1}
+
+
+def test_multi_gpu_spawned_workers_merge_and_keep_the_callers_model():
+    """evaluate(num_gpus=2) with real spawned processes (stub model): order-stable merge, and the model object the caller
+    passed in is still there afterwards (the workers load their own replicas)."""
+    from eval_stubs import SpawnStub
+    rows = [{"audio": {"path": p}, "text": p.upper()} for p in ("aaaa", "b", "ccc", "dd", "eeeeee")]
+    marker = object()
+    ev = SpawnStub(model=marker)
+    out = ev.evaluate(dataset=rows, num_gpus=2)
+    assert [r["prediction"].split("@")[0] for r in out] == [r["text"] for r in rows]
+    assert {r["prediction"].split("@")[1] for r in out} == {"0", "1"}
+    assert ev.model is marker
+
+
+@pytest.mark.parametrize("how", ["raise", "die"])
+def test_multi_gpu_worker_failure_raises_instead_of_hanging(how):
+    """A worker that raises (e.g. load_model without a checkpoint) or dies silently makes evaluate() raise -- the
+    reference's datasets.map(num_proc=...) propagates worker errors too (pkg/evaluation/src/base.py:198-204)."""
+    from eval_stubs import SpawnStub
+    rows = [{"audio": {"path": p}, "text": p} for p in ("aaaa", "b", "ccc", "dd")]
+    ev = SpawnStub()
+    if how == "raise":
+        ev.fail_rank = 1
+    else:
+        ev.die_rank = 1
+    with pytest.raises(RuntimeError, match="no checkpoint on this rank" if how == "raise" else "exited with code 3"):
+        ev.evaluate(dataset=rows, num_gpus=2)

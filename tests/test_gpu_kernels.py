@@ -220,50 +220,26 @@ def test_windowed_decode_equals_sequential_kernel(tiny_engine, tiny_cfg, B, monk
             assert torch.equal(outs["2"][0][b, :n], outs[other][0][b, :n]) and torch.equal(outs["2"][1][b, :n], outs[other][1][b, :n]), f"mode {other} utt {b}"
 
 
-def decisions_from(tokens, frames, T, max_symbols, blank):
-    """Rebuild the greedy decision sequence (every joint evaluation's argmax) from the emitted
-    tokens and their frames: per frame the tokens emitted there, then a blank unless the frame was
-    left because max_symbols was reached."""
-    out, i = [], 0
-    for t in range(T):
-        n = 0
-        while i < len(tokens) and frames[i] == t:
-            out.append(tokens[i]); i += 1; n += 1
-        if n < max_symbols:
-            out.append(blank)
-    return out
-
-
-def check_tokens_against_oracle(got_tokens, got_frames, ref, T, cfg, tol, tag):
-    """Identical decision sequences, or a first difference at a decision whose ORACLE top-2 margin is < tol."""
-    got = decisions_from(got_tokens, got_frames, T, cfg.max_symbols, cfg.blank)
-    if got == ref.decisions:
-        return True
-    d = next((j for j, (a, b) in enumerate(zip(got, ref.decisions)) if a != b), min(len(got), len(ref.decisions)))
-    margin = ref.margins[d] if d < len(ref.margins) else float("nan")
-    print(f"{tag}: decision {d} differs (engine {got[d] if d < len(got) else None}, oracle {ref.decisions[d] if d < len(ref.decisions) else None}), oracle margin {margin:.3e}")
-    assert margin < tol, f"{tag}: decision {d} differs where the oracle margin is clear ({margin})"
-    return False
+from parity import check_decisions, decisions_from     # noqa: E402  (tests/ is on sys.path under pytest)
 
 
 def test_end_to_end_tokens(tiny_engine, tiny_cfg, tiny_sd):
-    """Whole path vs the oracle with the engine's bf16 storage points emulated.  Decision sequences must be
-    identical, except that a first difference is tolerated where the oracle's own top-2 logit margin at
-    that decision is below 5e-2 (near-tie flipped by accumulation order / bf16 rounding boundaries)."""
+    """Whole path vs the oracle with the engine's bf16 storage points emulated: the engine's decision sequence is walked
+    through the oracle teacher-forced to the LAST frame (tests/parity.py); any difference at an oracle logit gap >= 1e-2
+    fails, and so do more than 3 near-tie differences in one clip."""
     from oracle import nemo_restated as O
     eng = tiny_engine
     waves = [padded(synth_clip(10 + i, s)) for i, s in enumerate((3.0, 5.0, 1.2, 4.4))]
     x, lens = pad_batch(waves, "cuda")
     tokens, frames, ntok = eng.transcribe_device(x, lens)
     torch.cuda.synchronize()
-    exact = 0
+    ties = []
     for i, w in enumerate(waves):
-        r = O.transcribe_tokens(torch.from_numpy(w), tiny_sd, tiny_cfg, emulate=True)
+        with torch.no_grad():
+            enc = O.encoder(O.log_mel(torch.from_numpy(w), tiny_cfg), tiny_sd, tiny_cfg, emulate=True)
         n = int(ntok[i])
-        exact += check_tokens_against_oracle(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), r,
-                                             tiny_cfg.enc_frames(len(w)), tiny_cfg, 5e-2, f"utt{i}")
-    print(f"exact decision sequences: {exact}/{len(waves)}")
-    assert exact >= len(waves) // 2
+        ties.append(check_decisions(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), enc, tiny_sd, tiny_cfg, f"utt{i}"))
+    print(f"near-tie differences per clip: {ties} (0 = decision sequence identical to the oracle)")
 
 
 @pytest.mark.parametrize("B", [16, 19])
@@ -309,7 +285,7 @@ def test_long_form_clip_in_one_call(tiny_engine, tiny_cfg, tiny_sd):
     """the reference feeds audio of any length to the model in one shot (transcribe.py:44-53,
     relying on local attention).  A 150 s clip (1 882 encoder frames = 15 query tiles of the tensor-core attention,
     ~470 decode windows) goes through the engine in one call, next to a short one: encoder within 2e-2 relative L2 of the
-    fp32 oracle, decisions equal to the oracle's up to the first near-tie."""
+    fp32 oracle, decision sequence walked through the oracle to the last frame (tests/parity.py)."""
     from oracle import nemo_restated as O
     eng = tiny_engine
     waves = [padded(synth_clip(90, 150.0)), padded(synth_clip(91, 2.0))]
@@ -321,11 +297,12 @@ def test_long_form_clip_in_one_call(tiny_engine, tiny_cfg, tiny_sd):
     for i, w in enumerate(waves):
         with torch.no_grad():
             ref = O.encoder(O.log_mel(torch.from_numpy(w), tiny_cfg), tiny_sd, tiny_cfg)
-            emu = O.transcribe_tokens(torch.from_numpy(w), tiny_sd, tiny_cfg, emulate=True)
+            emu = O.encoder(O.log_mel(torch.from_numpy(w), tiny_cfg), tiny_sd, tiny_cfg, emulate=True)
         T = ref.shape[0]
         assert int(enc_len[i]) == T == tiny_cfg.enc_frames(len(w))
         r = _rel(enc[i, :T].cpu(), ref)
         n = int(ntok[i])
-        print(f"utt{i}: T={T}, encoder rel-L2 {r:.3e}, {n} tokens (oracle {len(emu.tokens)})")
         assert r < 2e-2
-        check_tokens_against_oracle(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), emu, T, tiny_cfg, 5e-2, f"utt{i}")
+        ties = check_decisions(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), emu, tiny_sd, tiny_cfg, f"utt{i}",
+                               max_near_ties=3 + T // 200)      # 1 882 frames: the near-tie allowance scales with the clip
+        print(f"utt{i}: T={T}, encoder rel-L2 {r:.3e}, {n} tokens, {ties} near-tie differences")

@@ -166,3 +166,38 @@ def test_greedy_matches_stock_module_implementation(tiny_cfg, tiny_sd):
                     break
                 tokens.append(k); frames.append(t); state, last = new_state, k
     assert tokens == ref.tokens and frames == ref.frames
+
+
+def test_greedy_follow_resynchronises(tiny_cfg, tiny_sd):
+    """oracle.greedy_follow (the re-synchronising comparison used by every token-identity test, tests/parity.py): the
+    oracle's own decisions give no difference; a flipped decision is reported with the amount it loses by and the walk
+    goes on teacher-forced to the last frame; truncated / over-long sequences are flagged; a decision sequence rebuilt
+    from tokens + frames equals the recorded one."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from parity import check_decisions, decisions_from
+    import pytest
+    cfg, sd = tiny_cfg, tiny_sd
+    w = torch.from_numpy(np.pad(synth_clip(3, 2.5), 8000))
+    with torch.no_grad():
+        enc = O.encoder(O.log_mel(w, cfg), sd, cfg)
+    ref = O.rnnt_greedy(enc, sd, cfg)
+    assert len(ref.tokens) > 3
+    assert decisions_from(ref.tokens, ref.frames, enc.shape[0], cfg.max_symbols, cfg.blank) == ref.decisions
+    r = O.greedy_follow(enc, sd, cfg, ref.decisions)
+    assert r.complete and not r.gaps and r.n_decisions == len(ref.decisions)
+    assert abs(r.min_margin - min(ref.margins)) < 1e-6
+    assert check_decisions(ref.tokens, ref.frames, enc, sd, cfg, "self", emulate=False) == 0
+    # flip one emission to another token: reported once, with a positive gap, and the walk continues to the end
+    j = next(i for i, k in enumerate(ref.decisions) if k != cfg.blank)
+    bad = list(ref.decisions)
+    bad[j] = (bad[j] + 1) % cfg.vocab_size
+    r = O.greedy_follow(enc, sd, cfg, bad)
+    assert r.complete and r.gaps and r.gaps[0][0] == j and r.gaps[0][2] == bad[j] and r.gaps[0][3] == ref.decisions[j] and r.gaps[0][4] > 0
+    # a wrong token changes the predictor state, later oracle decisions may differ too -- but every one is examined
+    assert r.n_decisions == len(bad)
+    tok = [k for k in bad if k != cfg.blank]
+    with pytest.raises(AssertionError):
+        check_decisions(tok, ref.frames, enc, sd, cfg, "flipped", emulate=False, tol=0.0)
+    assert not O.greedy_follow(enc, sd, cfg, ref.decisions[:-3]).complete
+    assert not O.greedy_follow(enc, sd, cfg, ref.decisions + [cfg.blank]).complete
