@@ -300,7 +300,7 @@ def main():
     n_ln = kernel_ms.get("launch_layernorm", {}).get("launches", 0)
     n_dw = kernel_ms.get("launch_conv_dw", {}).get("launches", 0)
     roofline_hbm = [r for r in (
-        hbm_line("launch_logmel_b" if "launch_logmel_b" in kernel_ms else "launch_logmel", B * (L * 4 + eng.cfg.mel_valid(L) * eng.cfg.n_mels * 4), "log-mel frontend: fp32 samples in, fp32 normalised features out (2.98 MB per clip)"),
+        hbm_line("launch_logmel_fused", B * (L * 4 + eng.cfg.mel_valid(L) * eng.cfg.n_mels * 4), "log-mel frontend, one kernel: fp32 samples in, fp32 log-mel features + per-feature statistics out (2.98 MB per clip; the normalisation is applied by the consumer's load)"),
         hbm_line("launch_layernorm", n_ln * B * valid_T * dm * 6, "LayerNorm: fp32 row in, bf16 row out, per launch"),
         hbm_line("launch_conv_dw", n_dw * B * valid_T * dm * 4, "depthwise conv + BN + Swish: bf16 in, bf16 out, per launch"),
     ) if r is not None]

@@ -104,7 +104,9 @@ int rs_enc_valid(const rs_engine* e, int n_samples);
 
 /* ---- stages (each is also a parity-test seam) --------------------------------------------- */
 /* N1 AudioToMelSpectrogramPreprocessor: wav f32[B,L_max] + len -> mel f32[B,F_max,n_mels]
- * (time-major, per-feature normalised, rows >= mel_len zero) + mel_len i32[B]. */
+ * (time-major, per-feature normalised, rows >= mel_len zero) + mel_len i32[B].  Needs the workspace
+ * (rs_set_workspace) for the per-feature statistics.  On the fused paths below the features stay
+ * un-normalised in the workspace and the normalisation is applied by the first subsampling kernel's load. */
 int rs_logmel(rs_engine* e, const float* wav_dev, const int32_t* len_dev, int B, int L_max,
               float* mel_dev, int32_t* mel_len_dev, void* stream);
 /* N2-N7 ConformerEncoder: mel -> enc f32[B,T_max,d_model] + enc_len i32[B].

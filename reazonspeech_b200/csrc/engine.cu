@@ -14,17 +14,13 @@
 
 #include "../../include/rs_engine.h"
 #include "kernels.h"
+#include "logmel.h"
 
 namespace {
 
 thread_local char g_create_error[512] = "";
 
 struct Tensor { const void* p = nullptr; int dtype = 0; int64_t numel = 0; };
-
-struct FeTablesHost {   // must match rs::FeTables in frontend.cu
-  const float* window; const float* tw256; const float* tw512;
-  const int32_t* mel_start; const int32_t* mel_count; const float* mel_w;
-};
 
 struct LayerW {
   const float *ln_ff1_g, *ln_ff1_b, *ff1_b1, *ff1_b2;
@@ -43,7 +39,7 @@ struct LayerW {
 
 struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   int B, L_max, F_max, T1, F1, T2, F2, T3, F3, M;
-  size_t wav, len, mel, mel_len, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, vt, enc, encp;
+  size_t wav, len, mel, mel_len, mel_part, mel_stats, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, vt, enc, encp;
   int n_rel_pad, ld_vt;
   size_t tokens, frames, ntok, dec_ws, total;
   size_t stats;   // RS_LN_FOLD experiment: per-row partial (sum, sum of squares) of the residual stream, [M][fold_slots][2] f32
@@ -65,9 +61,9 @@ struct rs_engine {
   int device = 0;
   int num_sms = 148;
   std::map<std::string, Tensor> w;
-  FeTablesHost fe;
-  rs::FeTablesB fe_b{};       // RS_LOGMEL_VARIANT=B (experiment, unmeasured): tables of logmel_b_kernel
-  bool logmel_b = false;
+  rs::LmTables fe{};          // tables of the fused log-mel kernel (logmel_tables.py)
+  unsigned int* lm_tickets = nullptr;   // per-utterance CTA tickets of the log-mel statistics (engine-owned, kept zero between launches)
+  static constexpr int kMaxBatch = 1 << 16;
   struct { const float *c0w, *c0b, *d1w, *d1b, *p1b, *d2w, *d2b, *p2b, *ob; const void *p1w, *p2w, *ow; } sub;
   std::vector<LayerW> layers;
   struct { const void *enc_w, *out_w, *lstm_w, *pred_w; const float *enc_b, *out_b, *embed, *lstm_b, *pred_b; } dec;
@@ -142,6 +138,8 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.len = take(static_cast<size_t>(B) * 4);
   p.mel = take(static_cast<size_t>(B) * p.F_max * c.n_mels * 4);
   p.mel_len = take(static_cast<size_t>(B) * 4);
+  p.mel_part = take(static_cast<size_t>(B) * rs::logmel_tiles(L_max, c.n_window_stride) * c.n_mels * 2 * 4);   // per-CTA (sum, sum of squares)
+  p.mel_stats = take(static_cast<size_t>(B) * c.n_mels * 2 * 4);                                               // (mean, 1 / (std + eps))
   p.enc_len = take(static_cast<size_t>(B) * 4);
   p.sub1 = take(static_cast<size_t>(B) * p.T2 * p.F2 * C * 2);
   p.sub2 = take(static_cast<size_t>(B) * p.T2 * p.F2 * C * 2);
@@ -196,15 +194,15 @@ int bind_weights(rs_engine* e) {
   const int64_t n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32, k = c.conv_kernel;
   const int64_t F3 = conv_len(conv_len(conv_len(c.n_mels)));
   NEED(e->fe.window, "fe.window", RS_F32, c.n_fft);
-  NEED(e->fe.tw256, "fe.tw256", RS_F32, c.n_fft);
-  NEED(e->fe.tw512, "fe.tw512", RS_F32, c.n_fft + 2);
-  NEED(e->fe.mel_start, "fe.mel_start", RS_I32, c.n_mels);
-  NEED(e->fe.mel_count, "fe.mel_count", RS_I32, c.n_mels);
-  NEED(e->fe.mel_w, "fe.mel_w", RS_F32, static_cast<int64_t>(c.n_mels) * 40);
-  if (e->logmel_b) {
-    NEED(e->fe_b.tw_b, "fe.b.tw_b", RS_F32, 512); NEED(e->fe_b.tw_x, "fe.b.tw_x", RS_F32, 512);
-    NEED(e->fe_b.lane_w, "fe.b.lane_w", RS_F32, 16 * 47); NEED(e->fe_b.lane_bins, "fe.b.lane_bins", RS_I32, 16 * 8);
-    NEED(e->fe_b.lane_nb, "fe.b.lane_nb", RS_I32, 16);
+  NEED(e->fe.tw_b, "fe.tw_b", RS_F32, 512);
+  NEED(e->fe.tw_x, "fe.tw_x", RS_F32, 256);
+  NEED(e->fe.mel_meta, "fe.mel_meta", RS_I32, rs::kLmMetaInts);
+  {
+    auto it = e->w.find("fe.mel_w");
+    if (it == e->w.end() || it->second.dtype != RS_F32 || it->second.numel <= 0 || it->second.numel % 16)
+      return fail(e, RS_ERR_MISSING_WEIGHT, "weight 'fe.mel_w' (f32 [taps, 16]) missing from the table or misshapen");
+    e->fe.mel_w = static_cast<const float*>(it->second.p);
+    e->fe.n_taps = static_cast<int>(it->second.numel / 16);
   }
   NEED(e->sub.c0w, "sub.conv0.w", RS_F32, C * 9); NEED(e->sub.c0b, "sub.conv0.b", RS_F32, C);
   NEED(e->sub.d1w, "sub.dw1.w", RS_F32, C * 9); NEED(e->sub.d1b, "sub.dw1.b", RS_F32, C);
@@ -333,31 +331,38 @@ void mark(rs_engine* e, int i, cudaStream_t s) {
   if (e->timing && e->ev_ok) cudaEventRecord(e->ev[i], s);
 }
 
-int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, cudaStream_t s) {
+// Log-mel of utterances [b0, b0 + nb) of a batch whose statistics live at plan offsets (absolute utterance index).
+// normalise = false leaves `mel` un-normalised for sub_conv0_dw1_kernel (the transcribe path); rs_logmel passes true.
+int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int nb, int L_max, float* mel, int32_t* mel_len,
+              float* partials, float* stats, int b0, bool normalise, cudaStream_t s) {
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
-  if (e->logmel_b) {
-    RS_K(e, rs::launch_logmel_b(wav, len, B, L_max, mel, mel_len, &e->fe, e->fe_b, c.n_mels, c.n_window_stride, c.n_fft,
-                                c.n_window_size, c.preemph, c.log_zero_guard, c.norm_eps, s), 2);
-    return RS_OK;
-  }
-  RS_K(e, rs::launch_logmel(wav, len, B, L_max, mel, mel_len, nullptr, &e->fe, c.n_mels, c.n_window_stride, c.n_fft,
-                           c.n_window_size, c.preemph, c.log_zero_guard, c.norm_eps, s), 2);
+  if (b0 + nb > rs_engine::kMaxBatch) return fail(e, RS_ERR_INVALID_ARG, "batch of %d utterances exceeds the engine limit of %d", b0 + nb, rs_engine::kMaxBatch);
+  rs::LogmelArgs a{};
+  a.wav = wav; a.len = len; a.B = nb; a.L_max = L_max; a.mel = mel; a.mel_len = mel_len;
+  a.partials = partials + static_cast<size_t>(b0) * rs::logmel_tiles(L_max, c.n_window_stride) * c.n_mels * 2;
+  a.stats = stats + static_cast<size_t>(b0) * c.n_mels * 2;
+  a.tickets = e->lm_tickets + b0;
+  a.tb = e->fe; a.n_mels = c.n_mels; a.hop = c.n_window_stride; a.n_fft = c.n_fft; a.win = c.n_window_size;
+  a.preemph = c.preemph; a.guard = c.log_zero_guard; a.eps = c.norm_eps; a.normalise_in_place = normalise;
+  RS_K(e, rs::launch_logmel_fused(a, s), normalise ? 2 : 1);
   return RS_OK;
 }
 
-int do_sub_conv0(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, int b0, int nb, cudaStream_t s) {
+// mel_stats == nullptr: `mel` is already normalised (rs_encode takes rs_logmel's output)
+int do_sub_conv0(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, const float* mel_stats, int b0, int nb, cudaStream_t s) {
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   const int C = c.sub_channels;
-  rs::SubsampleArgs sa{mel + static_cast<size_t>(b0) * p.F_max * c.n_mels, mel_len + b0, nb, p.F_max, c.n_mels, C,
+  rs::SubsampleArgs sa{mel + static_cast<size_t>(b0) * p.F_max * c.n_mels, mel_len + b0,
+                       mel_stats ? mel_stats + static_cast<size_t>(b0) * c.n_mels * 2 : nullptr, nb, p.F_max, c.n_mels, C,
                        e->sub.c0w, e->sub.c0b, e->sub.d1w, e->sub.d1b,
                        at<uint16_t>(e, p.sub1) + static_cast<size_t>(b0) * p.T2 * p.F2 * C, p.T1, p.F1, p.T2, p.F2};
   RS_K(e, rs::launch_sub_conv0_dw1(sa, s), 1);
   return RS_OK;
 }
 
-int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, float* enc, int32_t* enc_len,
+int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, const float* mel_stats, float* enc, int32_t* enc_len,
               int n_layers, cudaStream_t s, bool conv0_done = false) {
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
@@ -366,7 +371,7 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
   enc_len_kernel<<<(B + 127) / 128, 128, 0, s>>>(mel_len, enc_len, B);
   RS_K(e, cudaGetLastError(), 1);
   // ---- ConvSubsampling
-  if (!conv0_done) RS_TRY(do_sub_conv0(e, p, mel, mel_len, 0, B, s));
+  if (!conv0_done) RS_TRY(do_sub_conv0(e, p, mel, mel_len, mel_stats, 0, B, s));
   RS_TRY(gemm(e, at<void>(e, p.sub1), e->sub.p1w, e->sub.p1b, nullptr, at<void>(e, p.sub2), B * p.T2 * p.F2, C, C,
               RS_EPI_BIAS_RELU_BF16, 1.f, s));
   RS_K(e, rs::launch_sub_dw(at<void>(e, p.sub2), at<void>(e, p.sub3), e->sub.d2w, e->sub.d2b, mel_len, 2, B, p.T2, p.F2,
@@ -514,8 +519,6 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   {   // RS_LN_FOLD=1: EXPERIMENT, unmeasured -- fold three of the five LayerNorms of a layer into their consumer GEMMs
     const char* f = getenv("RS_LN_FOLD");
     e->ln_fold = f != nullptr && atoi(f) == 1 && cfg->d_model % 256 == 0 && e->w.count("L0.att.wqkv.fold") != 0;
-    const char* lv = getenv("RS_LOGMEL_VARIANT");
-    e->logmel_b = lv != nullptr && lv[0] == 'B' && e->w.count("fe.b.tw_b") != 0;
   }
   int r = bind_weights(e);
   if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }
@@ -529,6 +532,13 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
       delete e;
       return RS_ERR_CUDA;
     }
+  }
+  if (cudaMalloc(&e->lm_tickets, rs_engine::kMaxBatch * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(e->lm_tickets, 0, rs_engine::kMaxBatch * sizeof(unsigned int)) != cudaSuccess) {
+    snprintf(g_create_error, sizeof g_create_error, "cannot allocate the log-mel ticket array (%s)", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(e->lm_tickets); cudaFree(e->sk_partials); cudaFree(e->sk_flags);
+    delete e;
+    return RS_ERR_CUDA;
   }
   e->ev_ok = true;
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) e->ev_ok = false;
@@ -547,6 +557,7 @@ void rs_engine_destroy(rs_engine* e) {
   for (auto& ev : e->k_ev) cudaEventDestroy(ev);
   cudaFree(e->sk_partials);
   cudaFree(e->sk_flags);
+  cudaFree(e->lm_tickets);
   delete e;
 }
 
@@ -575,7 +586,10 @@ int rs_enc_valid(const rs_engine* e, int n) { return conv_len(conv_len(conv_len(
 int rs_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len, void* stream) {
   if (!e || !wav || !len || !mel || !mel_len || B <= 0 || L_max <= 0) return fail(e, RS_ERR_INVALID_ARG, "rs_logmel: bad arguments");
   RS_CUDA(e, cudaSetDevice(e->device));
-  return do_logmel(e, wav, len, B, L_max, mel, mel_len, static_cast<cudaStream_t>(stream));
+  Plan p = make_plan(e, B, L_max, 1);               // the statistics scratch lives in the workspace
+  RS_TRY(check_ws(e, p));
+  return do_logmel(e, wav, len, B, L_max, mel, mel_len, at<float>(e, p.mel_part), at<float>(e, p.mel_stats), 0, true,
+                   static_cast<cudaStream_t>(stream));
 }
 
 int rs_encode(rs_engine* e, const float* mel, const int32_t* mel_len, int B, int F_max, float* enc, int32_t* enc_len,
@@ -585,7 +599,7 @@ int rs_encode(rs_engine* e, const float* mel, const int32_t* mel_len, int B, int
   const int L_max = (F_max - 1) * e->cfg.n_window_stride;
   Plan p = make_plan(e, B, L_max, 1);
   RS_TRY(check_ws(e, p));
-  return do_encode(e, p, mel, mel_len, enc, enc_len, n_layers, static_cast<cudaStream_t>(stream));
+  return do_encode(e, p, mel, mel_len, nullptr, enc, enc_len, n_layers, static_cast<cudaStream_t>(stream));
 }
 
 int rs_rnnt_greedy(rs_engine* e, const float* enc, const int32_t* enc_len, int B, int T_max, int32_t* tokens,
@@ -614,9 +628,9 @@ int rs_transcribe_device(rs_engine* e, const float* wav, const int32_t* len, int
   Plan p = make_plan(e, B, L_max, U_max);
   RS_TRY(check_ws(e, p));
   mark(e, 0, s);
-  RS_TRY(do_logmel(e, wav, len, B, L_max, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), s));
+  RS_TRY(do_logmel(e, wav, len, B, L_max, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.mel_part), at<float>(e, p.mel_stats), 0, false, s));
   mark(e, 1, s);
-  RS_TRY(do_encode(e, p, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s));
+  RS_TRY(do_encode(e, p, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.mel_stats), at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s));
   mark(e, 3, s);
   RS_TRY(do_greedy(e, p, at<float>(e, p.enc), at<int32_t>(e, p.enc_len), p.T3, tokens, frames, n_tok, U_max, s));
   mark(e, 5, s);
@@ -659,10 +673,10 @@ int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_
       const int nb = (B - b0 < per) ? B - b0 : per;
       RS_CUDA(e, cudaStreamWaitEvent(s, e->copy_ev[c], 0));
       RS_TRY(do_logmel(e, wav + static_cast<size_t>(b0) * L_max, len + b0, nb, L_max,
-                       mel + static_cast<size_t>(b0) * p.F_max * e->cfg.n_mels, mel_len + b0, s));
-      RS_TRY(do_sub_conv0(e, p, mel, mel_len, b0, nb, s));
+                       mel + static_cast<size_t>(b0) * p.F_max * e->cfg.n_mels, mel_len + b0, at<float>(e, p.mel_part), at<float>(e, p.mel_stats), b0, false, s));
+      RS_TRY(do_sub_conv0(e, p, mel, mel_len, at<float>(e, p.mel_stats), b0, nb, s));
     }
-    RS_TRY(do_encode(e, p, mel, mel_len, at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s, true));
+    RS_TRY(do_encode(e, p, mel, mel_len, at<float>(e, p.mel_stats), at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s, true));
     RS_TRY(do_greedy(e, p, at<float>(e, p.enc), at<int32_t>(e, p.enc_len), p.T3, at<int32_t>(e, p.tokens),
                      at<int32_t>(e, p.frames), at<int32_t>(e, p.ntok), U_max, s));
   }

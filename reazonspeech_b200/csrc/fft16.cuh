@@ -1,7 +1,7 @@
-// 16-point complex FFT held entirely in one thread's registers, the building block of the log-mel experiment
-// (frontend.cu, logmel_b_kernel: a 256-point complex FFT as 16 x 16, sixteen lanes per frame, two frames per warp).
-// Host + device code: tests/test_logmel_b_host.py compiles this header with g++ and runs the kernel's whole per-frame
-// arithmetic (both FFT16 passes, inter-pass twiddles, the real-FFT split with its partner-lane mapping) on the CPU
+// 16-point complex FFT held entirely in one thread's registers, the building block of the fused log-mel kernel
+// (logmel.cu: a 256-point complex FFT as 16 x 16, sixteen lanes per frame, two frames per warp).
+// Host + device code: tests/test_logmel_host.py compiles this header with g++ and runs the kernel's whole per-frame
+// arithmetic (both FFT16 passes, inter-pass twiddles, the paired real-FFT split with its partner-lane mapping) on the CPU
 // against numpy, so the index algebra is checked without a GPU.
 #pragma once
 #if defined(__CUDACC__)

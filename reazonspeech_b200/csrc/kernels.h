@@ -73,25 +73,14 @@ inline size_t splitk_flag_bytes(int ncl) { return static_cast<size_t>(ncl) * 2 *
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
 
-struct FrontendTables;   // device tables of the log-mel frontend (window, twiddles, sparse mel)
-cudaError_t launch_logmel(const float* wav, const int32_t* len, int B, int L_max, float* mel,
-                          int32_t* mel_len, float* partials, const void* tables, int n_mels,
-                          int hop, int n_fft, int win, float preemph, float guard, float eps,
-                          cudaStream_t stream);
-
-// EXPERIMENT (RS_LOGMEL_VARIANT=B, unmeasured): the log-mel kernel with a register-resident 16 x 16 FFT, sixteen lanes per
-// frame and two frames per warp (frontend.cu logmel_b_kernel); tables from engine.py::frontend_tables_b.
-struct FeTablesB { const float* tw_b; const float* tw_x; const float* lane_w; const int32_t* lane_bins; const int32_t* lane_nb; };
-cudaError_t launch_logmel_b(const float* wav, const int32_t* len, int B, int L_max, float* mel, int32_t* mel_len,
-                            const void* tables, const FeTablesB& tb, int n_mels, int hop, int n_fft, int win,
-                            float preemph, float guard, float eps, cudaStream_t stream);
-
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out_f32,
                              void* out_bf16, const float* gamma2, const float* beta2, int rows, int d,
                              float eps, cudaStream_t stream);
 
 struct SubsampleArgs {
-  const float* mel; const int32_t* mel_len; int B, F_max, n_mels, C;
+  const float* mel; const int32_t* mel_len;   // un-normalised log-mel [B, F_max, n_mels] and valid frames
+  const float* mel_stats;                     // [B, n_mels, 2] (mean, 1 / (std + eps)) from the log-mel kernel
+  int B, F_max, n_mels, C;
   const float* w0; const float* b0;      // conv.0  [C,9], [C]
   const float* wd1; const float* bd1;    // conv.2  [C,9], [C]
   void* out1;                            // bf16 [B,T2,F2,C]

@@ -3,7 +3,8 @@
 // pkg/nemo-asr/src/transcribe.py:48-53).  The 1x1 convs and the output Linear run on the
 // tcgen05 GEMM over channels-last activations; this file holds the HBM-bound 3x3 convs.
 //
-// Kernel A fuses conv.0 (1->C, 3x3, s2, p1) + ReLU + conv.2 (depthwise 3x3, s2, p1): the
+// Kernel A fuses the per-feature normalisation of the log-mel features (statistics from logmel.cu), conv.0
+// (1->C, 3x3, s2, p1) + ReLU + conv.2 (depthwise 3x3, s2, p1): the
 // [B, T1, 40, C] intermediate (1 GB at 32 x 30 s in bf16) never reaches HBM.  One thread per
 // channel; the mel patch of the tile sits in shared memory and is read as a warp broadcast.
 // Every stage treats frames at or beyond the utterance's length at that stage as zero, which is
@@ -25,7 +26,8 @@ constexpr int kMelOff = 4;    // smem column of mel bin 0 (bin -1 sits at column
 // together with the previous step's last three columns, and conv.0 at f1 = 2*f2-1 is carried over from
 // the previous step: per output 7 LDS.128 + 63 FMA instead of 54 scalar shared loads.
 __global__ void __launch_bounds__(256)
-sub_conv0_dw1_kernel(const float* __restrict__ mel, const int32_t* __restrict__ mel_len, int F_max, int n_mels, int C,
+sub_conv0_dw1_kernel(const float* __restrict__ mel, const int32_t* __restrict__ mel_len, const float* __restrict__ mel_stats,
+                     int F_max, int n_mels, int C,
                      const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ wd,
                      const float* __restrict__ bd, __nv_bfloat16* __restrict__ out, int T2, int F1, int F2) {
   extern __shared__ __align__(16) float s_mel[];         // [(4*TT+3)][ld], column kMelOff + bin
@@ -37,12 +39,18 @@ sub_conv0_dw1_kernel(const float* __restrict__ mel, const int32_t* __restrict__ 
   const int rows = 4 * kSubTT + 3;
   const int ld = ((n_mels + kMelOff + 4 + 3) / 4) * 4;   // bins -4 .. n_mels+3 addressable, multiple of 4 floats
   const int t0_base = 4 * t2_0 - 3;                      // first mel row needed: 2*(2*t2_0-1)-1
+  // The log-mel kernel leaves the features un-normalised next to their per-utterance statistics (logmel.cu): NeMo's
+  // per-feature normalisation (x - mean) / (std + eps) and its zero tail (frames >= len read as 0, which is also the
+  // convolution's zero padding at batch = 1) are applied here, while the patch is staged.
+  const float* st = mel_stats != nullptr ? mel_stats + static_cast<size_t>(b) * n_mels * 2 : nullptr;   // nullptr: already normalised (rs_encode)
   for (int i = threadIdx.x; i < rows * ld; i += blockDim.x) {
     const int r = i / ld, bin = i % ld - kMelOff;
     const int t0 = t0_base + r;
     float v = 0.f;
-    if (t0 >= 0 && t0 < len0 && t0 < F_max && bin >= 0 && bin < n_mels)
+    if (t0 >= 0 && t0 < len0 && t0 < F_max && bin >= 0 && bin < n_mels) {
       v = mel[(static_cast<size_t>(b) * F_max + t0) * n_mels + bin];
+      if (st != nullptr) v = (v - __ldg(st + 2 * bin)) * __ldg(st + 2 * bin + 1);
+    }
     s_mel[i] = v;
   }
   __syncthreads();
@@ -114,7 +122,7 @@ cudaError_t launch_sub_conv0_dw1(const SubsampleArgs& a, cudaStream_t stream) {
   const int ld = ((a.n_mels + kMelOff + 4 + 3) / 4) * 4;
   const size_t smem = static_cast<size_t>(4 * kSubTT + 3) * ld * sizeof(float);
   const dim3 grid((a.T2 + kSubTT - 1) / kSubTT, a.B);
-  sub_conv0_dw1_kernel<<<grid, 256, smem, stream>>>(a.mel, a.mel_len, a.F_max, a.n_mels, a.C, a.w0, a.b0, a.wd1, a.bd1,
+  sub_conv0_dw1_kernel<<<grid, 256, smem, stream>>>(a.mel, a.mel_len, a.mel_stats, a.F_max, a.n_mels, a.C, a.w0, a.b0, a.wd1, a.bd1,
                                                    static_cast<__nv_bfloat16*>(a.out1), a.T2, a.F1, a.F2);
   return cudaGetLastError();
 }

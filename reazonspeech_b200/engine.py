@@ -16,10 +16,10 @@ import numpy as np
 import torch
 
 from .config import ModelConfig, conv_out_len, xscale
-from .weights import StateDict, hann_window, mel_filterbank, rel_pos_table
+from .logmel_tables import logmel_tables
+from .weights import StateDict, rel_pos_table
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librs_engine.so")
-MEL_MAX_W = 40
 
 EPI_BIAS_BF16, EPI_BIAS_RELU_BF16, EPI_BIAS_SWISH_BF16, EPI_BIAS_GLU_BF16, EPI_RESID_F32, EPI_BIAS_F32, EPI_BIAS_F16 = range(7)
 
@@ -123,83 +123,11 @@ def glu_interleave_index(d: int) -> torch.Tensor:
     return torch.where(within < 16, blk * 16 + within, d + blk * 16 + within - 16)
 
 
-def frontend_tables(cfg: ModelConfig) -> Dict[str, torch.Tensor]:
-    if cfg.n_fft != 512:
-        raise ValueError("frontend kernel is built for n_fft == 512")
-    win = torch.zeros(cfg.n_fft, dtype=torch.float32)
-    lo = (cfg.n_fft - cfg.n_window_size) // 2
-    win[lo:lo + cfg.n_window_size] = hann_window(cfg)
-    k = np.arange(cfg.n_fft // 2, dtype=np.float64)
-    tw256 = np.stack([np.cos(2 * np.pi * k / 256), -np.sin(2 * np.pi * k / 256)], axis=1)
-    k2 = np.arange(cfg.n_fft // 2 + 1, dtype=np.float64)
-    tw512 = np.stack([np.cos(2 * np.pi * k2 / 512), -np.sin(2 * np.pi * k2 / 512)], axis=1)
-    fb = mel_filterbank(cfg).numpy()
-    start = np.zeros(cfg.n_mels, dtype=np.int32)
-    count = np.zeros(cfg.n_mels, dtype=np.int32)
-    w = np.zeros((cfg.n_mels, MEL_MAX_W), dtype=np.float32)
-    for m in range(cfg.n_mels):
-        nz = np.nonzero(fb[m])[0]
-        if len(nz) == 0:
-            continue
-        s, e = int(nz[0]), int(nz[-1])
-        if e - s + 1 > MEL_MAX_W:
-            raise ValueError(f"mel filter {m} spans {e - s + 1} bins > {MEL_MAX_W}")
-        start[m], count[m] = s, e - s + 1
-        w[m, : e - s + 1] = fb[m, s:e + 1]
-    return {
-        "fe.window": win, "fe.tw256": torch.from_numpy(tw256.astype(np.float32)).reshape(-1),
-        "fe.tw512": torch.from_numpy(tw512.astype(np.float32)).reshape(-1),
-        "fe.mel_start": torch.from_numpy(start), "fe.mel_count": torch.from_numpy(count),
-        "fe.mel_w": torch.from_numpy(w).reshape(-1),
-    }
-
-
-# Tables of the log-mel EXPERIMENT (RS_LOGMEL_VARIANT=B, frontend.cu logmel_b_kernel; unmeasured): 256-point FFT as 16 x 16
-# with sixteen lanes per frame.  Lane t of a frame holds the inter-pass twiddles W256^(t k1) and the real-split twiddles
-# W512^(t + 16 k2) in [k][t] order (conflict-free rows), and owns a fixed set of mel filters chosen so that every lane sums
-# about the same number of taps (longest-filter-first dealing); a filter is never split across lanes, so the order of
-# its sum is fixed.
-LOGMEL_B_LANES, LOGMEL_B_LANE_BINS, LOGMEL_B_LANE_TAPS = 16, 8, 47
-
-
-def frontend_tables_b(cfg: ModelConfig, base: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-    t = np.arange(16, dtype=np.float64)[None, :]
-    k = np.arange(16, dtype=np.float64)[:, None]
-    ang_b = 2 * np.pi * (t * k) / 256.0
-    ang_x = 2 * np.pi * (t + 16 * k) / 512.0
-    tw_b = np.stack([np.cos(ang_b), -np.sin(ang_b)], axis=-1).astype(np.float32)           # [k1][t][2]
-    tw_x = np.stack([np.cos(ang_x), -np.sin(ang_x)], axis=-1).astype(np.float32)           # [k2][t][2]
-    start, count = base["fe.mel_start"].numpy(), base["fe.mel_count"].numpy()
-    w = base["fe.mel_w"].numpy().reshape(cfg.n_mels, MEL_MAX_W)
-    lanes = [[] for _ in range(LOGMEL_B_LANES)]
-    load = [0] * LOGMEL_B_LANES
-    for m in sorted(range(cfg.n_mels), key=lambda m: (-int(count[m]), m)):
-        i = min(range(LOGMEL_B_LANES), key=lambda i: (load[i], i))
-        lanes[i].append(m)
-        load[i] += int(count[m])
-    if max(len(l) for l in lanes) > LOGMEL_B_LANE_BINS or max(load) > LOGMEL_B_LANE_TAPS:
-        raise ValueError(f"log-mel variant B: {max(len(l) for l in lanes)} filters / {max(load)} taps on one lane exceed the kernel's limits")
-    lane_w = np.zeros((LOGMEL_B_LANES, LOGMEL_B_LANE_TAPS), dtype=np.float32)
-    lane_bins = np.zeros((LOGMEL_B_LANES, LOGMEL_B_LANE_BINS), dtype=np.int32)
-    lane_nb = np.zeros(LOGMEL_B_LANES, dtype=np.int32)
-    for i, ms in enumerate(lanes):
-        pos = 0
-        for j, m in enumerate(sorted(ms)):
-            c = int(count[m])
-            lane_w[i, pos:pos + c] = w[m, :c]
-            lane_bins[i, j] = m | (int(start[m]) << 8) | (c << 18)
-            pos += c
-        lane_nb[i] = len(ms)
-    return {"fe.b.tw_b": torch.from_numpy(tw_b).reshape(-1), "fe.b.tw_x": torch.from_numpy(tw_x).reshape(-1),
-            "fe.b.lane_w": torch.from_numpy(lane_w).reshape(-1), "fe.b.lane_bins": torch.from_numpy(lane_bins).reshape(-1),
-            "fe.b.lane_nb": torch.from_numpy(lane_nb)}
-
-
 def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     """NeMo-named fp32 state dict -> packed host tensors (bf16 GEMM weights, folded BN, ...)."""
     bf = lambda t: t.to(torch.bfloat16).contiguous()
     f32 = lambda t: t.to(torch.float32).contiguous()
-    out: Dict[str, torch.Tensor] = dict(frontend_tables(cfg))
+    out: Dict[str, torch.Tensor] = dict(logmel_tables(cfg))
     d, H, dk, Cc = cfg.d_model, cfg.n_heads, cfg.d_head, cfg.sub_channels
     pe = "encoder.pre_encode."
     out["sub.conv0.w"] = f32(sd[pe + "conv.0.weight"].reshape(Cc, 9)); out["sub.conv0.b"] = f32(sd[pe + "conv.0.bias"])
@@ -305,8 +233,6 @@ class Engine:
         packed = pack_weights(state_dict, cfg)
         if os.environ.get("RS_LN_FOLD", "0") == "1":        # experiment, off by default: see ln_fold_tensors
             packed.update(ln_fold_tensors(packed, cfg))
-        if os.environ.get("RS_LOGMEL_VARIANT", "") == "B":  # experiment, off by default: see frontend_tables_b
-            packed.update(frontend_tables_b(cfg, packed))
         self.weights = {k: v.to(self.device) for k, v in packed.items()}
         self._names = [k.encode() for k in self.weights]
         arr = (RsTensor * len(self.weights))()
@@ -364,6 +290,7 @@ class Engine:
     def log_mel(self, wav: torch.Tensor, lens: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         B, L = wav.shape
         assert wav.dtype == torch.float32 and wav.is_contiguous() and lens.dtype == torch.int32
+        self.ensure_workspace(B, L)                  # the per-feature statistics are reduced in the workspace
         F = self.mel_frames(L)
         mel = torch.empty(B, F, self.cfg.n_mels, dtype=torch.float32, device=self.device)
         mel_len = torch.empty(B, dtype=torch.int32, device=self.device)
