@@ -128,56 +128,101 @@ def dist_setup(gpus: int):
     return world, rank, local
 
 
-def cpu_oracle_rtfx(seconds: float, repeats: int = 1):
-    """The reference algorithm (oracle port, fp32 PyTorch, batch=1 like transcribe.py:48-50) on the host cores."""
+CPU_CLIPS = 8          # bounded CPU sample: the first clips of the SAME 32 x 30 s set, one transcribe() each (batch = 1)
+
+
+def _cpu_setup(pin: bool):
     from oracle import nemo_restated as O
+    from oracle.cpu_threads import physical_threads
     from reazonspeech_b200.config import ModelConfig
     from reazonspeech_b200.synth import synth_clip
     from reazonspeech_b200.weights import random_state_dict
     cfg = ModelConfig()
     sd = random_state_dict(cfg, seed=0)
-    from oracle.cpu_threads import tune_threads
-    cores = tune_threads()
-    wave = torch.from_numpy(np.pad(synth_clip(0, seconds), PAD))
-    O.transcribe_tokens(torch.from_numpy(np.pad(synth_clip(1, 1.0), PAD)), sd, cfg)      # warm-up
-    times = []
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        O.transcribe_tokens(wave, sd, cfg)
-        times.append(time.perf_counter() - t0)
-    return seconds / float(np.median(times)), cores, float(np.median(times))
+    cores, how = physical_threads(pin=pin)          # deterministic: one thread per physical core of one NUMA node
+    clip = lambda i, seconds: torch.from_numpy(np.pad(synth_clip(i, seconds), PAD))
+    return O, cfg, sd, cores, how, clip
+
+
+def cpu_oracle_rtfx(seconds: float, n_clips: int = CPU_CLIPS):
+    """The reference algorithm (oracle port, fp32 PyTorch, batch=1 like transcribe.py:48-50) on the host cores, on the first
+    ``n_clips`` clips of the GPU arm's own clip set."""
+    O, cfg, sd, cores, how, clip = _cpu_setup(pin=False)
+    n_before = torch.get_num_threads()
+    O.transcribe_tokens(clip(1, 2.0), sd, cfg)                                  # warm-up (thread pool, oneDNN primitives)
+    t0 = time.perf_counter()
+    for i in range(n_clips):
+        O.transcribe_tokens(clip(i, seconds), sd, cfg)
+    dt = time.perf_counter() - t0
+    torch.set_num_threads(n_before)
+    return n_clips * seconds / dt, cores, how, dt
 
 
 def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; NeMo itself cannot be installed offline)
+    on the SAME clips as the GPU arm.  A step = one transcribe() of one 30 s clip of the set (batch = 1 is the only way
+    the reference calls NeMo, pkg/nemo-asr/src/transcribe.py:48-50); K steps walk K clips of the 32."""
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    seconds = args.cpu_seconds
-    from oracle import nemo_restated as O
-    from reazonspeech_b200.config import ModelConfig
-    from reazonspeech_b200.synth import synth_clip
-    from reazonspeech_b200.weights import random_state_dict
-    cfg = ModelConfig()
-    sd = random_state_dict(cfg, seed=0)
-    from oracle.cpu_threads import tune_threads
-    cores = tune_threads()
-    wave = torch.from_numpy(np.pad(synth_clip(0, seconds), PAD))
-    for _ in range(max(args.warmup, 1)):
-        O.transcribe_tokens(torch.from_numpy(np.pad(synth_clip(1, 1.0), PAD)), sd, cfg)
+    seconds = args.seconds
+    O, cfg, sd, cores, how, clip = _cpu_setup(pin=True)
+    for i in range(max(min(args.warmup, 3), 1)):
+        O.transcribe_tokens(clip(31 - i, 2.0 if i else seconds), sd, cfg)       # first warm-up at full length, the rest short
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.transcribe_tokens(wave, sd, cfg)
+    for k in range(args.steps):
+        O.transcribe_tokens(clip(k % args.batch, seconds), sd, cfg)
     dt = time.perf_counter() - t0
     v = args.steps * seconds / dt
-    sample = f"{args.steps} x one {seconds:g} s clip (batch=1, fp32, greedy), oracle port of the NeMo path"
+    sample = (f"{args.steps} steps x one {seconds:g} s clip of the same {args.batch}-clip set (batch=1, fp32, greedy), oracle port of the "
+              f"NeMo path; {how}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic 16 kHz AM/FM clips; seeded random weights (619 M architecture)",
-        "config": {"workload": "nemo-asr FastConformer-RNNT 619M, 32x30 s per GPU (reference arm: bounded CPU sample)", "sample": sample},
+        "config": {"workload": f"nemo-asr FastConformer-RNNT 619M, batch={args.batch}x{seconds:g} s clips per GPU", "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
+
+
+def decode_sensitivity(eng, run_step, n_tok_of, steps: int, targets=(50, 150, 250)):
+    """Step time as a function of the decode load: the synthetic checkpoint's blank bias is shifted (device tensor, in place)
+    until the batch emits about `target` tokens per 30 s clip, the step is timed, the bias is restored.  The emission rate of
+    random weights is a property of one calibration; this makes the RTFx's dependence on it visible."""
+    bias = eng.weights["joint.out.b"]
+    blank = eng.cfg.blank
+    base = float(bias[blank])
+    out = []
+
+    def tokens_at(shift):
+        bias[blank] = base + shift
+        run_step()
+        torch.cuda.synchronize()
+        return float(n_tok_of().float().mean())
+
+    try:
+        for target in targets:
+            lo, hi = -12.0, 12.0                                   # tokens decrease as the blank bias rises
+            for _ in range(16):
+                mid = 0.5 * (lo + hi)
+                if tokens_at(mid) > target:
+                    lo = mid
+                else:
+                    hi = mid
+            shift = 0.5 * (lo + hi)
+            tok = tokens_at(shift)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(steps):
+                run_step()
+            ev1.record()
+            torch.cuda.synchronize()
+            out.append({"target_tokens_per_clip": target, "tokens_per_clip": tok, "blank_shift": shift, "max_tokens_in_a_clip": int(n_tok_of().max()),
+                        "ms_per_step": ev0.elapsed_time(ev1) / steps})
+    finally:
+        bias[blank] = base
+    return out
 
 
 def main():
@@ -188,8 +233,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
     ap.add_argument("--seconds", type=float, default=NOMINAL_SECONDS)
-    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="clip length of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip python_api / decode_sensitivity / config2 (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -279,13 +324,13 @@ def main():
     torch.cuda.synchronize(dev)
     stages = eng.stage_times_ms()
     eng.enable_stage_timing(False)
-    decode_prof = eng.decode_cycles(B, L, U) if os.environ.get("RS_DECODE_MODE", "0") != "1" else None
+    decode_prof = eng.decode_cycles(B, L, U)
     # per-kernel device time inside the pipeline (event pair around every launch; one extra, untimed step)
     eng.kernel_timing(True)
     eng.transcribe_device(wav_dev, len_dev, U, out_dev)
     kernel_ms = {k: {"launches": n, "ms": round(ms, 4)} for k, (n, ms) in sorted(eng.kernel_timing().items(), key=lambda kv: -kv[1][1])}
     eng.kernel_timing(False)
-    attn_cycles = eng.attention_cycles() if os.environ.get("RS_ATTN_MODE", "0") != "1" else None
+    attn_cycles = eng.attention_cycles()
     # memory-bound kernels against the measured copy bandwidth: ALGORITHMIC bytes over the
     # in-pipeline time of their launches (event pairs above, so warm-L2 effects are included: a fraction can exceed 1)
     valid_T = eng.cfg.enc_frames(L)
@@ -308,28 +353,61 @@ def main():
     # frames); the roofline numerator keeps only the valid rows
     g_flops *= eng.cfg.enc_frames(L) / max(eng.enc_frames(L), 1)
     achieved = g_flops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    # DRAM bytes per launch of the dominant kernel: mean of dram__bytes_read.sum + dram__bytes_write.sum over the
-    # six consecutive launches of the `ncu --set full` capture in profiles/r01_v4_gemm_ncu.md (not re-measured here)
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": 1.176e8,
-                "traffic_source": "profiles/r01_v4_gemm_ncu.md (dram read + write, mean over 6 consecutive launches, bytes)",
+    # DRAM bytes per launch of the dominant kernel cannot be measured without a profiler: they are read from the committed
+    # summary of this round's `ncu --set full` capture of the same command (profiles/r02_gemm_traffic.json, written by
+    # scripts/summarize_ncu.py); null when that file is absent
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": sus, "unit": "TFLOP/s", "frac": achieved / sus, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "kernel": "gemm_bf16_tn_kernel (tcgen05.mma, all encoder/joint GEMMs)", "peak_source": f"{src} bf16_tflops_sustained",
                 "launches_per_step": g_n // max(args.steps, 1), "gemm_ms_per_step": g_ms / max(args.steps, 1),
                 "algorithmic_gflop_per_step": g_flops / max(args.steps, 1) / 1e9,
                 "how": "CUDA events around every GEMM launch on its stream, separate pass of the same K steps"}
 
+    # configs[2] of BASELINE.json (1024 clips sharded over 8 GPUs = 128 per GPU) next to the 32-per-GPU weak-scaling value
+    config2 = None
+    if world == 8 and not args.no_extras:
+        B2 = 128
+        w2, l2 = make_batch(B2, args.seconds, rank)
+        w2d, l2d = w2.to(dev), l2.to(dev)
+        o2 = (torch.zeros(B2, U, dtype=torch.int32, device=dev), torch.zeros(B2, U, dtype=torch.int32, device=dev), torch.zeros(B2, dtype=torch.int32, device=dev))
+        eng.ensure_workspace(B2, L)
+        for _ in range(2):
+            eng.transcribe_device(w2d, l2d, U, o2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n2 = max(args.steps // 4, 3)
+        e0.record()
+        for _ in range(n2):
+            eng.transcribe_device(w2d, l2d, U, o2)
+        e1.record()
+        barrier()
+        ms2 = max_over_ranks(e0.elapsed_time(e1)) / n2
+        config2 = {"workload": f"nemo-asr FastConformer-RNNT 619M, {world * B2} x {args.seconds:g} s clips sharded by utterance across {world} GPUs ({B2} per GPU)",
+                   "value": world * B2 * args.seconds / (ms2 / 1e3), "unit": UNIT, "ms_per_step": ms2, "steps": n2}
+        del w2d, l2d, o2
     if rank != 0:
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # the CPU arm is timed at N=1 only (it is the same host either way)
-        v, cores, secs = cpu_oracle_rtfx(args.cpu_seconds)
+        v, cores, how, secs = cpu_oracle_rtfx(args.seconds)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"one {args.cpu_seconds:g} s clip, batch=1 fp32 greedy through the oracle port ({secs:.1f} s of CPU work)"}
-    api = None
-    if world == 1:
+               "sample": f"the first {CPU_CLIPS} clips of the same {B} x {args.seconds:g} s set, one transcribe() each (batch=1, fp32, greedy) "
+                         f"through the oracle port: {secs:.1f} s of CPU work on {how}"}
+    api = sens = None
+    if world == 1 and not args.no_extras:
         try:
             api = python_api_rtfx(eng, B, args.seconds, rank)
         except Exception as exc:      # an extra: reported, never fatal to the contract keys
             api = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            sens = decode_sensitivity(eng, lambda: eng.transcribe_device(wav_dev, len_dev, U, out_dev), lambda: out_dev[2].cpu(), max(args.steps // 2, 3))
+        except Exception as exc:
+            sens = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -342,6 +420,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu, "python_api": api,
+        "decode_sensitivity": sens, "config2": config2,
     }), flush=True)
 
 

@@ -150,8 +150,6 @@ int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches);
 /* Per-kernel CUDA-event timing of EVERY launch inside the real pipeline (warm caches, back-to-back launches, unlike
  * the cold, serialised launches ncu reports).  rs_kernel_timing() synchronises the device and writes one line per
  * kernel name, "name<TAB>launches<TAB>total_ms", into buf; the log is reset. */
-/* Host-only (no device needed): work list of the RS_GEMM_SPLITK experiment -- see reazonspeech_b200/csrc/kernels.h. */
-int rs_debug_splitk_schedule(int num_tiles, int n_clusters, int num_k, int32_t* rows7, int max_rows, int* split);
 int rs_enable_kernel_timing(rs_engine* e, int on);
 int rs_kernel_timing(rs_engine* e, char* buf, int buf_bytes);
 

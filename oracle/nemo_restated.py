@@ -290,18 +290,26 @@ class FollowResult:
     complete: bool = True                                  # the sequence accounts for every frame, no more, no less
     gaps: List[tuple] = field(default_factory=list)        # (decision index, frame, given, oracle argmax, logit gap) where they differ
     min_margin: float = float("inf")                       # smallest oracle top-2 margin met on the way
+    margins: List[float] = field(default_factory=list)     # oracle top-2 margin of every decision
+    noise: List[float] = field(default_factory=list)       # with enc_ref: change of that top-2 gap when enc_ref replaces enc
 
 
-def greedy_follow(enc: torch.Tensor, sd: StateDict, cfg: ModelConfig, decisions: List[int], emulate: bool = False) -> FollowResult:
+def greedy_follow(enc: torch.Tensor, sd: StateDict, cfg: ModelConfig, decisions: List[int], emulate: bool = False,
+                  enc_ref: Optional[torch.Tensor] = None) -> FollowResult:
     """Re-synchronising comparison with a greedy decode produced elsewhere (the sm_100a engine).
 
     Walks ``decisions`` (the argmax of EVERY joint evaluation, blanks included, as rebuilt from tokens + frames) through
     the same control flow as ``rnnt_greedy`` but TEACHER-FORCED: the predictor state always follows the given decision.
     Wherever the oracle's own argmax differs, the entry records ``logit[oracle argmax] - logit[given]`` -- the amount by
     which the given decision loses under the oracle's arithmetic -- and the walk goes on, so one near-tie cannot hide the
-    rest of the sequence.  A decode is greedy-identical to the oracle iff ``gaps`` is empty and ``complete`` is true."""
+    rest of the sequence.  A decode is greedy-identical to the oracle iff ``gaps`` is empty and ``complete`` is true.
+
+    ``enc_ref`` (a second evaluation of the SAME encoder, e.g. the fp32 one next to the bf16-emulated ``enc``) turns the walk
+    into a noise measurement as well: at every decision the gap between the oracle's two best classes is re-evaluated with
+    ``enc_ref``'s frame and the change is recorded in ``noise`` -- how far storage rounding alone moves a decision gap."""
     res = FollowResult()
     ep = joint_enc_proj(_q(enc, emulate), sd)
+    ep_ref = joint_enc_proj(_q(enc_ref, emulate), sd) if enc_ref is not None else None
     n_threads = torch.get_num_threads()
     torch.set_num_threads(1)
     try:
@@ -319,7 +327,12 @@ def greedy_follow(enc: torch.Tensor, sd: StateDict, cfg: ModelConfig, decisions:
                     return res
                 logits = F.linear(torch.relu(ep[t] + pp), W, b)
                 top2 = torch.topk(logits, 2)
-                res.min_margin = min(res.min_margin, float(top2.values[0] - top2.values[1]))
+                m = float(top2.values[0] - top2.values[1])
+                res.min_margin = min(res.min_margin, m)
+                res.margins.append(m)
+                if ep_ref is not None:
+                    alt = F.linear(torch.relu(ep_ref[t] + pp), W, b)
+                    res.noise.append(float(alt[top2.indices[0]] - alt[top2.indices[1]]) - m)
                 k = int(decisions[i]); i += 1
                 if k != int(top2.indices[0]):
                     res.gaps.append((i - 1, t, k, int(top2.indices[0]), float(top2.values[0] - logits[k])))

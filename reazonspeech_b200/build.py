@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "librs_engine.so")
-SOURCES = ["gemm_tcgen05.cu", "logmel.cu", "subsample.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "decode.cu", "decode_batched.cu", "decode_spec.cu", "engine.cu"]
+SOURCES = ["gemm_tcgen05.cu", "logmel.cu", "subsample.cu", "elementwise.cu", "attention_tc.cu", "decode_spec.cu", "engine.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -33,17 +33,8 @@ def _headers_mtime() -> float:
     return max(os.path.getmtime(h) for h in hs)
 
 
-# Compile-time variants of the library (EXPERIMENTS; the default library is what every test and the bench load unless
-# RS_ENGINE_VARIANT names one).  "pdl": programmatic dependent launch in the encoder's kernels, see csrc/common.cuh.
-VARIANTS = {"pdl": ["-DRS_PDL=1"]}
-
-
-def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
-    if variant and variant not in VARIANTS:
-        raise ValueError(f"unknown variant {variant!r} (known: {sorted(VARIANTS)})")
-    obj_dir = OBJ + ("_" + variant if variant else "")
-    lib = LIB.replace(".so", f"_{variant}.so") if variant else LIB
-    defines = VARIANTS.get(variant, [])
+def build(force: bool = False, verbose: bool = False) -> str:
+    obj_dir, lib = OBJ, LIB
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     hm = _headers_mtime()
@@ -56,7 +47,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc, *ARCH, *FLAGS, *defines, "-c", s, "-o", o]
+        cmd = [nvcc, *ARCH, *FLAGS, "-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -77,7 +68,4 @@ def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
 
 
 if __name__ == "__main__":
-    _variant = ""
-    if "--variant" in sys.argv:
-        _variant = sys.argv[sys.argv.index("--variant") + 1]
-    print(build(force="--force" in sys.argv, verbose=True, variant=_variant))
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -89,7 +89,6 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
 __global__ void __launch_bounds__(kAtcThreads, 1)
 local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, const AtcDev p) {
   extern __shared__ uint8_t atc_raw[];
-  RS_PDL_TRIGGER(); RS_PDL_WAIT();      // (-DRS_PDL variant only) before enc_len: nothing above the wait may read activations
   const uint32_t base = (smem_u32(atc_raw) + 1023u) & ~1023u;
   uint8_t* gen = atc_raw + (base - smem_u32(atc_raw));          // generic pointer to the aligned base
   const uint32_t bar_qk = base + kOffBar, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_o = bar_qk + 24, tmem_slot = bar_qk + 32;
@@ -405,7 +404,6 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
 __global__ void __launch_bounds__(256)
 global_row_attention_tc_kernel(const AtcDev p) {
   extern __shared__ __align__(16) float gs[];        // [T_pad] scores | [8] reduction scratch | [128] q
-  RS_PDL_TRIGGER(); RS_PDL_WAIT();
   const int h = blockIdx.x, b = blockIdx.y;
   const int len = p.enc_len[b];
   if (len <= 0) return;
@@ -542,13 +540,13 @@ cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     attr_once.set();
   }
   const dim3 grid((a.T_max + TQ - 1) / TQ, a.H, a.B);
-  RS_LAUNCH(local_attention_tc_kernel, grid, kAtcThreads, kAtcSmem, stream, tm_qk, tm_vt, p);
+  local_attention_tc_kernel<<<grid, kAtcThreads, kAtcSmem, stream>>>(tm_qk, tm_vt, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.n_global > 0) {
     const size_t gsmem = (static_cast<size_t>(((a.T_max > 1024 ? a.T_max : 1024) + 7) & ~7) + 8 + TDK) * sizeof(float);
     if (gsmem > 200 * 1024) return cudaErrorInvalidValue;
-    RS_LAUNCH(global_row_attention_tc_kernel, dim3(a.H, a.B), 256, gsmem, stream, p);
+    global_row_attention_tc_kernel<<<dim3(a.H, a.B), 256, gsmem, stream>>>(p);
     e = cudaGetLastError();
   }
   return e;

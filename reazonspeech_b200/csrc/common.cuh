@@ -8,38 +8,7 @@
 
 #include <atomic>
 
-// EXPERIMENT (variant library built with -DRS_PDL=1, see build.py --variant pdl): programmatic
-// dependent launch.  A kernel launched with the programmatic-stream-serialization attribute may start while its
-// predecessor in the stream is still running; RS_PDL_WAIT() is where it blocks until that predecessor has completed
-// and its writes are visible -- everything above it (barrier init, TMEM allocation, descriptor prefetch, the launch
-// itself) overlaps the predecessor's tail.  RS_PDL_TRIGGER() lets the NEXT kernel in the stream do the same with
-// this one.  In the default build all three macros compile to nothing / a plain <<<>>> launch.
-#ifdef RS_PDL
-#define RS_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
-#define RS_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
-#else
-#define RS_PDL_WAIT() ((void)0)
-#define RS_PDL_TRIGGER() ((void)0)
-#endif
-
 namespace rs {
-
-#ifdef RS_PDL
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-// kernel names containing commas go in parentheses: RS_LAUNCH((k<A, B>), grid, block, smem, stream, args...)
-#define RS_LAUNCH(kernel, grid, block, smem, stream, ...) ::rs::launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__)
-#else
-#define RS_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
-#endif
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is PER DEVICE: a second engine on another GPU of the same process
 // (load_model("cuda:1") after "cuda:0", or the one-process multi-GPU model) must opt in again.  One bit per device

@@ -1,8 +1,6 @@
-// Windowed ("blank-run speculative") batched RNN-T greedy decode on the legacy tensor path.
-//
-// Same algorithm and results as decode_batched.cu / decode.cu (NeMo GreedyRNNTInfer._greedy_decode,
-// RNNTDecoder.predict, RNNTJoint.joint; the reference reaches it at pkg/nemo-asr/src/transcribe.py:48-53),
-// reorganised around two facts about greedy transducer decoding:
+// Windowed ("blank-run speculative") batched RNN-T greedy decode: NeMo GreedyRNNTInfer._greedy_decode, RNNTDecoder.predict
+// and RNNTJoint.joint (the reference reaches them at pkg/nemo-asr/src/transcribe.py:48-53) as ONE persistent cooperative
+// kernel, organised around two facts about greedy transducer decoding:
 //
 //  1. A blank leaves the prediction-network state untouched, so the joint of the NEXT frames can be
 //     evaluated against the same state before the current decision is known.  Every iteration scores a
@@ -13,11 +11,10 @@
 //  2. With kFrames x B rows per iteration the joint is a real (small) GEMM.  The CTAs form a 2-D grid,
 //     kGroups utterance groups x S vocabulary slices: a CTA keeps its ~82 rows of W_out in shared memory
 //     for the whole decode and multiplies them with the relu(enc_proj + pred_proj) rows of its group
-//     (32 rows per pass) on mma.sync m16n8k16.  Activations keep 22 mantissa bits: every fp32 value is split into
-//     two IEEE-half terms (hi + lo), the bf16 weights are exact in half, accumulation is fp32 (a three-term bf16
-//     split gave 24 bits but cost 1.5x: the legacy tensor path issues one m16n8k16 per ~19 cycles and scheduler).
+//     (32 rows per pass) on tcgen05 (see the kernel's comment).  Activations keep 22 mantissa bits: every fp32 value is
+//     split into two IEEE-half terms (hi + lo), the bf16 weights are exact in half, accumulation is fp32.
 //     The LSTM step and joint.pred of the utterances that emitted are the same kind of GEMM (rows =
-//     utterances, K split over the warps, A fragments loaded straight from L2).
+//     utterances, K split over the warps, A fragments loaded straight from L2) on mma.sync m16n8k16.
 //
 //   phase J  kGroups x S CTAs: window logits of the CTA's vocabulary slice -> per (utterance, frame) a grid-wide
 //            64-bit red.max of (ordered logit bits | ~row)
@@ -37,7 +34,6 @@ constexpr int kFrames = 4;                       // frames scored per utterance 
 constexpr int kGroups = 4;                       // utterance groups (utterance b belongs to group b % kGroups)
 constexpr int kPassRows = 32;                    // (utterance, frame) rows per pass: two m16 tiles
 constexpr int kPassUtts = kPassRows / kFrames;
-constexpr int kMaxTilesPerWarp = 3;              // vocabulary n8-tiles per warp (4 warps share an m16 tile)
 
 struct SpecDev {
   const float* enc_proj; const int32_t* enc_len;
@@ -109,7 +105,7 @@ __device__ __forceinline__ unsigned long long pack_best(float v, int row) {
   return (static_cast<unsigned long long>(fb) << 32) | (0xffffffffu - static_cast<unsigned int>(row));   // ties -> lower row
 }
 
-// TCJ = true: the joint window runs on tcgen05 instead of mma.sync.  A = the CTA's W_out rows as IEEE half in
+// The joint window runs on tcgen05.  A = the CTA's W_out rows as IEEE half in
 // 128B-swizzled K-major slabs of 64 columns (88 rows stored per slab; the M = 128 instruction reads on into the next slab /
 // region, whose rows land in accumulator lanes nobody looks at), B = the 32 (utterance, frame) activation rows as two half
 // planes (hi, lo) staged one k-half at a time, D = [128 vocabulary rows x (32 hi | 32 lo)] fp32 in tensor memory.  40 UMMAs
@@ -123,12 +119,10 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
   umma_bf16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);      // same instruction (kind::f16); the operand formats live in idesc
 }
 
-template <int HJ, int HP, bool TCJ>
+template <int HJ, int HP>
 __global__ void __launch_bounds__(kSpThreads, 1)
 rnnt_greedy_spec_kernel(const SpecDev p) {
   constexpr int KH = HJ / 2;                 // joint k-half staged in shared memory at a time
-  constexpr int GS = KH + 8;                 // s_g row stride in floats   (stride % 32 == 8: conflict-free LDS.64 fragments)
-  constexpr int WS = HJ + 8;                 // W_out / W_pred row stride in bf16 (word stride % 32 == 4: conflict-free B fragments)
   constexpr int LS = 2 * HP + 8;             // W_lstm row stride in bf16
   constexpr int KS_H = KH / 16;              // k16 steps per joint half
   constexpr int KSW_L = (2 * HP / 16) / kSpWarps;   // k16 steps per warp, LSTM
@@ -136,7 +130,6 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   constexpr int V4_ROW = KH / 4;             // float4 per staged row
   constexpr int ITEMS = kPassUtts * V4_ROW;  // loader items per k-half: (utterance, float4 column)
   constexpr int PERU = (ITEMS + kSpThreads - 1) / kSpThreads;
-  constexpr int G_FLOATS = (kPassRows * GS > kSpWarps * 16 * 24) ? kPassRows * GS : kSpWarps * 16 * 24;   // s_g doubles as the L / P reduction buffer
   static_assert(HJ % 32 == 0 && (2 * HP / 16) % kSpWarps == 0 && (HP / 16) % kSpWarps == 0, "shape");
 
   extern __shared__ __align__(16) uint8_t ssm[];
@@ -149,7 +142,6 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   const bool has_j = grp < kGroups;
   const int j0 = min(NC, slice * p.rows_j), j1 = min(NC, j0 + p.rows_j);
   const int nj = has_j ? j1 - j0 : 0;
-  const int n_tiles = (p.rows_j + 7) / 8;
   const int u0 = min(HP, cta * p.units), u1 = min(HP, u0 + p.units);
   const int nu = u1 - u0;
   const int p0 = min(HJ, cta * p.rows_p), p1 = min(HJ, p0 + p.rows_p);
@@ -157,32 +149,25 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 
   // ---- shared memory carve-up.  B fragments of a partial last n8-tile read past the end of a weight array
   // into the next one; those columns are masked, and every array is followed by at least 8 more rows of bytes.
-  // TCJ: [A slabs | B planes (also the L / P reduction buffer)] first, 1024-byte aligned, then the same arrays as before.
   constexpr int KSLABS = HJ / 64;                                  // 64-column slabs of A
   constexpr int NSLAB_H = KH / 64;                                 // slabs per staged k-half
   const int rows_a8 = (p.rows_j + 7) & ~7;
   const uint32_t a_slab = static_cast<uint32_t>(rows_a8) * 128u;   // bytes per A slab
   constexpr uint32_t kBSlab = 8192u;                               // B slab: 64 rows x 128 B = hi plane (rows 0-31) | lo plane (rows 32-63)
   constexpr uint32_t kBRegion = (NSLAB_H * kBSlab > 16384u) ? NSLAB_H * kBSlab : 16384u;   // >= what an M = 128 read of the last A slab overruns
-  // TCJ order: [A slabs | W_lstm | W_pred | pad to 1024 | B slabs | bias, state ...].  The mma.sync B fragments of the LSTM /
+  // Order: [A slabs | W_lstm | W_pred | pad to 1024 | B slabs (also the L / P reduction buffer) | bias, state ...].  The mma.sync B fragments of the LSTM /
   // joint.pred phases read up to 8 rows past the end of their (5- or 20-row) arrays: those reads must land inside the
   // allocation, so the big B region follows the weight arrays (a 2-utterance batch otherwise read past the end of shared memory).
-  uint32_t tc_base = 0, b_off = 0;
   const uint32_t wlp_bytes = static_cast<uint32_t>((static_cast<size_t>(4 * p.units) * LS + static_cast<size_t>(p.rows_p) * (HP + 8)) * 2);
-  if constexpr (TCJ) {
-    tc_base = (smem_u32(ssm) + 1023u) & ~1023u;
-    b_off = (KSLABS * a_slab + wlp_bytes + 1023u) & ~1023u;
-  }
-  uint8_t* gA = ssm + (tc_base - smem_u32(ssm));                   // TCJ: generic pointers to the A slabs / B slabs
+  const uint32_t tc_base = (smem_u32(ssm) + 1023u) & ~1023u;
+  const uint32_t b_off = (KSLABS * a_slab + wlp_bytes + 1023u) & ~1023u;
+  uint8_t* gA = ssm + (tc_base - smem_u32(ssm));                   // generic pointers to the A slabs / B slabs
   uint8_t* gB = gA + b_off;
-  __nv_bfloat16* s_wout = reinterpret_cast<__nv_bfloat16*>(ssm);                      // [rows_j][WS]   (not TCJ)
-  __nv_bfloat16* s_wlstm = TCJ ? reinterpret_cast<__nv_bfloat16*>(gA + KSLABS * a_slab)
-                               : s_wout + static_cast<size_t>(p.rows_j) * WS;         // [4*units][LS] gate-major
-  __nv_bfloat16* s_wpred = s_wlstm + static_cast<size_t>(4 * p.units) * LS;           // [rows_p][WS']  (WS' = HP + 8)
-  float* s_g = TCJ ? reinterpret_cast<float*>(gB)
-                   : reinterpret_cast<float*>(s_wpred + static_cast<size_t>(p.rows_p) * (HP + 8));   // [32][GS]; also the L / P reduction buffer
-  float* s_bout = TCJ ? reinterpret_cast<float*>(gB + kBRegion) : s_g + G_FLOATS;    // -inf beyond nj
-  const int n_bout = TCJ ? 128 : n_tiles * 8;
+  __nv_bfloat16* s_wlstm = reinterpret_cast<__nv_bfloat16*>(gA + KSLABS * a_slab);    // [4*units][LS] gate-major
+  __nv_bfloat16* s_wpred = s_wlstm + static_cast<size_t>(4 * p.units) * LS;           // [rows_p][HP + 8]
+  float* s_g = reinterpret_cast<float*>(gB);                                          // B planes; also the L / P reduction buffer
+  float* s_bout = reinterpret_cast<float*>(gB + kBRegion);                            // -inf beyond nj
+  constexpr int n_bout = 128;
   float* s_c = s_bout + n_bout;                                                      // [B][units]
   unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_c + ((static_cast<size_t>(B) * p.units + 1) & ~static_cast<size_t>(1)));   // [32][4]
   int* s_t = reinterpret_cast<int*>(s_best + kPassRows * 4);
@@ -190,14 +175,14 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   int* s_emit = s_tok + B; int* s_len = s_emit + B;
   int* s_act = s_len + B;                                                            // ordered list of the utterances with frames left
   int* s_cnt = s_act + B;                                                            // [0] n_emit, [1] n_active, [2..2+8) warp counts x2
-  // TCJ: one mbarrier (MMA completion) + the tensor-memory slot, 8-byte aligned after s_cnt
+  // one mbarrier (MMA completion) + the tensor-memory slot, 8-byte aligned after s_cnt
   const uint32_t tc_bar = (smem_u32(s_cnt + 2 + 2 * kSpWarps) + 7u) & ~7u;
   const uint32_t tc_slot = tc_bar + 8;
 
   {
     const uint32_t zero = 0;
     // W_out slice (rows beyond nj zero-filled)
-    if constexpr (TCJ) {
+    {
       for (int i = tid; i < rows_a8 * (HJ / 8); i += kSpThreads) {
         const int r = i / (HJ / 8), c = i % (HJ / 8);          // c: 16-byte chunk (8 columns) of the row
         uint4 v = make_uint4(zero, zero, zero, zero);
@@ -205,13 +190,6 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
         *reinterpret_cast<uint4*>(gA + (c >> 3) * a_slab + (r >> 3) * 1024 + (r & 7) * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
       }
       if (tid == 0) { mbar_init(tc_bar, 1); fence_barrier_init(); }
-    } else {
-      for (int i = tid; i < p.rows_j * (HJ / 8); i += kSpThreads) {
-        const int r = i / (HJ / 8), c = i % (HJ / 8);
-        uint4 v = make_uint4(zero, zero, zero, zero);
-        if (r < nj) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_out + static_cast<size_t>(j0 + r) * HJ)[c]);
-        *reinterpret_cast<uint4*>(s_wout + static_cast<size_t>(r) * WS + c * 8) = v;
-      }
     }
     for (int i = tid; i < 4 * p.units * (2 * HP / 8); i += kSpThreads) {
       const int r = i / (2 * HP / 8), c = i % (2 * HP / 8);
@@ -234,15 +212,11 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
     if (tid == 0) { s_cnt[0] = B; s_cnt[1] = 0; }
   }
   uint32_t tmem_d = 0, mma_phase = 0;
-  if constexpr (TCJ) {
-    if (warp == 0) tmem_alloc<64>(tc_slot);
-    tcgen05_fence_before();
-  }
+  if (warp == 0) tmem_alloc<64>(tc_slot);
+  tcgen05_fence_before();
   __syncthreads();
-  if constexpr (TCJ) {
-    tcgen05_fence_after();
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_d) : "r"(tc_slot));
-  }
+  tcgen05_fence_after();
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_d) : "r"(tc_slot));
 
   unsigned int target = 0;
   int iter = 0;
@@ -290,7 +264,9 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
 #pragma unroll
           for (int n = 0; n < 3; ++n) {
             if (n * 8 < 4 * p.units) {                 // warp-uniform
-              const __nv_bfloat16* wr = s_wlstm + static_cast<size_t>(n * 8 + gid) * LS + ks * 16 + tig * 2;
+              // rows beyond the CTA's 4 * units gate rows feed accumulator columns nobody reads: clamped so the fragment load stays
+              // inside the array (it used to run on into the reduction buffer, which compute-sanitizer racecheck rightly flags)
+              const __nv_bfloat16* wr = s_wlstm + static_cast<size_t>(min(n * 8 + gid, 4 * p.units - 1)) * LS + ks * 16 + tig * 2;
               const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
               mma_f16_16816(acc[n], ah, b0, b1); mma_f16_16816(acc[n], al, b0, b1);
             }
@@ -352,7 +328,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
           uint32_t ah[4], al[4];
           split2(xa[i][0], ah[0], al[0]); split2(xb[i][0], ah[1], al[1]);
           split2(xa[i][1], ah[2], al[2]); split2(xb[i][1], ah[3], al[3]);
-          const __nv_bfloat16* wr = s_wpred + static_cast<size_t>(gid) * (HP + 8) + ks * 16 + tig * 2;
+          const __nv_bfloat16* wr = s_wpred + static_cast<size_t>(min(gid, p.rows_p - 1)) * (HP + 8) + ks * 16 + tig * 2;   // clamped like the LSTM rows
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
           mma_f16_16816(acc, ah, b0, b1); mma_f16_16816(acc, al, b0, b1);
         }
@@ -409,7 +385,6 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   __syncthreads();
   compact();
 
-  const int mt = warp & 1, ng = warp >> 1;                   // this warp's m16 tile and n8-tile residue class
 
   for (;;) {
     // ---- phase J
@@ -460,49 +435,10 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
             }
           }
         };
-        auto store_half = [&]() {
-#pragma unroll
-          for (int i = 0; i < PERU; ++i) {
-            int it = tid + kSpThreads * i;
-            if (it < ITEMS) {
-              it = (it + slice * 29) % ITEMS;
-              const int ul = it / V4_ROW, c4 = it % V4_ROW;
-#pragma unroll
-              for (int j = 0; j < kFrames; ++j) *reinterpret_cast<float4*>(s_g + (ul * kFrames + j) * GS + 4 * c4) = gv[i][j];
-            }
-          }
-        };
-        float acc[kMaxTilesPerWarp][4];
-#pragma unroll
-        for (int n = 0; n < kMaxTilesPerWarp; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
-        const bool tile_on = ((mask >> (mt * 16)) & 0xffffu) != 0u;
-        auto mma_half = [&](int h) {
-          if (!tile_on) return;
-          const float* ga = s_g + (mt * 16 + gid) * GS + tig * 2;
-#pragma unroll 4
-          for (int ks = 0; ks < KS_H; ++ks) {
-            const float2 x0 = *reinterpret_cast<const float2*>(ga + ks * 16);
-            const float2 x1 = *reinterpret_cast<const float2*>(ga + 8 * GS + ks * 16);
-            const float2 x2 = *reinterpret_cast<const float2*>(ga + ks * 16 + 8);
-            const float2 x3 = *reinterpret_cast<const float2*>(ga + 8 * GS + ks * 16 + 8);
-            uint32_t ah[4], al[4];
-            split2(x0, ah[0], al[0]); split2(x1, ah[1], al[1]);
-            split2(x2, ah[2], al[2]); split2(x3, ah[3], al[3]);
-#pragma unroll
-            for (int n = 0; n < kMaxTilesPerWarp; ++n) {
-              const int nt = ng + 4 * n;
-              if (nt < n_tiles) {                            // warp-uniform
-                const __nv_bfloat16* wr = s_wout + static_cast<size_t>(nt * 8 + gid) * WS + h * KH + ks * 16 + tig * 2;
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-                mma_f16_16816(acc[n], ah, b0, b1); mma_f16_16816(acc[n], al, b0, b1);
-              }
-            }
-          }
-        };
         long long tj = 0;
         if (cta == 0 && tid == 0) tj = clock64();
         auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
-        if constexpr (TCJ) {
+        {
           // ---- tcgen05 joint: D[vocabulary row, (utterance, frame) row] in tensor memory
           auto write_planes = [&]() {                         // gv -> two IEEE-half planes, 128B-swizzled K-major, 32 rows per slab
 #pragma unroll
@@ -582,45 +518,6 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
                                           : 0ull;
           }
           tcgen05_fence_before();
-        } else {
-        load_half(0);
-          store_half();
-          __syncthreads();
-          jtick(8);
-          load_half(1);                                         // in flight under the MMAs of half 0
-          mma_half(0);
-          __syncthreads();
-          store_half();
-          __syncthreads();
-          mma_half(1);
-          jtick(9);
-          // ---- argmax of this warp's columns per row, then across the 4 lanes of a row, then across the 4 warps of the tile
-          {
-            float bv[2] = {-INFINITY, -INFINITY};
-            int bi[2] = {0x7fffffff, 0x7fffffff};
-#pragma unroll
-            for (int n = 0; n < kMaxTilesPerWarp; ++n) {
-              const int nt = ng + 4 * n;
-              if (nt < n_tiles) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int col = nt * 8 + tig * 2 + (q & 1), hrow = q >> 1;
-                  const float v = acc[n][q] + s_bout[col];
-                  if (col < nj && (v > bv[hrow] || (v == bv[hrow] && j0 + col < bi[hrow]))) { bv[hrow] = v; bi[hrow] = j0 + col; }
-                }
-              }
-            }
-#pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-#pragma unroll
-              for (int o = 1; o <= 2; o <<= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv[hrow], o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi[hrow], o);
-                if (ov > bv[hrow] || (ov == bv[hrow] && oi < bi[hrow])) { bv[hrow] = ov; bi[hrow] = oi; }
-              }
-              if (tig == 0) s_best[(mt * 16 + hrow * 8 + gid) * 4 + ng] = (bi[hrow] != 0x7fffffff) ? pack_best(bv[hrow], bi[hrow]) : 0ull;
-            }
-          }
         }
         __syncthreads();
         if (warp == 0 && row_b >= 0) {
@@ -683,11 +580,9 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   }
   if (cta == 0) for (int b = tid; b < B; b += kSpThreads) p.n_tok[b] = s_n[b];
   if (cta == 0 && tid == 0) for (int i = 0; i < 12; ++i) p.prof[i] = prof[i];
-  if constexpr (TCJ) {
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem_d); }
-  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem_d); }
 }
 
 // workspace: hbuf | ppbuf | (3*B*8 pad, keeps the counter/prof offset of decode_batched.cu) | counter + prof (256 B) | best
@@ -696,19 +591,19 @@ size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int /*num_sms*/) {
          static_cast<size_t>(3) * B * kFrames * 8;
 }
 
-template <int HJ, int HP, bool TCJ>
+template <int HJ, int HP>
 static cudaError_t launch_sp(SpecDev p, int grid, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(rnnt_greedy_spec_kernel<HJ, HP, TCJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = cudaFuncSetAttribute(rnnt_greedy_spec_kernel<HJ, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_greedy_spec_kernel<HJ, HP, TCJ>, kSpThreads, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rnnt_greedy_spec_kernel<HJ, HP>, kSpThreads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorLaunchOutOfResources;
   void* args[] = {&p};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_spec_kernel<HJ, HP, TCJ>), dim3(grid), dim3(kSpThreads), args, smem, stream);
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(rnnt_greedy_spec_kernel<HJ, HP>), dim3(grid), dim3(kSpThreads), args, smem, stream);
 }
 
-cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream, bool tc_joint) {
+cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream) {
   if (a.B <= 0 || num_sms < kGroups) return cudaErrorInvalidValue;
   const int G = num_sms;
   SpecDev p;
@@ -731,31 +626,21 @@ cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int nu
   p.rows_j = (a.V + 1 + p.S - 1) / p.S;
   p.units = (a.Hp + G - 1) / G;
   p.rows_p = (a.Hj + G - 1) / G;
-  const int n_tiles = (p.rows_j + 7) / 8;
-  if (n_tiles > 4 * kMaxTilesPerWarp || 4 * p.units > 24 || p.rows_p > 8 || 16 * p.units > kSpThreads) return cudaErrorInvalidValue;
+  if (4 * p.units > 24 || p.rows_p > 8 || 16 * p.units > kSpThreads) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(workspace, 0, rnnt_spec_workspace_bytes(a.B, a.Hj, a.Hp, num_sms), stream);
   if (e != cudaSuccess) return e;
   const size_t state = ((static_cast<size_t>(a.B) * p.units + 1) & ~static_cast<size_t>(1)) * 4 + kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 8 * 4 +
                        (2 + 2 * kSpWarps) * 4 + 64;
   const size_t w_lp = (static_cast<size_t>(4 * p.units) * (2 * a.Hp + 8) + static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
-  if (tc_joint) {
-    if (p.rows_j > 128) return cudaErrorInvalidValue;
-    const size_t rows_a8 = (p.rows_j + 7) & ~7;
-    const size_t b_bytes = static_cast<size_t>(a.Hj / 2 / 64) * 8192;
-    const size_t b_region = b_bytes > 16384 ? b_bytes : 16384;
-    const size_t ab = ((static_cast<size_t>(a.Hj / 64) * rows_a8 * 128 + w_lp + 1023) & ~static_cast<size_t>(1023));   // A slabs, W_lstm, W_pred, pad
-    const size_t smem = 1024 + ab + b_region + 128 * 4 + state + 16;
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640, true>(p, G, smem, stream);
-    if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128, true>(p, G, smem, stream);
-    return cudaErrorInvalidValue;
-  }
-  const size_t gs = a.Hj / 2 + 8;
-  const size_t g_floats = kPassRows * gs > static_cast<size_t>(kSpWarps) * 16 * 24 ? kPassRows * gs : static_cast<size_t>(kSpWarps) * 16 * 24;
-  const size_t smem = static_cast<size_t>(p.rows_j) * (a.Hj + 8) * 2 + w_lp + (g_floats + n_tiles * 8) * 4 + state;
+  if (p.rows_j > 128) return cudaErrorInvalidValue;
+  const size_t rows_a8 = (p.rows_j + 7) & ~7;
+  const size_t b_bytes = static_cast<size_t>(a.Hj / 2 / 64) * 8192;
+  const size_t b_region = b_bytes > 16384 ? b_bytes : 16384;
+  const size_t ab = ((static_cast<size_t>(a.Hj / 64) * rows_a8 * 128 + w_lp + 1023) & ~static_cast<size_t>(1023));   // A slabs, W_lstm, W_pred, pad
+  const size_t smem = 1024 + ab + b_region + 128 * 4 + state + 16;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640, false>(p, G, smem, stream);
-  if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128, false>(p, G, smem, stream);
+  if (a.Hj == 640 && a.Hp == 640) return launch_sp<640, 640>(p, G, smem, stream);
+  if (a.Hj == 128 && a.Hp == 128) return launch_sp<128, 128>(p, G, smem, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -20,7 +20,6 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, cons
   // Persistent: a warp walks rows (stride = warps in the grid) with the NEXT row's loads already in flight while
   // the current one is reduced and stored -- short-lived one-row warps left HBM at ~40 % (profiles/r01_v2_other_ncu.md).
   constexpr int D = 128 * NV;
-  RS_PDL_TRIGGER(); RS_PDL_WAIT();                       // (-DRS_PDL variant only) x is the previous kernel's output
   const int lane = lane_id();
   const int wstride = gridDim.x * (blockDim.x >> 5);
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -79,88 +78,21 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, cons
   }
 }
 
-// Variant B: one row per warp, registers capped so that 32 warps are resident per SM (the persistent variant holds 16):
-// with the residual stream still in L2 from the producing GEMM the kernel is bound by how many row-sized requests an
-// SM keeps in flight, not by HBM (scripts/probes/ln_probe.py).
-template <int NV>
-__global__ void __launch_bounds__(256, 4)
-layernorm_rowwarp_kernel(const float* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
-                         float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-                         const float* __restrict__ g2, const float* __restrict__ b2, int rows, float eps) {
-  constexpr int D = 128 * NV;
-  RS_PDL_TRIGGER(); RS_PDL_WAIT();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = lane_id();
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
-  float4 v[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
-  auto normalize = [&](const float* __restrict__ g, const float* __restrict__ b) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    const float mean = warp_sum(s) * (1.0f / D);
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, dd = v[i].w - mean;
-      ss += (a * a + bb * bb) + (c * c + dd * dd);
-    }
-    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / D) + eps);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * i);
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
-      v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
-      v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
-      v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
-      v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
-    }
-  };
-  normalize(g1, b1);
-  if (out_f32 != nullptr) {
-    float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) o[lane + 32 * i] = v[i];
-  }
-  if (g2 != nullptr) normalize(g2, b2);
-  if (out_bf16 != nullptr) {
-    uint2* o = reinterpret_cast<uint2*>(out_bf16 + static_cast<size_t>(row) * D);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) o[lane + 32 * i] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-  }
-}
-
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                              const float* gamma2, const float* beta2, int rows, int d, float eps, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   const int wpb = 8;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  int num_sms = 0, dev = 0;                                    // per call: engines on different devices share this code
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   const int need = (rows + wpb - 1) / wpb;
   const int cap = num_sms * 2;                                 // 2 resident CTAs per SM (16 warps x 2 rows in flight)
   auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
-  const char* variant = getenv("RS_LN_VARIANT");               // A (default): persistent, B: one row per warp, 32 warps per SM
-  if (variant != nullptr && variant[0] == 'B') {                // measured within 1 us of each other (scripts/probes/ln_probe.py)
-    const dim3 gridb(need), blockb(32 * wpb);
-    switch (d) {
-      case 256: RS_LAUNCH(layernorm_rowwarp_kernel<2>, gridb, blockb, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-      case 512: RS_LAUNCH(layernorm_rowwarp_kernel<4>, gridb, blockb, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-      case 1024: RS_LAUNCH(layernorm_rowwarp_kernel<8>, gridb, blockb, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-      default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-  }
   const dim3 grid(need < cap ? need : cap), block(32 * wpb);
   switch (d) {
-    case 256: RS_LAUNCH(layernorm_kernel<2>, grid, block, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-    case 512: RS_LAUNCH(layernorm_kernel<4>, grid, block, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
-    case 1024: RS_LAUNCH(layernorm_kernel<8>, grid, block, 0, stream, x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 256: layernorm_kernel<2><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 512: layernorm_kernel<4><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 1024: layernorm_kernel<8><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -180,7 +112,6 @@ conv_dw_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ 
   // unpacked into the KW-row sliding window as it advances.
   constexpr int PAD = (KW - 1) / 2;
   constexpr int ROWS = TT + KW - 1;
-  RS_PDL_TRIGGER(); RS_PDL_WAIT();
   const int b = blockIdx.z;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= d) return;
@@ -224,7 +155,7 @@ cudaError_t launch_conv_dw(const void* u, void* out, const float* w, const float
   constexpr int TT = 8;
   const int threads = d / 4 < 256 ? d / 4 : 256;
   const dim3 block(threads), grid((d / 4 + threads - 1) / threads, (T_max + TT - 1) / TT, B);
-  RS_LAUNCH((conv_dw_kernel<9, TT>), grid, block, 0, stream, static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
+  conv_dw_kernel<9, TT><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
             w, shift, enc_len, T_max, d);
   return cudaGetLastError();
 }

@@ -32,9 +32,6 @@ struct LayerW {
   const float *ln_ff2_g, *ln_ff2_b, *ff2_b1, *ff2_b2;
   const void *ff2_w1, *ff2_w2;
   const float *ln_out_g, *ln_out_b;
-  // RS_LN_FOLD experiment (engine.py ln_fold_tensors): gamma-scaled weights and the (c, d) vectors of the folded LayerNorms
-  const void *wqkv_f = nullptr, *pw1_wf = nullptr, *ff2_w1f = nullptr;
-  const float *qkv_c = nullptr, *qkv_d = nullptr, *pw1_c = nullptr, *pw1_d = nullptr, *ff2_c = nullptr, *ff2_d = nullptr;
 };
 
 struct Plan {           // workspace offsets (bytes) for one (B, L_max)
@@ -42,15 +39,12 @@ struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   size_t wav, len, mel, mel_len, mel_part, mel_stats, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, vt, enc, encp;
   int n_rel_pad, ld_vt;
   size_t tokens, frames, ntok, dec_ws, total;
-  size_t stats;   // RS_LN_FOLD experiment: per-row partial (sum, sum of squares) of the residual stream, [M][fold_slots][2] f32
 };
 
 inline int conv_len(int n) { return n > 0 ? (n - 1) / 2 + 1 : 0; }   // floor division as in NeMo's calc_length: 0 stays 0
 // Encoder-frame capacity of the padded activation tensors: the subsampled length rounded up to a multiple of 8, so that
 // every utterance starts at a 16-byte-aligned column of the transposed V buffer (TMA wants the innermost coordinate
 // 16-byte aligned: an odd T_max raised "illegal instruction" on the V^T tile loads of the attention kernel).
-// LayerNorm-fold experiment: one (sum, sum of squares) slot per 256-column tile of the producer GEMM and column half
-inline int fold_slots(int d_model) { return 2 * (d_model / 256); }
 constexpr int kBdSkewPitch = 384;   // 2 * 128 + 1 relative offsets + 127 of skew, rounded up: columns of a 128-query tile's key window
 inline int enc_capacity(int mel_frames) { return (conv_len(conv_len(conv_len(mel_frames))) + 7) & ~7; }
 
@@ -70,10 +64,6 @@ struct rs_engine {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int U_cap = 0;
-  // RS_GEMM_SPLITK=1 (experiment, unmeasured): engine-owned workspace of the split-K tail of the 2-CTA GEMM
-  float* sk_partials = nullptr;
-  unsigned int* sk_flags = nullptr;
-  bool ln_fold = false;   // RS_LN_FOLD=1 and the folded tensors are in the weight table (experiment, unmeasured)
   mutable char err[512] = "";
   int64_t launches = 0;
   bool timing = false;
@@ -115,10 +105,8 @@ int fail(const rs_engine* e, int code, const char* fmt, ...) {
 
 size_t align_up(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 
-inline size_t dec_ws_bytes(const rs_engine* e, int B) {   // the decode kernels share one region: size it for the larger
-  const size_t a = rs::rnnt_batched_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms);
-  const size_t b = rs::rnnt_spec_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms);
-  return a > b ? a : b;
+inline size_t dec_ws_bytes(const rs_engine* e, int B) {
+  return rs::rnnt_spec_workspace_bytes(B, e->cfg.joint_hidden, e->cfg.pred_hidden, e->num_sms);
 }
 
 Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
@@ -162,7 +150,6 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.frames = take(static_cast<size_t>(B) * U_max * 4);
   p.ntok = take(static_cast<size_t>(B) * 4);
   p.dec_ws = take(dec_ws_bytes(e, B));
-  if (e->ln_fold) p.stats = take(static_cast<size_t>(p.M) * fold_slots(c.d_model) * 2 * 4);   // appended: the default layout is unchanged
   p.total = off;
   return p;
 }
@@ -231,11 +218,6 @@ int bind_weights(rs_engine* e) {
     NEED(L.ff2_w1, N("ff2.w1"), RS_BF16, ff * d); NEED(L.ff2_b1, N("ff2.b1"), RS_F32, ff);
     NEED(L.ff2_w2, N("ff2.w2"), RS_BF16, d * ff); NEED(L.ff2_b2, N("ff2.b2"), RS_F32, d);
     NEED(L.ln_out_g, N("ln_out.g"), RS_F32, d); NEED(L.ln_out_b, N("ln_out.b"), RS_F32, d);
-    if (e->ln_fold) {
-      NEED(L.wqkv_f, N("att.wqkv.fold"), RS_BF16, 3 * d * d); NEED(L.qkv_c, N("att.wqkv.fold_c"), RS_F32, 3 * d); NEED(L.qkv_d, N("att.wqkv.fold_d"), RS_F32, 3 * d);
-      NEED(L.pw1_wf, N("conv.pw1.w.fold"), RS_BF16, 2 * d * d); NEED(L.pw1_c, N("conv.pw1.w.fold_c"), RS_F32, 2 * d); NEED(L.pw1_d, N("conv.pw1.w.fold_d"), RS_F32, 2 * d);
-      NEED(L.ff2_w1f, N("ff2.w1.fold"), RS_BF16, ff * d); NEED(L.ff2_c, N("ff2.w1.fold_c"), RS_F32, ff); NEED(L.ff2_d, N("ff2.w1.fold_d"), RS_F32, ff);
-    }
   }
   const int64_t Hj = c.joint_hidden, Hp = c.pred_hidden, NC = c.vocab_size + 1;
   NEED(e->dec.enc_w, "joint.enc.w", RS_BF16, Hj * d); NEED(e->dec.enc_b, "joint.enc.b", RS_F32, Hj);
@@ -278,8 +260,7 @@ void ktime_end(rs_engine* e) {
 }
 
 int gemm_args(rs_engine* e, const rs::GemmArgs& g_in, cudaStream_t s) {
-  rs::GemmArgs g = g_in;
-  g.sk_partials = e->sk_partials; g.sk_flags = e->sk_flags;      // nullptr unless RS_GEMM_SPLITK=1
+  const rs::GemmArgs& g = g_in;
   const int M = g.M, N = g.N, K = g.K;
   char msg[256] = "";
   bool timed = false;
@@ -387,68 +368,40 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     const LayerW& L0 = e->layers[0];
     RS_K(e, rs::launch_layernorm(x, L0.ln_ff1_g, L0.ln_ff1_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
   }
-  // LayerNorm-fold experiment: the residual GEMM in front of a folded LayerNorm also leaves bf16(x) in xn and the row sums
-  // in `stats`; the GEMM behind it reads xn with gamma-scaled weights and finishes the normalisation in its epilogue.
-  const bool fold = e->ln_fold;
-  float* stats = fold ? at<float>(e, p.stats) : nullptr;
-  auto resid_gemm = [&](const void* a, const void* w, const float* bias, int K, float alpha, bool producer) -> int {
-    rs::GemmArgs g{a, w, bias, x, x, M, d, K, RS_EPI_RESID_F32, alpha};
-    if (producer) { g.stats_out = stats; g.xb = xn; g.stats_slots = fold_slots(d); }
-    return gemm_args(e, g, s);
-  };
-  auto consumer = [&](rs::GemmArgs& g, const void* wf, const float* fc, const float* fd) {
-    g.w = wf; g.bias = nullptr; g.fold_c = fc; g.fold_d = fd; g.stats_in = stats; g.stats_slots = fold_slots(d); g.fold_n = d; g.ln_eps = c.ln_eps;
+  auto resid_gemm = [&](const void* a, const void* w, const float* bias, int K, float alpha) -> int {
+    return gemm(e, a, w, bias, x, x, M, d, K, RS_EPI_RESID_F32, alpha, s);
   };
   for (int i = 0; i < n_layers; ++i) {
     const LayerW& L = e->layers[i];
     RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
-    RS_TRY(resid_gemm(hb, L.ff1_w2, L.ff1_b2, c.d_ff, 0.5f, fold));
-    if (!fold) RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(resid_gemm(hb, L.ff1_w2, L.ff1_b2, c.d_ff, 0.5f));
+    RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
     aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt; aa.bd_pitch = kBdSkewPitch;
-    // RS_ATTN_MODE=1 keeps the mma.sync kernels (also the path for windows wider than 128)
-    const char* attn_env = getenv("RS_ATTN_MODE");
-    const int attn_mode = attn_env ? atoi(attn_env) : 0;
-    const bool attn_tc = attn_mode != 1 && rs::attention_tc_supported(aa);
-    if (attn_tc) {     // q | k row-major, V transposed (keys contiguous) for the tensor-core kernel's P.V product
+    {   // q | k row-major, V transposed (keys contiguous) for the attention's P.V product
       rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_QKV_VT, 1.f};
       g.out2 = at<void>(e, p.vt); g.split = 2 * d; g.ld2 = p.ld_vt;
-      if (fold) consumer(g, L.wqkv_f, L.qkv_c, L.qkv_d);
-      RS_TRY(gemm_args(e, g, s));
-    } else {
-      rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_BIAS_BF16, 1.f};
-      if (fold) consumer(g, L.wqkv_f, L.qkv_c, L.qkv_d);
       RS_TRY(gemm_args(e, g, s));
     }
     {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
-      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16, 1.f};
-      g.lda = 3 * d; g.ldo = c.n_heads * p.n_rel_pad; g.n_batch = c.n_heads;
-      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad; g.out_col_stride = p.n_rel_pad;
-      if (attn_tc) {   // row-skewed layout: column c + (t mod 128), see RS_EPI_BIAS_F16_SKEW
-        g.epilogue = RS_EPI_BIAS_F16_SKEW; g.ldo = c.n_heads * kBdSkewPitch; g.out_col_stride = kBdSkewPitch;
-        g.split = c.att_left + c.att_right + 1; g.ld2 = p.T3;
-        g.alpha = 1.4426950408889634f / sqrtf(static_cast<float>(d / c.n_heads));   // scores leave the GEMM in the softmax's log2 domain
-      }
+      // written row-skewed (column c + (t mod 128), see RS_EPI_BIAS_F16_SKEW) in IEEE half
+      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16_SKEW, 1.f};
+      g.lda = 3 * d; g.n_batch = c.n_heads;
+      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad;
+      g.ldo = c.n_heads * kBdSkewPitch; g.out_col_stride = kBdSkewPitch;
+      g.split = c.att_left + c.att_right + 1; g.ld2 = p.T3;
+      g.alpha = 1.4426950408889634f / sqrtf(static_cast<float>(d / c.n_heads));   // scores leave the GEMM in the softmax's log2 domain
       RS_TRY(gemm_args(e, g, s));
     }
-    if (attn_tc) RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);
-    else RS_K(e, rs::launch_attention(aa, s), c.global_tokens > 0 ? 2 : 1);
-    RS_TRY(resid_gemm(ab, L.wo, L.bo, d, 1.f, fold));
-    if (!fold) RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
-    {
-      rs::GemmArgs g{xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f};
-      if (fold) consumer(g, L.pw1_wf, L.pw1_c, L.pw1_d);
-      RS_TRY(gemm_args(e, g, s));
-    }
+    RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);
+    RS_TRY(resid_gemm(ab, L.wo, L.bo, d, 1.f));
+    RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f, s));
     RS_K(e, rs::launch_conv_dw(ab, cb, L.dw_w, L.dw_shift, enc_len, B, p.T3, d, c.conv_kernel, s), 1);
-    RS_TRY(resid_gemm(cb, L.pw2_w, L.pw2_b, d, 1.f, fold));
-    if (!fold) RS_K(e, rs::launch_layernorm(x, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
-    {
-      rs::GemmArgs g{xn, L.ff2_w1, L.ff2_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f};
-      if (fold) consumer(g, L.ff2_w1f, L.ff2_c, L.ff2_d);
-      RS_TRY(gemm_args(e, g, s));
-    }
-    RS_TRY(resid_gemm(hb, L.ff2_w2, L.ff2_b2, c.d_ff, 0.5f, false));
+    RS_TRY(resid_gemm(cb, L.pw2_w, L.pw2_b, d, 1.f));
+    RS_K(e, rs::launch_layernorm(x, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.ff2_w1, L.ff2_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
+    RS_TRY(resid_gemm(hb, L.ff2_w2, L.ff2_b2, c.d_ff, 0.5f));
     if (i + 1 < n_layers) {   // norm_out chained with the next layer's norm_feed_forward1
       const LayerW& Ln = e->layers[i + 1];
       RS_K(e, rs::launch_layernorm(x, L.ln_out_g, L.ln_out_b, x, xn, Ln.ln_ff1_g, Ln.ln_ff1_b, M, d, c.ln_eps, s), 1);
@@ -473,16 +426,10 @@ int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_
   rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b,
                     e->dec.pred_w, e->dec.pred_b, tokens, frames, ntok, p.B, T_max, c.joint_hidden, c.pred_hidden,
                     c.vocab_size, U_max, c.max_symbols};
-  // One decode kernel for every batch size (windowed, weights-stationary, decode_spec.cu): an utterance's logits
-  // are accumulated in the same order whether it is decoded alone or inside a batch, so results do not depend on
-  // batch composition.  RS_DECODE_MODE selects the earlier kernels for A/B measurements:
-  //   0/unset/4: windowed kernel, joint on tcgen05 (default); 3: windowed kernel, joint on mma.sync; 1: one cluster per
-  //   utterance; 2: batched one-frame-per-iteration kernel
-  const char* m = getenv("RS_DECODE_MODE");
-  const int mode = m ? atoi(m) : 0;
-  if (mode == 1) RS_K(e, rs::launch_rnnt_greedy(da, e->num_sms, s), 1);
-  else if (mode == 2) RS_K(e, rs::launch_rnnt_greedy_batched(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
-  else RS_K(e, rs::launch_rnnt_greedy_spec(da, at<void>(e, p.dec_ws), e->num_sms, s, mode != 3), 2);
+  // One decode kernel for every batch size (windowed, weights-stationary, joint on tcgen05: decode_spec.cu): an utterance's
+  // logits are accumulated in the same order whether it is decoded alone or inside a batch, so results do not depend on
+  // batch composition.
+  RS_K(e, rs::launch_rnnt_greedy_spec(da, at<void>(e, p.dec_ws), e->num_sms, s), 2);
   return RS_OK;
 }
 
@@ -501,8 +448,8 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   if (cfg->conv_kernel != 9) return fail(nullptr, RS_ERR_UNSUPPORTED, "conv_kernel=%d unsupported (9)", cfg->conv_kernel);
   if (cfg->global_tokens < 0 || cfg->global_tokens > 1)
     return fail(nullptr, RS_ERR_UNSUPPORTED, "global_tokens=%d unsupported (the attention kernels implement 0 or 1)", cfg->global_tokens);
-  if (cfg->att_left < 0 || cfg->att_right < 0)
-    return fail(nullptr, RS_ERR_UNSUPPORTED, "att context (%d, %d) unsupported (limited local context only)", cfg->att_left, cfg->att_right);
+  if (cfg->att_left < 0 || cfg->att_right < 0 || cfg->att_left > 128 || cfg->att_right > 128 || (cfg->att_left & 7))
+    return fail(nullptr, RS_ERR_UNSUPPORTED, "att context (%d, %d) unsupported: the attention kernel covers limited local context with 0 <= left, right <= 128 and left %% 8 == 0 (the shipped model is [128, 128])", cfg->att_left, cfg->att_right);
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -516,27 +463,12 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   rs_engine* e = new rs_engine();
   e->cfg = *cfg; e->device = device; e->num_sms = prop.multiProcessorCount;
   for (int i = 0; i < n_weights; ++i) e->w[weights[i].name] = Tensor{weights[i].dev_ptr, weights[i].dtype, weights[i].numel};
-  {   // RS_LN_FOLD=1: EXPERIMENT, unmeasured -- fold three of the five LayerNorms of a layer into their consumer GEMMs
-    const char* f = getenv("RS_LN_FOLD");
-    e->ln_fold = f != nullptr && atoi(f) == 1 && cfg->d_model % 256 == 0 && e->w.count("L0.att.wqkv.fold") != 0;
-  }
   int r = bind_weights(e);
   if (r != RS_OK) { snprintf(g_create_error, sizeof g_create_error, "%s", e->err); delete e; return r; }
-  if (const char* sk = getenv("RS_GEMM_SPLITK"); sk != nullptr && atoi(sk) == 1) {
-    const int ncl = e->num_sms / 2;
-    if (cudaMalloc(&e->sk_partials, rs::splitk_partial_bytes(ncl)) != cudaSuccess ||
-        cudaMalloc(&e->sk_flags, rs::splitk_flag_bytes(ncl)) != cudaSuccess ||
-        cudaMemset(e->sk_flags, 0, rs::splitk_flag_bytes(ncl)) != cudaSuccess) {
-      snprintf(g_create_error, sizeof g_create_error, "RS_GEMM_SPLITK: cannot allocate the split-K workspace (%s)", cudaGetErrorString(cudaGetLastError()));
-      cudaFree(e->sk_partials); cudaFree(e->sk_flags);
-      delete e;
-      return RS_ERR_CUDA;
-    }
-  }
   if (cudaMalloc(&e->lm_tickets, rs_engine::kMaxBatch * sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(e->lm_tickets, 0, rs_engine::kMaxBatch * sizeof(unsigned int)) != cudaSuccess) {
     snprintf(g_create_error, sizeof g_create_error, "cannot allocate the log-mel ticket array (%s)", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(e->lm_tickets); cudaFree(e->sk_partials); cudaFree(e->sk_flags);
+    cudaFree(e->lm_tickets);
     delete e;
     return RS_ERR_CUDA;
   }
@@ -555,8 +487,6 @@ void rs_engine_destroy(rs_engine* e) {
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
   for (auto& ev : e->k_ev) cudaEventDestroy(ev);
-  cudaFree(e->sk_partials);
-  cudaFree(e->sk_flags);
   cudaFree(e->lm_tickets);
   delete e;
 }
@@ -740,25 +670,6 @@ int rs_enable_kernel_timing(rs_engine* e, int on) {
 }
 
 // Text summary "name\tcount\ttotal_ms\n..." of every launch since rs_enable_kernel_timing(e, 1); resets the log.
-// Host-only: the work list of the split-K tail experiment (kernels.h) for `num_tiles` tiles on `ncl` clusters, as rows
-// (cluster, position, tile, k0, k1, kind, part).  Returns the number of rows (also when it exceeds max_rows).
-int rs_debug_splitk_schedule(int num_tiles, int ncl, int num_k, int32_t* rows7, int max_rows, int* split) {
-  if (num_tiles <= 0 || ncl <= 0 || num_k <= 0) return -1;
-  const rs::SplitKPlan plan = rs::splitk_plan(num_tiles, ncl, num_k);
-  if (split) *split = plan.S;
-  int n = 0;
-  for (int cid = 0; cid < ncl; ++cid) {
-    rs::SplitKItem w;
-    for (int it = 0; rs::splitk_item(plan, it, cid, ncl, num_k, w); ++it, ++n) {
-      if (rows7 != nullptr && n < max_rows) {
-        int32_t* r = rows7 + 7 * n;
-        r[0] = cid; r[1] = it; r[2] = w.tile; r[3] = w.k0; r[4] = w.k1; r[5] = w.kind; r[6] = w.part;
-      }
-    }
-  }
-  return n;
-}
-
 int rs_kernel_timing(rs_engine* e, char* buf, int buf_bytes) {
   if (!e || !buf || buf_bytes <= 0) return RS_ERR_INVALID_ARG;
   RS_CUDA(e, cudaDeviceSynchronize());

@@ -41,21 +41,6 @@ struct GemmDev {
   int n_batch, a_col_stride, w_row_stride, bias_stride, out_col_stride;
   void* out2; int split, ld2;    // RS_EPI_QKV_VT
 };
-// LayerNorm fold (RS_LN_FOLD experiment, see GemmArgs): the extra fields live in a derived struct that only the EG 3 / 4
-// instances take, so the kernel parameter block -- and with it the generated code -- of the default instances is untouched.
-struct GemmDevFold : GemmDev {
-  const float* fold_c; const float* fold_d; const float* stats_in; float* stats_out; void* xb; int stats_slots; float fold_inv_n; float ln_eps;
-};
-template <int EG> struct DevOf { using type = GemmDev; };
-template <> struct DevOf<3> { using type = GemmDevFold; };
-template <> struct DevOf<4> { using type = GemmDevFold; };
-
-// Per-thread state of the LayerNorm-fold epilogues: the row's (r, r * mu) for a consumer, running row sums for a producer.
-struct EpiRow {
-  float r = 1.f, rm = 0.f;
-  float rs[8], rss[8];
-};
-
 template <int BN>
 struct GemmCfg {
   static constexpr int kBBytes = BN * BK * 2;
@@ -88,25 +73,13 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
 
 // EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT, 2: RS_EPI_BIAS_F16_SKEW.
 // (One kernel with every path spilled registers in the common ones: 166 -> 168 registers + a stack frame, GEMMs 10-20 % slower.)
-// SWZ: the fp32 staging uses 32-float rows with the float4 index XOR-ed by (row & 7) instead of 36-float padded rows: both
-// are conflict-free for the row-per-lane writes and the 4-rows-per-instruction reads, the swizzled form fits 4 KB per warp,
-// which is what leaves room for a 6th pipeline stage (RS_GEMM_STAGES=6 experiment).
-template <int EG, bool SWZ = false>
-__device__ __forceinline__ void epilogue_store(const typename DevOf<EG>::type& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
-                                               int col0, int bt, const float4 (&rr)[8], EpiRow& er) {
+template <int EG>
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
+                                               int col0, int bt, const float4 (&rr)[8]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if constexpr (EG == 3) {                                     // folded LayerNorm: y = r * acc - r * mu * c[n] + d[n]
-    const float4* c4 = reinterpret_cast<const float4*>(p.fold_c + col0);
-    const float4* d4 = reinterpret_cast<const float4*>(p.fold_d + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 c = __ldg(c4 + j), dd = __ldg(d4 + j);
-      v[4 * j] = fmaf(er.r, v[4 * j], fmaf(-er.rm, c.x, dd.x)); v[4 * j + 1] = fmaf(er.r, v[4 * j + 1], fmaf(-er.rm, c.y, dd.y));
-      v[4 * j + 2] = fmaf(er.r, v[4 * j + 2], fmaf(-er.rm, c.z, dd.z)); v[4 * j + 3] = fmaf(er.r, v[4 * j + 3], fmaf(-er.rm, c.w, dd.w));
-    }
-  } else if (p.bias != nullptr) {
+  if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -117,7 +90,7 @@ __device__ __forceinline__ void epilogue_store(const typename DevOf<EG>::type& p
   const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
   uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
   int epi = p.epilogue;
-  if constexpr (EG == 1 || EG == 3) if (EG == 1 || p.epilogue == RS_EPI_QKV_VT) {
+  if constexpr (EG == 1) {
     if (col0 < p.split) {
       epi = RS_EPI_BIAS_BF16;                                  // q | k columns: plain row-major bf16
     } else {
@@ -161,7 +134,6 @@ __device__ __forceinline__ void epilogue_store(const typename DevOf<EG>::type& p
   }
   switch (epi) {
     case RS_EPI_BIAS_F16: {                                    // same 16-bit store pattern as the bf16 epilogues
-      if constexpr (EG == 3) break;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(stage_u + lane * 20 + 4 * j) =
@@ -226,10 +198,9 @@ __device__ __forceinline__ void epilogue_store(const typename DevOf<EG>::type& p
       break;
     }
     default: {  // RS_EPI_RESID_F32 / RS_EPI_BIAS_F32
-      if constexpr (EG == 3) break;                            // fold consumers write bf16 only (launcher-checked)
-      constexpr int LD = SWZ ? 32 : kStageLd;
+      constexpr int LD = kStageLd;
       for (int j = 0; j < 8; ++j)                              // (fully unrolled by the compiler: constant trip count)
-        *reinterpret_cast<float4*>(stage + lane * LD + 4 * (SWZ ? (j ^ (lane & 7)) : j)) =
+        *reinterpret_cast<float4*>(stage + lane * LD + 4 * j) =
             make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
       __syncwarp();
       const bool add = p.epilogue == RS_EPI_RESID_F32;
@@ -237,19 +208,10 @@ __device__ __forceinline__ void epilogue_store(const typename DevOf<EG>::type& p
       for (int i = 0; i < 8; ++i) {                            // 4 rows x 128 B per instruction
         const int rl = i * 4 + (lane >> 3), cw = (lane & 7) * 4;
         const int row = tile_row0 + rl;
-        float4 a = *reinterpret_cast<const float4*>(stage + rl * LD + (SWZ ? 4 * ((cw >> 2) ^ (rl & 7)) : cw));
+        float4 a = *reinterpret_cast<const float4*>(stage + rl * LD + cw);
         if (add) { a.x += rr[i].x; a.y += rr[i].y; a.z += rr[i].z; a.w += rr[i].w; }
         if (row < p.M)
           *reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col_off + col0 + cw) = a;
-        if constexpr (EG == 4) {                               // producer of a folded LayerNorm: bf16 copy + row sums
-          if (row < p.M)
-            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.xb) + static_cast<size_t>(row) * p.ldo + col0 + cw) =
-                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
-          float s1 = (a.x + a.y) + (a.z + a.w), s2 = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
-#pragma unroll
-          for (int o = 1; o <= 4; o <<= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-          er.rs[i] += s1; er.rss[i] += s2;                     // the 8 lanes of a row all hold its chunk sums
-        }
       }
       break;
     }
@@ -262,7 +224,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  RS_PDL_TRIGGER();
   // 128B-swizzled operand tiles need 1024 B alignment.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -296,7 +257,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  RS_PDL_WAIT();                                             // (-DRS_PDL variant only) operands come from the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -370,8 +330,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        EpiRow er_unused;
-        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur, er_unused);
+        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -395,23 +354,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // is bound by L2 bandwidth (87 FLOP/B against ~12 TB/s), not by the tensor pipe; it also leaves room
 // for a 6-deep ring.  Barriers: full[] on the leader (both producers arrive, both TMAs credit it),
 // empty[] / tmem_full[] per CTA (commit multicast to both), tmem_empty[] on the leader.
-template <int BN, int ST = 0>
+template <int BN>
 struct Gemm2Cfg {
   static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
-  static constexpr int kStages = ST > 0 ? ST : ((BN == 256) ? 5 : 7);
-  static constexpr bool kSwz = ST == 6;                                   // 6 stages need the 4 KB-per-warp staging
-  static constexpr int kStagingPerWarp = kSwz ? 32 * 32 * 4 : kStageBytesPerWarp;
+  static constexpr int kStages = (BN == 256) ? 5 : 7;
+  static constexpr int kStagingPerWarp = kStageBytesPerWarp;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiWarps * kStagingPerWarp /*epilogue staging*/;
 };
 
-template <int BN, int EG, int ST = 0>
+template <int BN, int EG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const typename DevOf<EG>::type p) {
-  using Cfg = Gemm2Cfg<BN, ST>;
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
+  using Cfg = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  RS_PDL_TRIGGER();
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -447,7 +404,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  RS_PDL_WAIT();                                             // (-DRS_PDL variant only) operands come from the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -505,25 +461,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (tile % num_n) * BN;
       const int tile_row0 = m0 + q * 32;
-      const bool pre = EG != 3 && p.epilogue == RS_EPI_RESID_F32;   // a fold consumer never carries a residual
+      const bool pre = p.epilogue == RS_EPI_RESID_F32;
       float4 rr[8], cur[8];
       resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
-      EpiRow er;
-      if constexpr (EG == 3) {                                   // (mu, r) of this thread's row from the producer's partial sums
-        const int row = tile_row0 + lane;
-        float s1 = 0.f, s2 = 0.f;
-        if (row < p.M) {
-          const float2* st = reinterpret_cast<const float2*>(p.stats_in) + static_cast<size_t>(row) * p.stats_slots;
-          for (int k = 0; k < p.stats_slots; ++k) { const float2 t = __ldg(st + k); s1 += t.x; s2 += t.y; }
-        }
-        const float mu = s1 * p.fold_inv_n;
-        er.r = rsqrtf(fmaxf(s2 * p.fold_inv_n - mu * mu, 0.f) + p.ln_eps);
-        er.rm = er.r * mu;
-      }
-      if constexpr (EG == 4) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { er.rs[i] = 0.f; er.rss[i] = 0.f; }
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -535,17 +475,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store<EG, Cfg::kSwz>(p, r, stage, tile_row0, lane, col0, 0, cur, er);
-      }
-      if constexpr (EG == 4) {                                   // one (sum, sum of squares) per row and (column tile, half)
-        if ((lane & 7) == 0) {
-          const int slot = (n0 / BN) * 2 + half;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = tile_row0 + i * 4 + (lane >> 3);
-            if (row < p.M) reinterpret_cast<float2*>(p.stats_out)[static_cast<size_t>(row) * p.stats_slots + slot] = make_float2(er.rs[i], er.rss[i]);
-          }
-        }
+        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -557,325 +487,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   }
   tcgen05_fence_before();
   cluster_sync_all();                                        // both CTAs done with TMEM and with each other's barriers
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------- 4-CTA variant: A multicast
-// Cluster of FOUR CTAs = two SM pairs that work on the SAME 256 rows of A and on two neighbouring 256-column tiles of W.
-// EXPERIMENT, not the default (see g_gemm_mode): measured slower than the 2-CTA kernel.
-// The 2-CTA kernel moves ~760 MB from L2 per FFN launch (~10 TB/s at 71 % tensor-pipe activity,
-// profiles/r01_v3_gemm_ncu.md): every pair pulls its own copy of the A rows.  Here each CTA loads 64 of the 128 A rows it
-// needs and TMA multicasts them to the CTA of the other pair that needs the same rows (ranks r and r+2), so a pair
-// receives 32 KB of A per k-block for 16 KB of L2 reads: 48 KB instead of 64 KB per pair and k-block.
-// Barriers: full[] per pair leader as before (every destination credits its own leader); empty[] now counts the commits of
-// BOTH pairs (a stage is rewritten in two pairs' shared memory at once), each commit multicast to all four CTAs.
-// ---------------------------------------------------------------------------------------------------------------
-// EXPERIMENT (RS_GEMM_SPLITK=1, unmeasured): the 2-CTA kernel with the last, partial wave of tiles split along K
-// (kernels.h: SplitKPlan / splitk_item).  A separate kernel so that the default instances stay untouched; common
-// epilogues only (EG 0).  A work item is a (tile, k range): the three roles walk the same item list.
-struct GemmDevSk : GemmDev {
-  float* sk_partials; unsigned int* sk_flags; SplitKPlan plan;
-};
-
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_2cta_sk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDevSk p) {
-  using Cfg = Gemm2Cfg<BN, 0>;
-  extern __shared__ uint8_t smem_raw[];
-  RS_PDL_TRIGGER();
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
-  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));
-  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
-  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
-
-  const int warp = warp_id_uniform();
-  const int lane = lane_id();
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-  const int num_n = p.N / BN;
-  const int num_k = p.K / BK;
-  const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
-  const SplitKPlan plan = p.plan;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
-    fence_barrier_init();
-  }
-  cluster_sync_all();
-  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
-  tcgen05_fence_before();
-  cluster_sync_all();
-  tcgen05_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  RS_PDL_WAIT();                                             // (-DRS_PDL variant only) operands come from the previous kernel
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      SplitKItem w;
-      for (int it = 0; splitk_item(plan, it, cid, ncl, num_k, w); ++it) {
-        const int m0 = (w.tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
-        const int n0 = (w.tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = w.k0; kb < w.k1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          tma_load_2d_2sm(smem_a(stage), &tm_a, kb * BK, m0, full_bar(stage));
-          tma_load_2d_2sm(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
-          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          else mbar_arrive_remote(full_bar(stage), 0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
-      int stage = 0; uint32_t phase = 0;
-      SplitKItem w;
-      for (int it = 0; splitk_item(plan, it, cid, ncl, num_k, w); ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = w.k0; kb < w.k1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_a(stage));
-          const uint64_t db = umma_desc_k_sw128(smem_b(stage));
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb != w.k0 || k != 0) ? 1u : 0u);
-          umma_commit_2sm(empty_bar(stage));
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit_2sm(tfull_bar(acc));
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ epilogue warps (both CTAs, own TMEM half)
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * Cfg::kStagingPerWarp);
-    SplitKItem w;
-    for (int it = 0; splitk_item(plan, it, cid, ncl, num_k, w); ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = (w.tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (w.tile % num_n) * BN;
-      const int tile_row0 = m0 + q * 32;
-      const bool pre = w.kind != 1 && p.epilogue == RS_EPI_RESID_F32;
-      float4 rr[8], cur[8];
-      resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);
-      // this warp's slice of a tail tile's partial accumulators: [tail tile][part - 1][rank][warp][chunk][j][lane]
-      auto partial = [&](int part, int ci) {
-        return p.sk_partials + ((((static_cast<size_t>(w.tail_idx) * (plan.S - 1) + (part - 1)) * 2 + rank) * kEpiWarps + (warp - 2)) * (BN / 64) + ci) * 1024 + lane;
-      };
-      unsigned int* flag = p.sk_flags + (static_cast<size_t>(w.tail_idx) * 2 + rank) * kEpiWarps + (warp - 2);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      if (w.kind == 2) {                                         // owner: every contributor of this warp's slice has published
-        if (lane == 0) {
-          unsigned int v;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-          } while (v < static_cast<unsigned int>(plan.S - 1));
-        }
-        __syncwarp();
-      }
-#pragma unroll 1
-      for (int chunk = half, ci = 0; chunk < BN / 32; chunk += 2, ++ci) {
-        const int col0 = n0 + chunk * 32;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-        resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
-        tmem_ld_wait();
-        if (w.kind == 1) {                                       // contributor: raw accumulators, coalesced over the lanes
-          float* dst = partial(w.part, ci);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) __stcg(dst + j * 32, __uint_as_float(r[j]));
-          continue;
-        }
-        if (w.kind == 2) {
-          for (int part = 1; part < plan.S; ++part) {            // fixed order: the sum does not depend on timing
-            const float* src = partial(part, ci);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(src + j * 32));
-          }
-        }
-        EpiRow er_unused;
-        epilogue_store<0, Cfg::kSwz>(p, r, stage, tile_row0, lane, col0, 0, cur, er_unused);
-      }
-      if (w.kind == 1) {                                         // publish: data first, then the flag
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
-      } else if (w.kind == 2) {
-        __syncwarp();
-        if (lane == 0) *flag = 0u;                               // ready for the next launch (launches are stream-ordered)
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_remote(tempty_bar(acc), 0);
-      }
-    }
-  }
-  tcgen05_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
-  }
-}
-
-template <int BN, int EG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_4cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
-  using Cfg = Gemm2Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
-  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));
-  auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
-  auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
-
-  const int warp = warp_id_uniform();
-  const int lane = lane_id();
-  const uint32_t rank = cluster_ctarank();                   // 0..3
-  const uint32_t pair = rank >> 1, r = rank & 1u;
-  const bool leader = r == 0;
-  const uint32_t lead_rank = rank & ~1u;
-  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
-  const int num_n2 = p.N / (2 * BN);                         // pairs of column tiles
-  const int num_tiles = num_m * num_n2;
-  const int num_k = p.K / BK;
-  const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_a);
-    tma_prefetch_desc(&tm_b);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 2); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps); }
-    fence_barrier_init();
-  }
-  cluster_sync_all();
-  if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
-  tcgen05_fence_before();
-  cluster_sync_all();
-  tcgen05_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (all four CTAs)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint16_t a_mask = static_cast<uint16_t>((1u << r) | (1u << (r + 2)));      // the two CTAs that consume these A rows
-      for (int tile = cid; tile < num_tiles; tile += ncl) {
-        const int a_row = (tile / num_n2) * 2 * BM + static_cast<int>(r) * BM + static_cast<int>(pair) * (BM / 2);
-        const int n0 = ((tile % num_n2) * 2 + static_cast<int>(pair)) * BN + static_cast<int>(r) * (BN / 2);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);           // both pairs have consumed this stage
-          tma_load_2d_2sm_mc(smem_a(stage) + pair * (kABytes / 2), &tm_a, kb * BK, a_row, full_bar(stage), a_mask);
-          tma_load_2d_2sm(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
-          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          else mbar_arrive_remote(full_bar(stage), lead_rank);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (the leader of each pair)
-    if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
-      const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pair));
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tcgen05_fence_after();
-          const uint64_t da = umma_desc_k_sw128(smem_a(stage));
-          const uint64_t db = umma_desc_k_sw128(smem_b(stage));
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_ss_2sm(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm_mask(empty_bar(stage), 0xF);       // every CTA of the cluster writes into / is written by this stage
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit_2sm_mask(tfull_bar(acc), pair_mask);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ epilogue warps (own TMEM half of own pair's tile)
-    const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * kStageBytesPerWarp);
-    int it = 0;
-    for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1u;
-      const int m0 = (tile / num_n2) * 2 * BM + static_cast<int>(r) * BM;
-      const int n0 = ((tile % num_n2) * 2 + static_cast<int>(pair)) * BN;
-      const int tile_row0 = m0 + q * 32;
-      const bool pre = p.epilogue == RS_EPI_RESID_F32;
-      float4 rr[8], cur[8];
-      resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int chunk = half; chunk < BN / 32; chunk += 2) {
-        const int col0 = n0 + chunk * 32;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-        resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
-        uint32_t rg[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, rg);
-        tmem_ld_wait();
-        EpiRow er_unused;
-        epilogue_store<EG>(p, rg, stage, tile_row0, lane, col0, 0, cur, er_unused);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_remote(tempty_bar(acc), lead_rank);
-      }
-    }
-  }
-  tcgen05_fence_before();
-  cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
@@ -915,7 +526,6 @@ static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint6
 }
 
 inline int epilogue_group(int epilogue) { return epilogue == RS_EPI_QKV_VT ? 1 : (epilogue == RS_EPI_BIAS_F16_SKEW ? 2 : 0); }
-inline bool ln_fold_args(const GemmArgs& g) { return g.fold_c != nullptr || g.stats_out != nullptr; }
 
 template <int BN, int EG>
 static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
@@ -937,7 +547,7 @@ static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t str
   GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, nb, g.a_col_stride, g.w_row_stride, g.bias_stride, g.out_col_stride, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * nb;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  RS_LAUNCH((gemm_bf16_tn_kernel<BN, EG>), grid, kGemmThreads, Cfg::kSmemBytes, stream, tm_a, tm_b, p);
+  gemm_bf16_tn_kernel<BN, EG><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
@@ -952,12 +562,12 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
   }
 }
 
-template <int BN, int EG, int ST = 0>
+template <int BN, int EG>
 static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  using Cfg = Gemm2Cfg<BN, ST>;
+  using Cfg = Gemm2Cfg<BN>;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
     attr_once.set();
   }
@@ -966,131 +576,26 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
-  typename DevOf<EG>::type p{};
-  static_cast<GemmDev&>(p) = GemmDev{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
-  if constexpr (EG == 3 || EG == 4) {
-    p.fold_c = g.fold_c; p.fold_d = g.fold_d; p.stats_in = g.stats_in; p.stats_out = g.stats_out; p.xb = g.xb;
-    p.stats_slots = g.stats_slots; p.fold_inv_n = g.fold_n > 0 ? 1.0f / static_cast<float>(g.fold_n) : 0.f; p.ln_eps = g.ln_eps;
-  }
-  if constexpr (EG == 4) {
-    if (g.epilogue != RS_EPI_RESID_F32 || g.xb == nullptr || g.stats_slots != 2 * (g.N / BN)) {
-      snprintf(err, 256, "LayerNorm-fold producer needs RS_EPI_RESID_F32, xb and stats_slots == 2 * N / %d (got %d)", BN, g.stats_slots);
-      return cudaErrorInvalidValue;
-    }
-  }
-  if constexpr (EG == 3) {
-    const bool bf16_out = g.epilogue == RS_EPI_BIAS_BF16 || g.epilogue == RS_EPI_BIAS_RELU_BF16 || g.epilogue == RS_EPI_BIAS_SWISH_BF16 ||
-                          g.epilogue == RS_EPI_BIAS_GLU_BF16 || g.epilogue == RS_EPI_QKV_VT;
-    if (g.fold_d == nullptr || g.stats_in == nullptr || g.stats_slots <= 0 || g.fold_n <= 0 || !bf16_out) {
-      snprintf(err, 256, "LayerNorm-fold consumer needs fold_c, fold_d, stats_in, stats_slots, fold_n and a bf16 epilogue");
-      return cudaErrorInvalidValue;
-    }
-  }
+  const GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  RS_LAUNCH((gemm_bf16_tn_2cta_kernel<BN, EG, ST>), 2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream, tm_a, tm_b, p);
+  gemm_bf16_tn_2cta_kernel<BN, EG><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm 2cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
 }
 
-// RS_GEMM_SPLITK experiment: true when the split-K kernel took the launch (rc then holds its result)
-template <int BN>
-static bool try_launch_2cta_sk(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err, cudaError_t* rc) {
-  using Cfg = Gemm2Cfg<BN, 0>;
-  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
-  const int clusters = num_sms / 2;                                // all of them: fewer tiles than clusters is a tail, too
-  const SplitKPlan plan = splitk_plan(tiles, clusters, g.K / BK);
-  if (plan.S <= 1 || g.K / BK < 32) return false;                  // nothing to gain, or k ranges too short to pay for the fix-up
-  static DeviceOnce attr_once;
-  if (attr_once.pending()) {
-    *rc = cudaFuncSetAttribute(gemm_bf16_tn_2cta_sk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (*rc != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta split-K smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(*rc)); return true; }
-    attr_once.set();
-  }
-  CUtensorMap tm_a, tm_b;
-  const int lda = g.lda > 0 ? g.lda : g.K;
-  const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
-  *rc = cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return true;
-  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return true;
-  GemmDevSk p{};
-  static_cast<GemmDev&>(p) = GemmDev{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
-  p.sk_partials = g.sk_partials; p.sk_flags = g.sk_flags; p.plan = plan;
-  RS_LAUNCH(gemm_bf16_tn_2cta_sk_kernel<BN>, 2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream, tm_a, tm_b, p);
-  *rc = cudaGetLastError();
-  if (*rc != cudaSuccess) snprintf(err, 256, "gemm 2cta split-K launch (M=%d N=%d K=%d S=%d): %s", g.M, g.N, g.K, plan.S, cudaGetErrorString(*rc));
-  return true;
-}
-
 template <int BN>
 static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  // RS_GEMM_STAGES=6: EXPERIMENT (not yet measured) -- a 6-deep ring for the common epilogues, made possible by the 4 KB
-  // swizzled fp32 staging; the default is the 5-deep ring with padded staging
-  static const int stages = getenv("RS_GEMM_STAGES") ? atoi(getenv("RS_GEMM_STAGES")) : 0;
-  if (g.sk_partials != nullptr && g.sk_flags != nullptr && !ln_fold_args(g) && epilogue_group(g.epilogue) == 0 && stages != 6) {
-    cudaError_t rc;                                                                       // RS_GEMM_SPLITK experiment
-    if (try_launch_2cta_sk<BN>(g, num_sms, stream, err, &rc)) return rc;
-  }
-  if (g.fold_c != nullptr) return launch_2cta_eg<BN, 3>(g, num_sms, stream, err);      // RS_LN_FOLD experiment (consumer)
-  if (g.stats_out != nullptr) return launch_2cta_eg<BN, 4>(g, num_sms, stream, err);   // RS_LN_FOLD experiment (producer)
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
     case 2: return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
-    default: return stages == 6 ? launch_2cta_eg<BN, 0, 6>(g, num_sms, stream, err) : launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
+    default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
   }
 }
-
-template <int BN, int EG>
-static cudaError_t launch_4cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  using Cfg = Gemm2Cfg<BN>;
-  static DeviceOnce attr_once;
-  if (attr_once.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_4cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(4cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
-    attr_once.set();
-  }
-  CUtensorMap tm_a, tm_b;
-  const int lda = g.lda > 0 ? g.lda : g.K;
-  const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
-  if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM / 2, err)) return cudaErrorInvalidValue;     // 64-row boxes: half of a CTA's A rows
-  if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
-  GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
-  const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / (2 * BN));
-  int clusters = num_sms / 4;
-  if (tiles < clusters) clusters = tiles;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(4 * clusters); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_4cta_kernel<BN, EG>, tm_a, tm_b, p);
-  if (e != cudaSuccess) snprintf(err, 256, "gemm 4cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
-  return e;
-}
-
-template <int BN>
-static cudaError_t launch_4cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  switch (epilogue_group(g.epilogue)) {
-    case 1: return launch_4cta_eg<BN, 1>(g, num_sms, stream, err);
-    case 2: return launch_4cta_eg<BN, 2>(g, num_sms, stream, err);
-    default: return launch_4cta_eg<BN, 0>(g, num_sms, stream, err);
-  }
-}
-
-// RS_GEMM_MODE: 0 = 1-CTA kernels only, 1 (default) = 2-CTA pairs, 2 = 4-CTA clusters with A multicast where N % 512 == 0.
-// Mode 2 is correct (all GEMM / model tests pass with it) but measured 1.3-1.7x SLOWER than mode 1 on every encoder shape
-// (FFN W1 139.6 vs 82.8 us): with a 5-stage ring of 32 KB per CTA the loop "MMA retires -> commit -> producer -> TMA -> full"
-// is latency-bound, and coupling two pairs through cluster-wide empty barriers and multicast lengthens exactly that loop.
-static int g_gemm_mode = -1;
 
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  if (g_gemm_mode < 0) {
-    const char* m = getenv("RS_GEMM_MODE");
-    g_gemm_mode = m ? atoi(m) : 1;
-  }
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.K % BK != 0 || g.N % 32 != 0) {
     snprintf(err, 256, "gemm shape unsupported: M=%d N=%d K=%d (need K%%64==0, N%%32==0)", g.M, g.N, g.K);
     return cudaErrorInvalidValue;
@@ -1108,16 +613,10 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, ld2 >= M rounded up to 256");
     return cudaErrorInvalidValue;
   }
-  if (ln_fold_args(g) && !(g_gemm_mode == 1 && g.n_batch <= 1 && g.N % 256 == 0)) {
-    snprintf(err, 256, "gemm: the LayerNorm-fold epilogues exist in the 2-CTA kernel only (RS_GEMM_MODE=1, N %% 256 == 0)");
-    return cudaErrorInvalidValue;
-  }
   // kernel choice depends on N only (never on M): a row's result must not depend on the batch it sits in
-  if (g_gemm_mode == 2 && g.n_batch <= 1 && g.N % 512 == 0)
-    return launch_4cta<256>(g, num_sms, stream, err);
-  if (g_gemm_mode >= 1 && g.n_batch <= 1 && g.N % 256 == 0)
+  if (g.n_batch <= 1 && g.N % 256 == 0)                       // 2-CTA pairs (cta_group::2), 256 x 256 tiles
     return launch_2cta<256>(g, num_sms, stream, err);
-  // Widest tile that still yields at least ~one wave of tiles; narrow N uses a narrower tile.
+  // 1-CTA kernel: the column-batched launch and N not divisible by 256; the widest tile that divides N
   if (g.N >= 256 && g.N % 256 == 0) return launch_bn<256>(g, num_sms, stream, err);
   if (g.N >= 128 && g.N % 128 == 0) return launch_bn<128>(g, num_sms, stream, err);
   return launch_bn<64>(g, num_sms, stream, err);

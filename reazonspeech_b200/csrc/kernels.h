@@ -19,56 +19,7 @@ struct GemmArgs {
   int n_batch = 1, a_col_stride = 0, w_row_stride = 0, bias_stride = 0, out_col_stride = 0;
   // RS_EPI_QKV_VT: columns >= split go, transposed, to out2 (bf16 [N - split, ld2]; ld2 >= M rounded up to 256)
   void* out2 = nullptr; int split = 0, ld2 = 0;
-  // EXPERIMENT (RS_LN_FOLD=1): LayerNorm folded into its consumer GEMM.
-  //   producer (RS_EPI_RESID_F32 with stats_out): also writes bf16(x) to xb and, per row and per (column tile, column half),
-  //     the partial sums (sum x, sum x^2) of its 128 columns to stats_out[row][stats_slots][2];
-  //   consumer (fold_c != nullptr): A = bf16(x), W = bf16(W * gamma); the epilogue applies
-  //     y = r * acc - r * mu * fold_c[n] + fold_d[n] with (mu, r) of the row from stats_in, then its usual activation.
-  const float* fold_c = nullptr; const float* fold_d = nullptr; const float* stats_in = nullptr;
-  float* stats_out = nullptr; void* xb = nullptr; int stats_slots = 0; int fold_n = 0; float ln_eps = 1e-5f;
-  // EXPERIMENT (RS_GEMM_SPLITK=1): workspace of the split-K tail (see SplitKPlan below); nullptr = off
-  float* sk_partials = nullptr; unsigned int* sk_flags = nullptr;
 };
-// EXPERIMENT (RS_GEMM_SPLITK=1): split-K of the LAST, partial wave of a persistent GEMM.
-// With T tiles on C clusters the last wave runs T mod C tiles while the other clusters idle (N = 1024 at 32 clips:
-// 196 tiles on 74 clusters = 2.65 waves, paid as 3).  The tail tiles are cut into S parts along K; parts 1..S-1
-// ("contributors") dump their fp32 accumulators to a workspace and raise a flag, part 0 (the "owner") adds them in a
-// fixed order and runs the normal epilogue: deterministic, no atomics on data.  Contributors are scheduled before
-// owners and never wait, so an owner only ever waits for clusters that are making progress.
-struct SplitKItem { int tile, k0, k1, kind, tail_idx, part; };   // kind: 0 full tile, 1 contributor, 2 owner
-struct SplitKPlan { int full_rounds, tail, S; };
-#if defined(__CUDACC__)
-#define RS_HD __host__ __device__
-#else
-#define RS_HD
-#endif
-// S in 1..4 minimising ceil(tail * S / C) / S, the duration of the tail in tile times (ties: the smaller S).
-RS_HD inline SplitKPlan splitk_plan(int num_tiles, int ncl, int num_k) {
-  SplitKPlan pl{num_tiles / ncl, num_tiles % ncl, 1};
-  if (pl.tail == 0) return pl;
-  int best_num = 1, best_den = 1;                                 // cost of S = 1 is 1 tile time
-  for (int s = 2; s <= 4 && s * 8 <= num_k; ++s) {
-    const int rounds = (pl.tail * s + ncl - 1) / ncl;             // cost = rounds / s
-    if (rounds * best_den < best_num * s) { best_num = rounds; best_den = s; pl.S = s; }
-  }
-  return pl;
-}
-// it-th work item of cluster cid; false when the cluster is done.
-RS_HD inline bool splitk_item(const SplitKPlan& pl, int it, int cid, int ncl, int num_k, SplitKItem& w) {
-  if (it < pl.full_rounds) { w = SplitKItem{cid + it * ncl, 0, num_k, 0, 0, 0}; return true; }
-  const int g = cid + (it - pl.full_rounds) * ncl;
-  if (g >= pl.tail * pl.S) return false;
-  const int n_contrib = pl.tail * (pl.S - 1);
-  if (g < n_contrib) { w.kind = 1; w.tail_idx = g % pl.tail; w.part = 1 + g / pl.tail; }
-  else { w.kind = pl.S > 1 ? 2 : 0; w.tail_idx = g - n_contrib; w.part = 0; }
-  w.tile = pl.full_rounds * ncl + w.tail_idx;
-  w.k0 = static_cast<int>(static_cast<long long>(w.part) * num_k / pl.S);
-  w.k1 = static_cast<int>(static_cast<long long>(w.part + 1) * num_k / pl.S);
-  return true;
-}
-// Workspace of the split-K experiment: partial accumulators [tail < C][S - 1 <= 3][256 x 256] f32, then the flags.
-inline size_t splitk_partial_bytes(int ncl) { return static_cast<size_t>(ncl) * 3 * 256 * 256 * 4; }
-inline size_t splitk_flag_bytes(int ncl) { return static_cast<size_t>(ncl) * 2 * 8 * 4; }
 
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
@@ -109,7 +60,6 @@ struct AttnArgs {
   // tensor-core path: `bd` is row-skewed (RS_EPI_BIAS_F16_SKEW), bd_pitch halves per (row, head)
   int bd_pitch = 0;
 };
-cudaError_t launch_attention(const AttnArgs& a, cudaStream_t stream);
 bool attention_tc_supported(const AttnArgs& a);
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream);
 cudaError_t attention_tc_debug_cycles(long long* out16);   // clock64 stamps of CTA (1,0,0) of the last launch
@@ -127,14 +77,9 @@ struct DecodeArgs {
   int32_t* tokens; int32_t* frames; int32_t* n_tok;
   int B, T_max, Hj, Hp, V, U_max, max_symbols;
 };
-cudaError_t launch_rnnt_greedy(const DecodeArgs& a, int num_sms, cudaStream_t stream);
-// batched, weights-stationary variant (decode_batched.cu); workspace from rnnt_batched_workspace_bytes()
-size_t rnnt_batched_workspace_bytes(int B, int Hj, int Hp, int num_sms);
-cudaError_t launch_rnnt_greedy_batched(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream);
-
-// windowed (kFrames per iteration) tensor-path variant (decode_spec.cu); workspace from rnnt_spec_workspace_bytes()
+// windowed (kFrames per iteration) persistent decode, joint on tcgen05 (decode_spec.cu); workspace from rnnt_spec_workspace_bytes()
 size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int num_sms);
-cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream, bool tc_joint = false);
+cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream);
 
 // small utility kernels
 cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);

@@ -49,7 +49,7 @@ EXPORTS = [
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
-    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles", "rs_debug_splitk_schedule",
+    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
 ]
 
 
@@ -59,12 +59,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _LIB_PATH
-    variant = os.environ.get("RS_ENGINE_VARIANT", "")      # experiments only: a compile-time variant, e.g. "pdl" (build.py)
-    if variant:
-        path = _LIB_PATH.replace(".so", f"_{variant}.so")
-        if not os.path.exists(path):
-            raise FileNotFoundError(f"{path}: build it first with `python -m reazonspeech_b200.build --variant {variant}`")
-    elif not os.path.exists(_LIB_PATH):
+    if not os.path.exists(_LIB_PATH):
         if not build_if_missing:
             raise FileNotFoundError(_LIB_PATH)
         from .build import build
@@ -98,8 +93,6 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_debug_decode_cycles.restype = ip
     lib.rs_enable_kernel_timing.argtypes = [vp, ip]
     lib.rs_enable_kernel_timing.restype = ip
-    lib.rs_debug_splitk_schedule.argtypes = [ip, ip, ip, vp, ip, C.POINTER(C.c_int)]
-    lib.rs_debug_splitk_schedule.restype = ip
     lib.rs_kernel_timing.argtypes = [vp, C.c_char_p, ip]
     lib.rs_kernel_timing.restype = ip
     lib.rs_enable_gemm_timing.argtypes = [vp, ip]
@@ -182,29 +175,6 @@ def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     return out
 
 
-def ln_fold_tensors(packed: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
-    """EXPERIMENT (RS_LN_FOLD=1, unmeasured): LayerNorm folded into the GEMM that consumes it.
-
-    For y = LN(x) W^T + b with LN(x) = (x - mu) r * g + beta:
-        y[n] = r * sum_k x[k] W'[n,k]  -  r * mu * c[n]  +  dd[n],
-        W' = bf16(W * g),  c[n] = sum_k W'[n,k],  dd[n] = sum_k beta[k] W[n,k] + b[n].
-    The GEMM then reads bf16(x) (written, with the row sums that give mu and r, by the epilogue of the GEMM that
-    produced x) and the three LayerNorm launches per layer whose input comes straight out of a residual GEMM --
-    norm_self_att, norm_conv, norm_feed_forward2 -- disappear.  Works on the PACKED matrices, so the q|k|v fusion, the
-    folded pos_bias_u and the GLU row interleave carry over unchanged."""
-    out: Dict[str, torch.Tensor] = {}
-    for i in range(cfg.n_layers):
-        o = f"L{i}."
-        for ln, w, b in (("ln_att", "att.wqkv", "att.bqkv"), ("ln_conv", "conv.pw1.w", "conv.pw1.b"), ("ln_ff2", "ff2.w1", "ff2.b1")):
-            W = packed[o + w].float()
-            g, beta = packed[o + ln + ".g"].float(), packed[o + ln + ".b"].float()
-            Wf = (W * g[None, :]).to(torch.bfloat16).contiguous()
-            out[o + w + ".fold"] = Wf
-            out[o + w + ".fold_c"] = Wf.float().sum(1).contiguous()
-            out[o + w + ".fold_d"] = (W @ beta + packed[o + b].float()).contiguous()
-    return out
-
-
 def to_rs_config(cfg: ModelConfig) -> RsModelConfig:
     return RsModelConfig(
         cfg.sample_rate, cfg.n_window_size, cfg.n_window_stride, cfg.n_fft, cfg.n_mels,
@@ -231,8 +201,6 @@ class Engine:
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", self.dev_index)
         packed = pack_weights(state_dict, cfg)
-        if os.environ.get("RS_LN_FOLD", "0") == "1":        # experiment, off by default: see ln_fold_tensors
-            packed.update(ln_fold_tensors(packed, cfg))
         self.weights = {k: v.to(self.device) for k, v in packed.items()}
         self._names = [k.encode() for k in self.weights]
         arr = (RsTensor * len(self.weights))()

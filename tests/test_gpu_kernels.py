@@ -161,13 +161,10 @@ def test_encoder_vs_oracle(tiny_engine, tiny_cfg, tiny_sd, n_layers):
 
 
 # ------------------------------------------------------------------------------------ decode
-@pytest.mark.parametrize("mode", ["1", "2", "3", "4"])
-def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd, mode, monkeypatch):
-    """Decode kernels alone (1: one cluster per utterance, 2: batched weights-stationary grid, 3: windowed
-    grid with the joint on mma.sync, 4: the same with the joint on tcgen05): fed the ORACLE's encoder output, tokens
-    and frames must be identical."""
+def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd):
+    """The decode kernel alone (windowed, weights stationary, joint on tcgen05): fed the ORACLE's encoder output, tokens and
+    frames must be identical."""
     from oracle import nemo_restated as O
-    monkeypatch.setenv("RS_DECODE_MODE", mode)
     eng = tiny_engine
     waves = [padded(synth_clip(6, 4.0)), padded(synth_clip(7, 2.5)), padded(synth_clip(8, 6.0))]
     refs, encs = [], []
@@ -189,35 +186,6 @@ def test_greedy_teacher_forced(tiny_engine, tiny_cfg, tiny_sd, mode, monkeypatch
         assert n == len(r.tokens)
         assert tokens[i, :n].cpu().tolist() == r.tokens
         assert frames[i, :n].cpu().tolist() == r.frames
-
-
-@pytest.mark.parametrize("B", [1, 3, 5, 33, 70])
-def test_windowed_decode_equals_sequential_kernel(tiny_engine, tiny_cfg, B, monkeypatch):
-    """The windowed kernel (4 frames per iteration, utterance groups x vocabulary slices, bf16x3 tensor path)
-    against the one-frame-per-iteration fp32 kernel on random encoder outputs, ragged lengths (incl. a
-    zero-length utterance), batch sizes that are not multiples of the group count and span several passes:
-    tokens, frames and counts identical."""
-    eng = tiny_engine
-    g = torch.Generator().manual_seed(B)
-    T = 61
-    enc = torch.randn(B, T, tiny_cfg.d_model, generator=g) * 2.0
-    enc_len = torch.randint(1, T + 1, (B,), generator=g, dtype=torch.int32)
-    enc_len[0] = T
-    if B > 2:
-        enc_len[2] = 0
-    outs = {}
-    for mode in ("2", "3", "4"):
-        monkeypatch.setenv("RS_DECODE_MODE", mode)
-        t, f, n = eng.greedy(enc.cuda(), enc_len.cuda())
-        torch.cuda.synchronize()
-        outs[mode] = (t.cpu(), f.cpu(), n.cpu())
-    n2 = outs["2"][2]
-    print("tokens per utterance:", n2.tolist()[:12], "lens", enc_len.tolist()[:12])
-    for other in ("3", "4"):
-        assert torch.equal(n2, outs[other][2]), f"mode {other}"
-        for b in range(B):
-            n = int(n2[b])
-            assert torch.equal(outs["2"][0][b, :n], outs[other][0][b, :n]) and torch.equal(outs["2"][1][b, :n], outs[other][1][b, :n]), f"mode {other} utt {b}"
 
 
 from parity import check_decisions, decisions_from     # noqa: E402  (tests/ is on sys.path under pytest)
@@ -258,27 +226,6 @@ def test_host_entry_chunked_copies_equal_device_entry(tiny_engine, B):
         n = int(nh[b])
         assert torch.equal(th[b, :n], td[b, :n].cpu()) and torch.equal(fh[b, :n], fd[b, :n].cpu())
     assert int(nh.sum()) > 0
-
-
-def test_tensor_core_attention_matches_mma_sync_attention(tiny_engine, monkeypatch):
-    """The tcgen05 attention (default) against the mma.sync kernels (RS_ATTN_MODE=1) through the whole encoder, ragged
-    batch with an utterance spanning several 128-row query tiles: relative L2 <= 5e-3 (both are bf16-operand,
-    fp32-accumulate evaluations of the same scores; P is rounded to bf16 at different points)."""
-    eng = tiny_engine
-    waves = [padded(synth_clip(80, 13.0)), padded(synth_clip(81, 0.9)), padded(synth_clip(82, 5.5)), padded(synth_clip(83, 10.3))]
-    mel, mel_len = _mel_batch(eng, waves)
-    outs = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("RS_ATTN_MODE", mode)
-        enc, enc_len = eng.encode(mel, mel_len)
-        torch.cuda.synchronize()
-        outs[mode] = enc.clone()
-    for i in range(len(waves)):
-        T = int(enc_len[i])
-        r = _rel(outs["0"][i, :T].cpu(), outs["1"][i, :T].cpu())
-        print(f"utt{i} T={T}: tcgen05 vs mma.sync attention, encoder rel-L2 {r:.3e}")
-        assert r < 5e-3
-        assert outs["0"][i, T:].abs().max().item() == 0.0 if T < outs["0"].shape[1] else True
 
 
 def test_long_form_clip_in_one_call(tiny_engine, tiny_cfg, tiny_sd):
