@@ -126,6 +126,17 @@ int rs_transcribe_device(rs_engine* e, const float* wav_dev, const int32_t* len_
 int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_host, int B,
                         int L_max, int32_t* tokens_host, int32_t* frames_host,
                         int32_t* n_tok_host, int U_max, void* stream);
+/* The same two entry points for 16-bit PCM (what audio files hold): samples are scaled by 2^-15 inside the
+ * log-mel kernel's staging load -- the value decoding a 16-bit WAV to float32 gives (the reference loads files
+ * through librosa.load, pkg/nemo-asr/src/audio.py:32-42) -- so the results equal the float entry points' on
+ * the converted samples, for half the host-to-device and HBM bytes.  L_max must be a multiple of 4 for the
+ * vectorised load (any value works, unaligned rows fall back to scalar loads). */
+int rs_transcribe_device_pcm16(rs_engine* e, const int16_t* wav_dev, const int32_t* len_dev, int B,
+                               int L_max, int32_t* tokens_dev, int32_t* frames_dev,
+                               int32_t* n_tok_dev, int U_max, void* stream);
+int rs_transcribe_batch_pcm16(rs_engine* e, const int16_t* wav_host, const int32_t* len_host, int B,
+                              int L_max, int32_t* tokens_host, int32_t* frames_host,
+                              int32_t* n_tok_host, int U_max, void* stream);
 
 /* ---- kernel-level seams (parity tests and roofline measurement) --------------------------- */
 int rs_gemm_bf16(rs_engine* e, const void* a_bf16, const void* w_bf16, const float* bias,

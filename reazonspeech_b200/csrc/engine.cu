@@ -314,13 +314,13 @@ void mark(rs_engine* e, int i, cudaStream_t s) {
 
 // Log-mel of utterances [b0, b0 + nb) of a batch whose statistics live at plan offsets (absolute utterance index).
 // normalise = false leaves `mel` un-normalised for sub_conv0_dw1_kernel (the transcribe path); rs_logmel passes true.
-int do_logmel(rs_engine* e, const float* wav, const int32_t* len, int nb, int L_max, float* mel, int32_t* mel_len,
+int do_logmel(rs_engine* e, const void* wav, bool i16, const int32_t* len, int nb, int L_max, float* mel, int32_t* mel_len,
               float* partials, float* stats, int b0, bool normalise, cudaStream_t s) {
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   if (b0 + nb > rs_engine::kMaxBatch) return fail(e, RS_ERR_INVALID_ARG, "batch of %d utterances exceeds the engine limit of %d", b0 + nb, rs_engine::kMaxBatch);
   rs::LogmelArgs a{};
-  a.wav = wav; a.len = len; a.B = nb; a.L_max = L_max; a.mel = mel; a.mel_len = mel_len;
+  a.wav = wav; a.wav_i16 = i16; a.len = len; a.B = nb; a.L_max = L_max; a.mel = mel; a.mel_len = mel_len;
   a.partials = partials + static_cast<size_t>(b0) * rs::logmel_tiles(L_max, c.n_window_stride) * c.n_mels * 2;
   a.stats = stats + static_cast<size_t>(b0) * c.n_mels * 2;
   a.tickets = e->lm_tickets + b0;
@@ -518,7 +518,7 @@ int rs_logmel(rs_engine* e, const float* wav, const int32_t* len, int B, int L_m
   RS_CUDA(e, cudaSetDevice(e->device));
   Plan p = make_plan(e, B, L_max, 1);               // the statistics scratch lives in the workspace
   RS_TRY(check_ws(e, p));
-  return do_logmel(e, wav, len, B, L_max, mel, mel_len, at<float>(e, p.mel_part), at<float>(e, p.mel_stats), 0, true,
+  return do_logmel(e, wav, false, len, B, L_max, mel, mel_len, at<float>(e, p.mel_part), at<float>(e, p.mel_stats), 0, true,
                    static_cast<cudaStream_t>(stream));
 }
 
@@ -549,16 +549,17 @@ int rs_rnnt_greedy(rs_engine* e, const float* enc, const int32_t* enc_len, int B
   return do_greedy(e, p, enc, enc_len, T_max, tokens, frames, n_tok, U_max, static_cast<cudaStream_t>(stream));
 }
 
-int rs_transcribe_device(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, int32_t* tokens,
-                         int32_t* frames, int32_t* n_tok, int U_max, void* stream) {
-  if (!e || !wav || !len || !tokens || !frames || !n_tok || B <= 0 || L_max <= 0 || U_max <= 0)
-    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_device: bad arguments");
-  RS_CUDA(e, cudaSetDevice(e->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+}  // extern "C"
+
+namespace {
+
+// Device-resident whole path; `wav` holds f32 samples, or int16 PCM (scaled by 2^-15 inside the log-mel kernel) when i16.
+int transcribe_device(rs_engine* e, const void* wav, bool i16, const int32_t* len, int B, int L_max, int32_t* tokens,
+                      int32_t* frames, int32_t* n_tok, int U_max, cudaStream_t s) {
   Plan p = make_plan(e, B, L_max, U_max);
   RS_TRY(check_ws(e, p));
   mark(e, 0, s);
-  RS_TRY(do_logmel(e, wav, len, B, L_max, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.mel_part), at<float>(e, p.mel_stats), 0, false, s));
+  RS_TRY(do_logmel(e, wav, i16, len, B, L_max, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.mel_part), at<float>(e, p.mel_stats), 0, false, s));
   mark(e, 1, s);
   RS_TRY(do_encode(e, p, at<float>(e, p.mel), at<int32_t>(e, p.mel_len), at<float>(e, p.mel_stats), at<float>(e, p.enc), at<int32_t>(e, p.enc_len), -1, s));
   mark(e, 3, s);
@@ -567,24 +568,24 @@ int rs_transcribe_device(rs_engine* e, const float* wav, const int32_t* len, int
   return RS_OK;
 }
 
-int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_host, int B, int L_max,
-                        int32_t* tokens_host, int32_t* frames_host, int32_t* n_tok_host, int U_max, void* stream) {
-  if (!e || !wav_host || !len_host || !tokens_host || !frames_host || !n_tok_host || B <= 0 || L_max <= 0 || U_max <= 0)
-    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_batch: bad arguments");
-  RS_CUDA(e, cudaSetDevice(e->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+// Host buffers in, host buffers out (the model.transcribe seam): H2D in utterance chunks on the copy stream, overlapped with
+// the frontend of the chunks that have landed; D2H of the tokens; synchronises before returning.
+int transcribe_batch(rs_engine* e, const void* wav_host, bool i16, const int32_t* len_host, int B, int L_max,
+                     int32_t* tokens_host, int32_t* frames_host, int32_t* n_tok_host, int U_max, cudaStream_t s) {
   Plan p = make_plan(e, B, L_max, U_max);
   RS_TRY(check_ws(e, p));
-  float* wav = at<float>(e, p.wav);
+  const size_t esz = i16 ? 2 : 4;                       // the waveform region of the workspace is sized for f32
+  char* wav = at<char>(e, p.wav);
+  const char* wav_h = static_cast<const char*>(wav_host);
   int32_t* len = at<int32_t>(e, p.len);
   float* mel = at<float>(e, p.mel);
   int32_t* mel_len = at<int32_t>(e, p.mel_len);
   const int n_chunks = (e->copy_ok && B >= 2 * rs_engine::kCopyChunks) ? rs_engine::kCopyChunks : 1;
   if (n_chunks == 1) {
-    RS_CUDA(e, cudaMemcpyAsync(wav, wav_host, static_cast<size_t>(B) * L_max * 4, cudaMemcpyHostToDevice, s));
+    RS_CUDA(e, cudaMemcpyAsync(wav, wav_h, static_cast<size_t>(B) * L_max * esz, cudaMemcpyHostToDevice, s));
     RS_CUDA(e, cudaMemcpyAsync(len, len_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
-    RS_TRY(rs_transcribe_device(e, wav, len, B, L_max, at<int32_t>(e, p.tokens), at<int32_t>(e, p.frames),
-                                at<int32_t>(e, p.ntok), U_max, s));
+    RS_TRY(transcribe_device(e, wav, i16, len, B, L_max, at<int32_t>(e, p.tokens), at<int32_t>(e, p.frames),
+                             at<int32_t>(e, p.ntok), U_max, s));
   } else {
     // copies on the copy stream, chunk by chunk; log-mel and the first (fused) subsampling conv of a chunk start as
     // soon as its samples have landed.  The copy stream first waits for everything already queued on the caller's
@@ -595,14 +596,14 @@ int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_
     RS_CUDA(e, cudaMemcpyAsync(len, len_host, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, e->copy_stream));
     for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
       const int nb = (B - b0 < per) ? B - b0 : per;
-      RS_CUDA(e, cudaMemcpyAsync(wav + static_cast<size_t>(b0) * L_max, wav_host + static_cast<size_t>(b0) * L_max,
-                                 static_cast<size_t>(nb) * L_max * 4, cudaMemcpyHostToDevice, e->copy_stream));
+      RS_CUDA(e, cudaMemcpyAsync(wav + static_cast<size_t>(b0) * L_max * esz, wav_h + static_cast<size_t>(b0) * L_max * esz,
+                                 static_cast<size_t>(nb) * L_max * esz, cudaMemcpyHostToDevice, e->copy_stream));
       RS_CUDA(e, cudaEventRecord(e->copy_ev[c], e->copy_stream));
     }
     for (int c = 0, b0 = 0; b0 < B; ++c, b0 += per) {
       const int nb = (B - b0 < per) ? B - b0 : per;
       RS_CUDA(e, cudaStreamWaitEvent(s, e->copy_ev[c], 0));
-      RS_TRY(do_logmel(e, wav + static_cast<size_t>(b0) * L_max, len + b0, nb, L_max,
+      RS_TRY(do_logmel(e, wav + static_cast<size_t>(b0) * L_max * esz, i16, len + b0, nb, L_max,
                        mel + static_cast<size_t>(b0) * p.F_max * e->cfg.n_mels, mel_len + b0, at<float>(e, p.mel_part), at<float>(e, p.mel_stats), b0, false, s));
       RS_TRY(do_sub_conv0(e, p, mel, mel_len, at<float>(e, p.mel_stats), b0, nb, s));
     }
@@ -615,6 +616,42 @@ int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_
   RS_CUDA(e, cudaMemcpyAsync(n_tok_host, at<int32_t>(e, p.ntok), static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
   RS_CUDA(e, cudaStreamSynchronize(s));
   return RS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rs_transcribe_device(rs_engine* e, const float* wav, const int32_t* len, int B, int L_max, int32_t* tokens,
+                         int32_t* frames, int32_t* n_tok, int U_max, void* stream) {
+  if (!e || !wav || !len || !tokens || !frames || !n_tok || B <= 0 || L_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_device: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  return transcribe_device(e, wav, false, len, B, L_max, tokens, frames, n_tok, U_max, static_cast<cudaStream_t>(stream));
+}
+
+int rs_transcribe_device_pcm16(rs_engine* e, const int16_t* wav, const int32_t* len, int B, int L_max, int32_t* tokens,
+                               int32_t* frames, int32_t* n_tok, int U_max, void* stream) {
+  if (!e || !wav || !len || !tokens || !frames || !n_tok || B <= 0 || L_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_device_pcm16: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  return transcribe_device(e, wav, true, len, B, L_max, tokens, frames, n_tok, U_max, static_cast<cudaStream_t>(stream));
+}
+
+int rs_transcribe_batch(rs_engine* e, const float* wav_host, const int32_t* len_host, int B, int L_max,
+                        int32_t* tokens_host, int32_t* frames_host, int32_t* n_tok_host, int U_max, void* stream) {
+  if (!e || !wav_host || !len_host || !tokens_host || !frames_host || !n_tok_host || B <= 0 || L_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_batch: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  return transcribe_batch(e, wav_host, false, len_host, B, L_max, tokens_host, frames_host, n_tok_host, U_max, static_cast<cudaStream_t>(stream));
+}
+
+int rs_transcribe_batch_pcm16(rs_engine* e, const int16_t* wav_host, const int32_t* len_host, int B, int L_max,
+                              int32_t* tokens_host, int32_t* frames_host, int32_t* n_tok_host, int U_max, void* stream) {
+  if (!e || !wav_host || !len_host || !tokens_host || !frames_host || !n_tok_host || B <= 0 || L_max <= 0 || U_max <= 0)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_batch_pcm16: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  return transcribe_batch(e, wav_host, true, len_host, B, L_max, tokens_host, frames_host, n_tok_host, U_max, static_cast<cudaStream_t>(stream));
 }
 
 int rs_gemm_bf16(rs_engine* e, const void* a, const void* w, const float* bias, const float* resid, void* out, int M,

@@ -64,9 +64,19 @@ __device__ __forceinline__ void split_step(const float2 (&v)[16], int t, int par
   s_pw[lm::bin_minus(t, K2)] = pm;
 }
 
-template <int kFrames, int kSlots>
+// PCM16 ingest: the staging loop reads int16 samples (half the HBM and PCIe bytes) and scales by 2^-15, which is exactly
+// what decoding a 16-bit WAV to float32 does (soundfile / librosa: sample / 32768), so both input types give identical features.
+template <bool kI16> struct LmSample { using type = float; };
+template <> struct LmSample<true> { using type = int16_t; };
+template <bool kI16>
+__device__ __forceinline__ float lm_load(const typename LmSample<kI16>::type* p) {
+  if constexpr (kI16) return static_cast<float>(__ldg(p)) * (1.0f / 32768.0f);
+  else return __ldg(p);
+}
+
+template <int kFrames, int kSlots, bool kI16>
 __global__ void __launch_bounds__(kLmThreads, kFrames <= 32 ? 3 : 2)
-logmel_fused_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, int L_max, float* __restrict__ mel,
+logmel_fused_kernel(const typename LmSample<kI16>::type* __restrict__ wav, const int32_t* __restrict__ len, int L_max, float* __restrict__ mel,
                     int32_t* __restrict__ mel_len, LmTables tb, float* __restrict__ partials, float* __restrict__ stats,
                     unsigned int* __restrict__ tickets, int F_max, int tiles_max, int n_mels, int hop, float preemph,
                     float guard, float eps) {
@@ -97,17 +107,26 @@ logmel_fused_kernel(const float* __restrict__ wav, const int32_t* __restrict__ l
   {
     const int n_stage = (kFrames - 1) * hop + lm::kNfft;
     const int start = f0 * hop - lm::kHalf;                // global sample index of s_y[0]
-    const float* xw = wav + static_cast<size_t>(b) * L_max;
-    const bool vec = ((reinterpret_cast<uintptr_t>(xw) | static_cast<uintptr_t>(start * 4)) & 15) == 0;
+    using Sample = typename LmSample<kI16>::type;
+    const Sample* xw = wav + static_cast<size_t>(b) * L_max;
+    const bool vec = ((reinterpret_cast<uintptr_t>(xw) | static_cast<uintptr_t>(start * sizeof(Sample))) & (4 * sizeof(Sample) - 1)) == 0;
     for (int i = threadIdx.x * 4; i < n_stage; i += kLmThreads * 4) {
       const int idx = start + i;
       float x[5];                                          // x[idx-1 .. idx+3]
       if (vec && idx >= 4 && idx + 3 < n && i + 3 < n_stage) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(xw + idx));
-        x[0] = __ldg(xw + idx - 1); x[1] = q.x; x[2] = q.y; x[3] = q.z; x[4] = q.w;
+        x[0] = lm_load<kI16>(xw + idx - 1);
+        if constexpr (kI16) {
+          const uint2 q = __ldg(reinterpret_cast<const uint2*>(xw + idx));       // four int16 samples
+          constexpr float k = 1.0f / 32768.0f;
+          x[1] = static_cast<float>(static_cast<int16_t>(q.x & 0xffffu)) * k; x[2] = static_cast<float>(static_cast<int16_t>(q.x >> 16)) * k;
+          x[3] = static_cast<float>(static_cast<int16_t>(q.y & 0xffffu)) * k; x[4] = static_cast<float>(static_cast<int16_t>(q.y >> 16)) * k;
+        } else {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(xw + idx));
+          x[1] = q.x; x[2] = q.y; x[3] = q.z; x[4] = q.w;
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { const int g = idx - 1 + k; x[k] = (g >= 0 && g < n) ? __ldg(xw + g) : 0.0f; }
+        for (int k = 0; k < 5; ++k) { const int g = idx - 1 + k; x[k] = (g >= 0 && g < n) ? lm_load<kI16>(xw + g) : 0.0f; }
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -254,14 +273,14 @@ mel_apply_norm_kernel(float* __restrict__ mel, const int32_t* __restrict__ mel_l
   }
 }
 
-template <int kFrames, int kSlots>
+template <int kFrames, int kSlots, bool kI16>
 cudaError_t launch_fused(const LogmelArgs& a, cudaStream_t stream) {
   const LmSmem L = lm_layout(kFrames, a.hop, a.tb.n_taps);
   const size_t smem = static_cast<size_t>(L.total) * 4;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(logmel_fused_kernel<kFrames, kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(logmel_fused_kernel<kFrames, kSlots, kI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     attr_once.set();
   }
@@ -269,7 +288,7 @@ cudaError_t launch_fused(const LogmelArgs& a, cudaStream_t stream) {
   const int tiles = logmel_tiles(a.L_max, a.hop);
   if (tiles * kLmTileFrames < F_max - 1) return cudaErrorInvalidValue;
   const dim3 grid((F_max - 1 + kFrames - 1) / kFrames > 0 ? (F_max - 1 + kFrames - 1) / kFrames : 1, a.B);
-  logmel_fused_kernel<kFrames, kSlots><<<grid, kLmThreads, smem, stream>>>(a.wav, a.len, a.L_max, a.mel, a.mel_len, a.tb, a.partials, a.stats,
+  logmel_fused_kernel<kFrames, kSlots, kI16><<<grid, kLmThreads, smem, stream>>>(static_cast<const typename LmSample<kI16>::type*>(a.wav), a.len, a.L_max, a.mel, a.mel_len, a.tb, a.partials, a.stats,
                                                                    a.tickets, F_max, tiles, a.n_mels, a.hop, a.preemph, a.guard, a.eps);
   return cudaGetLastError();
 }
@@ -280,7 +299,9 @@ cudaError_t launch_logmel_fused(const LogmelArgs& a, cudaStream_t stream) {
   if (a.n_fft != lm::kNfft || a.win > lm::kNfft || a.n_mels > lm::kLanes * lm::kMaxSlots || a.hop <= 0 || (a.hop & 1) ||
       a.tb.n_taps <= 0 || a.tb.n_taps > 128)
     return cudaErrorInvalidValue;
-  cudaError_t e = a.n_mels <= 5 * lm::kLanes ? launch_fused<kLmTileFrames, 5>(a, stream) : launch_fused<kLmTileFrames, lm::kMaxSlots>(a, stream);
+  cudaError_t e;
+  if (a.n_mels <= 5 * lm::kLanes) e = a.wav_i16 ? launch_fused<kLmTileFrames, 5, true>(a, stream) : launch_fused<kLmTileFrames, 5, false>(a, stream);
+  else e = a.wav_i16 ? launch_fused<kLmTileFrames, lm::kMaxSlots, true>(a, stream) : launch_fused<kLmTileFrames, lm::kMaxSlots, false>(a, stream);
   if (e != cudaSuccess || !a.normalise_in_place) return e;
   const int F_max = a.L_max / a.hop + 1;
   mel_apply_norm_kernel<<<dim3(64, a.B), 256, 0, stream>>>(a.mel, a.mel_len, a.stats, F_max, a.n_mels);

@@ -23,7 +23,9 @@ struct LmTables {             // device pointers into the packed weights (logmel
 };
 
 struct LogmelArgs {
-  const float* wav; const int32_t* len; int B, L_max;
+  const void* wav;            // f32 [B, L_max], or int16 PCM [B, L_max] when wav_i16 (scaled by 2^-15 on load)
+  bool wav_i16;
+  const int32_t* len; int B, L_max;
   float* mel;                 // [B, L_max / hop + 1, n_mels] f32: log-mel, un-normalised unless normalise_in_place
   int32_t* mel_len;           // [B] valid frames
   float* partials;            // [B, logmel_tiles, n_mels, 2] f32 workspace

@@ -47,7 +47,7 @@ _lib = None
 EXPORTS = [
     "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
-    "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
+    "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
     "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
 ]
@@ -83,6 +83,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_rnnt_greedy.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_transcribe_device.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_transcribe_batch.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_transcribe_device_pcm16.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_transcribe_batch_pcm16.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, C.c_float, vp]
     lib.rs_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, vp]
     lib.rs_launch_count.argtypes = [vp]
@@ -98,7 +100,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_enable_gemm_timing.argtypes = [vp, ip]
     lib.rs_gemm_timing.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for fn in ("rs_workspace_bytes", "rs_set_workspace", "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode",
-               "rs_rnnt_greedy", "rs_transcribe_device", "rs_transcribe_batch", "rs_gemm_bf16", "rs_layernorm",
+               "rs_rnnt_greedy", "rs_transcribe_device", "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16",
+               "rs_gemm_bf16", "rs_layernorm",
                "rs_enable_stage_timing", "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing"):
         getattr(lib, fn).restype = ip
     _lib = lib
@@ -190,7 +193,9 @@ def to_rs_config(cfg: ModelConfig) -> RsModelConfig:
 class Engine:
     """One engine per device: packed weights + workspace + the C-ABI handle."""
 
-    def __init__(self, cfg: ModelConfig, state_dict: StateDict, device: str = "cuda"):
+    def __init__(self, cfg: ModelConfig, state_dict: Optional[StateDict], device: str = "cuda", packed: Optional[Dict[str, torch.Tensor]] = None):
+        """``packed``: the result of ``pack_weights(state_dict, cfg)`` when several engines share one checkpoint (one replica
+        per device): the repack is done once, every engine uploads its own copy."""
         if not torch.cuda.is_available():
             raise RuntimeError("reazonspeech_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = load_library()
@@ -200,7 +205,8 @@ class Engine:
             raise RuntimeError(f"device {device!r}: the B200 engine has no CPU path")
         self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", self.dev_index)
-        packed = pack_weights(state_dict, cfg)
+        if packed is None:
+            packed = pack_weights(state_dict, cfg)
         self.weights = {k: v.to(self.device) for k, v in packed.items()}
         self._names = [k.encode() for k in self.weights]
         arr = (RsTensor * len(self.weights))()
@@ -298,22 +304,25 @@ class Engine:
                    torch.zeros(B, U, dtype=torch.int32, device=self.device),
                    torch.zeros(B, dtype=torch.int32, device=self.device))
         tokens, frames, ntok = out
-        self._check(self.lib.rs_transcribe_device(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(),
-                                                  frames.data_ptr(), ntok.data_ptr(), U, self._stream()), "rs_transcribe_device")
+        assert wav.dtype in (torch.float32, torch.int16) and wav.is_contiguous()
+        fn, name = ((self.lib.rs_transcribe_device_pcm16, "rs_transcribe_device_pcm16") if wav.dtype == torch.int16
+                    else (self.lib.rs_transcribe_device, "rs_transcribe_device"))        # int16: PCM, scaled by 2^-15 on the device
+        self._check(fn(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(), frames.data_ptr(), ntok.data_ptr(), U, self._stream()), name)
         return tokens, frames, ntok
 
     def transcribe_host(self, wav: torch.Tensor, lens: torch.Tensor, U_max: Optional[int] = None, out=None):
-        """wav: host float32 [B, L] (pinned for speed), lens: host int32 [B] -> host tokens/frames/n_tok."""
+        """wav: host float32 or int16 (PCM) [B, L] (pinned for speed), lens: host int32 [B] -> host tokens/frames/n_tok."""
         B, L = wav.shape
-        assert wav.device.type == "cpu" and wav.dtype == torch.float32 and wav.is_contiguous()
+        assert wav.device.type == "cpu" and wav.dtype in (torch.float32, torch.int16) and wav.is_contiguous()
         self.ensure_workspace(B, L)
         U = U_max or self.u_max(L)
         if out is None:
             out = (torch.zeros(B, U, dtype=torch.int32).pin_memory(), torch.zeros(B, U, dtype=torch.int32).pin_memory(),
                    torch.zeros(B, dtype=torch.int32).pin_memory())
         tokens, frames, ntok = out
-        self._check(self.lib.rs_transcribe_batch(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(),
-                                                 frames.data_ptr(), ntok.data_ptr(), U, self._stream()), "rs_transcribe_batch")
+        fn, name = ((self.lib.rs_transcribe_batch_pcm16, "rs_transcribe_batch_pcm16") if wav.dtype == torch.int16
+                    else (self.lib.rs_transcribe_batch, "rs_transcribe_batch"))
+        self._check(fn(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(), frames.data_ptr(), ntok.data_ptr(), U, self._stream()), name)
         return tokens, frames, ntok
 
     # -- kernel seams

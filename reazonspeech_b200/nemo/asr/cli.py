@@ -11,9 +11,11 @@ Same contract as the reference's ``reazonspeech-nemo-asr`` entry point (pkg/nemo
   unknown option       getopt.GetoptError propagates, as in the reference
 
 One extension: several AUDIO arguments are transcribed as one batch on the GPU (the reference reads exactly one);
-their segments are written one file after the other through the same writer.
-Audio decoding: WAV through scipy (or soundfile when installed); other containers need librosa, see audio_from_path.
+their segments are written one file after the other through the same writer, every file's times shifted by the total
+duration of the files before it, i.e. the transcript of the files played back to back (subtitle formats need monotonic times).
+Audio decoding: soundfile when installed, scipy for WAV, librosa for compressed containers, see audio.audio_from_path.
 """
+import dataclasses
 import getopt
 import sys
 import warnings
@@ -63,9 +65,12 @@ def run(opt: Options) -> None:
     with sink:
         out = get_writer(sink, opt.fmt)
         out.write_header()
-        for result in results:
+        offset = 0.0
+        for clip, result in zip(clips, results):
             for segment in result.segments:
-                out.write(segment)
+                out.write(segment if offset == 0.0 else
+                          dataclasses.replace(segment, start_seconds=segment.start_seconds + offset, end_seconds=segment.end_seconds + offset))
+            offset += clip.seconds
 
 
 def main(argv=None):

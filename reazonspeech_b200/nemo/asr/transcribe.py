@@ -61,18 +61,32 @@ class HostStaging:
         return buf
 
     def stage(self, waves: Sequence[np.ndarray], pad: int):
-        """Rows ``[zeros(pad) | wave | zeros(pad) | zeros to L]`` (pad_audio, audio.py:70-83, written in place) -> (wav [B, L], lens [B])."""
+        """Rows ``[zeros(pad) | wave | zeros(pad) | zeros to L]`` (pad_audio, audio.py:70-83, written in place) -> (wav [B, L], lens [B]).
+
+        A batch whose waveforms are ALL 16-bit PCM (int16 arrays, e.g. ``audio_from_path(..., pcm16=True)``) is staged as
+        int16 and scaled by 2^-15 on the device (rs_transcribe_batch_pcm16): half the pinned memory and PCIe bytes.  A mixed
+        batch is staged as float32, int16 members converted the way a file decoder would (sample / 32768)."""
         B = len(waves)
         L = max(len(w) for w in waves) + 2 * pad
-        self._wav = self._grown(self._wav, B * L, torch.float32)
+        L = (L + 3) & ~3                                # rows start 8 / 16-byte aligned: the kernel's vectorised staging load
+        pcm = all(w.dtype == np.int16 for w in waves)
+        if pcm:
+            self._wav16 = self._grown(getattr(self, "_wav16", None), B * L, torch.int16)
+            wav = self._wav16[: B * L].view(B, L)
+        else:
+            self._wav = self._grown(self._wav, B * L, torch.float32)
+            wav = self._wav[: B * L].view(B, L)
         self._lens = self._grown(self._lens, B, torch.int32)
-        wav, lens = self._wav[: B * L].view(B, L), self._lens[:B]
+        lens = self._lens[:B]
         rows = wav.numpy()
         for r, w in enumerate(waves):
             n = len(w)
-            rows[r, :pad] = 0.0
-            rows[r, pad:pad + n] = w                    # casts to float32 on the way in
-            rows[r, pad + n:] = 0.0
+            rows[r, :pad] = 0
+            if not pcm and w.dtype == np.int16:
+                np.multiply(w, np.float32(1.0 / 32768.0), out=rows[r, pad:pad + n], dtype=np.float32)
+            else:
+                rows[r, pad:pad + n] = w                # float inputs cast to float32 on the way in
+            rows[r, pad + n:] = 0
             lens[r] = n + 2 * pad
         return wav, lens
 
@@ -109,7 +123,7 @@ class B200RnntModel:
         order = sorted(range(len(waveforms)), key=lambda i: len(waveforms[i]))
         batches = [order[lo:lo + self.max_batch] for lo in range(0, len(order), self.max_batch)]
         eng = self.engine
-        eng.ensure_workspace(len(batches[0]), len(waveforms[order[-1]]) + 2 * pad)        # once, on this thread
+        eng.ensure_workspace(len(batches[0]), (len(waveforms[order[-1]]) + 2 * pad + 3) & ~3)   # once, on this thread (stage() rounds rows up to 4 samples)
 
         def run(staging, idx):
             wav, lens = staging.stage([waveforms[i] for i in idx], pad)
@@ -162,11 +176,13 @@ def _find_checkpoint() -> Optional[str]:
 
 
 def load_model(device=None, *, checkpoint: Optional[str] = None, synthetic: Optional[bool] = None,
-               config: Optional[ModelConfig] = None, seed: int = 0, max_batch: int = 64):
+               config: Optional[ModelConfig] = None, seed: int = 0, max_batch: int = 64, devices: Optional[Sequence] = None):
     """Load the ReazonSpeech FastConformer-RNNT onto a B200.
 
     ``device``: None / "cuda" / "cuda:N" as in the reference (transcribe.py:9-22, eval.py:26).
-    "cpu" raises: this engine has no CPU path.  Weights come from ``checkpoint`` (a .nemo file),
+    "cpu" raises: this engine has no CPU path.  ``devices`` (e.g. ``range(8)`` or ``["cuda:0", "cuda:1"]``) loads one
+    replica per listed GPU into THIS process and returns a model that deals every call's utterances across them
+    (``multi_gpu.MultiGpuRnntModel``; same surface, results in input order).  Weights come from ``checkpoint`` (a .nemo file),
     $REAZONSPEECH_NEMO_CHECKPOINT or the local Hugging Face cache of reazonspeech-nemo-v2.
     With ``synthetic=True`` (or $REAZONSPEECH_B200_SYNTHETIC=1) seeded random weights of the same
     architecture are used instead -- the only option offline."""
@@ -188,11 +204,20 @@ def load_model(device=None, *, checkpoint: Optional[str] = None, synthetic: Opti
         raise FileNotFoundError(
             f"no .nemo checkpoint for {HF_REPO}: pass checkpoint=..., set ${ENV_CHECKPOINT}, populate the Hugging Face "
             f"cache, or request seeded synthetic weights with synthetic=True / ${ENV_SYNTHETIC}=1")
-    return B200RnntModel(Engine(cfg, sd, str(device)), tokenizer, max_batch=max_batch)
+    if devices is None:
+        return B200RnntModel(Engine(cfg, sd, str(device)), tokenizer, max_batch=max_batch)
+    names = [d if isinstance(d, str) else f"cuda:{int(d)}" for d in devices]
+    if len(names) == 0 or len(set(names)) != len(names):
+        raise ValueError(f"devices must name distinct GPUs, got {list(devices)!r}")
+    from ...engine import pack_weights
+    from .multi_gpu import MultiGpuRnntModel
+    packed = pack_weights(sd, cfg)                                   # repacked once, uploaded once per device
+    return MultiGpuRnntModel([B200RnntModel(Engine(cfg, None, n, packed=packed), tokenizer, max_batch=max_batch) for n in names])
 
 
 def _prepare(audio: AudioData) -> np.ndarray:
-    return pad_audio(norm_audio(audio), PAD_SECONDS).waveform.astype(np.float32, copy=False)
+    wave = pad_audio(norm_audio(audio), PAD_SECONDS).waveform
+    return wave if wave.dtype == np.int16 else wave.astype(np.float32, copy=False)     # int16 = PCM, scaled on the device
 
 
 def transcribe(model, audio: AudioData, config: Optional[TranscribeConfig] = None) -> TranscribeResult:

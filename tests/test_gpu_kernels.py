@@ -253,3 +253,27 @@ def test_long_form_clip_in_one_call(tiny_engine, tiny_cfg, tiny_sd):
         ties = check_decisions(tokens[i, :n].cpu().tolist(), frames[i, :n].cpu().tolist(), emu, tiny_sd, tiny_cfg, f"utt{i}",
                                max_near_ties=3 + T // 200)      # 1 882 frames: the near-tie allowance scales with the clip
         print(f"utt{i}: T={T}, encoder rel-L2 {r:.3e}, {n} tokens, {ties} near-tie differences")
+
+
+@pytest.mark.parametrize("L_pad", [0, 3])
+def test_pcm16_ingest_equals_float_path(tiny_engine, L_pad):
+    """rs_transcribe_device_pcm16 / rs_transcribe_batch_pcm16 (int16 samples scaled by 2^-15 inside the log-mel kernel's staging
+    load) against the float entry points on the converted samples: the same values in, so tokens and frames must be
+    bit-identical -- with rows that allow the 8-byte vector load (L % 4 == 0) and rows that force the scalar path."""
+    eng = tiny_engine
+    waves = [np.round(padded(synth_clip(150 + i, 0.9 + 0.8 * i)) * 32767.0).astype(np.int16) for i in range(5)]
+    L = max(len(w) for w in waves)
+    L = ((L + 3) & ~3) + L_pad
+    x16 = torch.zeros(len(waves), L, dtype=torch.int16)
+    for i, w in enumerate(waves):
+        x16[i, : len(w)] = torch.from_numpy(w)
+    lens = torch.tensor([len(w) for w in waves], dtype=torch.int32)
+    xf = x16.to(torch.float32) / 32768.0
+    tf, ff, nf = [a.cpu() for a in eng.transcribe_device(xf.cuda(), lens.cuda())]
+    ti, fi, ni = [a.cpu() for a in eng.transcribe_device(x16.cuda(), lens.cuda())]
+    th, fh, nh = eng.transcribe_host(x16.pin_memory(), lens)
+    assert int(nf.sum()) > 0 and torch.equal(nf, ni) and torch.equal(nf, nh)
+    for b in range(len(waves)):
+        n = int(nf[b])
+        assert torch.equal(tf[b, :n], ti[b, :n]) and torch.equal(ff[b, :n], fi[b, :n])
+        assert torch.equal(tf[b, :n], th[b, :n]) and torch.equal(ff[b, :n], fh[b, :n])

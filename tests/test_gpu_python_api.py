@@ -57,3 +57,43 @@ def test_nemo_call_shape(model, tiny_cfg):
     assert len(hyps[0].timestamp) == len(hyps[0].y_sequence) - 1
     texts = model.transcribe([w, w[: len(w) // 2]], batch_size=2, return_hypotheses=False, verbose=False)
     assert len(texts) == 2 and all(isinstance(t, str) for t in texts)
+
+
+def test_two_engines_on_one_device_and_second_device_are_independent(tiny_cfg, tiny_sd):
+    """include/rs_engine.h promises 'distinct engines are independent' and load_model accepts 'cuda:N': the opt-in to more
+    than 48 KB of dynamic shared memory is per DEVICE (cudaFuncSetAttribute), so an engine created on another GPU after one
+    on cuda:0 must work (it failed with 'invalid argument' while the flag was process-wide).  Runs the second engine on the
+    last visible device (the same one on a one-GPU box, where it still checks two engines side by side)."""
+    from reazonspeech_b200.engine import Engine
+    dev = torch.cuda.device_count() - 1
+    e0 = Engine(tiny_cfg, tiny_sd, "cuda:0")
+    e1 = Engine(tiny_cfg, tiny_sd, f"cuda:{dev}")
+    w = np.pad(synth_clip(130, 2.2), 8000).astype(np.float32)
+    x, ln = torch.from_numpy(w)[None], torch.tensor([len(w)], dtype=torch.int32)
+    t0, f0, n0 = e0.transcribe_device(x.to("cuda:0"), ln.to("cuda:0"))
+    with torch.cuda.device(dev):
+        t1, f1, n1 = e1.transcribe_device(x.to(f"cuda:{dev}"), ln.to(f"cuda:{dev}"))
+    n = int(n0[0])
+    assert n > 0 and int(n1[0]) == n and torch.equal(t0[0, :n].cpu(), t1[0, :n].cpu()) and torch.equal(f0[0, :n].cpu(), f1[0, :n].cpu())
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_one_process_multi_gpu_equals_single_gpu(model, tiny_cfg):
+    """load_model(devices=[0, 1]): one replica, worker thread and staging pair per device in ONE process; the merged result
+    equals the one-GPU result token for token and arrives in input order (the reference's
+    counterpart is one spawned process per GPU, pkg/evaluation/src/base.py:194-212)."""
+    from reazonspeech_b200.nemo import asr
+    multi = asr.load_model(synthetic=True, config=tiny_cfg, seed=0, max_batch=4, devices=[0, 1])
+    assert multi.devices == ["cuda:0", "cuda:1"]
+    cfgv = asr.TranscribeConfig(verbose=False, raw_hypothesis=True)
+    audios = [asr.audio_from_numpy(synth_clip(140 + i, 0.8 + 0.45 * (i % 9)), 16000) for i in range(23)]
+    one = asr.transcribe_batch(model, audios, cfgv)
+    for rep in range(2):
+        two = asr.transcribe_batch(multi, audios, cfgv)
+        assert len(two) == len(one)
+        for i, (a, b) in enumerate(zip(one, two)):
+            assert a.hypothesis.y_sequence.tolist() == b.hypothesis.y_sequence.tolist(), f"clip {i}, pass {rep}"
+            assert list(a.hypothesis.timestamp) == list(b.hypothesis.timestamp) and a.text == b.text
+    assert sum(len(r.subwords) for r in two) > 0
+    single = asr.transcribe(multi, audios[3], cfgv)                    # the reference's one-clip call shape on the multi-GPU model
+    assert single.text == one[3].text

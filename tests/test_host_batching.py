@@ -166,3 +166,46 @@ def test_random_batches_property():
         assert model.transcribe_tokens(clips[::-1], pad=pad) == [_alone(w, pad) for w in clips[::-1]]     # reused staging
 
     check()
+
+
+def test_pcm16_batches_are_staged_as_int16_and_mixed_batches_as_float():
+    """HostStaging.stage: an all-int16 batch stays 16-bit PCM (scaled by 2^-15 on the device, rs_transcribe_batch_pcm16), a
+    mixed batch becomes float32 with the int16 members converted the way a WAV decoder would (sample / 32768); padding and
+    lengths are the same in both."""
+    import numpy as np
+    import torch
+    from reazonspeech_b200.nemo.asr.transcribe import HostStaging
+    g = np.random.default_rng(0)
+    a = g.integers(-32768, 32767, 1000, dtype=np.int16)
+    b = g.integers(-32768, 32767, 333, dtype=np.int16)
+    st = HostStaging(pin=False)
+    wav, lens = st.stage([a, b], pad=8)
+    assert wav.dtype == torch.int16 and wav.shape[1] % 4 == 0 and lens.tolist() == [1016, 349]
+    assert torch.equal(wav[0, 8:1008], torch.from_numpy(a)) and int(wav[0, :8].abs().sum()) == 0 and int(wav[1, 341:].abs().sum()) == 0
+    f = (b.astype(np.float32) / 32768.0)
+    wav2, lens2 = st.stage([a, f], pad=8)
+    assert wav2.dtype == torch.float32 and lens2.tolist() == [1016, 349]
+    assert np.array_equal(wav2[0, 8:1008].numpy(), a.astype(np.float32) / 32768.0) and np.array_equal(wav2[1, 8:341].numpy(), f)
+    wav3, _ = st.stage([a, b], pad=8)                        # the int16 buffer is reused after a float batch
+    assert wav3.dtype == torch.int16 and torch.equal(wav3[1, 8:341], torch.from_numpy(b))
+
+
+def test_audio_from_path_pcm16_and_fallback_errors(tmp_path):
+    import numpy as np
+    from scipy.io import wavfile
+    from reazonspeech_b200.nemo.asr.audio import audio_from_path, norm_audio, pad_audio
+    x = (np.sin(np.arange(1600) * 0.05) * 20000).astype(np.int16)
+    p = tmp_path / "m.wav"
+    wavfile.write(p, 16000, x)
+    f = audio_from_path(str(p))
+    q = audio_from_path(str(p), pcm16=True)
+    assert f.waveform.dtype == np.float32 and q.waveform.dtype == np.int16 and q.samplerate == 16000
+    assert np.array_equal(f.waveform, x.astype(np.float32) / 32768.0)           # the values the device computes from the int16 samples
+    assert norm_audio(q).waveform.dtype == np.int16 and pad_audio(norm_audio(q), 0.5).waveform.shape == (1600 + 16000,)
+    wavfile.write(p, 8000, x)                                                    # resampling leaves PCM behind
+    assert norm_audio(audio_from_path(str(p), pcm16=True)).waveform.dtype == np.float32
+    bad = tmp_path / "x.webm"
+    bad.write_bytes(b"not audio at all")
+    import pytest
+    with pytest.raises(RuntimeError, match="cannot decode"):
+        audio_from_path(str(bad))

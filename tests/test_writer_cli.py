@@ -61,3 +61,28 @@ def test_cli_rejects_unknown_option():
     import getopt
     with pytest.raises(getopt.GetoptError):
         cli.main(["--nope", "a.wav"])
+
+
+def test_cli_several_inputs_give_monotonic_times(tmp_path, monkeypatch):
+    """The multi-file extension shifts every file's segments by the duration of the files before it (a subtitle file
+    with times restarting at 0 is invalid); a single input is written exactly as the reference writes it."""
+    import numpy as np
+    from scipy.io import wavfile
+    from reazonspeech_b200.nemo.asr import cli, transcribe as T
+    from reazonspeech_b200.nemo.asr.interface import Segment, TranscribeResult
+    paths = []
+    for i, secs in enumerate((2.0, 3.5, 1.0)):
+        p = tmp_path / f"a{i}.wav"
+        wavfile.write(p, 16000, (np.zeros(int(secs * 16000)) + i).astype(np.int16))
+        paths.append(str(p))
+    fake = lambda n: TranscribeResult(f"t{n}", [], [Segment(0.5, 1.0, f"t{n}")])
+    monkeypatch.setattr(T, "load_model", lambda *a, **k: object())
+    monkeypatch.setattr(T, "transcribe", lambda model, audio, config=None: fake(0))
+    monkeypatch.setattr(T, "transcribe_batch", lambda model, audios, config=None: [fake(i) for i in range(len(audios))])
+    out = tmp_path / "o.tsv"
+    assert cli.main(["--to=tsv", "-o", str(out), *paths]) is None
+    rows = [l.split("\t") for l in out.read_text().splitlines()[1:]]
+    starts = [int(r[0]) for r in rows]
+    assert starts == [500, 2500, 6000]                       # 0.5 s into each file, files of 2.0 and 3.5 s before the later ones
+    assert cli.main(["--to=tsv", "-o", str(out), paths[1]]) is None
+    assert out.read_text().splitlines()[1].split("\t")[:2] == ["500", "1000"]
