@@ -68,7 +68,9 @@ def test_cli_several_inputs_give_monotonic_times(tmp_path, monkeypatch):
     with times restarting at 0 is invalid); a single input is written exactly as the reference writes it."""
     import numpy as np
     from scipy.io import wavfile
-    from reazonspeech_b200.nemo.asr import cli, transcribe as T
+    import importlib
+    from reazonspeech_b200.nemo.asr import cli
+    T = importlib.import_module("reazonspeech_b200.nemo.asr.transcribe")     # the package re-exports a function of the same name
     from reazonspeech_b200.nemo.asr.interface import Segment, TranscribeResult
     paths = []
     for i, secs in enumerate((2.0, 3.5, 1.0)):
