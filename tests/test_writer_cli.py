@@ -84,7 +84,7 @@ def test_cli_several_inputs_give_monotonic_times(tmp_path, monkeypatch):
     out = tmp_path / "o.tsv"
     assert cli.main(["--to=tsv", "-o", str(out), *paths]) is None
     rows = [l.split("\t") for l in out.read_text().splitlines()[1:]]
-    starts = [int(r[0]) for r in rows]
-    assert starts == [500, 2500, 6000]                       # 0.5 s into each file, files of 2.0 and 3.5 s before the later ones
+    starts = [float(r[0]) for r in rows]
+    assert starts == [0.5, 2.5, 6.0]                         # 0.5 s into each file, files of 2.0 and 3.5 s before the later ones
     assert cli.main(["--to=tsv", "-o", str(out), paths[1]]) is None
-    assert out.read_text().splitlines()[1].split("\t")[:2] == ["500", "1000"]
+    assert [float(v) for v in out.read_text().splitlines()[1].split("\t")[:2]] == [0.5, 1.0]
