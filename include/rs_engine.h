@@ -69,11 +69,7 @@ typedef enum rs_epilogue {
   RS_EPI_BIAS_GLU_BF16 = 3,   /* out_bf16[M,N/2] = a * sigmoid(g); W rows interleaved 16/16    */
   RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias)   */
   RS_EPI_BIAS_F32 = 5,        /* out_f32[M,N]    = alpha * (acc + bias)                        */
-  RS_EPI_BIAS_F16 = 6,        /* out_f16[M,N]    = acc + bias  (IEEE half: attention positional scores) */
-  RS_EPI_BIAS_F16_SKEW = 8,   /* attention positional scores for the tensor-core attention kernel: out_f16[row, col + (t mod 128)]
-                                 = alpha * (acc + bias),
-                                 with t = row mod T_max (T_max passed as ld2), only columns < split are written: thread `row`
-                                 of a 128-row query tile then finds the score of key column jj at the SAME offset in every row */
+  RS_EPI_BIAS_F16 = 6,        /* out_f16[M,N]    = acc + bias  (IEEE half)                          */
   RS_EPI_QKV_VT = 7           /* fused QKV projection: columns [0, split) -> out_bf16[M, ldo] as RS_EPI_BIAS_BF16,
                                  columns [split, N) -> TRANSPOSED into out2_bf16[N - split, ld2] (V^T, keys contiguous:
                                  the K-major B operand of the attention kernel's P.V product)               */

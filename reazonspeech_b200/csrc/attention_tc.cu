@@ -9,22 +9,26 @@
 // One CTA = 128 query rows of one (utterance, head).  With a band of +-w (w <= 128) those rows see the
 // 384 keys [q0-128, q0+256), so the whole score tile lives in tensor memory and no online softmax is needed:
 //
-//   TMA   Q' [128 x 128] (q + pos_bias_u, folded into the QKV projection's bias at pack time),
-//         K  [384 x 128]  and  V^T [128 x 384]  (the QKV GEMM's epilogue writes V transposed, RS_EPI_QKV_VT)
-//         -> shared memory, 128-byte swizzle, K-major: every UMMA operand of this kernel is K-major
+//   TMA   Q' [128 x 128] (q + pos_bias_u, folded into the QKV projection's bias at pack time) and the head's positional
+//         table P [n_rel_pad x 128] (linear_pos(pos_emb), packed at load) -> shared memory, 128-byte swizzle, K-major
+//   UMMA  BD[128 x n_rel_pad] = Q' P^T     -> TMEM columns [0, n_rel_pad)   (the relative-position term; + the constant
+//         (pos_bias_v - pos_bias_u) . p[c] it equals (q + pos_bias_v) . p[c])
+//   8 softmax warps drain BD: (acc + bias[c]) / sqrt(dk) * log2 e -> IEEE half, row-major into shared memory
+//   TMA   K [384 x 128] over the positional table (dead once its product retired)
 //   UMMA  S[128 x 384] = Q' K^T            -> TMEM columns [0, 384)         (24 x tcgen05.mma 128x128x16)
-//   8 softmax warps, one thread per (row, column half): t = (S + BD[i, j-i+w]) / sqrt(dk) with the band /
-//         padding mask, row maximum (with the global key's score), p = exp2(t - m) -> bf16 P into the
-//         shared memory that held K (same swizzled K-major layout), row sums
+//   pass 1, one thread per (row, column half): t = S / sqrt(dk) + BD[i, j-i+w] (the rel_shift: row i reads its BD row at
+//         an offset that depends on i -- 32-bit shared loads + a funnel shift where the offset is odd) with the band /
+//         padding mask, row maximum (with the global key's score); t written back to tensor memory
+//   TMA   V^T [128 x 384] over the BD buffer (dead after pass 1; the QKV GEMM's epilogue writes V transposed, RS_EPI_QKV_VT)
+//   pass 2: p = exp2(t - m) -> bf16 P into the shared memory that held K (same swizzled K-major layout), row sums
 //   UMMA  O[128 x 128] = P V               -> TMEM columns [384, 512)       (24 x tcgen05.mma 128x128x16)
 //   epilogue  O + p_global * v_0, divided by the row sum -> bf16, staged and stored in whole 128-byte lines
 //
-// BD[i][c] = (q_i + pos_bias_v) . p[c] comes from the batched tcgen05 GEMM (IEEE half), whose epilogue stores it
-// row-skewed (RS_EPI_BIAS_F16_SKEW: column c + (i mod 128)) so that the score of a key column is at the same offset in
-// every row of a tile: one thread = one row reads it with 16-byte loads (the unskewed gather cost 32 cache lines per
-// load instruction and bound the whole kernel).  Rows of the
-// global token itself are overwritten afterwards by global_row_attention_tc_kernel (full attention, no
-// positional term).  Shared memory: 32 KB Q' + 96 KB K/P + 96 KB V^T; tensor memory: all 512 columns.
+// Round 1 computed BD with a separate batched GEMM that wrote a row-skewed IEEE-half tensor [M, H, 384] (77 MB per layer at
+// 32 x 30 s, 3.7 GB per step of pure intermediate traffic, 1.05 ms) which this kernel read back; the positional product is a
+// 128 x 288 x 128 UMMA here and its result never leaves the SM.  Rows of the global token itself are overwritten afterwards
+// by global_row_attention_tc_kernel (full attention, no positional term).  Shared memory: 32 KB Q' + 96 KB P-table / K /
+// probabilities + 96 KB BD / V^T; tensor memory: all 512 columns.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -40,9 +44,11 @@ constexpr int TDK = 128;                // head dim
 constexpr int kSlab = TQ * 128;         // bytes of one [128 rows x 64 bf16] swizzled slab
 constexpr int kAtcThreads = 32 * 9;     // warp 0: TMA + MMA issue; warps 1..8: softmax / epilogue
 constexpr uint32_t kOffQ = 0;                       // 2 slabs
-constexpr uint32_t kOffK = 2 * kSlab;               // 2 k-slabs x 3 row blocks; later P: 6 key-slabs
-constexpr uint32_t kOffV = kOffK + 6 * kSlab;       // 6 key-slabs of V^T
-constexpr uint32_t kOffBar = kOffV + 6 * kSlab;     // 4 mbarriers + tmem slot
+constexpr uint32_t kOffK = 2 * kSlab;               // positional table (2 k-slabs x n_rel_pad rows), then K: 2 k-slabs x 3 row blocks, then P: 6 key-slabs
+constexpr uint32_t kOffV = kOffK + 6 * kSlab;       // BD as IEEE half [128][kBdPitch], then 6 key-slabs of V^T
+constexpr uint32_t kOffBar = kOffV + 6 * kSlab;     // 8 mbarriers + tmem slot
+constexpr int kBdPitch = 296;                       // halves per BD row: 592 B = 37 x 16 B (odd: 16-byte stores of 8 consecutive rows hit 8 different bank groups)
+constexpr int kNrelPadMax = 288;                    // 2 * 128 + 1 relative offsets rounded up to 32
 constexpr uint32_t kAtcSmem = kOffBar + 1024 + 1024; // barriers, k_0 row, global-key scores, alignment slack
 // small arrays that alias the Q' tile once the S product has retired
 constexpr uint32_t kOffMax = kOffQ;                 // float [2][128]
@@ -55,11 +61,11 @@ constexpr int kStagePitch = 64 + 8;                 // bf16 per staged output ro
 struct AtcDev {
   const __nv_bfloat16* qk;      // [M, ld_qk]: q' at column h*128, k at column d + h*128
   const __nv_bfloat16* vt;      // [d, ld_vt]: V^T, column = global frame index
-  const __half* bd;             // [M, H, bd_pitch], row-skewed: score of relative offset c of frame t at column c + (t mod 128)
+  const float* bd_bias;         // [H, n_rel_pad]: (pos_bias_v - pos_bias_u) . p[h][c]
   const float* bias_u;          // [H, 128]
   __nv_bfloat16* out;           // [M, d]
   const int32_t* enc_len;
-  int T_max, H, w_left, w_right, n_global, bd_pitch, ld_qk, ld_vt;
+  int T_max, H, w_left, w_right, n_global, n_rel_pad, ld_qk, ld_vt;
 };
 
 // cycle stamps of CTA (1, 0, 0): [0..7] control thread, [8..15] first softmax thread (profiling aid, rs_debug_attention_cycles)
@@ -87,11 +93,13 @@ __device__ __forceinline__ uint32_t sw128(int row, int chunk) {
 }
 
 __global__ void __launch_bounds__(kAtcThreads, 1)
-local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt, const AtcDev p) {
+local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __grid_constant__ CUtensorMap tm_vt,
+                          const __grid_constant__ CUtensorMap tm_pos, const AtcDev p) {
   extern __shared__ uint8_t atc_raw[];
   const uint32_t base = (smem_u32(atc_raw) + 1023u) & ~1023u;
   uint8_t* gen = atc_raw + (base - smem_u32(atc_raw));          // generic pointer to the aligned base
   const uint32_t bar_qk = base + kOffBar, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_o = bar_qk + 24, tmem_slot = bar_qk + 32;
+  const uint32_t bar_bd = bar_qk + 40, bar_k = bar_qk + 48, bar_drained = bar_qk + 56, bar_p1 = bar_qk + 320;   // behind s_k0 ([64, 320)), before s_uk (448) and s_sg ([512, 1024))
   __nv_bfloat16* s_k0 = reinterpret_cast<__nv_bfloat16*>(gen + kOffBar + 64);   // [128] (fits: 64 + 256 <= 128 + slack)
 
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * TQ;
@@ -120,23 +128,24 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
   rb_lo = max(rb_lo, 0); rb_hi = min(rb_hi, 2);
 
   const int n_rb = rb_hi - rb_lo + 1;
+  const uint32_t pos_slab = static_cast<uint32_t>(p.n_rel_pad) * 128u;          // bytes of one k-slab of the positional table
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_qk);
       tma_prefetch_desc(&tm_vt);
+      tma_prefetch_desc(&tm_pos);
       mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+      mbar_init(bar_bd, 1); mbar_init(bar_k, 1); mbar_init(bar_drained, kAtcThreads - 32); mbar_init(bar_p1, kAtcThreads - 32);
       fence_barrier_init();
-      // ---- loads: issued before the tensor-memory allocation and the CTA-wide sync so they overlap both
+      // ---- first loads (Q' and the head's positional table): issued before the tensor-memory allocation and the CTA-wide
+      // sync so they overlap both.  The table is two k-slabs of n_rel_pad rows, each fetched as two boxes of n_rel_pad / 2 rows.
       ATC_STAMP(true, 1);
-      mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>((2 + 2 * n_rb) * kSlab));
+      mbar_arrive_expect_tx(bar_qk, static_cast<uint32_t>(2 * kSlab + 2 * pos_slab));
       for (int kb = 0; kb < 2; ++kb) {
         tma_load_2d(base + kOffQ + kb * kSlab, &tm_qk, h * TDK + kb * 64, static_cast<int>(row0) + q0, bar_qk);
-        for (int rb = rb_lo; rb <= rb_hi; ++rb)
-          tma_load_2d(base + kOffK + (kb * 3 + rb) * kSlab, &tm_qk, d + h * TDK + kb * 64, static_cast<int>(row0) + j_base + rb * 128, bar_qk);
+        for (int hh = 0; hh < 2; ++hh)
+          tma_load_2d(base + kOffK + kb * pos_slab + hh * (pos_slab / 2), &tm_pos, kb * 64, h * p.n_rel_pad + hh * (p.n_rel_pad / 2), bar_qk);
       }
-      mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(2 * n_rb * kSlab));
-      for (int ks = 2 * rb_lo; ks <= 2 * rb_hi + 1; ++ks)
-        tma_load_2d(base + kOffV + ks * kSlab, &tm_vt, static_cast<int>(row0) + j_base + ks * 64, h * TDK, bar_v);
     }
     __syncwarp();
     tmem_alloc<512>(tmem_slot);
@@ -149,10 +158,33 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---- S = Q' K^T
+      // ---- BD = Q' P^T: two column halves of n_rel_pad / 2 (a multiple of 16, at most 144) per k16 step
       constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
       mbar_wait(bar_qk, 0);
       ATC_STAMP(true, 2);
+      tcgen05_fence_after();
+      {
+        const uint32_t idesc_bd = umma_idesc_bf16(128, p.n_rel_pad / 2);
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t da = umma_desc_k_sw128(base + kOffQ + kb * kSlab);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint64_t db = umma_desc_k_sw128(base + kOffK + kb * pos_slab + hh * (pos_slab / 2));
+              umma_bf16_ss(tmem_base + hh * (p.n_rel_pad / 2), da + 2u * k, db + 2u * k, idesc_bd, (kb | k) != 0 ? 1u : 0u);
+            }
+        }
+        umma_commit(bar_bd);
+      }
+      // ---- K over the positional table once that product has retired
+      mbar_wait(bar_bd, 0);
+      mbar_arrive_expect_tx(bar_k, static_cast<uint32_t>(2 * n_rb * kSlab));
+      for (int kb = 0; kb < 2; ++kb)
+        for (int rb = rb_lo; rb <= rb_hi; ++rb)
+          tma_load_2d(base + kOffK + (kb * 3 + rb) * kSlab, &tm_qk, d + h * TDK + kb * 64, static_cast<int>(row0) + j_base + rb * 128, bar_k);
+      // ---- S = Q' K^T into the columns BD was drained from
+      mbar_wait(bar_drained, 0);
+      mbar_wait(bar_k, 0);
       tcgen05_fence_after();
       for (int kb = 0; kb < 2; ++kb) {
         const uint64_t da = umma_desc_k_sw128(base + kOffQ + kb * kSlab);
@@ -166,6 +198,11 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
       }
       umma_commit(bar_s);
       ATC_STAMP(true, 3);
+      // ---- V^T over the BD buffer once pass 1 has read it
+      mbar_wait(bar_p1, 0);
+      mbar_arrive_expect_tx(bar_v, static_cast<uint32_t>(2 * n_rb * kSlab));
+      for (int ks = 2 * rb_lo; ks <= 2 * rb_hi + 1; ++ks)
+        tma_load_2d(base + kOffV + ks * kSlab, &tm_vt, static_cast<int>(row0) + j_base + ks * 64, h * TDK, bar_v);
     }
     __syncwarp();
   } else {
@@ -215,9 +252,38 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
       }
     }
 
-    // Positional scores, row-skewed by the GEMM epilogue: the score of key column jj of the window sits at column
-    // jj - (128 - w_left) of EVERY row of the tile, so a thread fetches a chunk's 32 scores with four 16-byte loads.
-    const __half* bdrow = p.bd + ((row0 + min(i, p.T_max - 1)) * p.H + h) * static_cast<size_t>(p.bd_pitch) - (128 - p.w_left);
+    // ---- drain the positional product: BD[r][c] = ((q' . p[c]) + bias[c]) / sqrt(dk) * log2 e as IEEE half, row-major
+    // [128][kBdPitch] in the region V^T will use later.  Thread (r, hf) takes half of the 32-column chunks of row r.
+    __half* s_bd = reinterpret_cast<__half*>(gen + kOffV);
+    {
+      const int n_chunks = p.n_rel_pad >> 5;
+      const int c_lo = hf == 0 ? 0 : (n_chunks + 1) / 2, c_hi = hf == 0 ? (n_chunks + 1) / 2 : n_chunks;
+      const float* bias = p.bd_bias + h * p.n_rel_pad;
+      mbar_wait(bar_bd, 0);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int ch = c_lo; ch < c_hi; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + ch * 32, v);
+        tmem_ld_wait();
+        uint4* dst = reinterpret_cast<uint4*>(s_bd + r * kBdPitch + ch * 32);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + ch * 32 + q4 * 8 + 2 * e));
+            w[e] = pack_f16x2((__uint_as_float(v[q4 * 8 + 2 * e]) + b2.x) * scale2, (__uint_as_float(v[q4 * 8 + 2 * e + 1]) + b2.y) * scale2);
+          }
+          dst[q4] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_drained);                          // the S product may overwrite these tensor-memory columns
+    }
+    // rel_shift: key column jj of the window (rel = jj - 128 - r) is BD[r][jj - (128 - w_left) - r]; a chunk's 32 scores
+    // are 17 32-bit words of the row, realigned with a funnel shift where that start is odd
+    const uint32_t* bdwords = reinterpret_cast<const uint32_t*>(s_bd + r * kBdPitch);
     float mx = -INFINITY;
     unsigned live = 0;                                   // chunks of this warp that intersect the band
     // rel = j - i = 32m + e - 128 - r; warp rows r in [32qd, 32qd+31]: the chunk matters to this warp iff ... (warp-uniform)
@@ -229,15 +295,7 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     };
 #pragma unroll
     for (int k = 0; k < 6; ++k) live |= chunk_live(hf * 6 + k) ? (1u << k) : 0u;
-    // the positional scores of the NEXT live chunk are requested before the current one is processed: a chunk's four
-    // 16-byte loads touch 32 different lines and their L2 latency (not the arithmetic) was what pass 1 waited for
-    uint4 bnext[4];
-    auto fetch = [&](int m) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) bnext[c] = __ldg(reinterpret_cast<const uint4*>(bdrow + 32 * m) + c);
-    };
     unsigned todo = live;
-    if (todo) fetch(hf * 6 + __ffs(todo) - 1);
     ATC_STAMP(threadIdx.x == 32, 9);
     mbar_wait(bar_s, 0);
     ATC_STAMP(threadIdx.x == 32, 10);
@@ -254,10 +312,12 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
       todo &= todo - 1;
       const int m = hf * 6 + k;
       const int jlo = j_base + 32 * m;
-      uint4 braw[4];
+      const int cs = 32 * m - (128 - p.w_left) - r;     // first BD column of the chunk for this row (may lie outside [0, n_rel): masked below)
+      const uint32_t* wp = bdwords + (cs >> 1);
+      const int sh = (cs & 1) * 16;
+      uint32_t braw[17];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) braw[c] = bnext[c];
-      if (todo) fetch(hf * 6 + __ffs(todo) - 1);
+      for (int c = 0; c < 17; ++c) braw[c] = wp[c];
       // columns e of this chunk the row may attend to: band (-w_left <= j - i <= w_right) and 0 <= j < len
       const int e_lo = max(max(128 + r - p.w_left - 32 * m, -jlo), 0);
       const int e_hi = row_ok ? min(min(128 + r + p.w_right - 32 * m, len - 1 - jlo), 31) : -1;
@@ -267,7 +327,7 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 32; e += 2) {
-        const uint32_t pair = (e & 7) == 0 ? braw[e >> 3].x : (e & 7) == 2 ? braw[e >> 3].y : (e & 7) == 4 ? braw[e >> 3].z : braw[e >> 3].w;
+        const uint32_t pair = __funnelshift_r(braw[e >> 1], braw[(e >> 1) + 1], sh);
         const float2 bdv = __half22float2(*reinterpret_cast<const __half2*>(&pair));
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -282,6 +342,8 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     tmem_st_wait();
     ATC_STAMP(threadIdx.x == 32, 11);
     s_max[hf * 128 + r] = mx;
+    fence_proxy_async();                                 // BD was written and read through the generic proxy; V^T arrives through the async proxy
+    mbar_arrive(bar_p1);                                 // the BD buffer is dead for this thread: V^T may land on it
     softmax_bar();
     float m_row = fmaxf(fmaxf(s_max[r], s_max[128 + r]), sg2);
     if (m_row == -INFINITY) m_row = 0.f;
@@ -496,13 +558,13 @@ EncodeTiledFnA encode_fn() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] (row pitch ld elements) -> 2-D map, box 64 columns x 128 rows, 128B swizzle, zero fill
-bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+// bf16 row-major [rows, cols] (row pitch ld elements) -> 2-D map, box 64 columns x box_rows rows, 128B swizzle, zero fill
+bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows = 128) {
   EncodeTiledFnA fn = encode_fn();
   if (fn == nullptr) return false;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -515,20 +577,23 @@ cudaError_t attention_tc_debug_cycles(long long* out16) {
 }
 
 bool attention_tc_supported(const AttnArgs& a) {
-  return a.dk == TDK && a.w_left <= 128 && a.w_right <= 128 && (a.w_left & 7) == 0 && a.n_global >= 0 && a.n_global <= 1 &&
-         a.vt != nullptr && (a.T_max & 7) == 0;
+  return a.dk == TDK && a.w_left >= 0 && a.w_right >= 0 && a.w_left <= 128 && a.w_right <= 128 && (a.w_left & 7) == 0 && a.n_global >= 0 &&
+         a.n_global <= 1 && a.vt != nullptr && (a.T_max & 7) == 0 && a.n_rel_pad >= a.w_left + a.w_right + 1 && a.n_rel_pad % 32 == 0 &&
+         a.n_rel_pad <= kNrelPadMax;
 }
 
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
-  if (!attention_tc_supported(a) || a.bd_pitch < a.w_left + a.w_right + 128 || (a.bd_pitch & 7) || (a.ld_vt & 7)) return cudaErrorInvalidValue;
+  if (!attention_tc_supported(a) || a.pos == nullptr || a.bd_bias == nullptr || (a.ld_vt & 7)) return cudaErrorInvalidValue;
   const int d = a.H * TDK;
   const int64_t M = static_cast<int64_t>(a.B) * a.T_max;
   AtcDev p;
   p.qk = static_cast<const __nv_bfloat16*>(a.qkv); p.vt = static_cast<const __nv_bfloat16*>(a.vt);
-  p.bd = static_cast<const __half*>(a.bd); p.bias_u = a.bias_u; p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.bd_bias = a.bd_bias; p.bias_u = a.bias_u; p.out = static_cast<__nv_bfloat16*>(a.out);
   p.enc_len = a.enc_len; p.T_max = a.T_max; p.H = a.H; p.w_left = a.w_left; p.w_right = a.w_right;
-  p.n_global = a.n_global; p.bd_pitch = a.bd_pitch; p.ld_qk = 3 * d; p.ld_vt = a.ld_vt;
-  CUtensorMap tm_qk, tm_vt;
+  p.n_global = a.n_global; p.n_rel_pad = a.n_rel_pad; p.ld_qk = 3 * d; p.ld_vt = a.ld_vt;
+  CUtensorMap tm_qk, tm_vt, tm_pos;
+  // positional table [H * n_rel_pad, 128] bf16, fetched in boxes of n_rel_pad / 2 rows (<= 144; a TMA box holds at most 256)
+  if (!make_map(&tm_pos, a.pos, static_cast<uint64_t>(a.H) * a.n_rel_pad, TDK, TDK, static_cast<uint32_t>(a.n_rel_pad / 2))) return cudaErrorInvalidValue;
   if (!make_map(&tm_qk, p.qk, static_cast<uint64_t>(M), static_cast<uint64_t>(2 * d), static_cast<uint64_t>(p.ld_qk))) return cudaErrorInvalidValue;
   if (!make_map(&tm_vt, p.vt, static_cast<uint64_t>(d), static_cast<uint64_t>(M), static_cast<uint64_t>(p.ld_vt))) return cudaErrorInvalidValue;
   static DeviceOnce attr_once;
@@ -540,7 +605,7 @@ cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     attr_once.set();
   }
   const dim3 grid((a.T_max + TQ - 1) / TQ, a.H, a.B);
-  local_attention_tc_kernel<<<grid, kAtcThreads, kAtcSmem, stream>>>(tm_qk, tm_vt, p);
+  local_attention_tc_kernel<<<grid, kAtcThreads, kAtcSmem, stream>>>(tm_qk, tm_vt, tm_pos, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.n_global > 0) {

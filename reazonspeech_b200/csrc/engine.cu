@@ -36,7 +36,7 @@ struct LayerW {
 
 struct Plan {           // workspace offsets (bytes) for one (B, L_max)
   int B, L_max, F_max, T1, F1, T2, F2, T3, F3, M;
-  size_t wav, len, mel, mel_len, mel_part, mel_stats, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, bd, vt, enc, encp;
+  size_t wav, len, mel, mel_len, mel_part, mel_stats, enc_len, sub1, sub2, sub3, sub4, x, xn, hbuf, abuf, cbuf, vt, enc, encp;
   int n_rel_pad, ld_vt;
   size_t tokens, frames, ntok, dec_ws, total;
 };
@@ -45,7 +45,6 @@ inline int conv_len(int n) { return n > 0 ? (n - 1) / 2 + 1 : 0; }   // floor di
 // Encoder-frame capacity of the padded activation tensors: the subsampled length rounded up to a multiple of 8, so that
 // every utterance starts at a 16-byte-aligned column of the transposed V buffer (TMA wants the innermost coordinate
 // 16-byte aligned: an odd T_max raised "illegal instruction" on the V^T tile loads of the attention kernel).
-constexpr int kBdSkewPitch = 384;   // 2 * 128 + 1 relative offsets + 127 of skew, rounded up: columns of a 128-query tile's key window
 inline int enc_capacity(int mel_frames) { return (conv_len(conv_len(conv_len(mel_frames))) + 7) & ~7; }
 
 }  // namespace
@@ -139,9 +138,6 @@ Plan make_plan(const rs_engine* e, int B, int L_max, int U_max) {
   p.abuf = take(static_cast<size_t>(p.M) * d * 2);
   p.cbuf = take(static_cast<size_t>(p.M) * d * 2);
   p.n_rel_pad = ((c.att_left + c.att_right + 1 + 31) / 32) * 32;
-  // IEEE half positional scores; the tensor-core attention reads them row-skewed with a pitch of kBdSkewPitch per head
-  // (256 B of slack in front: its 16-byte loads may start up to 128 - w_left columns before a row)
-  p.bd = take(static_cast<size_t>(p.M) * c.n_heads * kBdSkewPitch * 2 + 512) + 256;
   p.ld_vt = ((p.M + 255) / 256) * 256 + 64;                               // V^T row pitch: covers the GEMM's 256-row tile overhang
   p.vt = take(static_cast<size_t>(d) * p.ld_vt * 2);
   p.enc = take(static_cast<size_t>(p.M) * d * 4);
@@ -376,21 +372,12 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
     RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
     RS_TRY(resid_gemm(hb, L.ff1_w2, L.ff1_b2, c.d_ff, 0.5f));
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
-    rs::AttnArgs aa{hb, at<void>(e, p.bd), p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
-    aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt; aa.bd_pitch = kBdSkewPitch;
+    // the relative-position term (q + pos_bias_v) . p[c] is a UMMA inside the attention kernel (attention_tc.cu): no score tensor in HBM
+    rs::AttnArgs aa{hb, L.att_pos, L.att_bdbias, p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
+    aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt;
     {   // q | k row-major, V transposed (keys contiguous) for the attention's P.V product
       rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_QKV_VT, 1.f};
       g.out2 = at<void>(e, p.vt); g.split = 2 * d; g.ld2 = p.ld_vt;
-      RS_TRY(gemm_args(e, g, s));
-    }
-    {   // BD[row, h, c] = (q + v_bias) . p[h][c] for every relative offset: one GEMM batched over the heads
-      // written row-skewed (column c + (t mod 128), see RS_EPI_BIAS_F16_SKEW) in IEEE half
-      rs::GemmArgs g{hb, L.att_pos, L.att_bdbias, nullptr, at<void>(e, p.bd), M, p.n_rel_pad, d / c.n_heads, RS_EPI_BIAS_F16_SKEW, 1.f};
-      g.lda = 3 * d; g.n_batch = c.n_heads;
-      g.a_col_stride = d / c.n_heads; g.w_row_stride = p.n_rel_pad; g.bias_stride = p.n_rel_pad;
-      g.ldo = c.n_heads * kBdSkewPitch; g.out_col_stride = kBdSkewPitch;
-      g.split = c.att_left + c.att_right + 1; g.ld2 = p.T3;
-      g.alpha = 1.4426950408889634f / sqrtf(static_cast<float>(d / c.n_heads));   // scores leave the GEMM in the softmax's log2 domain
       RS_TRY(gemm_args(e, g, s));
     }
     RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);

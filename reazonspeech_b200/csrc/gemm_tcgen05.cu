@@ -71,7 +71,7 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
   }
 }
 
-// EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT, 2: RS_EPI_BIAS_F16_SKEW.
+// EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT.
 // (One kernel with every path spilled registers in the common ones: 166 -> 168 registers + a stack frame, GEMMs 10-20 % slower.)
 template <int EG>
 __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
@@ -109,28 +109,6 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       __syncwarp();
       return;
     }
-  }
-  if constexpr (EG == 2) {
-    // row-skewed half output (2-byte stores: the skew breaks vector alignment; 64 contiguous bytes per instruction)
-    uint16_t* st16 = reinterpret_cast<uint16_t*>(stage);       // [32 rows][40] halves
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      *reinterpret_cast<uint32_t*>(st16 + lane * 40 + 2 * j) = pack_f16x2(p.alpha * v[2 * j], p.alpha * v[2 * j + 1]);
-    __syncwarp();
-    const int col = col0 + lane;
-    if (col < p.split) {
-      int t = tile_row0 % p.ld2;                               // frame index of the chunk's first row (one division per chunk)
-      uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + static_cast<size_t>(tile_row0) * p.ldo + static_cast<size_t>(bt) * p.out_col_stride + col;
-      const int n_rows = min(32, p.M - tile_row0);
-#pragma unroll 4
-      for (int rr = 0; rr < n_rows; ++rr) {
-        dst[t & 127] = st16[rr * 40 + lane];
-        dst += p.ldo;
-        if (++t == p.ld2) t = 0;
-      }
-    }
-    __syncwarp();
-    return;
   }
   switch (epi) {
     case RS_EPI_BIAS_F16: {                                    // same 16-bit store pattern as the bf16 epilogues
@@ -525,7 +503,7 @@ static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint6
   return true;
 }
 
-inline int epilogue_group(int epilogue) { return epilogue == RS_EPI_QKV_VT ? 1 : (epilogue == RS_EPI_BIAS_F16_SKEW ? 2 : 0); }
+inline int epilogue_group(int epilogue) { return epilogue == RS_EPI_QKV_VT ? 1 : 0; }
 
 template <int BN, int EG>
 static cudaError_t launch_bn_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
@@ -557,7 +535,6 @@ template <int BN>
 static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_bn_eg<BN, 1>(g, num_sms, stream, err);
-    case 2: return launch_bn_eg<BN, 2>(g, num_sms, stream, err);
     default: return launch_bn_eg<BN, 0>(g, num_sms, stream, err);
   }
 }
@@ -590,7 +567,6 @@ template <int BN>
 static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
-    case 2: return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
     default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
   }
 }
@@ -605,10 +581,6 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
-  if (g.epilogue == RS_EPI_BIAS_F16_SKEW && (g.ld2 <= 0 || g.split <= 0)) {
-    snprintf(err, 256, "gemm: RS_EPI_BIAS_F16_SKEW needs ld2 = T_max and split = valid columns");
-    return cudaErrorInvalidValue;
-  }
   if (g.epilogue == RS_EPI_QKV_VT && (g.out2 == nullptr || g.split % 32 || g.ld2 % 8 || g.ld2 < ((g.M + 255) / 256) * 256 || g.n_batch > 1)) {
     snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, ld2 >= M rounded up to 256");
     return cudaErrorInvalidValue;

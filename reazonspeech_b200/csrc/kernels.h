@@ -47,18 +47,15 @@ cudaError_t launch_conv_dw(const void* u, void* out, const float* w /*[k,d]*/, c
                            const int32_t* enc_len, int B, int T_max, int d, int k, cudaStream_t stream);
 
 struct AttnArgs {
-  const void* qkv;       // bf16 [B*T_max, 3*d]: q | k | v
-  const void* bd;        // f16 [B*T_max, H, n_rel_pad]: (q + v_bias) . p[c], from the batched tcgen05 GEMM
+  const void* qkv;       // bf16 [B*T_max, 3*d]: q + pos_bias_u | k | (unused; V goes to vt)
+  const void* pos;       // bf16 [H, n_rel_pad, dk]: linear_pos(pos_emb) per head, rows beyond the 2w+1 offsets zero (packed at load)
+  const float* bd_bias;  // f32 [H, n_rel_pad]: (pos_bias_v - pos_bias_u) . pos[h][c]
   int n_rel_pad;
   const float* bias_u;   // f32 [H, dk]
   void* out;             // bf16 [B*T_max, d]
   const int32_t* enc_len;
   int B, T_max, H, dk, w_left, w_right, n_global;
-  // tensor-core path (attention_tc.cu): V^T bf16 [H*dk, ld_vt] written by the QKV GEMM (RS_EPI_QKV_VT); the q columns
-  // of `qkv` hold q + pos_bias_u in BOTH paths (folded into the projection bias when the weights are packed)
-  const void* vt = nullptr; int ld_vt = 0;
-  // tensor-core path: `bd` is row-skewed (RS_EPI_BIAS_F16_SKEW), bd_pitch halves per (row, head)
-  int bd_pitch = 0;
+  const void* vt = nullptr; int ld_vt = 0;   // V^T bf16 [H*dk, ld_vt] written by the QKV GEMM (RS_EPI_QKV_VT)
 };
 bool attention_tc_supported(const AttnArgs& a);
 cudaError_t launch_attention_tc(const AttnArgs& a, cudaStream_t stream);

@@ -3,8 +3,7 @@ own formulas (oracle/nemo_restated.py::local_attention_core):
 
 * pos_bias_u is folded into the q bias of the fused QKV projection, and the positional GEMM's bias takes it out again:
   q' k = (q + u) k  and  q' p[c] + bdbias[c] = (q + v) p[c];
-* the row-skewed layout of the positional scores (RS_EPI_BIAS_F16_SKEW): thread = query row of a 128-row tile finds the
-  score of window column jj at the SAME column jj - (128 - w_left) in every row."""
+* the rel_shift of the positional term on the read side of the attention kernel's shared-memory BD tile."""
 import torch
 
 from reazonspeech_b200.config import ModelConfig
@@ -41,22 +40,25 @@ def test_pos_bias_u_fold_is_algebraically_neutral():
     assert ((qp - u) - q).abs().max() < 1e-4
 
 
-def test_skewed_positional_layout_index_contract():
-    """Writer (GEMM epilogue): score of relative offset c of frame t goes to column c + (t mod 128).
-    Reader (attention kernel): row r = t - q0 of the tile reads window column jj (key j = q0 - 128 + jj) at
-    jj - (128 - w_left).  Both must address the same cell for every in-band (t, j)."""
-    for w_left, w_right in ((128, 128), (16, 16), (64, 32)):
+def test_rel_shift_read_index_contract():
+    """attention_tc.cu keeps the positional product BD[r][c] (row r of a 128-query tile, relative offset index c) un-shifted in
+    shared memory and applies NeMo's rel_shift on the read side: for window column jj (key j = q0 - 128 + jj) row r reads
+    BD[r][jj - (128 - w_left) - r].  That must be the oracle's index (j - i) + w_left for every in-band (i, j), and the 17
+    32-bit words a chunk loads must cover its 32 columns for either parity of the start."""
+    for w_left, w_right in ((128, 128), (16, 16), (8, 24), (64, 32)):
         for q0 in (0, 128, 384):
             for r in (0, 1, 77, 127):
-                t = q0 + r
+                i = q0 + r
                 for rel in range(-w_left, w_right + 1):
-                    j = t + rel
+                    j = i + rel
                     if j < 0:
                         continue
-                    c = rel + w_left                               # relative-position index, oracle's `idx`
-                    written_col = c + (t % 128)
                     jj = j - (q0 - 128)
                     assert 0 <= jj < 384
-                    read_col = jj - (128 - w_left)
-                    assert read_col == written_col
-                    assert 0 <= written_col < 384                  # pitch of the skewed buffer
+                    m, e = jj // 32, jj % 32                       # chunk and element, as pass 1 walks them
+                    cs = 32 * m - (128 - w_left) - r                # first BD column of the chunk for this row
+                    assert cs + e == rel + w_left                   # the oracle's `idx`
+                    word, sh = cs >> 1, (cs & 1) * 16               # floor division also for negative starts
+                    pair = e >> 1                                   # funnelshift(w[pair], w[pair + 1], sh) holds elements e, e + 1 of the chunk
+                    first_half = 2 * (word + pair) + (1 if sh else 0)
+                    assert first_half == cs + 2 * pair and pair + 1 <= 16
