@@ -1,18 +1,21 @@
 #!/bin/bash
 # One GPU call of the development cycle:  gpurun --timeout 1800 -- 'bash scripts/gpu_cycle.sh <tag> [tests] [calib] [bench] [sanitize] [ncu:<regex>]'
-# Everything lands in gpurun_out/<tag>_*.  Sections run in the order given below regardless of argument order.
+# Everything lands in gpurun_out/<tag>_*.  Sections run in the order calib, tests, bench, sanitize, profiles regardless of argument order.
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 tag=$1; shift
 mkdir -p gpurun_out
 has() { for a in "$@"; do [ "$a" = "$want" ] && return 0; done; return 1; }
 args=("$@")
+want=calib; if has "${args[@]}"; then
+  echo "=== calibrate the synthetic checkpoints (tiny, then full config); the files come back as gpurun_out/${tag}_calib_*.json"
+  timeout -k 10 600 python scripts/calibrate_synthetic.py --config tiny > gpurun_out/${tag}_calib_tiny.log 2>&1; tail -2 gpurun_out/${tag}_calib_tiny.log | cut -c1-300
+  timeout -k 10 900 python scripts/calibrate_synthetic.py --config full > gpurun_out/${tag}_calib.log 2>&1; tail -2 gpurun_out/${tag}_calib.log | cut -c1-300
+  cp reazonspeech_b200/data/synth_calib_24x1024_v3000_p640_j640_seed0.json gpurun_out/${tag}_calib_full.json
+  cp reazonspeech_b200/data/synth_calib_2x256_v127_p128_j128_seed0.json gpurun_out/${tag}_calib_tiny.json
+fi
 want=tests; if has "${args[@]}"; then
   echo "=== pytest -m gpu"; timeout -k 10 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/${tag}_tests.log 2>&1; tail -3 gpurun_out/${tag}_tests.log
   grep -E "FAIL|whole path:|decode kernel alone|near-tie|Error" gpurun_out/${tag}_tests.log | cut -c1-260 | head -60
-fi
-want=calib; if has "${args[@]}"; then
-  echo "=== calibrate the synthetic checkpoint (full config)"; timeout -k 10 900 python scripts/calibrate_synthetic.py --config full > gpurun_out/${tag}_calib.log 2>&1; tail -4 gpurun_out/${tag}_calib.log
-  cp reazonspeech_b200/data/synth_calib_24x1024_v3000_p640_j640_seed0.json gpurun_out/${tag}_calib_full.json
 fi
 want=bench; if has "${args[@]}"; then
   echo "=== bench"; timeout -k 10 900 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || tail -5 gpurun_out/${tag}_bench.err
