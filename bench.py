@@ -107,6 +107,21 @@ def python_api_rtfx(eng, n_clips: int, seconds: float, rank: int, batches: int =
             "what": "transcribe_batch(model, audios): numpy clips in, TranscribeResult out, one GPU"}
 
 
+def python_api_multi_gpu_rtfx(cfg, n_gpus: int, n_clips: int, seconds: float):
+    """``load_model(devices=range(n_gpus))`` in THIS process, then ``transcribe_batch`` over n_gpus x n_clips clips."""
+    from reazonspeech_b200.nemo.asr import TranscribeConfig, audio_from_numpy, load_model, transcribe_batch
+    from reazonspeech_b200.synth import synth_clip
+    model = load_model(synthetic=True, config=cfg, seed=0, max_batch=n_clips, devices=list(range(n_gpus)))
+    audios = [audio_from_numpy(synth_clip(i, seconds), 16000) for i in range(n_gpus * n_clips)]
+    conf = TranscribeConfig(verbose=False)
+    transcribe_batch(model, audios, conf)                       # warm-up: workspaces and staging on every device
+    t0 = time.perf_counter()
+    res = transcribe_batch(model, audios * 2, conf)
+    dt = time.perf_counter() - t0
+    return {"value": len(res) * seconds / dt, "unit": UNIT, "clips": len(res), "devices": n_gpus, "seconds": dt,
+            "what": "one process, load_model(devices=[0..N-1]) + transcribe_batch(model, audios): numpy clips in, TranscribeResult out"}
+
+
 def make_batch(n_clips: int, seconds: float, rank: int):
     from reazonspeech_b200.synth import synth_clip
     L = int(seconds * 16000) + 2 * PAD
@@ -390,6 +405,17 @@ def main():
         config2 = {"workload": f"nemo-asr FastConformer-RNNT 619M, {world * B2} x {args.seconds:g} s clips sharded by utterance across {world} GPUs ({B2} per GPU)",
                    "value": world * B2 * args.seconds / (ms2 / 1e3), "unit": UNIT, "ms_per_step": ms2, "steps": n2}
         del w2d, l2d, o2
+    # the one-process multi-GPU model (load_model(devices=...)): rank 0 drives ALL `world` GPUs from its own process while the
+    # other ranks idle at the barrier below -- the call a user makes on an 8-GPU box without torchrun
+    api_multi = None
+    if world > 1 and not args.no_extras:
+        barrier()
+        if rank == 0:
+            try:
+                api_multi = python_api_multi_gpu_rtfx(eng.cfg, world, B, args.seconds)
+            except Exception as exc:
+                api_multi = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        barrier()
     if rank != 0:
         return
     cpu = None
@@ -420,7 +446,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu, "python_api": api,
-        "decode_sensitivity": sens, "config2": config2,
+        "decode_sensitivity": sens, "config2": config2, "python_api_multi_gpu": api_multi,
     }), flush=True)
 
 

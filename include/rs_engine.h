@@ -134,6 +134,15 @@ int rs_transcribe_batch_pcm16(rs_engine* e, const int16_t* wav_host, const int32
                               int L_max, int32_t* tokens_host, int32_t* frames_host,
                               int32_t* n_tok_host, int U_max, void* stream);
 
+/* norm_audio on the device (pkg/nemo-asr/src/audio.py:54-68: resample to 16 kHz, then average the channels) fused with
+ * transcribe()'s padding (audio.py:70-83): in [B, channels, L_in_max] f32 or int16 PCM at the native rate ->
+ * out f32 [B, L_out_row], row b = pad zeros | resampled mono utterance | zeros, len_out[b] = resampled length + 2 pad;
+ * feed out / len_out to rs_transcribe_device.  The polyphase FIR (taps [up][taps_per_phase], n_pre_remove) is
+ * scipy.signal.resample_poly's, designed by the host binding (reazonspeech_b200/engine.py::resample_taps). */
+int rs_resample_mono(rs_engine* e, const void* in_dev, int in_is_pcm16, const int32_t* len_in_dev, int B,
+                     int channels, int L_in_max, const float* taps_dev, int taps_per_phase, int up, int down,
+                     int n_pre_remove, int pad, float* out_dev, int L_out_row, int32_t* len_out_dev, void* stream);
+
 /* ---- kernel-level seams (parity tests and roofline measurement) --------------------------- */
 int rs_gemm_bf16(rs_engine* e, const void* a_bf16, const void* w_bf16, const float* bias,
                  const float* resid, void* out, int M, int N, int K, int epilogue, float alpha,

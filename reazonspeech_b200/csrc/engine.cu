@@ -2,6 +2,7 @@
 // launch sequence of the FastConformer-RNNT path.  Host-side orchestration only; every device
 // operation is one of the sm_100a kernels declared in kernels.h.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -19,6 +20,15 @@
 namespace {
 
 thread_local char g_create_error[512] = "";
+
+// NVTX range around the ENQUEUE of a stage (per-stage ranges for Nsight Systems / Compute).  Header-only
+// NVTX v3: a no-op unless a tool has injected itself into the process.
+struct Nvtx {
+  explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+  ~Nvtx() { nvtxRangePop(); }
+  Nvtx(const Nvtx&) = delete;
+  Nvtx& operator=(const Nvtx&) = delete;
+};
 
 struct Tensor { const void* p = nullptr; int dtype = 0; int64_t numel = 0; };
 
@@ -312,6 +322,7 @@ void mark(rs_engine* e, int i, cudaStream_t s) {
 // normalise = false leaves `mel` un-normalised for sub_conv0_dw1_kernel (the transcribe path); rs_logmel passes true.
 int do_logmel(rs_engine* e, const void* wav, bool i16, const int32_t* len, int nb, int L_max, float* mel, int32_t* mel_len,
               float* partials, float* stats, int b0, bool normalise, cudaStream_t s) {
+  Nvtx range("rs::logmel");
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   if (b0 + nb > rs_engine::kMaxBatch) return fail(e, RS_ERR_INVALID_ARG, "batch of %d utterances exceeds the engine limit of %d", b0 + nb, rs_engine::kMaxBatch);
@@ -328,6 +339,7 @@ int do_logmel(rs_engine* e, const void* wav, bool i16, const int32_t* len, int n
 
 // mel_stats == nullptr: `mel` is already normalised (rs_encode takes rs_logmel's output)
 int do_sub_conv0(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_len, const float* mel_stats, int b0, int nb, cudaStream_t s) {
+  Nvtx range("rs::subsampling.conv0_dw1");
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   const int C = c.sub_channels;
@@ -356,6 +368,7 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
   RS_TRY(gemm(e, at<void>(e, p.sub3), e->sub.p2w, e->sub.p2b, nullptr, at<void>(e, p.sub4), B * p.T3 * p.F3, C, C,
               RS_EPI_BIAS_RELU_BF16, 1.f, s));
   float* x = at<float>(e, p.x);
+  Nvtx layers_range("rs::conformer_layers");
   RS_TRY(gemm(e, at<void>(e, p.sub4), e->sub.ow, e->sub.ob, nullptr, x, M, d, p.F3 * C, RS_EPI_BIAS_F32, c.xscale, s));
   mark(e, 2, s);
   // ---- Conformer layers
@@ -369,6 +382,9 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
   };
   for (int i = 0; i < n_layers; ++i) {
     const LayerW& L = e->layers[i];
+    char layer_name[32];
+    snprintf(layer_name, sizeof layer_name, "rs::conformer_layer[%d]", i);
+    Nvtx layer_range(layer_name);
     RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
     RS_TRY(resid_gemm(hb, L.ff1_w2, L.ff1_b2, c.d_ff, 0.5f));
     RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
@@ -403,6 +419,7 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
 
 int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_len, int T_max, int32_t* tokens,
               int32_t* frames, int32_t* ntok, int U_max, cudaStream_t s) {
+  Nvtx range("rs::rnnt_greedy (joint.enc projection + persistent decode)");
   e->cur_stream = s;
   const rs_model_config& c = e->cfg;
   const int M = p.B * T_max;
@@ -639,6 +656,19 @@ int rs_transcribe_batch_pcm16(rs_engine* e, const int16_t* wav_host, const int32
     return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_batch_pcm16: bad arguments");
   RS_CUDA(e, cudaSetDevice(e->device));
   return transcribe_batch(e, wav_host, true, len_host, B, L_max, tokens_host, frames_host, n_tok_host, U_max, static_cast<cudaStream_t>(stream));
+}
+
+int rs_resample_mono(rs_engine* e, const void* in_dev, int in_is_pcm16, const int32_t* len_in_dev, int B, int channels, int L_in_max,
+                     const float* taps_dev, int taps_per_phase, int up, int down, int n_pre_remove, int pad, float* out_dev,
+                     int L_out_row, int32_t* len_out_dev, void* stream) {
+  if (!e || !in_dev || !len_in_dev || !taps_dev || !out_dev || !len_out_dev) return fail(e, RS_ERR_INVALID_ARG, "rs_resample_mono: bad arguments");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  Nvtx range("rs::resample_mono");
+  e->cur_stream = static_cast<cudaStream_t>(stream);
+  rs::ResampleArgs a{in_dev, in_is_pcm16 != 0, len_in_dev, B, channels, L_in_max, taps_dev, taps_per_phase, up, down, n_pre_remove, pad,
+                     out_dev, L_out_row, len_out_dev};
+  RS_K(e, rs::launch_resample_mono(a, static_cast<cudaStream_t>(stream)), 1);
+  return RS_OK;
 }
 
 int rs_gemm_bf16(rs_engine* e, const void* a, const void* w, const float* bias, const float* resid, void* out, int M,

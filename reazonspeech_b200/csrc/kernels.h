@@ -78,6 +78,18 @@ struct DecodeArgs {
 size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int num_sms);
 cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream);
 
+// norm_audio on the device: polyphase resampling to 16 kHz + channel average + transcribe()'s zero padding (resample.cu)
+struct ResampleArgs {
+  const void* in; bool in_i16;          // [B, C, L_in_max] f32, or int16 PCM (scaled by 2^-15)
+  const int32_t* len_in;                // [B] valid samples per utterance (per channel)
+  int B, C, L_in_max;
+  const float* taps; int taps_per_phase, up, down, n_pre_remove;   // polyphase FIR from engine.py::resample_taps: taps[up][taps_per_phase]
+  int pad;                              // zero samples in front of and behind every resampled utterance
+  float* out; int L_out_row;            // [B, L_out_row] f32, fully written (zeros outside the utterance)
+  int32_t* len_out;                     // [B] resampled length + 2 * pad
+};
+cudaError_t launch_resample_mono(const ResampleArgs& a, cudaStream_t stream);
+
 // small utility kernels
 cudaError_t launch_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);
 cudaError_t launch_zero_pad_rows(float* x, const int32_t* len, int B, int T_max, int d, cudaStream_t stream);

@@ -29,10 +29,12 @@ namespace {
 
 constexpr int kLmThreads = 256;
 constexpr int kLmHalfWarps = kLmThreads / lm::kLanes;      // 16 frames in flight per CTA
-constexpr int kScrFloats = 2 * lm::kLanes * lm::kTrPitch;  // per half-warp scratch: transpose buffer (544 floats), later power spectrum + mel row
+constexpr int kScrUsed = 2 * lm::kLanes * lm::kTrPitch;    // per half-warp scratch: transpose buffer (544 floats), later power spectrum + mel row
+constexpr int kScrFloats = kScrUsed + 16;                  // pitch = 16 mod 32 banks: the two half-warps of a warp run the same access pattern on
+                                                           // their own scratch, and with a pitch of 0 mod 32 every 32-bit access of theirs collided 2-way
 constexpr int kPwOff = 0;                                  // power spectrum: 257 floats
 constexpr int kMelRowOff = 264;                            // raw mel sums: up to 16 * kMaxSlots floats, then 16 parking rows
-static_assert(kMelRowOff + lm::kLanes * lm::kMaxSlots + lm::kLanes <= kScrFloats, "scratch layout");   // + 16 parking rows of empty slots
+static_assert(kMelRowOff + lm::kLanes * lm::kMaxSlots + lm::kLanes <= kScrUsed && kScrFloats % 32 == 16, "scratch layout");   // + 16 parking rows of empty slots
 
 struct LmSmem {          // float offsets into dynamic shared memory
   int y, win, twb, twx, mw, meta, scr, total;
@@ -110,6 +112,40 @@ logmel_fused_kernel(const typename LmSample<kI16>::type* __restrict__ wav, const
     using Sample = typename LmSample<kI16>::type;
     const Sample* xw = wav + static_cast<size_t>(b) * L_max;
     const bool vec = ((reinterpret_cast<uintptr_t>(xw) | static_cast<uintptr_t>(start * sizeof(Sample))) & (4 * sizeof(Sample) - 1)) == 0;
+    // all of the thread's loads are issued before the first value is used (the tile is (kFrames - 1) * hop + 512 samples: at most
+    // kStageIters groups of four per thread), so one trip to L2 / HBM covers the whole staging instead of one per group
+    constexpr int kStageIters = ((kFrames - 1) * 160 + lm::kNfft + 4 * kLmThreads - 1) / (4 * kLmThreads);
+    if (n_stage <= kStageIters * 4 * kLmThreads) {
+      float x[kStageIters][5];
+#pragma unroll
+      for (int it = 0; it < kStageIters; ++it) {
+        const int i = (threadIdx.x + it * kLmThreads) * 4, idx = start + i;
+        if (vec && idx >= 4 && idx + 3 < n && i + 3 < n_stage) {
+          x[it][0] = lm_load<kI16>(xw + idx - 1);
+          if constexpr (kI16) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(xw + idx));       // four int16 samples
+            constexpr float k = 1.0f / 32768.0f;
+            x[it][1] = static_cast<float>(static_cast<int16_t>(q.x & 0xffffu)) * k; x[it][2] = static_cast<float>(static_cast<int16_t>(q.x >> 16)) * k;
+            x[it][3] = static_cast<float>(static_cast<int16_t>(q.y & 0xffffu)) * k; x[it][4] = static_cast<float>(static_cast<int16_t>(q.y >> 16)) * k;
+          } else {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(xw + idx));
+            x[it][1] = q.x; x[it][2] = q.y; x[it][3] = q.z; x[it][4] = q.w;
+          }
+        } else if (i < n_stage) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) { const int g = idx - 1 + k; x[it][k] = (g >= 0 && g < n) ? lm_load<kI16>(xw + g) : 0.0f; }
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < kStageIters; ++it) {
+        const int i = (threadIdx.x + it * kLmThreads) * 4, idx = start + i;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int g = idx + k;
+          if (i + k < n_stage) s_y[i + k] = (g >= 0 && g < n) ? fmaf(-preemph, x[it][k], x[it][k + 1]) : 0.0f;
+        }
+      }
+    } else
     for (int i = threadIdx.x * 4; i < n_stage; i += kLmThreads * 4) {
       const int idx = start + i;
       float x[5];                                          // x[idx-1 .. idx+3]
@@ -236,8 +272,8 @@ logmel_fused_kernel(const typename LmSample<kI16>::type* __restrict__ wav, const
 #pragma unroll
     for (int h = 0; h < kLmHalfWarps; ++h) a += lm_smem[L.scr + h * kScrFloats + i];
     prow[i] = a;
+    __threadfence();                                       // by the writers only: the row is visible before this CTA's ticket is
   }
-  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(tickets + b, 1u) == static_cast<unsigned>(tiles_b - 1));
   __syncthreads();

@@ -47,7 +47,7 @@ _lib = None
 EXPORTS = [
     "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
-    "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
+    "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16", "rs_resample_mono", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
     "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
 ]
@@ -85,6 +85,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_transcribe_batch.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_transcribe_device_pcm16.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_transcribe_batch_pcm16.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_resample_mono.argtypes = [vp, vp, ip, vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, ip, vp, vp]
+    lib.rs_resample_mono.restype = ip
     lib.rs_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, C.c_float, vp]
     lib.rs_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, vp]
     lib.rs_launch_count.argtypes = [vp]
@@ -176,6 +178,30 @@ def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     out["pred.lstm.b"] = f32(sd[l + "bias_ih_l0"] + sd[l + "bias_hh_l0"])
     out["joint.pred.w"] = bf(sd["joint.pred.weight"]); out["joint.pred.b"] = f32(sd["joint.pred.bias"])
     return out
+
+
+def resample_taps(orig_sr: int, target_sr: int):
+    """The polyphase FIR of ``scipy.signal.resample_poly(x, up, down)`` (its default Kaiser-5 window design, restated here
+    step by step) in the layout rs_resample_mono wants: (taps float32 [up, taps_per_phase], up, down, n_pre_remove).
+    out[m] = sum_j taps[phase][j] * x[n_hi - j] with t = (m + n_pre_remove) * down, n_hi = t // up, phase = t % up."""
+    from math import gcd
+    from scipy.signal import firwin
+    g = gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g, int(orig_sr) // g
+    if up == down == 1:                                  # already at the target rate: the identity filter (down-mix / padding only)
+        return torch.ones(1, 1, dtype=torch.float32), 1, 1, 0
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    h = (firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0)) * up).astype(np.float32)
+    n_pre_pad = down - half_len % down
+    n_pre_remove = (half_len + n_pre_pad) // down
+    hp = np.concatenate((np.zeros(n_pre_pad, np.float32), h))
+    per = (len(hp) + up - 1) // up
+    taps = np.zeros((up, per), np.float32)
+    for p in range(up):
+        col = hp[p::up]
+        taps[p, : len(col)] = col
+    return torch.from_numpy(taps), up, down, n_pre_remove
 
 
 def to_rs_config(cfg: ModelConfig) -> RsModelConfig:
@@ -324,6 +350,28 @@ class Engine:
                     else (self.lib.rs_transcribe_batch, "rs_transcribe_batch"))
         self._check(fn(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(), frames.data_ptr(), ntok.data_ptr(), U, self._stream()), name)
         return tokens, frames, ntok
+
+    def resample_mono(self, raw: torch.Tensor, lens: torch.Tensor, samplerate: int, pad: int = 0):
+        """norm_audio on the device (pkg/nemo-asr/src/audio.py:54-68) + transcribe()'s padding: ``raw`` [B, C, L] float32 or
+        int16 (PCM) on this device at ``samplerate``, ``lens`` int32 [B] valid samples -> (wav float32 [B, L16] at 16 kHz mono
+        with ``pad`` zeros on both sides of every utterance, lens int32 [B]); feed both to ``transcribe_device``."""
+        assert raw.dim() == 3 and raw.is_contiguous() and raw.dtype in (torch.float32, torch.int16) and lens.dtype == torch.int32
+        key = int(samplerate)
+        if not hasattr(self, "_rs_taps"):
+            self._rs_taps = {}
+        if key not in self._rs_taps:
+            taps, up, down, pre = resample_taps(key, self.cfg.sample_rate)
+            self._rs_taps[key] = (taps.to(self.device), up, down, pre)
+        taps, up, down, pre = self._rs_taps[key]
+        B, Cn, L = raw.shape
+        n_out = (L * up + down - 1) // down
+        L16 = (n_out + 2 * pad + 3) & ~3
+        out = torch.empty(B, L16, dtype=torch.float32, device=self.device)
+        out_len = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._check(self.lib.rs_resample_mono(self.h, raw.data_ptr(), int(raw.dtype == torch.int16), lens.data_ptr(), B, Cn, L,
+                                              taps.data_ptr(), taps.shape[1], up, down, pre, pad, out.data_ptr(), L16, out_len.data_ptr(),
+                                              self._stream()), "rs_resample_mono")
+        return out, out_len
 
     # -- kernel seams
     def gemm(self, a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,

@@ -157,6 +157,38 @@ class B200RnntModel:
                 results[i] = item
         return results
 
+    def iter_token_batches_raw(self, waves: Sequence[np.ndarray], samplerate: int, pad: int = 0):
+        """Like ``iter_token_batches`` for audio that still needs ``norm_audio`` (pkg/nemo-asr/src/audio.py:54-68): waveforms
+        at ``samplerate`` (any rate), mono [n] or channels-first [c, n] with the SAME channel count, float or int16 PCM.  They
+        are staged as they are (pinned), copied to the GPU and resampled / down-mixed / padded there (rs_resample_mono)
+        straight into the buffer the engine transcribes from: the host never touches a sample arithmetically.  (scipy's
+        resample_poly, which this kernel restates, costs the host ~10 ms per 30 s 48 kHz clip -- more than the whole engine.)"""
+        if len(waves) == 0:
+            return
+        eng = self.engine
+        waves = [w if w.ndim == 2 else w[None] for w in waves]
+        C = waves[0].shape[0]
+        if any(w.shape[0] != C for w in waves):
+            raise ValueError("iter_token_batches_raw: all waveforms of a call must have the same number of channels")
+        pcm = all(w.dtype == np.int16 for w in waves)
+        order = sorted(range(len(waves)), key=lambda i: waves[i].shape[1])
+        for lo in range(0, len(order), self.max_batch):
+            idx = order[lo:lo + self.max_batch]
+            L = (max(waves[i].shape[1] for i in idx) + 3) & ~3
+            raw = torch.zeros(len(idx), C, L, dtype=torch.int16 if pcm else torch.float32)
+            if torch.cuda.is_available():
+                raw = raw.pin_memory()
+            rows = raw.numpy()
+            for r, i in enumerate(idx):
+                w = waves[i]
+                rows[r, :, : w.shape[1]] = w if (pcm or w.dtype != np.int16) else w.astype(np.float32) * np.float32(1.0 / 32768.0)
+            lens = torch.tensor([waves[i].shape[1] for i in idx], dtype=torch.int32)
+            with torch.cuda.device(eng.device):
+                wav, wl = eng.resample_mono(raw.to(eng.device, non_blocking=True), lens.to(eng.device, non_blocking=True), samplerate, pad)
+                tokens, frames, ntok = eng.transcribe_device(wav, wl)
+                tokens, frames, counts = tokens.cpu(), frames.cpu(), ntok.cpu().tolist()
+            yield idx, [(tokens[r, :n].tolist(), frames[r, :n].tolist()) for r, n in enumerate(counts)]
+
     # -- NeMo's call shape (transcribe.py:48-53): already padded tensors
     def transcribe(self, audio, batch_size: int = 1, return_hypotheses: bool = True, verbose: bool = True, **_):
         waves = [a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a) for a in audio]
@@ -250,9 +282,19 @@ def transcribe_batch(model, audios: Sequence[AudioData], config: Optional[Transc
         out[i] = r
 
     if hasattr(model, "iter_token_batches"):
-        waves = [np.asarray(norm_audio(a).waveform) for a in audios]
         blank = model.cfg.blank
-        for idx, items in model.iter_token_batches(waves, pad=int(PAD_SECONDS * SAMPLERATE)):
+        pad = int(PAD_SECONDS * SAMPLERATE)
+        # audio that still needs norm_audio (another rate, several channels) and is uniform in both goes to the GPU as it is:
+        # resampling, down-mixing and padding run there (iter_token_batches_raw); anything else is normalised on the host
+        raw_ok = (hasattr(model, "iter_token_batches_raw") and len(audios) > 0 and
+                  len({(a.samplerate, np.asarray(a.waveform).ndim, np.asarray(a.waveform).shape[0] if np.asarray(a.waveform).ndim == 2 else 1)
+                       for a in audios}) == 1 and
+                  (audios[0].samplerate != SAMPLERATE or np.asarray(audios[0].waveform).ndim == 2))
+        if raw_ok:
+            batches = model.iter_token_batches_raw([np.asarray(a.waveform) for a in audios], audios[0].samplerate, pad=pad)
+        else:
+            batches = model.iter_token_batches([np.asarray(norm_audio(a).waveform) for a in audios], pad=pad)
+        for idx, items in batches:
             for i, (tokens, frames) in zip(idx, items):
                 finish(i, Hypothesis.from_greedy(tokens, frames, blank))
     else:

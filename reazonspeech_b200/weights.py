@@ -166,6 +166,16 @@ def _structure_predictor(sd: StateDict, cfg: ModelConfig, suppress: float = 16.0
     clip that bursts to a thousand tokens not even the oracle agreed with itself across precisions, let alone with the
     engine.  A trained prediction network forgets its distant past; this one now does too."""
     hp, hj = cfg.pred_hidden, cfg.joint_hidden
+    # The blank row of the output layer is the constant vector 0.1875 / sqrt(hj).  A random blank row makes the blank logit
+    # swing from frame to frame like any token's while the SPREAD of the 3000 token logits follows the frame's activation norm:
+    # a frame then emits either nothing or -- where its norm is large -- max_symbols tokens at once, and a clip's token count
+    # is decided by a handful of such frames (one clip of the bench set decoded 50 to 3800 tokens depending on the last bit
+    # of the blank bias).  A constant positive row makes the blank logit proportional to the l1 norm of the (ReLU) activation,
+    # i.e. it sits a fixed number of standard deviations (about 3.3 at 0.1875) above the token logits of EVERY frame: the
+    # tokens that beat it are few and spread over the frames, like speech.  Values only; bf16-exact.
+    w_all = sd["joint.joint_net.2.weight"].clone()
+    w_all[cfg.blank] = _bf16_round(torch.full((hj,), 0.1875 / math.sqrt(hj)))
+    sd["joint.joint_net.2.weight"] = w_all
     if hp != hj:
         return                                           # construction needs the two widths to agree (640 == 640)
     l = "decoder.prediction.dec_rnn.lstm."

@@ -97,3 +97,40 @@ def test_one_process_multi_gpu_equals_single_gpu(model, tiny_cfg):
     assert sum(len(r.subwords) for r in two) > 0
     single = asr.transcribe(multi, audios[3], cfgv)                    # the reference's one-clip call shape on the multi-GPU model
     assert single.text == one[3].text
+
+
+def test_transcribe_batch_normalises_foreign_rates_on_the_gpu(model, tiny_cfg):
+    """A call whose clips all come at 44.1 kHz stereo PCM takes the device route (iter_token_batches_raw: H2D of the raw
+    samples, rs_resample_mono, rs_transcribe_device); its results equal the host route's (norm_audio on the CPU) up to the
+    two resamplers' fp32 rounding: same text on nearly all tokens, same count within a few."""
+    from reazonspeech_b200.nemo import asr
+    rate = 44100
+    g = np.random.default_rng(3)
+    clips = []
+    for i, secs in enumerate((1.4, 2.3, 0.8, 3.0, 1.9)):
+        t = np.arange(int(rate * secs)) / rate
+        x = np.stack([0.3 * np.sin(2 * np.pi * (200 + 70 * (i + c)) * t * (1 + 0.1 * np.sin(2 * np.pi * 4 * t))) + 0.02 * g.standard_normal(len(t))
+                      for c in range(2)])
+        clips.append(np.round(x * 32767.0).astype(np.int16))
+    audios = [asr.audio_from_numpy(c, rate) for c in clips]
+    cfgv = asr.TranscribeConfig(verbose=False, raw_hypothesis=True)
+    calls = {"raw": 0}
+    orig = model.iter_token_batches_raw
+
+    def spy(*a, **k):
+        calls["raw"] += 1
+        return orig(*a, **k)
+
+    model.iter_token_batches_raw = spy
+    try:
+        dev = asr.transcribe_batch(model, audios, cfgv)
+    finally:
+        del model.iter_token_batches_raw
+    assert calls["raw"] == 1
+    host = [asr.transcribe(model, a, cfgv) for a in audios]              # one clip per call: norm_audio on the host (scipy)
+    total = 0
+    for d, h in zip(dev, host):
+        nd, nh = len(d.hypothesis.y_sequence), len(h.hypothesis.y_sequence)
+        assert abs(nd - nh) <= max(2, nh // 10)
+        total += nd - 1
+    assert total > 0

@@ -49,5 +49,7 @@ def test_windowed_loop_equals_sequential(K, max_symbols):
         tok, fr, iters = windowed_greedy(O.joint_enc_proj(enc, sd), sd, cfg, K)
     assert len(ref.tokens) > 5
     assert tok == ref.tokens and fr == ref.frames
-    if K > 1:
-        assert iters < len(ref.decisions)
+    if K > 1:                                       # blanks are what a window saves iterations on
+        assert iters <= len(ref.decisions)
+        if ref.decisions.count(cfg.blank) >= 8:
+            assert iters < len(ref.decisions)
