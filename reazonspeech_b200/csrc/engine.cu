@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/rs_engine.h"
+#include "alsd.h"
 #include "kernels.h"
 #include "logmel.h"
 
@@ -65,6 +66,12 @@ struct rs_engine {
   int num_sms = 148;
   std::map<std::string, Tensor> w;
   rs::LmTables fe{};          // tables of the fused log-mel kernel (logmel_tables.py)
+  // ALSD beam search (decode_alsd.cu): fp32-accurate tripled weights (optional: present when the engine was created with them),
+  // an engine-owned workspace grown on demand, a pinned word for the periodic "all utterances finished" check
+  struct { const void *out_w3 = nullptr, *lstm_w3 = nullptr, *pred_w3 = nullptr; const float* out_b = nullptr; int n_pad = 0; } alsd;
+  void* alsd_ws = nullptr;
+  size_t alsd_ws_bytes = 0;
+  int* alsd_done_host = nullptr;
   unsigned int* lm_tickets = nullptr;   // per-utterance CTA tickets of the log-mel statistics (engine-owned, kept zero between launches)
   static constexpr int kMaxBatch = 1 << 16;
   struct { const float *c0w, *c0b, *d1w, *d1b, *p1b, *d2w, *d2b, *p2b, *ob; const void *p1w, *p2w, *ow; } sub;
@@ -226,6 +233,12 @@ int bind_weights(rs_engine* e) {
     NEED(L.ln_out_g, N("ln_out.g"), RS_F32, d); NEED(L.ln_out_b, N("ln_out.b"), RS_F32, d);
   }
   const int64_t Hj = c.joint_hidden, Hp = c.pred_hidden, NC = c.vocab_size + 1;
+  if (e->w.count("alsd.out.w3") != 0) {                  // optional: only an engine that was asked for beam search carries these
+    const int64_t n_pad = (NC + 63) / 64 * 64;
+    NEED(e->alsd.out_w3, "alsd.out.w3", RS_BF16, n_pad * 3 * Hj); NEED(e->alsd.out_b, "alsd.out.b", RS_F32, n_pad);
+    NEED(e->alsd.lstm_w3, "alsd.lstm.w3", RS_BF16, 4 * Hp * 6 * Hp); NEED(e->alsd.pred_w3, "alsd.pred.w3", RS_BF16, Hj * 3 * Hp);
+    e->alsd.n_pad = static_cast<int>(n_pad);
+  }
   NEED(e->dec.enc_w, "joint.enc.w", RS_BF16, Hj * d); NEED(e->dec.enc_b, "joint.enc.b", RS_F32, Hj);
   NEED(e->dec.out_w, "joint.out.w", RS_BF16, NC * Hj); NEED(e->dec.out_b, "joint.out.b", RS_F32, NC);
   NEED(e->dec.embed, "pred.embed", RS_F32, NC * Hp);
@@ -492,6 +505,8 @@ void rs_engine_destroy(rs_engine* e) {
   for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
   for (auto& ev : e->k_ev) cudaEventDestroy(ev);
   cudaFree(e->lm_tickets);
+  cudaFree(e->alsd_ws);
+  if (e->alsd_done_host) cudaFreeHost(e->alsd_done_host);
   delete e;
 }
 
@@ -656,6 +671,77 @@ int rs_transcribe_batch_pcm16(rs_engine* e, const int16_t* wav_host, const int32
     return fail(e, RS_ERR_INVALID_ARG, "rs_transcribe_batch_pcm16: bad arguments");
   RS_CUDA(e, cudaSetDevice(e->device));
   return transcribe_batch(e, wav_host, true, len_host, B, L_max, tokens_host, frames_host, n_tok_host, U_max, static_cast<cudaStream_t>(stream));
+}
+
+// ALSD beam search over encoder outputs (decode_alsd.cu; semantics: oracle/alsd_restated.py).  Synchronises: the host checks every
+// 32 steps whether every utterance's search has ended.
+int rs_rnnt_alsd(rs_engine* e, const float* enc, const int32_t* enc_len, int B, int T_max, int beam, float u_max_ratio, int score_norm,
+                 int recombine_returns_input, int32_t* y_dev, int32_t* step_dev, int32_t* n_dev, double* score_dev, int U_cap, void* stream) {
+  if (!e || !enc || !enc_len || !y_dev || !step_dev || !n_dev || !score_dev || B <= 0 || T_max <= 0 || U_cap <= 0 || beam < 1 || beam > 8 || u_max_ratio < 0.f)
+    return fail(e, RS_ERR_INVALID_ARG, "rs_rnnt_alsd: bad arguments (beam must be 1..8)");
+  if (e->alsd.out_w3 == nullptr)
+    return fail(e, RS_ERR_UNSUPPORTED, "rs_rnnt_alsd: the engine was created without the beam-search weight tensors (alsd.*)");
+  RS_CUDA(e, cudaSetDevice(e->device));
+  Nvtx range("rs::rnnt_alsd");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  e->cur_stream = s;
+  const rs_model_config& c = e->cfg;
+  const int Hj = c.joint_hidden, Hp = c.pred_hidden, d = c.d_model, V = c.vocab_size, blank = c.vocab_size, n_pad = e->alsd.n_pad;
+  const int M = B * T_max, R = B * beam;
+  const int total_steps = T_max + static_cast<int>(u_max_ratio * static_cast<float>(T_max));
+  const int max_nodes = 1 + beam * (total_steps + 1);
+  // ---- workspace
+  size_t off = 0;
+  auto take = [&](size_t bytes) { off = align_up(off); size_t o = off; off += bytes; return o; };
+  const size_t o_xn = take(static_cast<size_t>(M) * d * 2), o_encp = take(static_cast<size_t>(M) * Hj * 4);
+  const size_t plane_cols = static_cast<size_t>(3 * Hj > 6 * Hp ? 3 * Hj : 6 * Hp);
+  const size_t o_planes = take(static_cast<size_t>(R) * plane_cols * 2), o_logits = take(static_cast<size_t>(R) * n_pad * 4);
+  const size_t o_gates = take(static_cast<size_t>(R) * 4 * Hp * 4), o_pp = take(static_cast<size_t>(R) * Hj * 4);
+  const size_t state_bytes = rs::alsd_state_bytes(B, beam, Hp, Hj, max_nodes);
+  const size_t o_state = take(state_bytes);
+  const size_t need_bytes = align_up(off);
+  if (need_bytes > e->alsd_ws_bytes) {
+    RS_CUDA(e, cudaStreamSynchronize(s));
+    cudaFree(e->alsd_ws); e->alsd_ws = nullptr; e->alsd_ws_bytes = 0;
+    RS_CUDA(e, cudaMalloc(&e->alsd_ws, need_bytes));
+    e->alsd_ws_bytes = need_bytes;
+  }
+  if (e->alsd_done_host == nullptr) RS_CUDA(e, cudaMallocHost(reinterpret_cast<void**>(&e->alsd_done_host), sizeof(int)));
+  char* ws = static_cast<char*>(e->alsd_ws);
+  void* xn = ws + o_xn; float* encp = reinterpret_cast<float*>(ws + o_encp); void* planes = ws + o_planes;
+  float* logits = reinterpret_cast<float*>(ws + o_logits); float* gates = reinterpret_cast<float*>(ws + o_gates); float* ppn = reinterpret_cast<float*>(ws + o_pp);
+  RS_CUDA(e, cudaMemsetAsync(ws + o_state, 0, state_bytes, s));
+  rs::AlsdState st{};
+  rs::alsd_bind_state(st, ws + o_state, B, beam, Hp, Hj, max_nodes, score_norm != 0);
+  // ---- joint.enc over every frame (as in the greedy path)
+  RS_K(e, rs::launch_f32_to_bf16(enc, xn, static_cast<int64_t>(M) * d, s), 1);
+  RS_TRY(gemm(e, xn, e->dec.enc_w, e->dec.enc_b, nullptr, encp, M, Hj, d, RS_EPI_BIAS_F32, 1.f, s));
+  // predictor of the extended hypotheses of the beam being built (also the start: [blank] from the zero state)
+  auto predictor = [&]() -> int {
+    RS_K(e, rs::alsd_launch_lstm_in(st, B, e->dec.embed, Hp, planes, s), 1);
+    RS_TRY(gemm(e, planes, e->alsd.lstm_w3, e->dec.lstm_b, nullptr, gates, R, 4 * Hp, 6 * Hp, RS_EPI_BIAS_F32, 1.f, s));
+    RS_K(e, rs::alsd_launch_cell(st, B, gates, Hp, planes, s), 1);
+    RS_TRY(gemm(e, planes, e->alsd.pred_w3, e->dec.pred_b, nullptr, ppn, R, Hj, 3 * Hp, RS_EPI_BIAS_F32, 1.f, s));
+    RS_K(e, rs::alsd_launch_commit(st, B, ppn, Hp, Hj, s), 2);
+    return RS_OK;
+  };
+  RS_K(e, rs::alsd_launch_init(st, B, blank, s), 1);
+  RS_TRY(predictor());
+  for (int step = 0; step <= total_steps; ++step) {
+    RS_K(e, rs::alsd_launch_rows(st, B, encp, enc_len, T_max, Hj, step, planes, s), 1);
+    RS_TRY(gemm(e, planes, e->alsd.out_w3, e->alsd.out_b, nullptr, logits, R, n_pad, 3 * Hj, RS_EPI_BIAS_F32, 1.f, s));
+    RS_K(e, rs::alsd_launch_reduce(st, B, logits, n_pad, V, s), 1);
+    RS_K(e, rs::alsd_launch_select(st, B, enc_len, step, blank, u_max_ratio, recombine_returns_input != 0, s), 1);
+    RS_TRY(predictor());
+    if ((step & 31) == 31) {
+      RS_CUDA(e, cudaMemcpyAsync(e->alsd_done_host, st.n_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+      RS_CUDA(e, cudaStreamSynchronize(s));
+      if (*e->alsd_done_host >= B) break;
+    }
+  }
+  RS_K(e, rs::alsd_launch_output(st, B, blank, y_dev, step_dev, n_dev, score_dev, U_cap, s), 1);
+  RS_CUDA(e, cudaStreamSynchronize(s));
+  return RS_OK;
 }
 
 int rs_resample_mono(rs_engine* e, const void* in_dev, int in_is_pcm16, const int32_t* len_in_dev, int B, int channels, int L_in_max,

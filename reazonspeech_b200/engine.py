@@ -47,7 +47,7 @@ _lib = None
 EXPORTS = [
     "rs_engine_create", "rs_engine_destroy", "rs_last_error", "rs_workspace_bytes", "rs_set_workspace",
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
-    "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16", "rs_resample_mono", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
+    "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16", "rs_resample_mono", "rs_rnnt_alsd", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
     "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
 ]
@@ -85,6 +85,8 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_transcribe_batch.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_transcribe_device_pcm16.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
     lib.rs_transcribe_batch_pcm16.argtypes = [vp, vp, vp, ip, ip, vp, vp, vp, ip, vp]
+    lib.rs_rnnt_alsd.argtypes = [vp, vp, vp, ip, ip, ip, C.c_float, ip, ip, vp, vp, vp, vp, ip, vp]
+    lib.rs_rnnt_alsd.restype = ip
     lib.rs_resample_mono.argtypes = [vp, vp, ip, vp, ip, ip, ip, vp, ip, ip, ip, ip, ip, vp, ip, vp, vp]
     lib.rs_resample_mono.restype = ip
     lib.rs_gemm_bf16.argtypes = [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip, C.c_float, vp]
@@ -180,6 +182,21 @@ def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     return out
 
 
+def alsd_tensors(packed: Dict[str, torch.Tensor], cfg: ModelConfig) -> Dict[str, torch.Tensor]:
+    """Weights of the ALSD beam search (csrc/decode_alsd.cu): the predictor / joint matrices repeated three times along K, so
+    that activations split into three bf16 terms (24 mantissa bits) meet bf16-exact weights -- fp32-accurate log-probabilities
+    out of the bf16 tensor-core GEMM.  The output layer is padded to a multiple of 64 rows (zero rows, never read)."""
+    nc, hj = cfg.vocab_size + 1, cfg.joint_hidden
+    n_pad = (nc + 63) // 64 * 64
+    w = torch.zeros(n_pad, hj, dtype=torch.bfloat16)
+    w[:nc] = packed["joint.out.w"]
+    b = torch.zeros(n_pad, dtype=torch.float32)
+    b[:nc] = packed["joint.out.b"]
+    return {"alsd.out.w3": torch.cat([w] * 3, dim=1).contiguous(), "alsd.out.b": b,
+            "alsd.lstm.w3": torch.cat([packed["pred.lstm.w"]] * 3, dim=1).contiguous(),
+            "alsd.pred.w3": torch.cat([packed["joint.pred.w"]] * 3, dim=1).contiguous()}
+
+
 def resample_taps(orig_sr: int, target_sr: int):
     """The polyphase FIR of ``scipy.signal.resample_poly(x, up, down)`` (its default Kaiser-5 window design, restated here
     step by step) in the layout rs_resample_mono wants: (taps float32 [up, taps_per_phase], up, down, n_pre_remove).
@@ -219,7 +236,8 @@ def to_rs_config(cfg: ModelConfig) -> RsModelConfig:
 class Engine:
     """One engine per device: packed weights + workspace + the C-ABI handle."""
 
-    def __init__(self, cfg: ModelConfig, state_dict: Optional[StateDict], device: str = "cuda", packed: Optional[Dict[str, torch.Tensor]] = None):
+    def __init__(self, cfg: ModelConfig, state_dict: Optional[StateDict], device: str = "cuda", packed: Optional[Dict[str, torch.Tensor]] = None,
+                 alsd: bool = False):
         """``packed``: the result of ``pack_weights(state_dict, cfg)`` when several engines share one checkpoint (one replica
         per device): the repack is done once, every engine uploads its own copy."""
         if not torch.cuda.is_available():
@@ -233,6 +251,8 @@ class Engine:
         self.device = torch.device("cuda", self.dev_index)
         if packed is None:
             packed = pack_weights(state_dict, cfg)
+        if alsd and "alsd.out.w3" not in packed:             # beam search wanted: +34 MB of tripled predictor / joint weights
+            packed = dict(packed, **alsd_tensors(packed, cfg))
         self.weights = {k: v.to(self.device) for k, v in packed.items()}
         self._names = [k.encode() for k in self.weights]
         arr = (RsTensor * len(self.weights))()
@@ -350,6 +370,21 @@ class Engine:
                     else (self.lib.rs_transcribe_batch, "rs_transcribe_batch"))
         self._check(fn(self.h, wav.data_ptr(), lens.data_ptr(), B, L, tokens.data_ptr(), frames.data_ptr(), ntok.data_ptr(), U, self._stream()), name)
         return tokens, frames, ntok
+
+    def alsd(self, enc: torch.Tensor, enc_len: torch.Tensor, beam: int = 4, u_max_ratio: float = 2.0, score_norm: bool = True,
+             recombine_returns_input: bool = True, U_cap: Optional[int] = None):
+        """ALSD beam search over encoder outputs -> (y [B, U_cap + 1] with the leading blank, steps [B, U_cap], n [B], score [B])."""
+        B, T, _ = enc.shape
+        assert enc.dtype == torch.float32 and enc.is_contiguous() and enc_len.dtype == torch.int32
+        U = U_cap or (T + int(u_max_ratio * T) + 1)
+        y = torch.zeros(B, U + 1, dtype=torch.int32, device=self.device)
+        steps = torch.zeros(B, U, dtype=torch.int32, device=self.device)
+        n = torch.zeros(B, dtype=torch.int32, device=self.device)
+        score = torch.zeros(B, dtype=torch.float64, device=self.device)
+        self._check(self.lib.rs_rnnt_alsd(self.h, enc.data_ptr(), enc_len.data_ptr(), B, T, int(beam), float(u_max_ratio), int(score_norm),
+                                          int(recombine_returns_input), y.data_ptr(), steps.data_ptr(), n.data_ptr(), score.data_ptr(), U,
+                                          self._stream()), "rs_rnnt_alsd")
+        return y, steps, n, score
 
     def resample_mono(self, raw: torch.Tensor, lens: torch.Tensor, samplerate: int, pad: int = 0):
         """norm_audio on the device (pkg/nemo-asr/src/audio.py:54-68) + transcribe()'s padding: ``raw`` [B, C, L] float32 or

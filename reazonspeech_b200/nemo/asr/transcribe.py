@@ -100,11 +100,12 @@ class HostStaging:
 class B200RnntModel:
     """Engine + tokenizer behind NeMo's model surface."""
 
-    def __init__(self, engine: Engine, tokenizer, max_batch: int = 64):
+    def __init__(self, engine: Engine, tokenizer, max_batch: int = 64, decoding: str = "greedy", beam_size: int = 4):
         self.engine = engine
         self.cfg = engine.cfg
         self.tokenizer = tokenizer
         self.max_batch = max_batch
+        self.decoding, self.beam_size = decoding, beam_size       # "greedy" (north_star's parity target) or "alsd" (the checkpoint's default)
         pin = torch.cuda.is_available()
         self._staging = (HostStaging(pin), HostStaging(pin))      # double buffer: stage batch k+1 while batch k runs
 
@@ -190,9 +191,33 @@ class B200RnntModel:
             yield idx, [(tokens[r, :n].tolist(), frames[r, :n].tolist()) for r, n in enumerate(counts)]
 
     # -- NeMo's call shape (transcribe.py:48-53): already padded tensors
+    def transcribe_alsd(self, waveforms: Sequence[np.ndarray], pad: int = 0) -> List[Hypothesis]:
+        """ALSD beam search (NeMo's align_length_sync_decoding, the strategy reazonspeech-nemo-v2 ships with): hypotheses exactly
+        as NeMo hands them to the reference's decode.py -- y_sequence with the leading blank, timestamp = alignment steps."""
+        eng = self.engine
+        out: List[Optional[Hypothesis]] = [None] * len(waveforms)
+        order = sorted(range(len(waveforms)), key=lambda i: len(waveforms[i]))
+        for lo in range(0, len(order), self.max_batch):
+            idx = order[lo:lo + self.max_batch]
+            wav, lens = self._staging[0].stage([waveforms[i] for i in idx], pad)
+            with torch.cuda.device(eng.device):
+                x = wav.to(eng.device, non_blocking=True)
+                if x.dtype == torch.int16:
+                    x = x.to(torch.float32) * (1.0 / 32768.0)
+                mel, mel_len = eng.log_mel(x, lens.to(eng.device))
+                enc, enc_len = eng.encode(mel, mel_len)
+                y, steps, n, score = [a.cpu() for a in eng.alsd(enc, enc_len, beam=self.beam_size)]
+            for r, i in enumerate(idx):
+                k = int(n[r])
+                out[i] = Hypothesis(y[r, : k + 1].to(torch.long), steps[r, :k].tolist(), float(score[r]))
+        return out
+
     def transcribe(self, audio, batch_size: int = 1, return_hypotheses: bool = True, verbose: bool = True, **_):
         waves = [a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a) for a in audio]
-        out = [Hypothesis.from_greedy(t, f, self.cfg.blank) for t, f in self.transcribe_tokens(waves)]
+        if self.decoding == "alsd":
+            out = self.transcribe_alsd(waves)
+        else:
+            out = [Hypothesis.from_greedy(t, f, self.cfg.blank) for t, f in self.transcribe_tokens(waves)]
         if return_hypotheses:
             return out
         return [self.tokenizer.ids_to_text(h.y_sequence.tolist()[1:]) for h in out]
@@ -208,11 +233,14 @@ def _find_checkpoint() -> Optional[str]:
 
 
 def load_model(device=None, *, checkpoint: Optional[str] = None, synthetic: Optional[bool] = None,
-               config: Optional[ModelConfig] = None, seed: int = 0, max_batch: int = 64, devices: Optional[Sequence] = None):
+               config: Optional[ModelConfig] = None, seed: int = 0, max_batch: int = 64, devices: Optional[Sequence] = None,
+               decoding: str = "greedy", beam_size: int = 4):
     """Load the ReazonSpeech FastConformer-RNNT onto a B200.
 
     ``device``: None / "cuda" / "cuda:N" as in the reference (transcribe.py:9-22, eval.py:26).
-    "cpu" raises: this engine has no CPU path.  ``devices`` (e.g. ``range(8)`` or ``["cuda:0", "cuda:1"]``) loads one
+    "cpu" raises: this engine has no CPU path.  ``decoding``: "greedy" (default: BASELINE.json's parity target) or "alsd", NeMo's
+    align_length_sync_decoding beam search with ``beam_size`` -- the strategy the shipped checkpoint decodes with by default
+    (pkg/nemo-asr/src/decode.py:29); it runs on the GPU too (csrc/decode_alsd.cu).  ``devices`` (e.g. ``range(8)`` or ``["cuda:0", "cuda:1"]``) loads one
     replica per listed GPU into THIS process and returns a model that deals every call's utterances across them
     (``multi_gpu.MultiGpuRnntModel``; same surface, results in input order).  Weights come from ``checkpoint`` (a .nemo file),
     $REAZONSPEECH_NEMO_CHECKPOINT or the local Hugging Face cache of reazonspeech-nemo-v2.
@@ -236,8 +264,12 @@ def load_model(device=None, *, checkpoint: Optional[str] = None, synthetic: Opti
         raise FileNotFoundError(
             f"no .nemo checkpoint for {HF_REPO}: pass checkpoint=..., set ${ENV_CHECKPOINT}, populate the Hugging Face "
             f"cache, or request seeded synthetic weights with synthetic=True / ${ENV_SYNTHETIC}=1")
+    if decoding not in ("greedy", "alsd"):
+        raise ValueError(f"decoding must be 'greedy' or 'alsd', got {decoding!r}")
     if devices is None:
-        return B200RnntModel(Engine(cfg, sd, str(device)), tokenizer, max_batch=max_batch)
+        return B200RnntModel(Engine(cfg, sd, str(device), alsd=decoding == "alsd"), tokenizer, max_batch=max_batch, decoding=decoding, beam_size=beam_size)
+    if decoding != "greedy":
+        raise ValueError("the one-process multi-GPU model decodes greedily; load one model per device for beam search")
     names = [d if isinstance(d, str) else f"cuda:{int(d)}" for d in devices]
     if len(names) == 0 or len(set(names)) != len(names):
         raise ValueError(f"devices must name distinct GPUs, got {list(devices)!r}")
@@ -281,7 +313,7 @@ def transcribe_batch(model, audios: Sequence[AudioData], config: Optional[Transc
             r.hypothesis = hyp
         out[i] = r
 
-    if hasattr(model, "iter_token_batches"):
+    if hasattr(model, "iter_token_batches") and getattr(model, "decoding", "greedy") == "greedy":
         blank = model.cfg.blank
         pad = int(PAD_SECONDS * SAMPLERATE)
         # audio that still needs norm_audio (another rate, several channels) and is uniform in both goes to the GPU as it is:

@@ -134,3 +134,22 @@ def test_transcribe_batch_normalises_foreign_rates_on_the_gpu(model, tiny_cfg):
         assert abs(nd - nh) <= max(2, nh // 10)
         total += nd - 1
     assert total > 0
+
+
+def test_alsd_decoding_through_the_reference_call_shape(tiny_cfg):
+    """load_model(decoding="alsd"): model.transcribe hands back NeMo-shaped ALSD hypotheses (leading blank, alignment steps)
+    which decode_hypothesis -- byte-compatible with the reference's decode.py -- turns into subwords with non-negative,
+    non-decreasing times; beam 1 reproduces the greedy text where greedy's symbol cap does not bind."""
+    from reazonspeech_b200.nemo import asr
+    m = asr.load_model("cuda:0", synthetic=True, config=tiny_cfg, seed=0, max_batch=4, decoding="alsd", beam_size=4)
+    audios = [asr.audio_from_numpy(synth_clip(160 + i, 1.0 + 0.7 * i), 16000) for i in range(5)]
+    cfgv = asr.TranscribeConfig(verbose=False, raw_hypothesis=True)
+    res = asr.transcribe_batch(m, audios, cfgv)
+    assert len(res) == 5
+    for r in res:
+        h = r.hypothesis
+        assert int(h.y_sequence[0]) == tiny_cfg.blank and len(h.timestamp) == len(h.y_sequence) - 1
+        secs = [s.seconds for s in r.subwords]
+        assert all(s >= 0 for s in secs) and secs == sorted(secs)
+    one = asr.transcribe(m, audios[2], cfgv)
+    assert one.text == res[2].text
