@@ -107,6 +107,30 @@ def python_api_rtfx(eng, n_clips: int, seconds: float, rank: int, batches: int =
             "what": "transcribe_batch(model, audios): numpy clips in, TranscribeResult out, one GPU"}
 
 
+def alsd_rtfx(cfg, wav_dev, len_dev, seconds: float, beam: int = 4):
+    """The same batch with the reference checkpoint's DEFAULT decoding (ALSD beam search, pkg/nemo-asr/src/decode.py:29) instead of
+    greedy: log-mel + encoder + rs_rnnt_alsd, device-resident inputs, one warm-up + two timed passes (synchronous call)."""
+    from reazonspeech_b200.engine import Engine
+    from reazonspeech_b200.weights import random_state_dict
+    eng = Engine(cfg, random_state_dict(cfg, seed=0), str(wav_dev.device), alsd=True)
+
+    def one():
+        mel, mel_len = eng.log_mel(wav_dev, len_dev)
+        enc, enc_len = eng.encode(mel, mel_len)
+        return eng.alsd(enc, enc_len, beam=beam)
+
+    one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        y, steps, n, score = one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 2
+    B = wav_dev.shape[0]
+    return {"value": B * seconds / dt, "unit": UNIT, "ms_per_step": 1e3 * dt, "beam": beam, "tokens_per_clip": float(n.float().mean()),
+            "what": "log-mel + encoder + ALSD beam search (NeMo align_length_sync_decoding, u_max = 2 T, score_norm), same batch, device-resident"}
+
+
 def python_api_multi_gpu_rtfx(cfg, n_gpus: int, n_clips: int, seconds: float):
     """``load_model(devices=range(n_gpus))`` in THIS process, then ``transcribe_batch`` over n_gpus x n_clips clips."""
     from reazonspeech_b200.nemo.asr import TranscribeConfig, audio_from_numpy, load_model, transcribe_batch
@@ -424,8 +448,12 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"the first {CPU_CLIPS} clips of the same {B} x {args.seconds:g} s set, one transcribe() each (batch=1, fp32, greedy) "
                          f"through the oracle port: {secs:.1f} s of CPU work on {how}"}
-    api = sens = None
+    api = sens = alsd = None
     if world == 1 and not args.no_extras:
+        try:
+            alsd = alsd_rtfx(eng.cfg, wav_dev, len_dev, args.seconds)
+        except Exception as exc:
+            alsd = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         try:
             api = python_api_rtfx(eng, B, args.seconds, rank)
         except Exception as exc:      # an extra: reported, never fatal to the contract keys
@@ -446,7 +474,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3},
         "roofline": roofline, "roofline_hbm": roofline_hbm, "stage_ms": stages, "kernel_ms": kernel_ms, "attention_cycles_cta": attn_cycles, "decode_cycles_cta0": decode_prof, "cpu_baseline": cpu, "python_api": api,
-        "decode_sensitivity": sens, "config2": config2, "python_api_multi_gpu": api_multi,
+        "decode_sensitivity": sens, "alsd": alsd, "config2": config2, "python_api_multi_gpu": api_multi,
     }), flush=True)
 
 

@@ -26,7 +26,7 @@ print("RTFx", round(j["value"]), "e2e", round(j["e2e"]["value"]), "ms/step", rou
 print("stage_ms", j["stage_ms"], "tokens/clip", j["config"].get("tokens_per_clip"), "iterations", (j.get("decode_cycles_cta0") or {}).get("iterations"))
 print("roofline", {k: j["roofline"][k] for k in ("achieved", "frac", "gemm_ms_per_step")}, [(r["kernel"], round(r["frac"], 3)) for r in j["roofline_hbm"]])
 for k, v in list(j["kernel_ms"].items())[:18]: print("   ", k, v)
-for k in ("cpu_baseline", "python_api", "python_api_multi_gpu", "decode_sensitivity", "config2"):
+for k in ("cpu_baseline", "python_api", "python_api_multi_gpu", "decode_sensitivity", "alsd", "config2"):
     if j.get(k): print(k, j[k])
 PY
 fi

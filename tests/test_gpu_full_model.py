@@ -150,3 +150,30 @@ def test_full_batch_properties(full):
     n = int(na[0])
     assert n == int(n1[9]) and torch.equal(ta[0, :n], t1[9, :n])
     print("tokens per clip:", n1.tolist())
+
+
+def test_alsd_full_size_matches_the_oracle():
+    """ALSD beam search at the production size (V = 3000, 640-wide predictor / joint, tripled-weight GEMMs with K = 1920 /
+    3840): the winner equals the oracle's on the same encoder output."""
+    from oracle.alsd_restated import alsd_beam
+    from reazonspeech_b200.engine import Engine
+    from reazonspeech_b200.weights import random_state_dict
+    cfg = ModelConfig()
+    sd = random_state_dict(cfg, seed=0)
+    eng = Engine(cfg, sd, "cuda:0", alsd=True)
+    waves = [np.pad(synth_clip(60 + i, s), 8000) for i, s in enumerate((4.0, 6.5, 2.0))]
+    x, lens = _batch(waves)
+    mel, mel_len = eng.log_mel(x, lens)
+    enc, enc_len = eng.encode(mel, mel_len)
+    y, steps, n, score = [a.cpu() for a in eng.alsd(enc, enc_len, beam=4)]
+    enc = enc.cpu()
+    same = 0
+    for i in range(len(waves)):
+        T = int(enc_len[i])
+        ref = alsd_beam(enc[i, :T], sd, cfg, beam=4, emulate=True)
+        k = int(n[i])
+        ok = y[i, : k + 1].tolist() == ref.y_sequence and steps[i, :k].tolist() == ref.timestamp
+        print(f"utt{i}: T={T}, {k} tokens (oracle {len(ref.tokens)}), score {float(score[i]):.3f} (oracle {ref.score:.3f}), identical={ok}")
+        same += ok
+        assert abs(float(score[i]) / (k + 1) - ref.score / len(ref.y_sequence)) < 1e-3
+    assert same >= len(waves) - 1
