@@ -44,6 +44,7 @@ class ModelConfig:
     pred_hidden: int = 640
     joint_hidden: int = 640
     max_symbols: int = 10
+    checkpoint_decoding: str = dataclasses.field(default="greedy", compare=False)   # the strategy model_config.yaml asks for (informational: load_model decides what runs)
 
     # ---- derived ----
     @property
@@ -116,6 +117,16 @@ class ModelConfig:
                            pred_hidden=128, joint_hidden=128)
 
     @staticmethod
+    def decoding_strategy(cfg: dict) -> str:
+        """The checkpoint's configured decoding strategy ("greedy", "greedy_batch", "beam", "alsd", ...); the reference never
+        overrides it (pkg/nemo-asr/src/transcribe.py:26-28), reazonspeech-nemo-v2 ships ALSD (decode.py:29)."""
+        dec = cfg.get("decoding", {}) or {}
+        strategy = str(dec.get("strategy", "greedy_batch"))
+        if strategy == "beam" or "beam" in strategy:
+            return str((dec.get("beam", {}) or {}).get("search_type", strategy))
+        return strategy
+
+    @staticmethod
     def from_nemo_yaml(cfg: dict) -> "ModelConfig":
         """Map a parsed ``model_config.yaml`` (dict) onto ModelConfig.
 
@@ -144,6 +155,7 @@ class ModelConfig:
         require("preprocessor", pre, "highfreq", (None, sr / 2.0, sr // 2), None)
         require("preprocessor", pre, "mel_norm", ("slaney",), "slaney")
         require("preprocessor", pre, "frame_splicing", (1,), 1)
+        require("preprocessor", pre, "exact_pad", (False,), False)          # exact_pad changes the STFT padding and the frame count
         guard = pre.get("log_zero_guard_value", 2.0 ** -24)
         if isinstance(guard, str):                                   # NeMo also accepts "tiny" / "eps" of float32
             import numpy as np
@@ -161,6 +173,12 @@ class ModelConfig:
         require("encoder", enc, "global_tokens_spacing", (1,), 1)
         require("encoder", enc, "global_attn_separate", (False,), False)
         require("encoder", enc, "conv_context_size", (None,), None)
+        require("encoder", enc, "causal_downsampling", (False,), False)
+        require("encoder", enc, "att_context_style", ("regular",), "regular")  # "chunked_limited" masks by chunk, not by band
+        require("encoder", enc, "reduction", (None,), None)
+        if not jointnet_probe(cfg).get("dropout"):                            # without dropout NeMo builds joint_net as [act, Linear]: the
+            raise ValueError("model_config.yaml: joint.jointnet.dropout is absent or 0: NeMo then builds the output layer as joint_net.1, "
+                             "the engine binds joint.joint_net.2 (the layout with dropout, as reazonspeech-nemo-v2 ships)")
         n_mels = int(pre.get("features", 80))
         if int(enc.get("feat_in", n_mels)) != n_mels:
             raise ValueError(f"model_config.yaml: encoder.feat_in={enc.get('feat_in')} != preprocessor.features={n_mels}")
@@ -198,7 +216,12 @@ class ModelConfig:
             pred_hidden=pred_hidden,
             joint_hidden=int(jointnet["joint_hidden"]),
             max_symbols=int(cfg.get("decoding", {}).get("greedy", {}).get("max_symbols", 10) or 10),
+            checkpoint_decoding=ModelConfig.decoding_strategy(cfg),
         )
+
+
+def jointnet_probe(cfg: dict) -> dict:
+    return (cfg.get("joint", {}) or {}).get("jointnet", {}) or {}
 
 
 def conv_out_len(n: int) -> int:

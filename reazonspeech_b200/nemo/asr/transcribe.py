@@ -256,6 +256,10 @@ def load_model(device=None, *, checkpoint: Optional[str] = None, synthetic: Opti
     if path is not None:
         cfg, sd, tok = load_nemo_archive(path)
         tokenizer = SentencePieceTokenizer(tok) if tok else PieceTableTokenizer(synthetic_pieces(cfg.vocab_size))
+        if decoding == "greedy" and not cfg.checkpoint_decoding.startswith("greedy"):
+            import warnings                 # the reference never overrides the checkpoint's strategy (transcribe.py:26-28): say what differs
+            warnings.warn(f"{path}: the checkpoint is configured for '{cfg.checkpoint_decoding}' decoding; this model decodes greedily "
+                          f"(transcripts can differ from the reference's default).  Pass decoding='alsd' for NeMo's ALSD beam search.", stacklevel=2)
     elif synthetic:
         cfg = config or ModelConfig()
         sd = random_state_dict(cfg, seed)

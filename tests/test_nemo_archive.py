@@ -152,3 +152,26 @@ def test_nested_settings_are_refused_and_variants_are_understood(tiny):
     assert got.log_zero_guard == pytest.approx(1.1754943508222875e-38) and got.replace(log_zero_guard=cfg.log_zero_guard) == cfg
     full = ModelConfig.from_nemo_yaml(nemo_yaml(ModelConfig()))
     assert full == ModelConfig()                                    # the 619 M defaults of SURVEY.md App. A.1
+
+
+def test_unsupported_arithmetic_settings_are_rejected_and_the_strategy_is_reported():
+    """Settings that change the arithmetic but used to load silently: exact_pad, causal_downsampling,
+    chunked attention context, encoder reduction, a joint built without dropout (its output layer is then joint_net.1);
+    and the checkpoint's decoding strategy is surfaced (the shipped model asks for ALSD beam search)."""
+    import copy
+    cfg = ModelConfig.tiny()
+    base = nemo_yaml(cfg)
+    for block, key, value in (("preprocessor", "exact_pad", True), ("encoder", "causal_downsampling", True),
+                              ("encoder", "att_context_style", "chunked_limited"), ("encoder", "reduction", "pooling")):
+        y = copy.deepcopy(base)
+        y[block][key] = value
+        with pytest.raises(ValueError, match=key):
+            ModelConfig.from_nemo_yaml(y)
+    y = copy.deepcopy(base)
+    y["joint"]["jointnet"]["dropout"] = 0.0
+    with pytest.raises(ValueError, match="joint_net.1"):
+        ModelConfig.from_nemo_yaml(y)
+    y = copy.deepcopy(base)
+    y["decoding"] = {"strategy": "beam", "beam": {"search_type": "alsd", "beam_size": 4}, "greedy": {"max_symbols": 10}}
+    assert ModelConfig.from_nemo_yaml(y).checkpoint_decoding == "alsd"
+    assert ModelConfig.from_nemo_yaml(base).checkpoint_decoding.startswith("greedy")
