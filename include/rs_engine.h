@@ -154,6 +154,14 @@ int rs_resample_mono(rs_engine* e, const void* in_dev, int in_is_pcm16, const in
                      int channels, int L_in_max, const float* taps_dev, int taps_per_phase, int up, int down,
                      int n_pre_remove, int pad, float* out_dev, int L_out_row, int32_t* len_out_dev, void* stream);
 
+/* Host-side half of transcribe()'s padding (pkg/nemo-asr/src/audio.py:70-83) for a batch: row r of dst[B][L] (pinned host
+ * memory the caller then hands to rs_transcribe_batch / _pcm16) = zeros(pad) | src[r][0 .. n[r]) | zeros to L.
+ * dst_is_pcm16: rows are int16 and every source must be int16; otherwise rows are float32 and an int16 source
+ * (src_is_pcm16[r] != 0; the array may be NULL = all float32) is scaled by 1/32768.  No engine, no CUDA call: plain
+ * copies split over `threads` host threads, so a binding can stage a batch without holding its interpreter lock. */
+int rs_stage_rows(void* dst, int64_t L, const void* const* src, const int64_t* n, const int32_t* src_is_pcm16,
+                  int dst_is_pcm16, int B, int64_t pad, int threads);
+
 /* ---- kernel-level seams (parity tests and roofline measurement) --------------------------- */
 int rs_gemm_bf16(rs_engine* e, const void* a_bf16, const void* w_bf16, const float* bias,
                  const float* resid, void* out, int M, int N, int K, int epilogue, float alpha,
@@ -172,6 +180,7 @@ int rs_stage_times_ms(const rs_engine* e, float* ms /*[8]*/);
  * last read, and resets the accumulators. */
 int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* out8);   /* profiling aid, see engine.cu */
 int rs_debug_attention_cycles(rs_engine* e, int64_t* out16);   /* clock64 stamps of one CTA of the last attention launch */
+int rs_debug_gemm_cycles(rs_engine* e, int64_t* out64);        /* clock64 timeline of the last 2-CTA GEMM launch: first / last cluster x 32 stamps (gemm_tcgen05.cu) */
 int rs_enable_gemm_timing(rs_engine* e, int on);
 int rs_gemm_timing(rs_engine* e, double* ms, double* flops, int64_t* launches);
 /* Per-kernel CUDA-event timing of EVERY launch inside the real pipeline (warm caches, back-to-back launches, unlike

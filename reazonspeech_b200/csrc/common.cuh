@@ -102,6 +102,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* desc,
       ::"r"(smem_dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-D tiled store / reduce-add from shared memory (bulk async-group completion).  The reduction is performed by the
+// memory system at the destination: global[tile] += smem[tile], element type taken from the tensor map.
+__device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(desc), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(desc), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -838,6 +838,13 @@ int rs_debug_attention_cycles(rs_engine* e, int64_t* out16) {
   return RS_OK;
 }
 
+int rs_debug_gemm_cycles(rs_engine* e, int64_t* out64) {
+  if (!e || !out64) return RS_ERR_INVALID_ARG;
+  RS_CUDA(e, cudaDeviceSynchronize());
+  RS_CUDA(e, rs::gemm_debug_cycles(reinterpret_cast<long long*>(out64)));
+  return RS_OK;
+}
+
 int rs_enable_gemm_timing(rs_engine* e, int on) {
   if (!e) return RS_ERR_INVALID_ARG;
   e->gemm_timing = on != 0;

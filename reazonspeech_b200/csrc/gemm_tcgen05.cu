@@ -332,29 +332,45 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
 // is bound by L2 bandwidth (87 FLOP/B against ~12 TB/s), not by the tensor pipe; it also leaves room
 // for a 6-deep ring.  Barriers: full[] on the leader (both producers arrive, both TMAs credit it),
 // empty[] / tmem_full[] per CTA (commit multicast to both), tmem_empty[] on the leader.
-template <int BN>
+// EG 2 (in-place residual, out == resid): the epilogue never reads the residual.  Each warp writes alpha * (acc + bias) of
+// a 32 x 32 chunk into a 128B-swizzled 4 KB buffer and one lane hands it to the TMA unit as a reduce-add
+// (cp.reduce.async.bulk.tensor ... .add, fp32): the memory system performs x += tile at the destination, asynchronously.
+// The register path it replaces fetched the residual 4 KB per warp at a time and was bound by that round trip
+// (N = 1024, K = 1024: 39 us against a 20 us HBM floor).  Two buffers per warp, so a chunk is written while the
+// previous one is still being read out.  The sum is the same fp32 add as before (each element is reduced exactly once).
+constexpr int kReduceBufBytes = 32 * 32 * 4;
+
+// Timeline of the last 2-CTA launch (SM clock of the leader CTA), first and last cluster: [0] roles start, per tile i < 3
+// [1+4i] accumulator free, [2+4i] first operand stage landed, [3+4i] last MMA issued, [4+4i] accumulator complete as seen by
+// the epilogue, [16+2i] that epilogue warp done with the tile, [30] kernel entry, [31] after the closing cluster sync.
+__device__ long long g_gemm_prof[2][32];
+template <int BN, int EG = 0>
 struct Gemm2Cfg {
   static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
   static constexpr int kStages = (BN == 256) ? 5 : 7;
-  static constexpr int kStagingPerWarp = kStageBytesPerWarp;
+  static constexpr int kStagingPerWarp = EG == 2 ? 2 * kReduceBufBytes : kStageBytesPerWarp;
+  static constexpr int kStagingBytes = kEpiWarps * kStagingPerWarp;      // multiple of 1024: follows the operand ring, 1024-aligned
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiWarps * kStagingPerWarp /*epilogue staging*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStagingBytes % 1024 == 0 && kSmemBytes <= 227 * 1024, "shared memory layout");
 };
 
 template <int BN, int EG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmDev p) {
-  using Cfg = Gemm2Cfg<BN>;
+gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                         const __grid_constant__ CUtensorMap tm_o, const GemmDev p) {
+  using Cfg = Gemm2Cfg<BN, EG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t staging_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+  const uint32_t bar_base = staging_base + Cfg::kStagingBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 4);
-  uint8_t* stage_gen = smem_raw + ((bar_base + 256u) - smem_u32(smem_raw));   // generic pointer to the staging area
+  uint8_t* stage_gen = smem_raw + (staging_base - smem_u32(smem_raw));        // generic pointer to the staging area
   auto smem_a = [&](int s) { return smem_base + s * Cfg::kStageBytes; };
   auto smem_b = [&](int s) { return smem_base + s * Cfg::kStageBytes + kABytes; };
 
@@ -367,6 +383,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int num_tiles = num_m * num_n;
   const int num_k = p.K / BK;
   const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
+  const int prof_slot = !leader ? -1 : cid == 0 ? 0 : cid == ncl - 1 ? 1 : -1;
+  auto stamp = [&](int i) { if (prof_slot >= 0 && i < 32) g_gemm_prof[prof_slot][i] = clock64(); };
+  if (threadIdx.x == 0) stamp(30);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -407,15 +426,18 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
+      stamp(0);
       for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
+        if (it < 3) stamp(1 + 4 * it);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
+          if (kb == 0 && it < 3) stamp(2 + 4 * it);
           const uint64_t da = umma_desc_k_sw128(smem_a(stage));
           const uint64_t db = umma_desc_k_sw128(smem_b(stage));
 #pragma unroll
@@ -425,6 +447,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
         umma_commit_2sm(tfull_bar(acc));
+        if (it < 3) stamp(3 + 4 * it);
       }
     }
     __syncwarp();
@@ -434,26 +457,58 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     const int half = (warp - 2) >> 2;
     float* stage = reinterpret_cast<float*>(stage_gen + (warp - 2) * Cfg::kStagingPerWarp);
     int it = 0;
+    [[maybe_unused]] uint32_t nbuf = 0;
     for (int tile = cid; tile < num_tiles; tile += ncl, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (tile % num_n) * BN;
       const int tile_row0 = m0 + q * 32;
-      const bool pre = p.epilogue == RS_EPI_RESID_F32;
-      float4 rr[8], cur[8];
-      resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
+      if constexpr (EG == 2) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
 #pragma unroll 1
-      for (int chunk = half; chunk < BN / 32; chunk += 2) {
-        const int col0 = n0 + chunk * 32;
+        for (int chunk = half; chunk < BN / 32; chunk += 2, nbuf ^= 1u) {
+          const int col0 = n0 + chunk * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+          if (lane == 0) bulk_wait_group_read<1>();             // the buffer written two chunks ago has been read out
+          __syncwarp();
+          tmem_ld_wait();
+          uint8_t* buf = reinterpret_cast<uint8_t*>(stage) + nbuf * kReduceBufBytes + lane * 128;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-        resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
-        tmem_ld_wait();
-        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
+          for (int j = 0; j < 8; ++j) {                          // lane = row; 16-byte chunk j of the row sits at j ^ (row & 7)
+            const float4 b = p.bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(buf + ((j ^ (lane & 7)) << 4)) =
+                make_float4(p.alpha * (__uint_as_float(r[4 * j]) + b.x), p.alpha * (__uint_as_float(r[4 * j + 1]) + b.y),
+                            p.alpha * (__uint_as_float(r[4 * j + 2]) + b.z), p.alpha * (__uint_as_float(r[4 * j + 3]) + b.w));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tm_o, smem_u32(stage) + nbuf * kReduceBufBytes, col0, tile_row0);
+            bulk_commit_group();
+          }
+        }
+      } else {
+        const bool pre = p.epilogue == RS_EPI_RESID_F32;
+        float4 rr[8], cur[8];
+        resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
+#pragma unroll 1
+        for (int chunk = half; chunk < BN / 32; chunk += 2) {
+          const int col0 = n0 + chunk * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+          resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+          tmem_ld_wait();
+          epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
+        }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -461,10 +516,16 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
         if (leader) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_remote(tempty_bar(acc), 0);
       }
+      if (warp == 2 && lane == 0 && it < 3) stamp(16 + 2 * it);
+    }
+    if constexpr (EG == 2) {
+      if (lane == 0) bulk_wait_group_read<0>();                  // shared memory stays valid until the last tile has been read out
+      __syncwarp();
     }
   }
   tcgen05_fence_before();
   cluster_sync_all();                                        // both CTAs done with TMEM and with each other's barriers
+  if (threadIdx.x == 0) stamp(31);
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
@@ -502,6 +563,23 @@ static bool make_tmap_bf16(CUtensorMap* m, const void* ptr, uint64_t rows, uint6
   if (r != CUDA_SUCCESS) { snprintf(err, 256, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols); return false; }
   return true;
 }
+
+// fp32 row-major [rows, cols] -> 2-D map with a 32 x 32 box and 128B swizzle (one epilogue chunk; rows beyond `rows` are clipped).
+static bool make_tmap_f32_chunk(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, char* err) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { snprintf(err, 256, "cuTensorMapEncodeTiled entry point unavailable"); return false; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(err, 256, "cuTensorMapEncodeTiled(f32) failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols); return false; }
+  return true;
+}
+
+cudaError_t gemm_debug_cycles(long long* out64) { return cudaMemcpyFromSymbol(out64, g_gemm_prof, sizeof(long long) * 64); }
 
 inline int epilogue_group(int epilogue) { return epilogue == RS_EPI_QKV_VT ? 1 : 0; }
 
@@ -541,23 +619,25 @@ static cudaError_t launch_bn(const GemmArgs& g, int num_sms, cudaStream_t stream
 
 template <int BN, int EG>
 static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, EG>;
   static DeviceOnce attr_once;
   if (attr_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_2cta_kernel<BN, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { snprintf(err, 256, "cudaFuncSetAttribute(2cta smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e)); return e; }
     attr_once.set();
   }
-  CUtensorMap tm_a, tm_b;
+  CUtensorMap tm_a, tm_b, tm_o;
   const int lda = g.lda > 0 ? g.lda : g.K;
   const int ldo = g.ldo > 0 ? g.ldo : (g.epilogue == RS_EPI_BIAS_GLU_BF16 ? g.N / 2 : g.N);
   if (!make_tmap_bf16(&tm_a, g.a, g.M, g.K, lda, BM, err)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tm_b, g.w, g.N, g.K, g.K, BN / 2, err)) return cudaErrorInvalidValue;
+  if (EG == 2) { if (!make_tmap_f32_chunk(&tm_o, g.out, g.M, g.N, ldo, err)) return cudaErrorInvalidValue; }
+  else memset(&tm_o, 0, sizeof(tm_o));
   const GemmDev p{g.bias, g.resid, g.out, g.M, g.N, g.K, g.epilogue, g.alpha, ldo, 1, 0, 0, 0, 0, g.out2, g.split, g.ld2};
   const int tiles = ((g.M + 2 * BM - 1) / (2 * BM)) * (g.N / BN);
   int clusters = num_sms / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm_bf16_tn_2cta_kernel<BN, EG><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, p);
+  gemm_bf16_tn_2cta_kernel<BN, EG><<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, stream>>>(tm_a, tm_b, tm_o, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) snprintf(err, 256, "gemm 2cta launch (M=%d N=%d K=%d BN=%d): %s", g.M, g.N, g.K, BN, cudaGetErrorString(e));
   return e;
@@ -565,6 +645,9 @@ static cudaError_t launch_2cta_eg(const GemmArgs& g, int num_sms, cudaStream_t s
 
 template <int BN>
 static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err) {
+  // residual added in place: handed to the memory system as a TMA reduce-add (see Gemm2Cfg)
+  const int ldo = g.ldo > 0 ? g.ldo : g.N;
+  if (g.epilogue == RS_EPI_RESID_F32 && g.resid == g.out && ldo % 4 == 0) return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
     default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);

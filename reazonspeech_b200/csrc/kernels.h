@@ -23,6 +23,7 @@ struct GemmArgs {
 
 // Returns cudaSuccess or the failing CUDA error; err (>=256 B) receives a description.
 cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, char* err);
+cudaError_t gemm_debug_cycles(long long* out64);   // timeline of the last 2-CTA launch (see g_gemm_prof)
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out_f32,
                              void* out_bf16, const float* gamma2, const float* beta2, int rows, int d,

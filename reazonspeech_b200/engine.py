@@ -49,7 +49,7 @@ EXPORTS = [
     "rs_mel_frames", "rs_enc_frames", "rs_mel_valid", "rs_enc_valid", "rs_logmel", "rs_encode", "rs_rnnt_greedy", "rs_transcribe_device",
     "rs_transcribe_batch", "rs_transcribe_device_pcm16", "rs_transcribe_batch_pcm16", "rs_resample_mono", "rs_rnnt_alsd", "rs_gemm_bf16", "rs_layernorm", "rs_launch_count", "rs_enable_stage_timing",
     "rs_stage_times_ms", "rs_enable_gemm_timing", "rs_gemm_timing", "rs_debug_decode_cycles",
-    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles",
+    "rs_enable_kernel_timing", "rs_kernel_timing", "rs_debug_attention_cycles", "rs_debug_gemm_cycles", "rs_stage_rows",
 ]
 
 
@@ -97,6 +97,10 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     lib.rs_stage_times_ms.argtypes = [vp, f32p]
     lib.rs_debug_decode_cycles.argtypes = [vp, ip, ip, ip, C.POINTER(C.c_int64)]
     lib.rs_debug_decode_cycles.restype = ip
+    lib.rs_debug_gemm_cycles.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.rs_debug_gemm_cycles.restype = ip
+    lib.rs_stage_rows.argtypes = [vp, C.c_int64, C.POINTER(vp), C.POINTER(C.c_int64), i32p, ip, ip, C.c_int64, ip]
+    lib.rs_stage_rows.restype = ip
     lib.rs_enable_kernel_timing.argtypes = [vp, ip]
     lib.rs_enable_kernel_timing.restype = ip
     lib.rs_kernel_timing.argtypes = [vp, C.c_char_p, ip]
@@ -461,6 +465,21 @@ class Engine:
         names = ["start", "tma_issue", "qk_landed", "s_issued", "pv_wait", "pv_issued", "dealloc", "_",
                  "sm_start", "sm_gscore_done", "sm_s_ready", "sm_pass1", "sm_pass2", "sm_o_wait", "sm_o_ready", "sm_end"]
         return {n: int(x - v[0]) for n, x in zip(names, v) if n != "_"}
+
+    def gemm_cycles(self):
+        """Timeline (SM clocks relative to kernel entry) of the last 2-CTA GEMM launch, for its first and its last cluster."""
+        out = (C.c_int64 * 64)()
+        self._check(self.lib.rs_debug_gemm_cycles(self.h, out), "rs_debug_gemm_cycles")
+        res = {}
+        for c, tag in enumerate(("first_cluster", "last_cluster")):
+            v = list(out)[32 * c: 32 * c + 32]
+            d = {"roles_start": v[0] - v[30], "end": v[31] - v[30]}
+            for i in range(3):
+                if v[3 + 4 * i] > v[30]:
+                    d[f"tile{i}"] = {"acc_free": v[1 + 4 * i] - v[30], "operands": v[2 + 4 * i] - v[30], "mma_issued": v[3 + 4 * i] - v[30],
+                                     "acc_full": v[4 + 4 * i] - v[30], "epilogue_done": v[16 + 2 * i] - v[30]}
+            res[tag] = d
+        return res
 
     def decode_cycles(self, B: int, L_max: int, U_max: int):
         out = (C.c_int64 * 12)()

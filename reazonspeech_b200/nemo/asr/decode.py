@@ -50,11 +50,19 @@ def find_end_of_segment(subwords: Sequence[Subword], start: int) -> int:
 def build_result(tokenizer, token_ids: Sequence[int], steps: Sequence[int]) -> TranscribeResult:
     token_ids = [int(t) for t in token_ids]
     text = tokenizer.ids_to_text(token_ids)
+    # ids_to_text([tid]) is a pure function of tid: remembered per tokenizer object (a 30 s clip asks ~100 times, a batched
+    # run thousands of times per second -- with several GPUs behind one interpreter this loop is what they wait for)
+    try:
+        single = tokenizer.__dict__.setdefault("_single_id_text", {})
+    except AttributeError:                          # an object without __dict__: no cache
+        single = {}
     pieces: List[Subword] = []
     for index, (tid, step) in enumerate(zip(token_ids, steps)):
-        piece = tokenizer.ids_to_text([tid])
+        piece = single.get(tid)
+        if piece is None:
+            piece = single[tid] = tokenizer.ids_to_text([tid])
         if piece:                                   # a bare word-boundary mark decodes to "" (decode.py:51-53)
-            pieces.append(Subword(seconds=token_seconds(int(step), index), token_id=tid, token=piece))
+            pieces.append(Subword(max(SECONDS_PER_STEP * (int(step) - index - 1) - PAD_SECONDS, 0), tid, piece))   # token_seconds, inlined
     segments: List[Segment] = []
     begin = 0
     while begin < len(pieces):

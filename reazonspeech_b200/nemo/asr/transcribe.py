@@ -78,16 +78,18 @@ class HostStaging:
             wav = self._wav[: B * L].view(B, L)
         self._lens = self._grown(self._lens, B, torch.int32)
         lens = self._lens[:B]
-        rows = wav.numpy()
-        for r, w in enumerate(waves):
-            n = len(w)
-            rows[r, :pad] = 0
-            if not pcm and w.dtype == np.int16:
-                np.multiply(w, np.float32(1.0 / 32768.0), out=rows[r, pad:pad + n], dtype=np.float32)
-            else:
-                rows[r, pad:pad + n] = w                # float inputs cast to float32 on the way in
-            rows[r, pad + n:] = 0
-            lens[r] = n + 2 * pad
+        # the copies run in the library (rs_stage_rows: memcpy split over a few threads, interpreter lock released): the
+        # same loop as numpy slice assignments cost ~0.5 ms per 30 s clip, as much as the GPU spends on it
+        import ctypes as C
+        from ...engine import load_library
+        srcs = [np.ascontiguousarray(w if w.dtype in (np.int16, np.float32) else w.astype(np.float32)) for w in waves]
+        ptr = (C.c_void_p * B)(*[a.ctypes.data for a in srcs])
+        n = (C.c_int64 * B)(*[a.shape[0] for a in srcs])
+        is16 = (C.c_int32 * B)(*[int(a.dtype == np.int16) for a in srcs])
+        rc = load_library().rs_stage_rows(wav.data_ptr(), L, ptr, n, is16, int(pcm), B, pad, min(4, B))
+        if rc != 0:
+            raise RuntimeError(f"rs_stage_rows failed ({rc})")
+        lens.copy_(torch.tensor([a.shape[0] + 2 * pad for a in srcs], dtype=torch.int32))
         return wav, lens
 
     def outputs(self, B: int, U: int):

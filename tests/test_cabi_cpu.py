@@ -82,3 +82,37 @@ def test_create_rejects_unsupported_configs_before_touching_a_device():
         rc = lib.rs_engine_create(C.byref(cfg), arr, 0, 0, C.byref(h))
         assert rc == -5 and not h, field                             # RS_ERR_UNSUPPORTED
         assert needle in lib.rs_last_error(None), lib.rs_last_error(None)
+
+
+def test_stage_rows_host_helper():
+    """rs_stage_rows: pad | samples | zeros rows, float and PCM16, threads or not, argument errors -- no GPU involved."""
+    import ctypes as C
+    import numpy as np
+    from reazonspeech_b200.engine import load_library
+    lib = load_library()
+    rng = np.random.default_rng(0)
+    waves = [rng.standard_normal(n).astype(np.float32) for n in (0, 1, 17, 4000, 999)]
+    pcm = [(w * 1000).astype(np.int16) for w in waves]
+    B, pad, L = len(waves), 5, 4012
+
+    def call(dst, srcs, dst16, threads, is16=None, L_=L):
+        ptr = (C.c_void_p * B)(*[a.ctypes.data for a in srcs])
+        n = (C.c_int64 * B)(*[len(a) for a in srcs])
+        flags = (C.c_int32 * B)(*is16) if is16 is not None else None
+        return lib.rs_stage_rows(dst.ctypes.data, L_, ptr, n, flags, dst16, B, pad, threads)
+
+    for threads in (1, 3, 64):
+        dst = np.full((B, L), 7.0, np.float32)
+        assert call(dst, waves, 0, threads) == 0
+        for r, w in enumerate(waves):
+            assert np.array_equal(dst[r], np.pad(w, (pad, L - pad - len(w))))
+        d16 = np.full((B, L), 7, np.int16)
+        assert call(d16, pcm, 1, threads, [1] * B) == 0
+        for r, w in enumerate(pcm):
+            assert np.array_equal(d16[r], np.pad(w, (pad, L - pad - len(w))))
+        mixed = [pcm[0], waves[1], pcm[2], waves[3], pcm[4]]
+        assert call(dst, mixed, 0, threads, [1, 0, 1, 0, 1]) == 0
+        assert np.array_equal(dst[2, pad:pad + 17], pcm[2].astype(np.float32) / np.float32(32768.0))
+        assert np.array_equal(dst[3, pad:pad + 4000], waves[3])
+    assert call(np.zeros((B, L), np.float32), waves, 0, 1, L_=4000) != 0          # a row does not fit
+    assert call(np.zeros((B, L), np.int16), waves, 1, 1, [0] * B) != 0            # int16 rows from float sources

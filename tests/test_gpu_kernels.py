@@ -81,17 +81,26 @@ def test_gemm_epilogues(tiny_engine, epi):
     assert err < tol, f"epilogue {epi}: max scaled err {err}"
 
 
-def test_gemm_resid_in_place(tiny_engine):
+@pytest.mark.parametrize("M,N,K,with_bias,alpha", [(640, 256, 1024, False, 1.0), (1000, 1024, 256, True, 0.5), (12416 // 8 + 3, 1024, 1024, True, 1.0)])
+def test_gemm_resid_in_place(tiny_engine, M, N, K, with_bias, alpha):
+    """x += alpha * (A W^T + b) with out == resid takes the TMA reduce-add epilogue (the memory system performs the add);
+    it must equal the register-path result (resid != out) bit for bit: same fp32 operations, each element reduced once."""
     eng = tiny_engine
-    M, N, K = 640, 256, 1024
-    g = torch.Generator(device="cuda").manual_seed(5)
+    g = torch.Generator(device="cuda").manual_seed(5 + M)
     a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g) if with_bias else None
     x = torch.randn(M, N, device="cuda", generator=g)
-    ref = x + (a.float() @ w.float().T)
-    eng.gemm(a, w, None, E.EPI_RESID_F32, resid=x, alpha=1.0, out=x)
+    ref = x + alpha * (a.float() @ w.float().T + (bias if with_bias else 0.0))
+    separate = eng.gemm(a, w, bias, E.EPI_RESID_F32, resid=x.clone(), alpha=alpha)
+    guard = torch.full((64, N), 7.0, device="cuda")
+    buf = torch.cat([x, guard])                       # rows past M must not be touched by the clipped last tile
+    xin = buf[:M]
+    eng.gemm(a, w, bias, E.EPI_RESID_F32, resid=xin, alpha=alpha, out=xin)
     torch.cuda.synchronize()
-    assert (x - ref).abs().max().item() < 2e-3
+    assert (xin - ref).abs().max().item() < 2e-3
+    assert torch.equal(xin, separate)
+    assert torch.equal(buf[M:], guard)
 
 
 def test_layernorm(tiny_engine):
