@@ -15,6 +15,10 @@
 //     split into two IEEE-half terms (hi + lo), the bf16 weights are exact in half, accumulation is fp32.
 //     The LSTM step and joint.pred of the utterances that emitted are the same kind of GEMM (rows =
 //     utterances, K split over the warps, A fragments loaded straight from L2) on mma.sync m16n8k16.
+//  3. The input half of the LSTM gates depends on the emitted token only: W_ih . embed[k] + b_ih + b_hh is a table
+//     [V+1, 4*Hp] built once at load time (pred.gate_tab), so a step multiplies just the recurrent half W_hh . h -- half the
+//     shared memory, half the MMAs, and half of what every CTA pulls through L2 per step (all 148 CTAs read every
+//     emitting utterance's full input vector: that traffic, not the arithmetic, is what the phase costs).
 //
 //   phase J  kGroups x S CTAs: window logits of the CTA's vocabulary slice -> per (utterance, frame) a grid-wide
 //            64-bit red.max of (ordered logit bits | ~row)
@@ -38,26 +42,37 @@ constexpr int kPassUtts = kPassRows / kFrames;
 struct SpecDev {
   const float* enc_proj; const int32_t* enc_len;
   const __nv_bfloat16* w_out; const float* b_out; const float* embed;
-  const __nv_bfloat16* w_lstm; const float* b_lstm; const __nv_bfloat16* w_pred; const float* b_pred;
+  const __nv_bfloat16* w_lstm; const float* gate_tab; const __nv_bfloat16* w_pred; const float* b_pred;
   int32_t* tokens; int32_t* frames; int32_t* n_tok;
   unsigned long long* best;   // [3][B][kFrames] packed (ordered logit bits << 32 | ~row), 3-deep ring
   float* hbuf;                // [2][B][Hp]
   float* ppbuf;               // [B][Hj]
-  unsigned int* counter;      // grid barrier
+  unsigned int* counter;      // grid barrier: kBarCounters arrival counters, one per 128-byte line
   long long* prof;            // [12] cycle counters of CTA 0
   int B, T_max, V, U_max, max_symbols;
   int S, rows_j, units, rows_p;
 };
 
-__device__ __forceinline__ void sp_grid_barrier(unsigned int* counter, unsigned int& target, unsigned int nblocks) {
+// Grid barrier over kBarCounters arrival counters, each in its own 128-byte line: CTA i arrives on counter i % kBarCounters,
+// threads 0..kBarCounters-1 each poll one counter.  All 148 arrivals on ONE address are serialised by the L2 slice that
+// owns it (the barrier then costs ~1.5 us, three times per decode iteration); spread over several lines they proceed in
+// parallel.  `round` counts the barriers passed; counter c has seen round * (number of CTAs with i % kBarCounters == c) arrivals.
+constexpr int kBarCounters = 8;
+constexpr int kBarStride = 32;            // unsigned ints between counters
+__device__ __forceinline__ void sp_grid_barrier(unsigned int* counters, unsigned int& round, unsigned int nblocks) {
   __syncthreads();
+  ++round;
   if (threadIdx.x == 0) {
-    target += nblocks;
     __threadfence();
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + (blockIdx.x % kBarCounters) * kBarStride) : "memory");
+  }
+  if (threadIdx.x < kBarCounters) {
+    const unsigned int c = threadIdx.x;
+    const unsigned int arrivals = (nblocks + kBarCounters - 1 - c) / kBarCounters;      // CTAs with index % kBarCounters == c
+    const unsigned int target = round * arrivals;
     unsigned int v;
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counters + c * kBarStride) : "memory");
     } while (v < target);
   }
   __syncthreads();
@@ -123,14 +138,14 @@ template <int HJ, int HP>
 __global__ void __launch_bounds__(kSpThreads, 1)
 rnnt_greedy_spec_kernel(const SpecDev p) {
   constexpr int KH = HJ / 2;                 // joint k-half staged in shared memory at a time
-  constexpr int LS = 2 * HP + 8;             // W_lstm row stride in bf16
+  constexpr int LS = HP + 8;                 // W_hh row stride in halves
   constexpr int KS_H = KH / 16;              // k16 steps per joint half
-  constexpr int KSW_L = (2 * HP / 16) / kSpWarps;   // k16 steps per warp, LSTM
+  constexpr int KSW_L = (HP / 16) / kSpWarps;       // k16 steps per warp, LSTM (recurrent half only)
   constexpr int KSW_P = (HP / 16) / kSpWarps;       // k16 steps per warp, joint.pred
   constexpr int V4_ROW = KH / 4;             // float4 per staged row
   constexpr int ITEMS = kPassUtts * V4_ROW;  // loader items per k-half: (utterance, float4 column)
   constexpr int PERU = (ITEMS + kSpThreads - 1) / kSpThreads;
-  static_assert(HJ % 32 == 0 && (2 * HP / 16) % kSpWarps == 0 && (HP / 16) % kSpWarps == 0, "shape");
+  static_assert(HJ % 32 == 0 && (HP / 16) % kSpWarps == 0, "shape");
 
   extern __shared__ __align__(16) uint8_t ssm[];
   const int G = gridDim.x, cta = blockIdx.x;
@@ -154,11 +169,11 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   const int rows_a8 = (p.rows_j + 7) & ~7;
   const uint32_t a_slab = static_cast<uint32_t>(rows_a8) * 128u;   // bytes per A slab
   constexpr uint32_t kBSlab = 8192u;                               // B slab: 64 rows x 128 B = hi plane (rows 0-31) | lo plane (rows 32-63)
-  constexpr uint32_t kBRegion = (NSLAB_H * kBSlab > 16384u) ? NSLAB_H * kBSlab : 16384u;   // >= what an M = 128 read of the last A slab overruns
+  constexpr uint32_t kBRegion = (NSLAB_H * kBSlab > 24576u) ? NSLAB_H * kBSlab : 24576u;   // >= what an M = 128 read of the last A slab overruns, and the LSTM reduction buffer
   // Order: [A slabs | W_lstm | W_pred | pad to 1024 | B slabs (also the L / P reduction buffer) | bias, state ...].  The mma.sync B fragments of the LSTM /
   // joint.pred phases read up to 8 rows past the end of their (5- or 20-row) arrays: those reads must land inside the
   // allocation, so the big B region follows the weight arrays (a 2-utterance batch otherwise read past the end of shared memory).
-  const uint32_t wlp_bytes = static_cast<uint32_t>((static_cast<size_t>(4 * p.units) * LS + static_cast<size_t>(p.rows_p) * (HP + 8)) * 2);
+  const uint32_t wlp_bytes = static_cast<uint32_t>((static_cast<size_t>(4 * p.units) * LS + static_cast<size_t>(p.rows_p) * (HP + 8)) * 2);   // LS = HP + 8
   const uint32_t tc_base = (smem_u32(ssm) + 1023u) & ~1023u;
   const uint32_t b_off = (KSLABS * a_slab + wlp_bytes + 1023u) & ~1023u;
   uint8_t* gA = ssm + (tc_base - smem_u32(ssm));                   // generic pointers to the A slabs / B slabs
@@ -191,11 +206,11 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
       }
       if (tid == 0) { mbar_init(tc_bar, 1); fence_barrier_init(); }
     }
-    for (int i = tid; i < 4 * p.units * (2 * HP / 8); i += kSpThreads) {
-      const int r = i / (2 * HP / 8), c = i % (2 * HP / 8);
+    for (int i = tid; i < 4 * p.units * (HP / 8); i += kSpThreads) {      // the W_hh half of [W_ih | W_hh]
+      const int r = i / (HP / 8), c = i % (HP / 8);
       const int gate = r / p.units, u = r % p.units;
       uint4 v = make_uint4(zero, zero, zero, zero);
-      if (u < nu) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_lstm + (static_cast<size_t>(gate) * HP + u0 + u) * 2 * HP)[c]);
+      if (u < nu) v = bf16x8_to_f16x8(reinterpret_cast<const uint4*>(p.w_lstm + (static_cast<size_t>(gate) * HP + u0 + u) * 2 * HP + HP)[c]);
       *reinterpret_cast<uint4*>(s_wlstm + static_cast<size_t>(r) * LS + c * 8) = v;
     }
     for (int i = tid; i < p.rows_p * (HP / 8); i += kSpThreads) {
@@ -229,73 +244,85 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   // ------------------------------------------------------------------------------------------------
   auto lstm_and_pred = [&]() {
     const int n_emit = s_cnt[0];
-    float* red = s_g;                                  // [warps][16][24]
-    // ---- phase L: gates[utterance][4*units] = (embed[k] | h) . W_lstm[slice]^T, K split over the warps
+    float* red = s_g;                                  // [warps][32][24]: 24 KB of the B-plane region
+    // ---- phase L: gates[utterance][4*units] = gate_tab[token] + h . W_hh[slice]^T, K split over the warps.  Both 16-row
+    // tiles of a step (up to 32 emitting utterances) are loaded before the first MMA: one L2 round trip, one reduction.
     if (nu > 0) {
       const int kw = (warp + cta) % kSpWarps;          // which k-range this warp takes (rotated per CTA against L2 hot-spotting)
-      for (int m0 = 0; m0 < n_emit; m0 += 16) {
-        const int ea = m0 + gid, eb = ea + 8;
-        const bool va = ea < n_emit, vb = eb < n_emit;
-        const int ba = va ? s_emit[ea] : 0, bb = vb ? s_emit[eb] : 0;
-        const float* emb_a = p.embed + static_cast<size_t>(va ? s_tok[ba] : 0) * HP;
-        const float* emb_b = p.embed + static_cast<size_t>(vb ? s_tok[bb] : 0) * HP;
-        const float* h_a = p.hbuf + (static_cast<size_t>(s_par[ba]) * B + ba) * HP;
-        const float* h_b = p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * HP;
-        float2 xa[KSW_L][2], xb[KSW_L][2];
+      for (int m0 = 0; m0 < n_emit; m0 += 32) {
+        const bool two = m0 + 16 < n_emit;             // block-uniform
+        float2 x[2][KSW_L][4];                         // [tile][k-step][row a lo, row b lo, row a hi, row b hi]
 #pragma unroll
-        for (int i = 0; i < KSW_L; ++i) {
-          const int ks = kw * KSW_L + i;
-          const bool in_e = ks < HP / 16;
-          const int off = (in_e ? ks : ks - HP / 16) * 16 + tig * 2;
-          const float* pa = (in_e ? emb_a : h_a) + off;
-          const float* pb = (in_e ? emb_b : h_b) + off;
-          xa[i][0] = va ? ldcg2(pa) : make_float2(0.f, 0.f); xa[i][1] = va ? ldcg2(pa + 8) : make_float2(0.f, 0.f);
-          xb[i][0] = vb ? ldcg2(pb) : make_float2(0.f, 0.f); xb[i][1] = vb ? ldcg2(pb + 8) : make_float2(0.f, 0.f);
-        }
-        float acc[3][4];
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt == 1 && !two) break;
+          const int ea = m0 + 16 * mt + gid, eb = ea + 8;
+          const bool va = ea < n_emit, vb = eb < n_emit;
+          const int ba = va ? s_emit[ea] : 0, bb = vb ? s_emit[eb] : 0;
+          const float* h_a = p.hbuf + (static_cast<size_t>(s_par[ba]) * B + ba) * HP;
+          const float* h_b = p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * HP;
 #pragma unroll
-        for (int n = 0; n < 3; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
-#pragma unroll
-        for (int i = 0; i < KSW_L; ++i) {
-          const int ks = kw * KSW_L + i;
-          uint32_t ah[4], al[4];
-          split2(xa[i][0], ah[0], al[0]); split2(xb[i][0], ah[1], al[1]);
-          split2(xa[i][1], ah[2], al[2]); split2(xb[i][1], ah[3], al[3]);
-#pragma unroll
-          for (int n = 0; n < 3; ++n) {
-            if (n * 8 < 4 * p.units) {                 // warp-uniform
-              // rows beyond the CTA's 4 * units gate rows feed accumulator columns nobody reads: clamped so the fragment load stays
-              // inside the array (it used to run on into the reduction buffer, which compute-sanitizer racecheck rightly flags)
-              const __nv_bfloat16* wr = s_wlstm + static_cast<size_t>(min(n * 8 + gid, 4 * p.units - 1)) * LS + ks * 16 + tig * 2;
-              const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-              mma_f16_16816(acc[n], ah, b0, b1); mma_f16_16816(acc[n], al, b0, b1);
-            }
+          for (int i = 0; i < KSW_L; ++i) {
+            const int off = (kw * KSW_L + i) * 16 + tig * 2;
+            x[mt][i][0] = va ? ldcg2(h_a + off) : make_float2(0.f, 0.f); x[mt][i][2] = va ? ldcg2(h_a + off + 8) : make_float2(0.f, 0.f);
+            x[mt][i][1] = vb ? ldcg2(h_b + off) : make_float2(0.f, 0.f); x[mt][i][3] = vb ? ldcg2(h_b + off + 8) : make_float2(0.f, 0.f);
           }
         }
+        // the table row of this thread's (utterance, unit) -- the reducer threads below -- is requested now as well
+        float tab[4] = {0.f, 0.f, 0.f, 0.f};
+        const int el_r = tid / nu, u_r = tid % nu, e_r = m0 + el_r;
+        const bool red_on = tid < 32 * nu && e_r < n_emit;
+        int b_r = 0;
+        if (red_on) {
+          b_r = s_emit[e_r];
+          const float* tr = p.gate_tab + static_cast<size_t>(s_tok[b_r]) * 4 * HP + u0 + u_r;
 #pragma unroll
-        for (int n = 0; n < 3; ++n) {
-          float* r0 = red + (warp * 16 + gid) * 24 + n * 8 + tig * 2;
-          r0[0] = acc[n][0]; r0[1] = acc[n][1]; r0[8 * 24] = acc[n][2]; r0[8 * 24 + 1] = acc[n][3];
+          for (int gate = 0; gate < 4; ++gate) tab[gate] = __ldg(tr + gate * HP);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt == 1 && !two) break;
+          float acc[3][4];
+#pragma unroll
+          for (int n = 0; n < 3; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+#pragma unroll
+          for (int i = 0; i < KSW_L; ++i) {
+            const int ks = kw * KSW_L + i;
+            uint32_t ah[4], al[4];
+            split2(x[mt][i][0], ah[0], al[0]); split2(x[mt][i][1], ah[1], al[1]);
+            split2(x[mt][i][2], ah[2], al[2]); split2(x[mt][i][3], ah[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+              if (n * 8 < 4 * p.units) {                 // warp-uniform
+                // rows beyond the CTA's 4 * units gate rows feed accumulator columns nobody reads: clamped so the fragment load stays
+                // inside the array (it used to run on into the reduction buffer, which compute-sanitizer racecheck rightly flags)
+                const __nv_bfloat16* wr = s_wlstm + static_cast<size_t>(min(n * 8 + gid, 4 * p.units - 1)) * LS + ks * 16 + tig * 2;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+                mma_f16_16816(acc[n], ah, b0, b1); mma_f16_16816(acc[n], al, b0, b1);
+              }
+            }
+          }
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {                  // red: [warps][32 utterances][24]
+            float* r0 = red + ((warp * 32 + 16 * mt + gid) * 24) + n * 8 + tig * 2;
+            r0[0] = acc[n][0]; r0[1] = acc[n][1]; r0[8 * 24] = acc[n][2]; r0[8 * 24 + 1] = acc[n][3];
+          }
         }
         __syncthreads();
-        if (tid < 16 * nu) {
-          const int el = tid / nu, u = tid % nu, e = m0 + el;
-          if (e < n_emit) {
-            const int b = s_emit[e], unit = u0 + u;
-            float gsum[4];
+        if (red_on) {
+          const int unit = u0 + u_r;
+          float gsum[4];
 #pragma unroll
-            for (int gate = 0; gate < 4; ++gate) {
-              float s = 0.f;
+          for (int gate = 0; gate < 4; ++gate) {
+            float s = 0.f;
 #pragma unroll
-              for (int w = 0; w < kSpWarps; ++w) s += red[(w * 16 + el) * 24 + gate * p.units + u];
-              gsum[gate] = s + __ldg(p.b_lstm + gate * HP + unit);
-            }
-            const float ig = sigmoidf_accurate(gsum[0]), fg = sigmoidf_accurate(gsum[1]);
-            const float cg = tanhf(gsum[2]), og = sigmoidf_accurate(gsum[3]);
-            const float c2 = fg * s_c[b * p.units + u] + ig * cg;
-            s_c[b * p.units + u] = c2;
-            __stcg(p.hbuf + (static_cast<size_t>(s_par[b] ^ 1) * B + b) * HP + unit, og * tanhf(c2));
+            for (int w = 0; w < kSpWarps; ++w) s += red[(w * 32 + el_r) * 24 + gate * p.units + u_r];
+            gsum[gate] = s + tab[gate];
           }
+          const float ig = sigmoidf_accurate(gsum[0]), fg = sigmoidf_accurate(gsum[1]);
+          const float cg = tanhf(gsum[2]), og = sigmoidf_accurate(gsum[3]);
+          const float c2 = fg * s_c[b_r * p.units + u_r] + ig * cg;
+          s_c[b_r * p.units + u_r] = c2;
+          __stcg(p.hbuf + (static_cast<size_t>(s_par[b_r] ^ 1) * B + b_r) * HP + unit, og * tanhf(c2));
         }
         __syncthreads();
       }
@@ -308,41 +335,48 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
     __syncthreads();
     if (np > 0) {
       const int kw = (warp + cta) % kSpWarps;
-      for (int m0 = 0; m0 < n_emit; m0 += 16) {
-        const int ea = m0 + gid, eb = ea + 8;
-        const bool va = ea < n_emit, vb = eb < n_emit;
-        const int ba = va ? s_emit[ea] : 0, bb = vb ? s_emit[eb] : 0;
-        const float* h_a = p.hbuf + (static_cast<size_t>(s_par[ba]) * B + ba) * HP;
-        const float* h_b = p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * HP;
-        float2 xa[KSW_P][2], xb[KSW_P][2];
+      for (int m0 = 0; m0 < n_emit; m0 += 32) {
+        const bool two = m0 + 16 < n_emit;
+        float2 x[2][KSW_P][4];
 #pragma unroll
-        for (int i = 0; i < KSW_P; ++i) {
-          const int off = (kw * KSW_P + i) * 16 + tig * 2;
-          xa[i][0] = va ? ldcg2(h_a + off) : make_float2(0.f, 0.f); xa[i][1] = va ? ldcg2(h_a + off + 8) : make_float2(0.f, 0.f);
-          xb[i][0] = vb ? ldcg2(h_b + off) : make_float2(0.f, 0.f); xb[i][1] = vb ? ldcg2(h_b + off + 8) : make_float2(0.f, 0.f);
-        }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt == 1 && !two) break;
+          const int ea = m0 + 16 * mt + gid, eb = ea + 8;
+          const bool va = ea < n_emit, vb = eb < n_emit;
+          const int ba = va ? s_emit[ea] : 0, bb = vb ? s_emit[eb] : 0;
+          const float* h_a = p.hbuf + (static_cast<size_t>(s_par[ba]) * B + ba) * HP;
+          const float* h_b = p.hbuf + (static_cast<size_t>(s_par[bb]) * B + bb) * HP;
 #pragma unroll
-        for (int i = 0; i < KSW_P; ++i) {
-          const int ks = kw * KSW_P + i;
-          uint32_t ah[4], al[4];
-          split2(xa[i][0], ah[0], al[0]); split2(xb[i][0], ah[1], al[1]);
-          split2(xa[i][1], ah[2], al[2]); split2(xb[i][1], ah[3], al[3]);
-          const __nv_bfloat16* wr = s_wpred + static_cast<size_t>(min(gid, p.rows_p - 1)) * (HP + 8) + ks * 16 + tig * 2;   // clamped like the LSTM rows
-          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
-          mma_f16_16816(acc, ah, b0, b1); mma_f16_16816(acc, al, b0, b1);
+          for (int i = 0; i < KSW_P; ++i) {
+            const int off = (kw * KSW_P + i) * 16 + tig * 2;
+            x[mt][i][0] = va ? ldcg2(h_a + off) : make_float2(0.f, 0.f); x[mt][i][2] = va ? ldcg2(h_a + off + 8) : make_float2(0.f, 0.f);
+            x[mt][i][1] = vb ? ldcg2(h_b + off) : make_float2(0.f, 0.f); x[mt][i][3] = vb ? ldcg2(h_b + off + 8) : make_float2(0.f, 0.f);
+          }
         }
-        {
-          float* r0 = red + (warp * 16 + gid) * 8 + tig * 2;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          if (mt == 1 && !two) break;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < KSW_P; ++i) {
+            const int ks = kw * KSW_P + i;
+            uint32_t ah[4], al[4];
+            split2(x[mt][i][0], ah[0], al[0]); split2(x[mt][i][1], ah[1], al[1]);
+            split2(x[mt][i][2], ah[2], al[2]); split2(x[mt][i][3], ah[3], al[3]);
+            const __nv_bfloat16* wr = s_wpred + static_cast<size_t>(min(gid, p.rows_p - 1)) * (HP + 8) + ks * 16 + tig * 2;   // clamped like the LSTM rows
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wr), b1 = *reinterpret_cast<const uint32_t*>(wr + 8);
+            mma_f16_16816(acc, ah, b0, b1); mma_f16_16816(acc, al, b0, b1);
+          }
+          float* r0 = red + (warp * 32 + 16 * mt + gid) * 8 + tig * 2;
           r0[0] = acc[0]; r0[1] = acc[1]; r0[8 * 8] = acc[2]; r0[8 * 8 + 1] = acc[3];
         }
         __syncthreads();
-        if (tid < 16 * np) {
+        if (tid < 32 * np) {
           const int el = tid / np, r = tid % np, e = m0 + el;
           if (e < n_emit) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < kSpWarps; ++w) s += red[(w * 16 + el) * 8 + r];
+            for (int w = 0; w < kSpWarps; ++w) s += red[(w * 32 + el) * 8 + r];
             __stcg(p.ppbuf + static_cast<size_t>(s_emit[e]) * HJ + p0 + r, s + __ldg(p.b_pred + p0 + r));
           }
         }
@@ -585,10 +619,13 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   if (warp == 0) { tcgen05_fence_after(); tmem_dealloc<64>(tmem_d); }
 }
 
-// workspace: hbuf | ppbuf | (3*B*8 pad, keeps the counter/prof offset of decode_batched.cu) | counter + prof (256 B) | best
+// workspace: hbuf | ppbuf | pad to 128 | barrier counters (kBarCounters lines) | prof (128 B) | best
+static size_t spec_counter_offset(int B, int Hj, int Hp) {
+  return (static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + 127) & ~static_cast<size_t>(127);
+}
+size_t rnnt_spec_prof_offset(int B, int Hj, int Hp) { return spec_counter_offset(B, Hj, Hp) + static_cast<size_t>(kBarCounters) * kBarStride * 4; }
 size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int /*num_sms*/) {
-  return static_cast<size_t>(2) * B * Hp * 4 + static_cast<size_t>(B) * Hj * 4 + static_cast<size_t>(3) * B * 8 + 256 + 16 +
-         static_cast<size_t>(3) * B * kFrames * 8;
+  return rnnt_spec_prof_offset(B, Hj, Hp) + 128 + static_cast<size_t>(3) * B * kFrames * 8 + 128 /*base alignment slack*/;
 }
 
 template <int HJ, int HP>
@@ -609,33 +646,31 @@ cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int nu
   SpecDev p;
   p.enc_proj = a.enc_proj; p.enc_len = a.enc_len;
   p.w_out = static_cast<const __nv_bfloat16*>(a.w_out); p.b_out = a.b_out; p.embed = a.embed;
-  p.w_lstm = static_cast<const __nv_bfloat16*>(a.w_lstm); p.b_lstm = a.b_lstm;
+  p.w_lstm = static_cast<const __nv_bfloat16*>(a.w_lstm); p.gate_tab = a.gate_tab;
   p.w_pred = static_cast<const __nv_bfloat16*>(a.w_pred); p.b_pred = a.b_pred;
   p.tokens = a.tokens; p.frames = a.frames; p.n_tok = a.n_tok;
+  if (reinterpret_cast<uintptr_t>(workspace) & 15u) return cudaErrorInvalidValue;   // the window is read with 16-byte loads
   char* ws = static_cast<char*>(workspace);
-  p.hbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(2) * a.B * a.Hp * 4;
-  p.ppbuf = reinterpret_cast<float*>(ws); ws += static_cast<size_t>(a.B) * a.Hj * 4;
-  ws += static_cast<size_t>(3) * a.B * 8;
-  p.counter = reinterpret_cast<unsigned int*>(ws);
-  p.prof = reinterpret_cast<long long*>(ws + 64);
-  ws += 256;
-  ws += (16 - (reinterpret_cast<uintptr_t>(ws) & 15)) & 15;       // the window is read with 16-byte loads
-  p.best = reinterpret_cast<unsigned long long*>(ws);
+  p.hbuf = reinterpret_cast<float*>(ws);
+  p.ppbuf = reinterpret_cast<float*>(ws + static_cast<size_t>(2) * a.B * a.Hp * 4);
+  p.counter = reinterpret_cast<unsigned int*>(ws + spec_counter_offset(a.B, a.Hj, a.Hp));
+  p.prof = reinterpret_cast<long long*>(ws + rnnt_spec_prof_offset(a.B, a.Hj, a.Hp));
+  p.best = reinterpret_cast<unsigned long long*>(ws + rnnt_spec_prof_offset(a.B, a.Hj, a.Hp) + 128);
   p.B = a.B; p.T_max = a.T_max; p.V = a.V; p.U_max = a.U_max; p.max_symbols = a.max_symbols;
   p.S = G / kGroups;
   p.rows_j = (a.V + 1 + p.S - 1) / p.S;
   p.units = (a.Hp + G - 1) / G;
   p.rows_p = (a.Hj + G - 1) / G;
-  if (4 * p.units > 24 || p.rows_p > 8 || 16 * p.units > kSpThreads) return cudaErrorInvalidValue;
+  if (4 * p.units > 24 || p.rows_p > 8 || 32 * p.units > kSpThreads || 32 * p.rows_p > kSpThreads || a.gate_tab == nullptr) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(workspace, 0, rnnt_spec_workspace_bytes(a.B, a.Hj, a.Hp, num_sms), stream);
   if (e != cudaSuccess) return e;
   const size_t state = ((static_cast<size_t>(a.B) * p.units + 1) & ~static_cast<size_t>(1)) * 4 + kPassRows * 4 * 8 + static_cast<size_t>(a.B) * 8 * 4 +
                        (2 + 2 * kSpWarps) * 4 + 64;
-  const size_t w_lp = (static_cast<size_t>(4 * p.units) * (2 * a.Hp + 8) + static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
+  const size_t w_lp = (static_cast<size_t>(4 * p.units) * (a.Hp + 8) + static_cast<size_t>(p.rows_p) * (a.Hp + 8)) * 2;
   if (p.rows_j > 128) return cudaErrorInvalidValue;
   const size_t rows_a8 = (p.rows_j + 7) & ~7;
   const size_t b_bytes = static_cast<size_t>(a.Hj / 2 / 64) * 8192;
-  const size_t b_region = b_bytes > 16384 ? b_bytes : 16384;
+  const size_t b_region = b_bytes > 24576 ? b_bytes : 24576;     // also the [8 warps][32][24] fp32 reduction buffer of the LSTM phase
   const size_t ab = ((static_cast<size_t>(a.Hj / 64) * rows_a8 * 128 + w_lp + 1023) & ~static_cast<size_t>(1023));   // A slabs, W_lstm, W_pred, pad
   const size_t smem = 1024 + ab + b_region + 128 * 4 + state + 16;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;

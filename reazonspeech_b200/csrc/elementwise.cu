@@ -9,52 +9,28 @@
 namespace rs {
 
 // ------------------------------------------------------------------------------ LayerNorm
-// One warp per row of d = 128*NV fp32 values (two-pass mean / variance in registers).  Optional second LayerNorm chained
-// on the result (norm_out of layer i feeding norm_feed_forward1 of layer i+1) so the residual stream is read once.
-//
-// Rows reach the warp through its own ring of kLnStages row buffers in shared memory, filled by 1-D bulk copies
-// (cp.async.bulk, one 4 KB request per row, completion on an mbarrier): the warp always has kLnStages rows in flight
-// without holding them in registers.  The version this replaces prefetched ONE row ahead with eight LDG.128 per lane and
-// was bound by that round trip (~2.7 us per row and warp under load: 3.1 TB/s, 0.47 of the HBM peak, ncu r01_v4); more
-// resident warps did not help, the register file was full.
-constexpr int kLnWarps = 8;
-constexpr int kLnStages = 3;
-
-__device__ __forceinline__ void bulk_load_row(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
-}
-
+// One warp per row of d = 128*NV fp32 values held in registers (two-pass mean / variance).
+// Optional second LayerNorm chained on the result (norm_out of layer i feeding
+// norm_feed_forward1 of layer i+1) so the residual stream is read once.
 template <int NV>
-__global__ void __launch_bounds__(32 * kLnWarps)
+__global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, const float* __restrict__ b1,
                  float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
                  const float* __restrict__ g2, const float* __restrict__ b2, int rows, float eps) {
+  // Persistent: a warp walks rows (stride = warps in the grid) with the NEXT row's loads already in flight while
+  // the current one is reduced and stored -- short-lived one-row warps left HBM at ~40 % (profiles/r01_v2_other_ncu.md).
   constexpr int D = 128 * NV;
-  constexpr uint32_t kRowBytes = D * 4;
-  extern __shared__ __align__(128) uint8_t ln_smem[];
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int wstride = gridDim.x * kLnWarps;
-  const int row0 = blockIdx.x * kLnWarps + warp;
-  const uint32_t ring = smem_u32(ln_smem) + static_cast<uint32_t>(warp) * kLnStages * kRowBytes;
-  const uint32_t bars = smem_u32(ln_smem) + kLnWarps * kLnStages * kRowBytes + static_cast<uint32_t>(warp) * kLnStages * 8;
-  if (lane == 0) {
-    for (int s = 0; s < kLnStages; ++s) mbar_init(bars + 8 * s, 1);
-    fence_barrier_init();
-  }
-  __syncwarp();
-  if (row0 >= rows) return;
-  if (lane == 0) {
+  const int lane = lane_id();
+  const int wstride = gridDim.x * (blockDim.x >> 5);
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV], nx[NV];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * D);
 #pragma unroll
-    for (int s = 0; s < kLnStages; ++s) {
-      const int r = row0 + s * wstride;
-      if (r < rows) {
-        mbar_arrive_expect_tx(bars + 8 * s, kRowBytes);
-        bulk_load_row(ring + s * kRowBytes, x + static_cast<size_t>(r) * D, kRowBytes, bars + 8 * s);
-      }
-    }
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
   }
-  float4 v[NV];
+
   auto normalize = [&](const float* __restrict__ g, const float* __restrict__ b) {
     float s = 0.f;
 #pragma unroll
@@ -78,22 +54,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, cons
     }
   };
 
-  int stage = 0; uint32_t phase = 0;
-  for (int row = row0; row < rows; row += wstride) {
-    mbar_wait(bars + 8 * stage, phase);
-    {
-      const uint32_t src = ring + stage * kRowBytes + lane * 16;
+  for (; row < rows; row += wstride) {
+    const int nrow = row + wstride;
+    if (nrow < rows) {                                         // warp-uniform
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(nrow) * D);
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(src + 512 * i));
+      for (int i = 0; i < NV; ++i) nx[i] = xr[lane + 32 * i];
     }
-    __syncwarp();                                              // every lane has its part of the row: the buffer may be refilled
-    const int nrow = row + kLnStages * wstride;
-    if (lane == 0 && nrow < rows) {
-      mbar_arrive_expect_tx(bars + 8 * stage, kRowBytes);
-      bulk_load_row(ring + stage * kRowBytes, x + static_cast<size_t>(nrow) * D, kRowBytes, bars + 8 * stage);
-    }
-    if (++stage == kLnStages) { stage = 0; phase ^= 1u; }
     normalize(g1, b1);
     if (out_f32 != nullptr) {
       float4* o = reinterpret_cast<float4*>(out_f32 + static_cast<size_t>(row) * D);
@@ -106,138 +73,90 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g1, cons
 #pragma unroll
       for (int i = 0; i < NV; ++i) o[lane + 32 * i] = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = nx[i];
   }
-}
-
-template <int NV>
-static cudaError_t launch_ln(const float* x, const float* g1, const float* b1, float* out_f32, __nv_bfloat16* out_bf16,
-                             const float* g2, const float* b2, int rows, float eps, int num_sms, cudaStream_t stream) {
-  constexpr int kSmem = kLnWarps * kLnStages * (128 * NV * 4 + 8);
-  static DeviceOnce attr_once;
-  if (attr_once.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(layernorm_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return e;
-    attr_once.set();
-  }
-  const int need = (rows + kLnWarps - 1) / kLnWarps;
-  const int cap = num_sms * 2;                                 // two resident CTAs per SM at d = 1024 (2 x 96 KB of row buffers)
-  layernorm_kernel<NV><<<need < cap ? need : cap, 32 * kLnWarps, kSmem, stream>>>(x, g1, b1, out_f32, out_bf16, g2, b2, rows, eps);
-  return cudaGetLastError();
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16,
                              const float* gamma2, const float* beta2, int rows, int d, float eps, cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
-  if (reinterpret_cast<uintptr_t>(x) & 15u) return cudaErrorInvalidValue;      // bulk copies want 16-byte aligned rows
+  const int wpb = 8;
   int num_sms = 0, dev = 0;                                    // per call: engines on different devices share this code
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  const int need = (rows + wpb - 1) / wpb;
+  const int cap = num_sms * 2;                                 // 2 resident CTAs per SM (16 warps x 2 rows in flight)
   auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
+  const dim3 grid(need < cap ? need : cap), block(32 * wpb);
   switch (d) {
-    case 256: return launch_ln<2>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps, num_sms, stream);
-    case 512: return launch_ln<4>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps, num_sms, stream);
-    case 1024: return launch_ln<8>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps, num_sms, stream);
+    case 256: layernorm_kernel<2><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 512: layernorm_kernel<4><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
+    case 1024: layernorm_kernel<8><<<grid, block, 0, stream>>>(x, gamma, beta, out_f32, ob, gamma2, beta2, rows, eps); break;
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------ conv module middle
 // u: GLU output, bf16 [B, T_max, d].  Frames t >= len[b] read as zero (masked_fill before the
 // depthwise conv); t < 0 is the conv's own zero padding.  BatchNorm(eval) is folded at pack time:
 // w'[j][c] = w[c][j] * gamma/sqrt(var+eps),  shift[c] = (bias - mean) * gamma/sqrt(var+eps) + beta.
-//
-// Persistent CTAs of d/2 threads (two channels each) walk work items (utterance, TT output frames).  The TT + KW - 1 input
-// rows of an item are ONE contiguous block of [B, T_max, d], fetched with a single bulk copy into one of two shared-memory
-// buffers while the previous item is computed: the thread slides a KW-row register window down its two channels (one LDS.32
-// per output frame) and stores bf16x2, a warp covering 128 contiguous bytes.  The version this replaces had every thread
-// request its own TT + KW - 1 rows from L2 (2x read amplification, 1.6 TB/s: 0.31 of the HBM peak).
-constexpr int kDwTT = 16;
-
 template <int KW, int TT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 conv_dw_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ out, const float* __restrict__ w,
-               const float* __restrict__ shift, const int32_t* __restrict__ len, int B, int T_max, int d) {
+               const float* __restrict__ shift, const int32_t* __restrict__ len, int T_max, int d) {
+  // Four channels per thread (8-byte accesses), TT output frames per thread.  All TT + KW - 1 input rows of the
+  // thread are requested before the first one is used (one round trip to L2 / HBM instead of one per few frames:
+  // the earlier four-rows-at-a-time version sat at ~1.4 TB/s); they stay packed (bf16) in registers and are
+  // unpacked into the KW-row sliding window as it advances.
   constexpr int PAD = (KW - 1) / 2;
   constexpr int ROWS = TT + KW - 1;
-  extern __shared__ __align__(128) uint8_t dw_smem[];
-  const uint32_t row_bytes = static_cast<uint32_t>(d) * 2u;
-  const uint32_t buf_bytes = ROWS * row_bytes;
-  const uint32_t bars = smem_u32(dw_smem) + 2 * buf_bytes;
-  const int chunks = (T_max + TT - 1) / TT;
-  const int items = B * chunks;
-  const int c = threadIdx.x * 2;
-  if (threadIdx.x == 0) { mbar_init(bars, 1); mbar_init(bars + 8, 1); fence_barrier_init(); }
-  __syncthreads();
-  auto fetch = [&](int item, int buf) {                         // one thread: the item's rows that exist, at their place in the buffer
-    const int b = item / chunks, t0 = (item % chunks) * TT;
-    const int lo = max(t0 - PAD, 0), hi = min(t0 + TT + PAD, T_max);
-    const uint32_t bytes = static_cast<uint32_t>(hi - lo) * row_bytes;
-    mbar_arrive_expect_tx(bars + 8 * buf, bytes);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dw_smem) + buf * buf_bytes + static_cast<uint32_t>(lo - (t0 - PAD)) * row_bytes),
-                   "l"(u + (static_cast<size_t>(b) * T_max + lo) * d), "r"(bytes), "r"(bars + 8 * buf) : "memory");
-  };
-  if (threadIdx.x == 0) {
-    if (static_cast<int>(blockIdx.x) < items) fetch(blockIdx.x, 0);
-    if (static_cast<int>(blockIdx.x + gridDim.x) < items) fetch(blockIdx.x + gridDim.x, 1);
+  const int b = blockIdx.z;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= d) return;
+  const int t0 = blockIdx.y * TT;
+  const int n = len[b];
+  const __nv_bfloat16* base = u + (static_cast<size_t>(b) * T_max) * d + c;
+  uint2 raw[ROWS];
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    const int t = t0 - PAD + j;
+    raw[j] = (t >= 0 && t < n) ? __ldg(reinterpret_cast<const uint2*>(base + static_cast<size_t>(t) * d)) : make_uint2(0u, 0u);
   }
-  float2 wt[KW];
+  float4 wt[KW];
 #pragma unroll
-  for (int j = 0; j < KW; ++j) wt[j] = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(j) * d + c));
-  const float2 sh = __ldg(reinterpret_cast<const float2*>(shift + c));
-  int k = 0;
-  for (int item = blockIdx.x; item < items; item += gridDim.x, ++k) {
-    const int buf = k & 1;
-    const int b = item / chunks, t0 = (item % chunks) * TT;
-    const int n = len[b];
-    mbar_wait(bars + 8 * buf, (k >> 1) & 1u);
-    const uint32_t base = smem_u32(dw_smem) + buf * buf_bytes + static_cast<uint32_t>(c) * 2u;
-    auto row = [&](int r) -> float2 {                           // buffer row r holds frame t0 - PAD + r; masked / padded frames read as 0
-      const int t = t0 - PAD + r;
-      uint32_t v = 0;
-      if (t >= 0 && t < n) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + static_cast<uint32_t>(r) * row_bytes));
-      return make_float2(bf16_lo(v), bf16_hi(v));
-    };
-    float2 win[KW];
+  for (int j = 0; j < KW; ++j) wt[j] = __ldg(reinterpret_cast<const float4*>(w + static_cast<size_t>(j) * d + c));
+  const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+  auto unpack = [](uint2 v) { return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y)); };
+  float4 win[KW];
 #pragma unroll
-    for (int j = 0; j < KW - 1; ++j) win[j + 1] = row(j);
-    __nv_bfloat16* o = out + (static_cast<size_t>(b) * T_max + t0) * d + c;
+  for (int j = 0; j < KW - 1; ++j) win[j + 1] = unpack(raw[j]);
 #pragma unroll
-    for (int q = 0; q < TT; ++q) {
+  for (int q = 0; q < TT; ++q) {
 #pragma unroll
-      for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
-      win[KW - 1] = row(q + KW - 1);
-      float2 a = sh;
+    for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+    win[KW - 1] = unpack(raw[q + KW - 1]);
+    float4 a = sh;
 #pragma unroll
-      for (int j = 0; j < KW; ++j) { a.x = fmaf(win[j].x, wt[j].x, a.x); a.y = fmaf(win[j].y, wt[j].y, a.y); }
-      if (t0 + q < T_max) *reinterpret_cast<uint32_t*>(o + static_cast<size_t>(q) * d) = pack_bf16x2(swishf_fast(a.x), swishf_fast(a.y));
+    for (int j = 0; j < KW; ++j) {
+      a.x = fmaf(win[j].x, wt[j].x, a.x); a.y = fmaf(win[j].y, wt[j].y, a.y);
+      a.z = fmaf(win[j].z, wt[j].z, a.z); a.w = fmaf(win[j].w, wt[j].w, a.w);
     }
-    __syncthreads();                                            // everyone is done with this buffer
-    const int nxt = item + 2 * gridDim.x;
-    if (threadIdx.x == 0 && nxt < items) fetch(nxt, buf);
+    if (t0 + q < T_max)
+      *reinterpret_cast<uint2*>(out + (static_cast<size_t>(b) * T_max + t0 + q) * d + c) =
+          make_uint2(pack_bf16x2(swishf_fast(a.x), swishf_fast(a.y)), pack_bf16x2(swishf_fast(a.z), swishf_fast(a.w)));
   }
 }
 
 cudaError_t launch_conv_dw(const void* u, void* out, const float* w, const float* shift, const int32_t* enc_len,
                            int B, int T_max, int d, int k, cudaStream_t stream) {
-  if (k != 9 || (d & 63) || d > 1024 || (reinterpret_cast<uintptr_t>(u) & 15u)) return cudaErrorInvalidValue;
-  if (B <= 0 || T_max <= 0) return cudaSuccess;
-  constexpr int TT = kDwTT;
-  const int smem = 2 * (TT + 8) * d * 2 + 16;
-  int num_sms = 0, dev = 0;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  static DeviceOnce attr_once;
-  if (attr_once.pending()) {
-    cudaError_t e = cudaFuncSetAttribute(conv_dw_kernel<9, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (TT + 8) * 1024 * 2 + 16);
-    if (e != cudaSuccess) return e;
-    attr_once.set();
-  }
-  const int items = B * ((T_max + TT - 1) / TT);
-  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
-  const int cap = num_sms * per_sm;
-  conv_dw_kernel<9, TT><<<items < cap ? items : cap, d / 2, smem, stream>>>(static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
-            w, shift, enc_len, B, T_max, d);
+  if (k != 9 || (d & 3)) return cudaErrorInvalidValue;
+  constexpr int TT = 8;
+  const int threads = d / 4 < 256 ? d / 4 : 256;
+  const dim3 block(threads), grid((d / 4 + threads - 1) / threads, (T_max + TT - 1) / TT, B);
+  conv_dw_kernel<9, TT><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(u), static_cast<__nv_bfloat16*>(out),
+            w, shift, enc_len, T_max, d);
   return cudaGetLastError();
 }
 

@@ -76,7 +76,7 @@ struct rs_engine {
   static constexpr int kMaxBatch = 1 << 16;
   struct { const float *c0w, *c0b, *d1w, *d1b, *p1b, *d2w, *d2b, *p2b, *ob; const void *p1w, *p2w, *ow; } sub;
   std::vector<LayerW> layers;
-  struct { const void *enc_w, *out_w, *lstm_w, *pred_w; const float *enc_b, *out_b, *embed, *lstm_b, *pred_b; } dec;
+  struct { const void *enc_w, *out_w, *lstm_w, *pred_w; const float *enc_b, *out_b, *embed, *lstm_b, *pred_b, *gate_tab; } dec;
   void* ws = nullptr;
   size_t ws_bytes = 0;
   int U_cap = 0;
@@ -243,6 +243,7 @@ int bind_weights(rs_engine* e) {
   NEED(e->dec.out_w, "joint.out.w", RS_BF16, NC * Hj); NEED(e->dec.out_b, "joint.out.b", RS_F32, NC);
   NEED(e->dec.embed, "pred.embed", RS_F32, NC * Hp);
   NEED(e->dec.lstm_w, "pred.lstm.w", RS_BF16, 4 * Hp * 2 * Hp); NEED(e->dec.lstm_b, "pred.lstm.b", RS_F32, 4 * Hp);
+  NEED(e->dec.gate_tab, "pred.gate_tab", RS_F32, NC * 4 * Hp);     // W_ih . embed[k] + b_ih + b_hh per token k (decode_spec.cu)
   NEED(e->dec.pred_w, "joint.pred.w", RS_BF16, Hj * Hp); NEED(e->dec.pred_b, "joint.pred.b", RS_F32, Hj);
   return RS_OK;
 }
@@ -440,7 +441,7 @@ int do_greedy(rs_engine* e, const Plan& p, const float* enc, const int32_t* enc_
   RS_TRY(gemm(e, at<void>(e, p.xn), e->dec.enc_w, e->dec.enc_b, nullptr, at<void>(e, p.encp), M, c.joint_hidden, c.d_model,
               RS_EPI_BIAS_F32, 1.f, s));
   mark(e, 4, s);
-  rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b,
+  rs::DecodeArgs da{at<float>(e, p.encp), enc_len, e->dec.out_w, e->dec.out_b, e->dec.embed, e->dec.lstm_w, e->dec.lstm_b, e->dec.gate_tab,
                     e->dec.pred_w, e->dec.pred_b, tokens, frames, ntok, p.B, T_max, c.joint_hidden, c.pred_hidden,
                     c.vocab_size, U_max, c.max_symbols};
   // One decode kernel for every batch size (windowed, weights-stationary, joint on tcgen05: decode_spec.cu): an utterance's
@@ -796,8 +797,7 @@ int rs_debug_decode_cycles(rs_engine* e, int B, int L_max, int U_max, int64_t* o
   if (!e || !out8) return RS_ERR_INVALID_ARG;
   Plan p = make_plan(e, B, L_max, U_max);
   RS_CUDA(e, cudaDeviceSynchronize());
-  const size_t off = p.dec_ws + static_cast<size_t>(2) * B * e->cfg.pred_hidden * 4 + static_cast<size_t>(B) * e->cfg.joint_hidden * 4 +
-                     static_cast<size_t>(3) * B * 8 + 64;
+  const size_t off = p.dec_ws + rs::rnnt_spec_prof_offset(B, e->cfg.joint_hidden, e->cfg.pred_hidden);
   RS_CUDA(e, cudaMemcpy(out8, static_cast<char*>(e->ws) + off, 96, cudaMemcpyDeviceToHost));
   return RS_OK;
 }

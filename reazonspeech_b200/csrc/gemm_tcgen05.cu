@@ -47,7 +47,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int kTmemCols = 2 * BN;                       // power of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * (32 * 36 * 4 + 512) /*epilogue staging*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 32 * 36 * 4 * 8 /*epilogue staging*/;
 };
 
 // Fused epilogue of one 32-row x 32-column chunk (one epilogue warp): bias, activation / GLU / residual, store.
@@ -57,8 +57,8 @@ struct GemmCfg {
 // bf16: 8 rows x 64 B), and the residual is read -- and prefetched during the MMAs -- in that same
 // coalesced ownership.
 constexpr int kStageLd = 36;                                   // floats per staged row (144 B: 16 B-aligned, conflict-free)
-constexpr int kBiasSlotBytes = 512;                            // the bias of the warp's (up to) four chunks of a tile, read back as broadcasts
-constexpr int kStageBytesPerWarp = 32 * kStageLd * 4 + kBiasSlotBytes;
+constexpr int kStageBytesPerWarp = 32 * kStageLd * 4;
+constexpr int kStageBytesTotal = kEpiWarps * kStageBytesPerWarp;
 
 __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int tile_row0, int lane, int col0, int bt, float4 (&rr)[8]) {
   if (on) {
@@ -73,16 +73,19 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
 
 // EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT.
 // (One kernel with every path spilled registers in the common ones: 166 -> 168 registers + a stack frame, GEMMs 10-20 % slower.)
-// bias_s: the chunk's 32 bias values in shared memory (zeros without a bias), read as broadcasts.
 template <int EG>
-__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], const float* bias_s, float* stage, int tile_row0, int lane,
+__device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
                                                int col0, int bt, const float4 (&rr)[8]) {
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);
-    v[4 * j] = __uint_as_float(r[4 * j]) + b.x; v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z; v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
   }
   const size_t col_off = static_cast<size_t>(bt) * p.out_col_stride;
   uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
@@ -289,17 +292,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
       const int bt = tile / tiles_per_batch, tl = tile % tiles_per_batch;
       const int m0 = (tl / num_n) * BM, n0 = (tl % num_n) * BN;
       const int tile_row0 = m0 + q * 32;
-      // residual of the first chunk and the bias of all the warp's chunks are fetched while the tile's MMAs are still running
+      // residual of the first chunk is fetched while the tile's MMAs are still running
       const bool pre = p.epilogue == RS_EPI_RESID_F32;
       float4 rr[8], cur[8];
       resid_prefetch(p, pre && n0 + half * 32 < p.N, tile_row0, lane, n0 + half * 32, bt, rr);
-      float* bias_s = stage + 32 * kStageLd;
-#pragma unroll
-      for (int c = 0; c < (BN + 63) / 64; ++c) {
-        const int col = n0 + (half + 2 * c) * 32 + lane;
-        bias_s[c * 32 + lane] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + bt * p.bias_stride + col) : 0.f;
-      }
-      __syncwarp();
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -311,8 +307,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         resid_prefetch(p, pre && chunk + 2 < BN / 32 && col0 + 64 < p.N, tile_row0, lane, col0 + 64, bt, rr);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
-        tmem_ld_wait(r);
-        epilogue_store<EG>(p, r, bias_s + (chunk >> 1) * 32, stage, tile_row0, lane, col0, bt, cur);
+        tmem_ld_wait();
+        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -353,7 +349,7 @@ struct Gemm2Cfg {
   static constexpr int kBHalfBytes = (BN / 2) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBHalfBytes;
   static constexpr int kStages = (BN == 256) ? 5 : 7;
-  static constexpr int kStagingPerWarp = EG == 2 ? 2 * kReduceBufBytes : kStageBytesPerWarp;    // EG 2 keeps its bias in registers: no room for the slot
+  static constexpr int kStagingPerWarp = EG == 2 ? 2 * kReduceBufBytes : kStageBytesPerWarp;
   static constexpr int kStagingBytes = kEpiWarps * kStagingPerWarp;      // multiple of 1024: follows the operand ring, 1024-aligned
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -467,47 +463,23 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       const uint32_t acc_phase = (it >> 1) & 1u;
       const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM, n0 = (tile % num_n) * BN;
       const int tile_row0 = m0 + q * 32;
-      // the bias of the warp's four chunks -> its shared slot (and, EG 3, the residual of the first chunk -> registers) while the MMAs run
-      constexpr int kChunks = BN / 64;
-      [[maybe_unused]] float* bias_s = stage + 32 * kStageLd;
-      [[maybe_unused]] float4 rr[8], cur[8], bn[8], bc[8];      // EG 3: residual; EG 2: bias of the next / current chunk
-      auto bias_regs = [&](int col0, float4 (&b)[8]) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) b[j] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
       if constexpr (EG == 2) {
-        bias_regs(n0 + half * 32, bn);
-      } else {
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c)
-          bias_s[c * 32 + lane] = p.bias != nullptr ? __ldg(p.bias + n0 + (half + 2 * c) * 32 + lane) : 0.f;
-        if constexpr (EG == 3) resid_prefetch(p, true, tile_row0, lane, n0 + half * 32, 0, rr);
-        __syncwarp();
-      }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
-      // two register sets: chunk c + 1 leaves tensor memory while chunk c is processed
-      uint32_t ra[32], rb[32];
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 32;
-      tmem_ld_32x32(t_addr, ra);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int col0 = n0 + (half + 2 * c) * 32;
-        uint32_t (&r)[32] = (c & 1) ? rb : ra;
-        uint32_t (&rn)[32] = (c & 1) ? ra : rb;
-        tmem_ld_wait(r);
-        if (c + 1 < kChunks) tmem_ld_32x32(t_addr + (c + 1) * 64, rn);
-        if constexpr (EG == 2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bc[j] = bn[j];
-          if (c + 1 < kChunks) bias_regs(col0 + 64, bn);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
+#pragma unroll 1
+        for (int chunk = half; chunk < BN / 32; chunk += 2, nbuf ^= 1u) {
+          const int col0 = n0 + chunk * 32;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
           if (lane == 0) bulk_wait_group_read<1>();             // the buffer written two chunks ago has been read out
           __syncwarp();
+          tmem_ld_wait();
           uint8_t* buf = reinterpret_cast<uint8_t*>(stage) + nbuf * kReduceBufBytes + lane * 128;
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {                          // lane = row; 16-byte chunk j of the row sits at j ^ (row & 7)
-            const float4 b = bc[j];
+            const float4 b = p.bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4*>(buf + ((j ^ (lane & 7)) << 4)) =
                 make_float4(p.alpha * (__uint_as_float(r[4 * j]) + b.x), p.alpha * (__uint_as_float(r[4 * j + 1]) + b.y),
                             p.alpha * (__uint_as_float(r[4 * j + 2]) + b.z), p.alpha * (__uint_as_float(r[4 * j + 3]) + b.w));
@@ -518,14 +490,24 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             tma_reduce_add_2d(&tm_o, smem_u32(stage) + nbuf * kReduceBufBytes, col0, tile_row0);
             bulk_commit_group();
           }
-          nbuf ^= 1u;
-        } else {
-          if constexpr (EG == 3) {
+        }
+      } else {
+        const bool pre = p.epilogue == RS_EPI_RESID_F32;
+        float4 rr[8], cur[8];
+        resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
+#pragma unroll 1
+        for (int chunk = half; chunk < BN / 32; chunk += 2) {
+          const int col0 = n0 + chunk * 32;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-            resid_prefetch(p, c + 1 < kChunks, tile_row0, lane, col0 + 64, 0, rr);
-          }
-          epilogue_store<EG>(p, r, bias_s + c * 32, stage, tile_row0, lane, col0, 0, cur);
+          for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+          resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+          tmem_ld_wait();
+          epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
         }
       }
       tcgen05_fence_before();
@@ -666,7 +648,6 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   // residual added in place: handed to the memory system as a TMA reduce-add (see Gemm2Cfg)
   const int ldo = g.ldo > 0 ? g.ldo : g.N;
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == g.out && ldo % 4 == 0) return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
-  if (g.epilogue == RS_EPI_RESID_F32) return launch_2cta_eg<BN, 3>(g, num_sms, stream, err);   // residual from another buffer: read into registers
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
     default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);

@@ -70,6 +70,7 @@ struct DecodeArgs {
   const float* embed;         // f32 [V+1, Hp]
   const void* w_lstm;         // bf16 [4*Hp, 2*Hp]  (W_ih | W_hh, gate order i,f,g,o)
   const float* b_lstm;        // f32 [4*Hp]  (b_ih + b_hh)
+  const float* gate_tab;      // f32 [V+1, 4*Hp]: W_ih . embed[k] + b_ih + b_hh (the input half of the gates, per token)
   const void* w_pred;         // bf16 [Hj, Hp]
   const float* b_pred;        // f32 [Hj]
   int32_t* tokens; int32_t* frames; int32_t* n_tok;
@@ -77,6 +78,7 @@ struct DecodeArgs {
 };
 // windowed (kFrames per iteration) persistent decode, joint on tcgen05 (decode_spec.cu); workspace from rnnt_spec_workspace_bytes()
 size_t rnnt_spec_workspace_bytes(int B, int Hj, int Hp, int num_sms);
+size_t rnnt_spec_prof_offset(int B, int Hj, int Hp);        // where the kernel's 12 cycle counters sit inside that workspace
 cudaError_t launch_rnnt_greedy_spec(const DecodeArgs& a, void* workspace, int num_sms, cudaStream_t stream);
 
 // norm_audio on the device: polyphase resampling to 16 kHz + channel average + transcribe()'s zero padding (resample.cu)

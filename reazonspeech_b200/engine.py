@@ -182,6 +182,10 @@ def pack_weights(sd: StateDict, cfg: ModelConfig) -> Dict[str, torch.Tensor]:
     out["pred.embed"] = f32(sd["decoder.prediction.embed.weight"])
     out["pred.lstm.w"] = bf(torch.cat([sd[l + "weight_ih_l0"], sd[l + "weight_hh_l0"]], 1))
     out["pred.lstm.b"] = f32(sd[l + "bias_ih_l0"] + sd[l + "bias_hh_l0"])
+    # the input half of the LSTM gates is a function of the token alone: one row per token (decode_spec.cu), from the same
+    # bf16-rounded W_ih the kernels multiply with, accumulated in fp32
+    w_ih = sd[l + "weight_ih_l0"].to(torch.bfloat16).to(torch.float32)
+    out["pred.gate_tab"] = f32(out["pred.embed"] @ w_ih.T + out["pred.lstm.b"])
     out["joint.pred.w"] = bf(sd["joint.pred.weight"]); out["joint.pred.b"] = f32(sd["joint.pred.bias"])
     return out
 

@@ -180,7 +180,7 @@ def test_alsd_full_size_matches_the_oracle():
 
 
 def test_long_form_clip_at_full_size(full):
-    """SURVEY.md section 8(f).2 at the production size: a 150 s clip (1 882 encoder frames = 15 query tiles, ~95 k mel frames) in
+    """SURVEY.md section 8(f).2 at the production size: a 150 s clip (1 888 encoder frames = 15 query tiles, ~95 k mel frames) in
     ONE call next to a short one, as the reference feeds audio of any length to the model (transcribe.py:44-53): encoder within
     2e-2 of the fp32 oracle over the clip and for its worst frame, decisions under the noise-aware bar of tests/parity.py."""
     cfg, sd, eng = full
@@ -190,6 +190,6 @@ def test_long_form_clip_at_full_size(full):
     enc, enc_len = eng.encode(mel, mel_len)
     tokens, frames, ntok = [a.cpu() for a in eng.transcribe_device(x, lens)]
     enc = enc.cpu()
-    assert int(enc_len[0]) == cfg.enc_frames(len(waves[0])) == 1882
+    assert int(enc_len[0]) == cfg.enc_frames(len(waves[0])) == 1888
     for i, w in enumerate(waves):
         _oracle_check(cfg, sd, w, enc[i], int(enc_len[i]), tokens[i], frames[i], int(ntok[i]), f"long{i}")
