@@ -55,7 +55,16 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-__device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// 1 / (1 + 2^(-x log2 e)) on the two special-function instructions alone (ex2.approx.ftz, rcp.approx.ftz: 5 instructions
+// with the swish multiply).  __expf / __fdividef wrap the same two in range fix-ups for denormal results (8 instructions);
+// here a denormal e^-x flushes to 0 (sigmoid = 1 exactly) and an overflowing one gives rcp(inf) = 0, both the right limits.
+// The GEMM epilogues that apply Swish / GLU to every output element are bound by instruction issue, not by memory.
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 __device__ __forceinline__ float sigmoidf_accurate(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float swishf_fast(float x) { return x * sigmoidf_fast(x); }
 

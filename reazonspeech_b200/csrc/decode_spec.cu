@@ -62,10 +62,8 @@ constexpr int kBarStride = 32;            // unsigned ints between counters
 __device__ __forceinline__ void sp_grid_barrier(unsigned int* counters, unsigned int& round, unsigned int nblocks) {
   __syncthreads();
   ++round;
-  if (threadIdx.x == 0) {
-    __threadfence();
+  if (threadIdx.x == 0)     // release at gpu scope: covers the other threads' writes too (they reached thread 0 through the CTA barrier above)
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + (blockIdx.x % kBarCounters) * kBarStride) : "memory");
-  }
   if (threadIdx.x < kBarCounters) {
     const unsigned int c = threadIdx.x;
     const unsigned int arrivals = (nblocks + kBarCounters - 1 - c) / kBarCounters;      // CTAs with index % kBarCounters == c

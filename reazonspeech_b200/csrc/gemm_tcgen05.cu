@@ -73,7 +73,8 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
 
 // EG: epilogue group compiled into a kernel instance -- 0: the common epilogues, 1: RS_EPI_QKV_VT.
 // (One kernel with every path spilled registers in the common ones: 166 -> 168 registers + a stack frame, GEMMs 10-20 % slower.)
-template <int EG>
+// kResid: the instance may be asked for RS_EPI_RESID_F32 with the residual in rr (otherwise rr is never read).
+template <int EG, bool kResid>
 __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
                                                int col0, int bt, const float4 (&rr)[8]) {
   float v[32];
@@ -181,7 +182,7 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
         *reinterpret_cast<float4*>(stage + lane * LD + 4 * j) =
             make_float4(p.alpha * v[4 * j], p.alpha * v[4 * j + 1], p.alpha * v[4 * j + 2], p.alpha * v[4 * j + 3]);
       __syncwarp();
-      const bool add = p.epilogue == RS_EPI_RESID_F32;
+      const bool add = kResid && p.epilogue == RS_EPI_RESID_F32;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {                            // 4 rows x 128 B per instruction
         const int rl = i * 4 + (lane >> 3), cw = (lane & 7) * 4;
@@ -308,7 +309,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
         tmem_ld_wait();
-        epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, bt, cur);
+        epilogue_store<EG, true>(p, r, stage, tile_row0, lane, col0, bt, cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -395,6 +396,23 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     fence_barrier_init();
   }
   cluster_sync_all();                                        // peer barriers exist before any remote arrive / 2-SM alloc
+  // TMA producer state (lane 0 of warp 0, both CTAs).  The first ring of loads goes out BETWEEN the two set-up barriers: the
+  // tensor-memory allocation and the second cluster barrier (~0.5 us) then run under the first operands' DRAM latency (~1.8 us).
+  int p_tile = cid, p_kb = 0, p_stage = 0; uint32_t p_phase = 0;
+  auto produce = [&](int budget) {
+    while (p_tile < num_tiles && budget-- > 0) {
+      const int m0 = (p_tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
+      const int n0 = (p_tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
+      mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
+      tma_load_2d_2sm(smem_a(p_stage), &tm_a, p_kb * BK, m0, full_bar(p_stage));
+      tma_load_2d_2sm(smem_b(p_stage), &tm_b, p_kb * BK, n0, full_bar(p_stage));
+      if (leader) mbar_arrive_expect_tx(full_bar(p_stage), 2 * Cfg::kStageBytes);
+      else mbar_arrive_remote(full_bar(p_stage), 0);
+      if (++p_stage == Cfg::kStages) { p_stage = 0; p_phase ^= 1u; }
+      if (++p_kb == num_k) { p_kb = 0; p_tile += ncl; }
+    }
+  };
+  if (warp == 0 && lane == 0) produce(Cfg::kStages);
   if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
   tcgen05_fence_before();
   cluster_sync_all();
@@ -404,21 +422,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = cid; tile < num_tiles; tile += ncl) {
-        const int m0 = (tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
-        const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          tma_load_2d_2sm(smem_a(stage), &tm_a, kb * BK, m0, full_bar(stage));
-          tma_load_2d_2sm(smem_b(stage), &tm_b, kb * BK, n0, full_bar(stage));
-          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          else mbar_arrive_remote(full_bar(stage), 0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
-    }
+    if (lane == 0) produce(0x7fffffff);
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -492,22 +496,23 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           }
         }
       } else {
-        const bool pre = p.epilogue == RS_EPI_RESID_F32;
-        float4 rr[8], cur[8];
-        resid_prefetch(p, pre, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
+        [[maybe_unused]] float4 rr[8], cur[8];                                // EG 3 only: the residual, one chunk ahead
+        if constexpr (EG == 3) resid_prefetch(p, true, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
 #pragma unroll 1
         for (int chunk = half; chunk < BN / 32; chunk += 2) {
           const int col0 = n0 + chunk * 32;
+          if constexpr (EG == 3) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cur[j] = rr[j];
-          resid_prefetch(p, pre && chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
+            for (int j = 0; j < 8; ++j) cur[j] = rr[j];
+            resid_prefetch(p, chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
+          }
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
           tmem_ld_wait();
-          epilogue_store<EG>(p, r, stage, tile_row0, lane, col0, 0, cur);
+          epilogue_store<EG, EG == 3>(p, r, stage, tile_row0, lane, col0, 0, cur);
         }
       }
       tcgen05_fence_before();
@@ -648,6 +653,7 @@ static cudaError_t launch_2cta(const GemmArgs& g, int num_sms, cudaStream_t stre
   // residual added in place: handed to the memory system as a TMA reduce-add (see Gemm2Cfg)
   const int ldo = g.ldo > 0 ? g.ldo : g.N;
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == g.out && ldo % 4 == 0) return launch_2cta_eg<BN, 2>(g, num_sms, stream, err);
+  if (g.epilogue == RS_EPI_RESID_F32) return launch_2cta_eg<BN, 3>(g, num_sms, stream, err);   // residual from another buffer: read into registers
   switch (epilogue_group(g.epilogue)) {
     case 1: return launch_2cta_eg<BN, 1>(g, num_sms, stream, err);
     default: return launch_2cta_eg<BN, 0>(g, num_sms, stream, err);
