@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU call of the development cycle:  gpurun --timeout 1800 -- 'bash scripts/gpu_cycle.sh <tag> [tests] [calib] [bench] [sanitize] [ncu:<regex>]'
+# One GPU call of the development cycle:  gpurun --timeout 1800 -- 'bash scripts/gpu_cycle.sh <tag> [tests] [calib] [bench] [sanitize] [ncu:<regex>[:<skip>[:<count>]]] [launches]'
 # Everything lands in gpurun_out/<tag>_*.  Sections run in the order calib, tests, bench, sanitize, profiles regardless of argument order.
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 tag=$1; shift
@@ -39,9 +39,10 @@ want=sanitize; if has "${args[@]}"; then
 fi
 for a in "${args[@]}"; do
   case "$a" in ncu:*)
-    pat=${a#ncu:}; name=$(echo "$pat" | tr -c 'A-Za-z0-9' '_')
-    echo "=== ncu --set full on $pat"
-    timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 3 -f -o gpurun_out/${tag}_ncu_$name python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/${tag}_ncu_$name.log 2>&1; tail -2 gpurun_out/${tag}_ncu_$name.log;;
+    spec=${a#ncu:}; IFS=: read -r pat skip count <<< "$spec"; skip=${skip:-2}; count=${count:-3}     # ncu:<regex>[:<skip>[:<count>]]
+    name=$(echo "$pat" | tr -c 'A-Za-z0-9' '_')
+    echo "=== ncu --set full on $pat (skip $skip, capture $count)"
+    timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:$pat -s $skip -c $count -f -o gpurun_out/${tag}_ncu_$name python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/${tag}_ncu_$name.log 2>&1; tail -2 gpurun_out/${tag}_ncu_$name.log;;
   launches)
     echo "=== ncu launch list"
     timeout -k 10 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/${tag}_launches.log 2>&1; tail -1 gpurun_out/${tag}_launches.log;;

@@ -52,7 +52,7 @@ def test_blank_always_wins_and_small_output_buffer(tiny_cfg, tiny_sd):
     assert frames[0, :7].cpu().tolist() == [0] * 7 and tokens.shape[1] == 7
 
 
-@pytest.mark.parametrize("B", [1, 3, 5, 33, 70])
+@pytest.mark.parametrize("B", [1, 3, 5, 33, 70, 130])
 def test_windowed_decode_equals_the_sequential_loop(tiny_engine, tiny_cfg, tiny_sd, B):
     """The windowed kernel (4 frames per iteration, utterance groups x vocabulary slices) against the oracle's one-decision-
     at-a-time loop on random encoder outputs, ragged lengths (incl. a zero-length utterance), batch sizes that are not
