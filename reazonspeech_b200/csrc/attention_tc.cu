@@ -258,7 +258,17 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
     {
       const int n_chunks = p.n_rel_pad >> 5;
       const int c_lo = hf == 0 ? 0 : (n_chunks + 1) / 2, c_hi = hf == 0 ? (n_chunks + 1) / 2 : n_chunks;
-      const float* bias = p.bd_bias + h * p.n_rel_pad;
+      // The head's positional bias (n_rel_pad floats) is parked in the 16 spare bytes at the end of the BD rows -- four floats
+      // in the padding of row k -- and read back below as broadcasts: fetching it from global memory inside the drain loop put
+      // an L1 / L2 round trip in front of every chunk (16 % of the kernel's stall samples, profiles/r02_attention_ncu.md).
+      {
+        const int st = threadIdx.x - 32;
+        if (st < (p.n_rel_pad >> 2))
+          *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s_bd) + st * (kBdPitch * 2) + kNrelPadMax * 2) =
+              __ldg(reinterpret_cast<const float4*>(p.bd_bias + h * p.n_rel_pad) + st);
+        softmax_bar();
+      }
+      const uint8_t* bias_rows = reinterpret_cast<const uint8_t*>(s_bd) + kNrelPadMax * 2;
       mbar_wait(bar_bd, 0);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -269,12 +279,13 @@ local_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qk, const __gri
         uint4* dst = reinterpret_cast<uint4*>(s_bd + r * kBdPitch + ch * 32);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 ba = *reinterpret_cast<const float4*>(bias_rows + (ch * 8 + q4 * 2) * (kBdPitch * 2));
+          const float4 bb = *reinterpret_cast<const float4*>(bias_rows + (ch * 8 + q4 * 2 + 1) * (kBdPitch * 2));
+          const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + ch * 32 + q4 * 8 + 2 * e));
-            w[e] = pack_f16x2((__uint_as_float(v[q4 * 8 + 2 * e]) + b2.x) * scale2, (__uint_as_float(v[q4 * 8 + 2 * e + 1]) + b2.y) * scale2);
-          }
+          for (int e = 0; e < 4; ++e)
+            w[e] = pack_f16x2((__uint_as_float(v[q4 * 8 + 2 * e]) + bq[2 * e]) * scale2, (__uint_as_float(v[q4 * 8 + 2 * e + 1]) + bq[2 * e + 1]) * scale2);
           dst[q4] = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
