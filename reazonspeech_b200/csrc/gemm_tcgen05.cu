@@ -105,7 +105,8 @@ __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t 
       for (int i = 0; i < 4; ++i) {
         const int dim = i * 8 + (lane >> 2), f0 = (lane & 3) * 8;
         const uint4 a = *reinterpret_cast<const uint4*>(st16 + dim * 40 + f0);
-        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(col0 - p.split + dim) * p.ld2 + tile_row0 + f0) = a;
+        if (tile_row0 + f0 < p.M)      // M is a multiple of 8 (checked at launch): frames beyond it belong to another row range of the same buffer
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(col0 - p.split + dim) * p.ld2 + tile_row0 + f0) = a;
       }
       __syncwarp();
       return;
@@ -670,8 +671,8 @@ cudaError_t launch_gemm(const GemmArgs& g, int num_sms, cudaStream_t stream, cha
     return cudaErrorInvalidValue;
   }
   if (g.epilogue == RS_EPI_RESID_F32 && g.resid == nullptr) { snprintf(err, 256, "gemm: residual epilogue without resid"); return cudaErrorInvalidValue; }
-  if (g.epilogue == RS_EPI_QKV_VT && (g.out2 == nullptr || g.split % 32 || g.ld2 % 8 || g.ld2 < ((g.M + 255) / 256) * 256 || g.n_batch > 1)) {
-    snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, ld2 >= M rounded up to 256");
+  if (g.epilogue == RS_EPI_QKV_VT && (g.out2 == nullptr || g.split % 32 || g.ld2 % 8 || g.M % 8 || g.ld2 < g.M || g.n_batch > 1)) {
+    snprintf(err, 256, "gemm: RS_EPI_QKV_VT needs out2, split %% 32 == 0, ld2 %% 8 == 0, M %% 8 == 0, ld2 >= M");
     return cudaErrorInvalidValue;
   }
   // kernel choice depends on N only (never on M): a row's result must not depend on the batch it sits in
