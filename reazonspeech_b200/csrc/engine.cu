@@ -101,10 +101,6 @@ struct rs_engine {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[kCopyChunks + 1] = {};
   bool copy_ok = false;
-  // the Conformer layers of a batch run as two row ranges (utterance halves) on two streams: see do_encode
-  cudaStream_t half_stream[2] = {nullptr, nullptr};
-  cudaEvent_t fork_ev = nullptr, join_ev[2] = {nullptr, nullptr};
-  bool split_ok = false;
 };
 
 namespace {
@@ -390,89 +386,46 @@ int do_encode(rs_engine* e, const Plan& p, const float* mel, const int32_t* mel_
   RS_TRY(gemm(e, at<void>(e, p.sub4), e->sub.ow, e->sub.ob, nullptr, x, M, d, p.F3 * C, RS_EPI_BIAS_F32, c.xscale, s));
   mark(e, 2, s);
   // ---- Conformer layers
-  // Every activation is row-major [M, ...] with an utterance's rows contiguous, and nothing in a layer mixes utterances: the
-  // layers of utterances [0, B/2) and [B/2, B) are two independent kernel chains over disjoint row ranges of the SAME buffers.
-  // They are issued on two streams.  Each persistent kernel has a ~3 us start-up, a last wave that leaves a third of the SMs
-  // idle (2.65 waves at N = 1024) and an epilogue tail; with a second, independent chain resident the SMs one kernel leaves
-  // idle are picked up by the other chain's next kernel instead of waiting for the stream's successor.  Results are bit-identical
-  // to the one-chain order (a row's arithmetic never depends on M).  The per-kernel timing passes (rs_enable_kernel_timing /
-  // rs_enable_gemm_timing) keep ONE chain, so their event pairs time kernels that have the GPU to themselves.
-  const int n_chains = (e->split_ok && B >= 4 && n_layers > 0 && !e->ktiming && !e->gemm_timing) ? 2 : 1;
-  if (n_chains == 2) {
-    RS_CUDA(e, cudaEventRecord(e->fork_ev, s));
-    for (int h = 0; h < 2; ++h) RS_CUDA(e, cudaStreamWaitEvent(e->half_stream[h], e->fork_ev, 0));
+  void* xn = at<void>(e, p.xn); void* hb = at<void>(e, p.hbuf); void* ab = at<void>(e, p.abuf); void* cb = at<void>(e, p.cbuf);
+  if (n_layers > 0) {
+    const LayerW& L0 = e->layers[0];
+    RS_K(e, rs::launch_layernorm(x, L0.ln_ff1_g, L0.ln_ff1_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
   }
-  struct Chain { int b0, nb; cudaStream_t st; };
-  Chain chains[2];
-  chains[0] = {0, n_chains == 2 ? (B + 1) / 2 : B, n_chains == 2 ? e->half_stream[0] : s};
-  chains[1] = {chains[0].nb, B - chains[0].nb, e->half_stream[1]};
-  auto layer = [&](int i, const Chain& ch) -> int {      // i == -1: the first norm_feed_forward1
-    cudaStream_t st = ch.st;
-    e->cur_stream = st;
-    const size_t r0 = static_cast<size_t>(ch.b0) * p.T3;
-    const int Mh = ch.nb * p.T3;
-    float* xh = x + r0 * d;
-    auto* xn = at<uint16_t>(e, p.xn) + r0 * d;
-    auto* hb = at<uint16_t>(e, p.hbuf) + r0 * (static_cast<size_t>(c.d_ff) > 3 * static_cast<size_t>(d) ? c.d_ff : 3 * d);
-    auto* ab = at<uint16_t>(e, p.abuf) + r0 * d;
-    auto* cb = at<uint16_t>(e, p.cbuf) + r0 * d;
-    auto* vt = at<uint16_t>(e, p.vt) + r0;                 // V^T: column = row index
-    const int32_t* len_h = enc_len + ch.b0;
-    if (i < 0) {
-      const LayerW& L0 = e->layers[0];
-      RS_K(e, rs::launch_layernorm(xh, L0.ln_ff1_g, L0.ln_ff1_b, nullptr, xn, nullptr, nullptr, Mh, d, c.ln_eps, st), 1);
-      return RS_OK;
-    }
-    auto resid_gemm = [&](const void* a, const void* w, const float* bias, int K, float alpha) -> int {
-      return gemm(e, a, w, bias, xh, xh, Mh, d, K, RS_EPI_RESID_F32, alpha, st);
-    };
+  auto resid_gemm = [&](const void* a, const void* w, const float* bias, int K, float alpha) -> int {
+    return gemm(e, a, w, bias, x, x, M, d, K, RS_EPI_RESID_F32, alpha, s);
+  };
+  for (int i = 0; i < n_layers; ++i) {
     const LayerW& L = e->layers[i];
-    // NOTE hb is addressed with the row pitch of the call that writes / reads it: FFN hidden [Mh, d_ff], QKV [Mh, 3d]; a chain's
-    // region starts at r0 * max(d_ff, 3d) elements, which both pitches fit into
-    RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, Mh, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, st));
+    char layer_name[32];
+    snprintf(layer_name, sizeof layer_name, "rs::conformer_layer[%d]", i);
+    Nvtx layer_range(layer_name);
+    RS_TRY(gemm(e, xn, L.ff1_w1, L.ff1_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
     RS_TRY(resid_gemm(hb, L.ff1_w2, L.ff1_b2, c.d_ff, 0.5f));
-    RS_K(e, rs::launch_layernorm(xh, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, Mh, d, c.ln_eps, st), 1);
+    RS_K(e, rs::launch_layernorm(x, L.ln_att_g, L.ln_att_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     // the relative-position term (q + pos_bias_v) . p[c] is a UMMA inside the attention kernel (attention_tc.cu): no score tensor in HBM
-    rs::AttnArgs aa{hb, L.att_pos, L.att_bdbias, p.n_rel_pad, L.att_u, ab, len_h, ch.nb, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
-    aa.vt = vt; aa.ld_vt = p.ld_vt;
+    rs::AttnArgs aa{hb, L.att_pos, L.att_bdbias, p.n_rel_pad, L.att_u, ab, enc_len, B, p.T3, c.n_heads, d / c.n_heads, c.att_left, c.att_right, c.global_tokens};
+    aa.vt = at<void>(e, p.vt); aa.ld_vt = p.ld_vt;
     {   // q | k row-major, V transposed (keys contiguous) for the attention's P.V product
-      rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, Mh, 3 * d, d, RS_EPI_QKV_VT, 1.f};
-      g.out2 = vt; g.split = 2 * d; g.ld2 = p.ld_vt;
-      RS_TRY(gemm_args(e, g, st));
+      rs::GemmArgs g{xn, L.wqkv, L.bqkv, nullptr, hb, M, 3 * d, d, RS_EPI_QKV_VT, 1.f};
+      g.out2 = at<void>(e, p.vt); g.split = 2 * d; g.ld2 = p.ld_vt;
+      RS_TRY(gemm_args(e, g, s));
     }
-    RS_K(e, rs::launch_attention_tc(aa, st), c.global_tokens > 0 ? 2 : 1);
+    RS_K(e, rs::launch_attention_tc(aa, s), c.global_tokens > 0 ? 2 : 1);
     RS_TRY(resid_gemm(ab, L.wo, L.bo, d, 1.f));
-    RS_K(e, rs::launch_layernorm(xh, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, Mh, d, c.ln_eps, st), 1);
-    RS_TRY(gemm(e, xn, L.pw1_w, L.pw1_b, nullptr, ab, Mh, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f, st));
-    RS_K(e, rs::launch_conv_dw(ab, cb, L.dw_w, L.dw_shift, len_h, ch.nb, p.T3, d, c.conv_kernel, st), 1);
+    RS_K(e, rs::launch_layernorm(x, L.ln_conv_g, L.ln_conv_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.pw1_w, L.pw1_b, nullptr, ab, M, 2 * d, d, RS_EPI_BIAS_GLU_BF16, 1.f, s));
+    RS_K(e, rs::launch_conv_dw(ab, cb, L.dw_w, L.dw_shift, enc_len, B, p.T3, d, c.conv_kernel, s), 1);
     RS_TRY(resid_gemm(cb, L.pw2_w, L.pw2_b, d, 1.f));
-    RS_K(e, rs::launch_layernorm(xh, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, Mh, d, c.ln_eps, st), 1);
-    RS_TRY(gemm(e, xn, L.ff2_w1, L.ff2_b1, nullptr, hb, Mh, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, st));
+    RS_K(e, rs::launch_layernorm(x, L.ln_ff2_g, L.ln_ff2_b, nullptr, xn, nullptr, nullptr, M, d, c.ln_eps, s), 1);
+    RS_TRY(gemm(e, xn, L.ff2_w1, L.ff2_b1, nullptr, hb, M, c.d_ff, d, RS_EPI_BIAS_SWISH_BF16, 1.f, s));
     RS_TRY(resid_gemm(hb, L.ff2_w2, L.ff2_b2, c.d_ff, 0.5f));
     if (i + 1 < n_layers) {   // norm_out chained with the next layer's norm_feed_forward1
       const LayerW& Ln = e->layers[i + 1];
-      RS_K(e, rs::launch_layernorm(xh, L.ln_out_g, L.ln_out_b, xh, xn, Ln.ln_ff1_g, Ln.ln_ff1_b, Mh, d, c.ln_eps, st), 1);
+      RS_K(e, rs::launch_layernorm(x, L.ln_out_g, L.ln_out_b, x, xn, Ln.ln_ff1_g, Ln.ln_ff1_b, M, d, c.ln_eps, s), 1);
     } else {
-      RS_K(e, rs::launch_layernorm(xh, L.ln_out_g, L.ln_out_b, enc + r0 * d, nullptr, nullptr, nullptr, Mh, d, c.ln_eps, st), 1);
-    }
-    return RS_OK;
-  };
-  for (int i = -1; i < n_layers; ++i) {
-    if (i >= 0 || n_layers > 0) {
-      char layer_name[32];
-      snprintf(layer_name, sizeof layer_name, "rs::conformer_layer[%d]", i);
-      Nvtx layer_range(layer_name);
-      for (int h = 0; h < n_chains; ++h)
-        if (chains[h].nb > 0) RS_TRY(layer(i, chains[h]));
+      RS_K(e, rs::launch_layernorm(x, L.ln_out_g, L.ln_out_b, enc, nullptr, nullptr, nullptr, M, d, c.ln_eps, s), 1);
     }
   }
-  if (n_chains == 2) {
-    for (int h = 0; h < 2; ++h) {
-      RS_CUDA(e, cudaEventRecord(e->join_ev[h], e->half_stream[h]));
-      RS_CUDA(e, cudaStreamWaitEvent(s, e->join_ev[h], 0));
-    }
-  }
-  e->cur_stream = s;
   if (n_layers == 0) RS_CUDA(e, cudaMemcpyAsync(enc, x, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, s));
   RS_K(e, rs::launch_zero_pad_rows(enc, enc_len, B, p.T3, d, s), 1);
   return RS_OK;
@@ -540,10 +493,6 @@ int rs_engine_create(const rs_model_config* cfg, const rs_tensor* weights, int n
   e->ev_ok = true;
   for (auto& ev : e->ev) if (cudaEventCreate(&ev) != cudaSuccess) e->ev_ok = false;
   e->copy_ok = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-  e->split_ok = cudaEventCreateWithFlags(&e->fork_ev, cudaEventDisableTiming) == cudaSuccess;
-  for (int h = 0; h < 2; ++h)
-    e->split_ok = e->split_ok && cudaStreamCreateWithFlags(&e->half_stream[h], cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaEventCreateWithFlags(&e->join_ev[h], cudaEventDisableTiming) == cudaSuccess;
   for (auto& ev : e->copy_ev) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) e->copy_ok = false;
   *out = e;
   return RS_OK;
@@ -554,8 +503,6 @@ void rs_engine_destroy(rs_engine* e) {
   if (e->ev_ok) for (auto& ev : e->ev) cudaEventDestroy(ev);
   for (auto& ev : e->copy_ev) if (ev) cudaEventDestroy(ev);
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-  for (int h = 0; h < 2; ++h) { if (e->half_stream[h]) cudaStreamDestroy(e->half_stream[h]); if (e->join_ev[h]) cudaEventDestroy(e->join_ev[h]); }
-  if (e->fork_ev) cudaEventDestroy(e->fork_ev);
   for (auto& ev : e->gemm_ev) cudaEventDestroy(ev);
   for (auto& ev : e->k_ev) cudaEventDestroy(ev);
   cudaFree(e->lm_tickets);
