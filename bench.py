@@ -140,7 +140,7 @@ def python_api_multi_gpu_rtfx(cfg, n_gpus: int, n_clips: int, seconds: float):
     conf = TranscribeConfig(verbose=False)
     transcribe_batch(model, audios, conf)                       # warm-up: workspaces and staging on every device
     t0 = time.perf_counter()
-    res = transcribe_batch(model, audios * 2, conf)
+    res = transcribe_batch(model, audios * 4, conf)              # four engine batches per device
     dt = time.perf_counter() - t0
     return {"value": len(res) * seconds / dt, "unit": UNIT, "clips": len(res), "devices": n_gpus, "seconds": dt,
             "what": "one process, load_model(devices=[0..N-1]) + transcribe_batch(model, audios): numpy clips in, TranscribeResult out"}
@@ -164,7 +164,12 @@ def dist_setup(gpus: int):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        global HOST_GROUP                      # CPU-side rendezvous for the extras during which a rank must leave its GPU alone
+        HOST_GROUP = dist.new_group(backend="gloo")
     return world, rank, local
+
+
+HOST_GROUP = None
 
 
 CPU_CLIPS = 8          # bounded CPU sample: the first clips of the SAME 32 x 30 s set, one transcribe() each (batch = 1)
@@ -445,13 +450,17 @@ def main():
     # other ranks idle at the barrier below -- the call a user makes on an 8-GPU box without torchrun
     api_multi = None
     if world > 1 and not args.no_extras:
+        # The other ranks must not touch their GPUs meanwhile: an NCCL barrier is a kernel spinning on the device, and rank 0's
+        # in-process replica for that device would be time-sliced against it (measured: 8.6 k RTFx instead of 2 x 35 k at two
+        # GPUs).  They wait on the host (gloo) instead.
+        import torch.distributed as dist
         barrier()
         if rank == 0:
             try:
                 api_multi = python_api_multi_gpu_rtfx(eng.cfg, world, B, args.seconds)
             except Exception as exc:
                 api_multi = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-        barrier()
+        dist.barrier(group=HOST_GROUP)
     if rank != 0:
         return
     cpu = None
