@@ -9,6 +9,8 @@
 // channel; the mel patch of the tile sits in shared memory and is read as a warp broadcast.
 // Every stage treats frames at or beyond the utterance's length at that stage as zero, which is
 // what batch=1 execution sees as conv zero-padding (padding invariance, SURVEY.md finding 4).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,6 +27,9 @@ constexpr int kMelOff = 4;    // smem column of mel bin 0 (bin -1 sits at column
 // the 7 x 4 new mel values of a step are fetched with seven 128-bit broadcast loads and kept in registers
 // together with the previous step's last three columns, and conv.0 at f1 = 2*f2-1 is carried over from
 // the previous step: per output 7 LDS.128 + 63 FMA instead of 54 scalar shared loads.
+// LDC: the shared-memory row pitch as a compile-time constant (0: run-time).  With it the 7 row loads of a step are one base
+// register + immediates; the run-time pitch cost an IMAD / LEA pair per load (30 of the 140 instructions of a step).
+template <int LDC>
 __global__ void __launch_bounds__(256)
 sub_conv0_dw1_kernel(const float* __restrict__ mel, const int32_t* __restrict__ mel_len, const float* __restrict__ mel_stats,
                      int F_max, int n_mels, int C,
@@ -37,7 +42,7 @@ sub_conv0_dw1_kernel(const float* __restrict__ mel, const int32_t* __restrict__ 
   const int len1 = conv_len(len0);
   const int len2 = conv_len(len1);
   const int rows = 4 * kSubTT + 3;
-  const int ld = ((n_mels + kMelOff + 4 + 3) / 4) * 4;   // bins -4 .. n_mels+3 addressable, multiple of 4 floats
+  const int ld = LDC > 0 ? LDC : ((n_mels + kMelOff + 4 + 3) / 4) * 4;   // bins -4 .. n_mels+3 addressable, multiple of 4 floats
   const int t0_base = 4 * t2_0 - 3;                      // first mel row needed: 2*(2*t2_0-1)-1
   // The log-mel kernel leaves the features un-normalised next to their per-utterance statistics (logmel.cu): NeMo's
   // per-feature normalisation (x - mean) / (std + eps) and its zero tail (frames >= len read as 0, which is also the
@@ -80,40 +85,46 @@ sub_conv0_dw1_kernel(const float* __restrict__ mel, const int32_t* __restrict__ 
         m[i][3] = 0.f;
       }
       float left[3] = {0.f, 0.f, 0.f};                    // conv.0 at f1 = 2*f2-1 (carried from the previous step)
-      for (int f2 = 0; f2 < F2; ++f2) {
+      // interior frames (all three conv.0 rows exist, F1 == 2 * F2) take a path without the per-element validity selects
+      auto run = [&](auto all_valid) {
+        constexpr bool kAll = decltype(all_valid)::value;
+#pragma unroll 1
+        for (int f2 = 0; f2 < F2; ++f2) {
 #pragma unroll
-        for (int i = 0; i < 7; ++i) {
-          const float4 q = *reinterpret_cast<const float4*>(base + i * ld + 4 * f2);   // bins 4*f2 .. 4*f2+3
-          m[i][3] = q.x; m[i][4] = q.y; m[i][5] = q.z; m[i][6] = q.w;
-          if (f2 == 0) { m[i][2] = 0.f; }
+          for (int i = 0; i < 7; ++i) {
+            const float4 q = *reinterpret_cast<const float4*>(base + i * ld + 4 * f2);   // bins 4*f2 .. 4*f2+3
+            m[i][3] = q.x; m[i][4] = q.y; m[i][5] = q.z; m[i][6] = q.w;
+          }
+          // conv.0 at f1 = 2*f2 (bins 4f2-1..4f2+1 -> m cols 2..4) and f1 = 2*f2+1 (bins 4f2+1..4f2+3 -> m cols 4..6)
+          float mid[3], right[3];
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt) {
+            float a0 = bias0, a1 = bias0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                a0 = fmaf(m[2 * dt + i][2 + j], k0[i * 3 + j], a0);
+                a1 = fmaf(m[2 * dt + i][4 + j], k0[i * 3 + j], a1);
+              }
+            mid[dt] = (kAll || (tv[dt] && 2 * f2 < F1)) ? fmaxf(a0, 0.f) : 0.f;
+            right[dt] = (kAll || (tv[dt] && 2 * f2 + 1 < F1)) ? fmaxf(a1, 0.f) : 0.f;
+          }
+          float a = biasd;
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt) {
+            a = fmaf(left[dt], kd[dt * 3 + 0], a);
+            a = fmaf(mid[dt], kd[dt * 3 + 1], a);
+            a = fmaf(right[dt], kd[dt * 3 + 2], a);
+            left[dt] = right[dt];
+          }
+          orow[static_cast<size_t>(f2) * C] = __float2bfloat16_rn(a);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) { m[i][2] = m[i][6]; }  // bin 4*f2+3 becomes bin 4*(f2+1)-1 (bin -1 of the first step is the zero set above)
         }
-        // conv.0 at f1 = 2*f2 (bins 4f2-1..4f2+1 -> m cols 2..4) and f1 = 2*f2+1 (bins 4f2+1..4f2+3 -> m cols 4..6)
-        float mid[3], right[3];
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-          float a0 = bias0, a1 = bias0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              a0 = fmaf(m[2 * dt + i][2 + j], k0[i * 3 + j], a0);
-              a1 = fmaf(m[2 * dt + i][4 + j], k0[i * 3 + j], a1);
-            }
-          mid[dt] = (tv[dt] && 2 * f2 < F1) ? fmaxf(a0, 0.f) : 0.f;
-          right[dt] = (tv[dt] && 2 * f2 + 1 < F1) ? fmaxf(a1, 0.f) : 0.f;
-        }
-        float a = biasd;
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-          a = fmaf(left[dt], kd[dt * 3 + 0], a);
-          a = fmaf(mid[dt], kd[dt * 3 + 1], a);
-          a = fmaf(right[dt], kd[dt * 3 + 2], a);
-          left[dt] = right[dt];
-        }
-        orow[static_cast<size_t>(f2) * C] = __float2bfloat16_rn(a);
-#pragma unroll
-        for (int i = 0; i < 7; ++i) { m[i][2] = m[i][6]; }  // bin 4*f2+3 becomes bin 4*(f2+1)-1
-      }
+      };
+      if (tv[0] && tv[1] && tv[2] && F1 == 2 * F2) run(std::true_type{});
+      else run(std::false_type{});
     }
   }
 }
@@ -122,8 +133,12 @@ cudaError_t launch_sub_conv0_dw1(const SubsampleArgs& a, cudaStream_t stream) {
   const int ld = ((a.n_mels + kMelOff + 4 + 3) / 4) * 4;
   const size_t smem = static_cast<size_t>(4 * kSubTT + 3) * ld * sizeof(float);
   const dim3 grid((a.T2 + kSubTT - 1) / kSubTT, a.B);
-  sub_conv0_dw1_kernel<<<grid, 256, smem, stream>>>(a.mel, a.mel_len, a.mel_stats, a.F_max, a.n_mels, a.C, a.w0, a.b0, a.wd1, a.bd1,
-                                                   static_cast<__nv_bfloat16*>(a.out1), a.T2, a.F1, a.F2);
+  if (ld == 88)                                            // 80 mel bins: every shipped configuration
+    sub_conv0_dw1_kernel<88><<<grid, 256, smem, stream>>>(a.mel, a.mel_len, a.mel_stats, a.F_max, a.n_mels, a.C, a.w0, a.b0, a.wd1, a.bd1,
+                                                         static_cast<__nv_bfloat16*>(a.out1), a.T2, a.F1, a.F2);
+  else
+    sub_conv0_dw1_kernel<0><<<grid, 256, smem, stream>>>(a.mel, a.mel_len, a.mel_stats, a.F_max, a.n_mels, a.C, a.w0, a.b0, a.wd1, a.bd1,
+                                                        static_cast<__nv_bfloat16*>(a.out1), a.T2, a.F1, a.F2);
   return cudaGetLastError();
 }
 
