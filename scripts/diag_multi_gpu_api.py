@@ -14,8 +14,10 @@ import time
 import torch
 
 sys.path.insert(0, ".")
-import reazonspeech_b200.nemo.asr.multi_gpu as mg                                   # noqa: E402
-import reazonspeech_b200.nemo.asr.transcribe as tr                                  # noqa: E402
+import importlib                                                                    # noqa: E402
+
+mg = importlib.import_module("reazonspeech_b200.nemo.asr.multi_gpu")                # (asr.transcribe the attribute is the function)
+tr = importlib.import_module("reazonspeech_b200.nemo.asr.transcribe")
 from reazonspeech_b200.config import ModelConfig                                    # noqa: E402
 from reazonspeech_b200.engine import Engine                                         # noqa: E402
 from reazonspeech_b200.nemo.asr import TranscribeConfig, audio_from_numpy, load_model, transcribe_batch   # noqa: E402
