@@ -12,41 +12,13 @@ peer-to-peer traffic: an utterance never leaves its device.  The engine's C call
 """
 from __future__ import annotations
 
-import contextlib
 import queue
-import sys
 import threading
 from typing import List, Sequence
 
 import numpy as np
 
 from ...sharding import shard_indices
-
-
-_handoff_lock = threading.Lock()
-_handoff_users = 0
-_handoff_saved = None
-
-
-@contextlib.contextmanager
-def fast_thread_handoff(interval: float = 2e-4):
-    """While several threads feed GPUs from one interpreter, a thread returning from an engine call (made without the interpreter
-    lock) must get the lock back to submit the next batch; under the default 5 ms switch interval it waits that long whenever
-    another thread is post-processing, and a 25 ms GPU batch then sits behind several such waits.  The interval is lowered while
-    at least one such call is running (calls nest and overlap: counted) and restored when the last one ends."""
-    global _handoff_users, _handoff_saved
-    with _handoff_lock:
-        if _handoff_users == 0:
-            _handoff_saved = sys.getswitchinterval()
-            sys.setswitchinterval(min(_handoff_saved, interval))
-        _handoff_users += 1
-    try:
-        yield
-    finally:
-        with _handoff_lock:
-            _handoff_users -= 1
-            if _handoff_users == 0:
-                sys.setswitchinterval(_handoff_saved)
 
 
 class MultiGpuRnntModel:
@@ -83,20 +55,19 @@ class MultiGpuRnntModel:
                 out.put(None)
 
         threads = [threading.Thread(target=work, args=(r, s), daemon=True) for r, s in zip(self.replicas, shards) if s]
-        with fast_thread_handoff():
-            for t in threads:
-                t.start()
-            running, error = len(threads), None
-            while running:
-                item = out.get()
-                if item is None:
-                    running -= 1
-                elif isinstance(item, BaseException):
-                    error = error or item
-                elif error is None:
-                    yield item
-            for t in threads:
-                t.join()
+        for t in threads:
+            t.start()
+        running, error = len(threads), None
+        while running:
+            item = out.get()
+            if item is None:
+                running -= 1
+            elif isinstance(item, BaseException):
+                error = error or item
+            elif error is None:
+                yield item
+        for t in threads:
+            t.join()
         if error is not None:
             raise error
 

@@ -142,8 +142,7 @@ class B200RnntModel:
             wav, lens, out = run(self._staging[0], batches[0])
             yield collect(eng.transcribe_host(wav, lens, out[0].shape[1], out), batches[0])
             return
-        from .multi_gpu import fast_thread_handoff
-        with ThreadPoolExecutor(max_workers=1) as pool, fast_thread_handoff():
+        with ThreadPoolExecutor(max_workers=1) as pool:
             in_flight = None
             for k, idx in enumerate(batches):
                 wav, lens, out = run(self._staging[k & 1], idx)

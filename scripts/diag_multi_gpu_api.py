@@ -2,10 +2,9 @@
 
     python scripts/diag_multi_gpu_api.py [n_devices]        # on a box with that many B200s
 
-Wraps the staging call, the engine call and decode_hypothesis with timers (per thread), runs the same clip list with and
-without the lowered interpreter switch interval, prints one JSON line per variant.
+Wraps the staging call, the engine call and decode_hypothesis with timers (per thread), runs the same clip list three times,
+prints one JSON line per run.
 """
-import contextlib
 import json
 import sys
 import threading
@@ -49,17 +48,13 @@ def main():
     tr.HostStaging.stage = timed("stage (sum over threads)", tr.HostStaging.stage)
     Engine.transcribe_host = timed("engine call (sum over threads)", Engine.transcribe_host)
     tr.decode_hypothesis = timed("decode_hypothesis (caller thread)", tr.decode_hypothesis)
-    guard = mg.fast_thread_handoff
-    for variant in ("switch interval 0.2 ms", "default switch interval", "switch interval 0.2 ms", "default switch interval"):
-        mg.fast_thread_handoff = guard if variant.startswith("switch") else contextlib.nullcontext
-        tr_guard = guard if variant.startswith("switch") else contextlib.nullcontext
+    for variant in ("first call of this shape (allocates the second pinned staging set)", "steady state", "steady state"):
         acc.clear()
         t0 = time.perf_counter()
         res = transcribe_batch(model, audios * 4, conf)
         dt = time.perf_counter() - t0
         print(json.dumps({"variant": variant, "devices": n_dev, "clips": len(res), "seconds": round(dt, 4), "rtfx": round(len(res) * 30.0 / dt),
                           "ms_per_clip": round(dt / len(res) * 1e3, 3), **{k: round(v, 4) for k, v in acc.items()}}))
-        del tr_guard
 
 
 if __name__ == "__main__":
