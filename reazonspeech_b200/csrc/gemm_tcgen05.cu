@@ -386,7 +386,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int num_k = p.K / BK;
   const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
   const int prof_slot = !leader ? -1 : cid == 0 ? 0 : cid == ncl - 1 ? 1 : -1;
+#ifdef RS_GEMM_NO_PROF
+  auto stamp = [&](int) {};
+#else
   auto stamp = [&](int i) { if (prof_slot >= 0 && i < 32) g_gemm_prof[prof_slot][i] = clock64(); };
+#endif
   if (threadIdx.x == 0) stamp(30);
 
   if (warp == 0 && lane == 0) {
@@ -413,7 +417,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       if (++p_kb == num_k) { p_kb = 0; p_tile += ncl; }
     }
   };
+#ifndef RS_GEMM_NO_PREFILL
   if (warp == 0 && lane == 0) produce(Cfg::kStages);
+#endif
   if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
   tcgen05_fence_before();
   cluster_sync_all();
