@@ -369,12 +369,18 @@ def main():
     stages = eng.stage_times_ms()
     eng.enable_stage_timing(False)
     decode_prof = eng.decode_cycles(B, L, U)
+    if not any(v for k, v in decode_prof.items() if k != "iterations"):
+        # the per-phase cycle counters (and the attention / GEMM timelines) are compiled in only with RS_BUILD_FLAGS=-DRS_PROF: the
+        # shipped kernels do not carry them (profiles/r02_ab.md); the counters of a profiling build are in BASELINE.md
+        decode_prof = {"iterations": decode_prof["iterations"]}
     # per-kernel device time inside the pipeline (event pair around every launch; one extra, untimed step)
     eng.kernel_timing(True)
     eng.transcribe_device(wav_dev, len_dev, U, out_dev)
     kernel_ms = {k: {"launches": n, "ms": round(ms, 4)} for k, (n, ms) in sorted(eng.kernel_timing().items(), key=lambda kv: -kv[1][1])}
     eng.kernel_timing(False)
     attn_cycles = eng.attention_cycles()
+    if not any(attn_cycles.values()):
+        attn_cycles = None
     # memory-bound kernels against the measured copy bandwidth: ALGORITHMIC bytes over the
     # in-pipeline time of their launches (event pairs above, so warm-L2 effects are included: a fraction can exceed 1)
     valid_T = eng.cfg.enc_frames(L)

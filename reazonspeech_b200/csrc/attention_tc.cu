@@ -70,7 +70,11 @@ struct AtcDev {
 
 // cycle stamps of CTA (1, 0, 0): [0..7] control thread, [8..15] first softmax thread (profiling aid, rs_debug_attention_cycles)
 __device__ long long g_atc_prof[16];
+#ifdef RS_PROF      // RS_BUILD_FLAGS=-DRS_PROF python -m reazonspeech_b200.build --force; not in the shipped build
 #define ATC_STAMP(cond, slot) do { if (prof_cta && (cond)) g_atc_prof[slot] = clock64(); } while (0)
+#else
+#define ATC_STAMP(cond, slot) do { (void)prof_cta; } while (0)
+#endif
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(

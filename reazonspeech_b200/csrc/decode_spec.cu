@@ -234,8 +234,15 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   unsigned int target = 0;
   int iter = 0;
   long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // per-phase cycle counters of CTA 0: compiled in only with -DRS_PROF (RS_BUILD_FLAGS=-DRS_PROF python -m reazonspeech_b200.build
+  // --force); every CTA waits for CTA 0 at the next barrier, so the shipped kernel does not carry them.  prof[7] (iterations) always counts.
+#ifdef RS_PROF
   auto tick = [&](int slot, long long& t0) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; } };
   long long tk = clock64();
+#else
+  auto tick = [&](int, long long&) {};
+  long long tk = 0;
+#endif
 
   // ------------------------------------------------------------------------------------------------
   // LSTM step + joint.pred for the utterances listed in s_emit[0..n_emit): token s_tok[b], state parity s_par[b]
@@ -467,9 +474,13 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
             }
           }
         };
+#ifdef RS_PROF
         long long tj = 0;
         if (cta == 0 && tid == 0) tj = clock64();
         auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
+#else
+        auto jtick = [&](int) {};
+#endif
         {
           // ---- tcgen05 joint: D[vocabulary row, (utterance, frame) row] in tensor memory
           auto write_planes = [&]() {                         // gv -> two IEEE-half planes, 128B-swizzled K-major, 32 rows per slab

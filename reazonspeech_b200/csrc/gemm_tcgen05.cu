@@ -386,10 +386,13 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   const int num_k = p.K / BK;
   const int cid = static_cast<int>(cluster_id_x()), ncl = static_cast<int>(cluster_nctaid_x());
   const int prof_slot = !leader ? -1 : cid == 0 ? 0 : cid == ncl - 1 ? 1 : -1;
-#ifdef RS_GEMM_NO_PROF
-  auto stamp = [&](int) {};
-#else
+  // The stamps are compiled in only with -DRS_PROF (RS_BUILD_FLAGS=-DRS_PROF python -m reazonspeech_b200.build --force):
+  // measured on one box, the shipped kernel is 2-3 % faster without them (12.5 vs 12.8 ms of GEMM per step, profiles/r02_ab.md).
+#ifdef RS_PROF
   auto stamp = [&](int i) { if (prof_slot >= 0 && i < 32) g_gemm_prof[prof_slot][i] = clock64(); };
+#else
+  (void)prof_slot;
+  auto stamp = [&](int) {};
 #endif
   if (threadIdx.x == 0) stamp(30);
 
@@ -401,11 +404,11 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     fence_barrier_init();
   }
   cluster_sync_all();                                        // peer barriers exist before any remote arrive / 2-SM alloc
-  // TMA producer state (lane 0 of warp 0, both CTAs).  The first ring of loads goes out BETWEEN the two set-up barriers: the
-  // tensor-memory allocation and the second cluster barrier (~0.5 us) then run under the first operands' DRAM latency (~1.8 us).
+  // TMA producer state (lane 0 of warp 0, both CTAs).  (Issuing the first ring of loads between the two set-up barriers, to
+  // hide ~0.5 us of the first operands' latency, was measured 2 % SLOWER on the same box and removed: profiles/r02_ab.md.)
   int p_tile = cid, p_kb = 0, p_stage = 0; uint32_t p_phase = 0;
   auto produce = [&](int budget) {
-    while (p_tile < num_tiles && budget-- > 0) {
+    while (p_tile < num_tiles && budget-- > 0) {      // (budget: all of it, see above)
       const int m0 = (p_tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
       const int n0 = (p_tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
       mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
@@ -417,9 +420,6 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       if (++p_kb == num_k) { p_kb = 0; p_tile += ncl; }
     }
   };
-#ifndef RS_GEMM_NO_PREFILL
-  if (warp == 0 && lane == 0) produce(Cfg::kStages);
-#endif
   if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
   tcgen05_fence_before();
   cluster_sync_all();

@@ -1,7 +1,9 @@
 """Where a 2-CTA GEMM launch spends its time: clock64 timeline of the first and last cluster (Engine.gemm_cycles) for the
 encoder's shapes at the bench geometry (M = 32 x 388), next to the CUDA-event time of the same launch (warm, median of 20).
 
+    RS_BUILD_FLAGS=-DRS_PROF python -m reazonspeech_b200.build --force     # the stamps are not in the shipped build
     python scripts/diag_gemm_timeline.py            # on a B200
+    python -m reazonspeech_b200.build --force       # back to the shipped build
 """
 import json
 import statistics
