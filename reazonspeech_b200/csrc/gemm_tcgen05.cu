@@ -47,7 +47,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 7);
   static constexpr int kTmemCols = 2 * BN;                       // power of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + 32 * 36 * 4 * 8 /*epilogue staging*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * (32 * 36 * 4 + 512) /*epilogue staging*/;
 };
 
 // Fused epilogue of one 32-row x 32-column chunk (one epilogue warp): bias, activation / GLU / residual, store.
@@ -57,7 +57,7 @@ struct GemmCfg {
 // bf16: 8 rows x 64 B), and the residual is read -- and prefetched during the MMAs -- in that same
 // coalesced ownership.
 constexpr int kStageLd = 36;                                   // floats per staged row (144 B: 16 B-aligned, conflict-free)
-constexpr int kStageBytesPerWarp = 32 * kStageLd * 4;
+constexpr int kStageBytesPerWarp = 32 * kStageLd * 4 + 512;    // + the bias of the warp's (up to) four chunks of a tile
 constexpr int kStageBytesTotal = kEpiWarps * kStageBytesPerWarp;
 
 __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int tile_row0, int lane, int col0, int bt, float4 (&rr)[8]) {
@@ -76,11 +76,17 @@ __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int ti
 // kResid: the instance may be asked for RS_EPI_RESID_F32 with the residual in rr (otherwise rr is never read).
 template <int EG, bool kResid>
 __device__ __forceinline__ void epilogue_store(const GemmDev& p, const uint32_t (&r)[32], float* stage, int tile_row0, int lane,
-                                               int col0, int bt, const float4 (&rr)[8]) {
+                                               int col0, int bt, const float4 (&rr)[8], const float* bias_s = nullptr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias != nullptr) {
+  if (bias_s != nullptr) {                                     // the chunk's bias from shared memory (broadcast reads; zeros without a bias)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  } else if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + bt * p.bias_stride + col0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -490,7 +496,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {                          // lane = row; 16-byte chunk j of the row sits at j ^ (row & 7)
-            const float4 b = p.bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b = p.bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);   // (a register prefetch of the next chunk's bias measured slower)
             *reinterpret_cast<float4*>(buf + ((j ^ (lane & 7)) << 4)) =
                 make_float4(p.alpha * (__uint_as_float(r[4 * j]) + b.x), p.alpha * (__uint_as_float(r[4 * j + 1]) + b.y),
                             p.alpha * (__uint_as_float(r[4 * j + 2]) + b.z), p.alpha * (__uint_as_float(r[4 * j + 3]) + b.w));
@@ -505,9 +511,17 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
       } else {
         [[maybe_unused]] float4 rr[8], cur[8];                                // EG 3 only: the residual, one chunk ahead
         if constexpr (EG == 3) resid_prefetch(p, true, tile_row0, lane, n0 + half * 32, 0, rr);       // overlaps the tile's MMAs
+        // the bias of the warp's four chunks -> its shared slot while the MMAs run, read back as broadcasts: with the loads inside
+        // the chunk loop every chunk began with an L1 / L2 round trip (same box, three alternating runs: all GEMMs 12.12 ->
+        // 11.94 ms per step, N = 4096 3.79 -> 3.62 ms; profiles/r02_ab.md)
+        float* bias_s = stage + 32 * kStageLd;
+#pragma unroll
+        for (int c = 0; c < BN / 64; ++c) bias_s[c * 32 + lane] = p.bias != nullptr ? __ldg(p.bias + n0 + (half + 2 * c) * 32 + lane) : 0.f;
+        __syncwarp();
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         if (warp == 2 && lane == 0 && it < 3) stamp(4 + 4 * it);
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + half * 32;
 #pragma unroll 1
         for (int chunk = half; chunk < BN / 32; chunk += 2) {
           const int col0 = n0 + chunk * 32;
@@ -517,9 +531,9 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             resid_prefetch(p, chunk + 2 < BN / 32, tile_row0, lane, col0 + 64, 0, rr);
           }
           uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, r);
+          tmem_ld_32x32(t_addr + (chunk - half) * 32, r);
           tmem_ld_wait();
-          epilogue_store<EG, EG == 3>(p, r, stage, tile_row0, lane, col0, 0, cur);
+          epilogue_store<EG, EG == 3>(p, r, stage, tile_row0, lane, col0, 0, cur, bias_s + (chunk >> 1) * 32);
         }
       }
       tcgen05_fence_before();
