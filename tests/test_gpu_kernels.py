@@ -103,11 +103,14 @@ def test_gemm_resid_in_place(tiny_engine, M, N, K, with_bias, alpha):
     assert torch.equal(buf[M:], guard)
 
 
-def test_layernorm(tiny_engine):
+@pytest.mark.parametrize("rows", [333, 12419])
+def test_layernorm(tiny_engine, rows):
+    """rows = 12 419: more rows than resident warps, so every warp walks several rows (the prefetch path of the persistent kernel)."""
     eng = tiny_engine
     for d in (256, 1024):
-        x = torch.randn(333, d, device="cuda") * 3 + 1
-        g = torch.randn(d, device="cuda"); b = torch.randn(d, device="cuda")
+        g0 = torch.Generator(device="cuda").manual_seed(rows + d)
+        x = torch.randn(rows, d, device="cuda", generator=g0) * 3 + 1
+        g = torch.randn(d, device="cuda", generator=g0); b = torch.randn(d, device="cuda", generator=g0)
         ref = torch.nn.functional.layer_norm(x, (d,), g, b, eng.cfg.ln_eps)
         out = eng.layernorm(x, g, b, bf16_out=False)
         assert (out - ref).abs().max().item() < 2e-5
