@@ -111,12 +111,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* desc,
       ::"r"(smem_dst), "l"(desc), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// 2-D tiled store / reduce-add from shared memory (bulk async-group completion).  The reduction is performed by the
-// memory system at the destination: global[tile] += smem[tile], element type taken from the tensor map.
-__device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(desc), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
-}
+// 2-D tiled reduce-add from shared memory (bulk async-group completion).  The reduction is performed by the memory system
+// at the destination: global[tile] += smem[tile], element type taken from the tensor map.
 __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(desc), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
@@ -181,16 +177,6 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// The same wait, tied to the registers a tcgen05.ld is filling: no use of r can be scheduled ahead of it (with several loads in
-// flight the plain form above leaves that to the compiler's goodwill).
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
-                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :: "memory");
-}
 
 // ---------------------------------------------------------------- 2-CTA (cta_group::2) variants
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA

@@ -58,7 +58,6 @@ struct GemmCfg {
 // coalesced ownership.
 constexpr int kStageLd = 36;                                   // floats per staged row (144 B: 16 B-aligned, conflict-free)
 constexpr int kStageBytesPerWarp = 32 * kStageLd * 4 + 512;    // + the bias of the warp's (up to) four chunks of a tile
-constexpr int kStageBytesTotal = kEpiWarps * kStageBytesPerWarp;
 
 __device__ __forceinline__ void resid_prefetch(const GemmDev& p, bool on, int tile_row0, int lane, int col0, int bt, float4 (&rr)[8]) {
   if (on) {
@@ -413,8 +412,8 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
   // TMA producer state (lane 0 of warp 0, both CTAs).  (Issuing the first ring of loads between the two set-up barriers, to
   // hide ~0.5 us of the first operands' latency, was measured 2 % SLOWER on the same box and removed: profiles/r02_ab.md.)
   int p_tile = cid, p_kb = 0, p_stage = 0; uint32_t p_phase = 0;
-  auto produce = [&](int budget) {
-    while (p_tile < num_tiles && budget-- > 0) {      // (budget: all of it, see above)
+  auto produce = [&]() {
+    while (p_tile < num_tiles) {
       const int m0 = (p_tile / num_n) * 2 * BM + static_cast<int>(rank) * BM;
       const int n0 = (p_tile % num_n) * BN + static_cast<int>(rank) * (BN / 2);
       mbar_wait(empty_bar(p_stage), p_phase ^ 1u);
@@ -435,7 +434,7 @@ gemm_bf16_tn_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) produce(0x7fffffff);
+    if (lane == 0) produce();
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
