@@ -370,8 +370,7 @@ def main():
     eng.enable_stage_timing(False)
     decode_prof = eng.decode_cycles(B, L, U)
     if not any(v for k, v in decode_prof.items() if k != "iterations"):
-        # the per-phase cycle counters (and the attention / GEMM timelines) are compiled in only with RS_BUILD_FLAGS=-DRS_PROF: the
-        # shipped kernels do not carry them (profiles/r02_ab.md); the counters of a profiling build are in BASELINE.md
+        # (a build with -DRS_NO_DECODE_COUNTERS; the attention / GEMM timelines are compiled in only with RS_BUILD_FLAGS=-DRS_PROF)
         decode_prof = {"iterations": decode_prof["iterations"]}
     # per-kernel device time inside the pipeline (event pair around every launch; one extra, untimed step)
     eng.kernel_timing(True)

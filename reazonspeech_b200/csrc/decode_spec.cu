@@ -234,9 +234,10 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
   unsigned int target = 0;
   int iter = 0;
   long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  // per-phase cycle counters of CTA 0: compiled in only with -DRS_PROF (RS_BUILD_FLAGS=-DRS_PROF python -m reazonspeech_b200.build
-  // --force); every CTA waits for CTA 0 at the next barrier, so the shipped kernel does not carry them.  prof[7] (iterations) always counts.
-#ifdef RS_PROF
+  // per-phase cycle counters of CTA 0 (rs_debug_decode_cycles).  They stay in the shipped kernel: on the same box, three alternating
+  // runs each, the kernel compiled WITH them decodes the bench batch in 5.30-5.35 ms and the one without in 5.62-5.70 ms (238 against
+  // 231 registers: the counters change the schedule ptxas picks, not the work; profiles/r02_ab.md).  -DRS_NO_DECODE_COUNTERS drops them.
+#ifndef RS_NO_DECODE_COUNTERS
   auto tick = [&](int slot, long long& t0) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; } };
   long long tk = clock64();
 #else
@@ -474,7 +475,7 @@ rnnt_greedy_spec_kernel(const SpecDev p) {
             }
           }
         };
-#ifdef RS_PROF
+#ifndef RS_NO_DECODE_COUNTERS
         long long tj = 0;
         if (cta == 0 && tid == 0) tj = clock64();
         auto jtick = [&](int slot) { if (cta == 0 && tid == 0) { const long long t1 = clock64(); prof[slot] += t1 - tj; tj = t1; } };
