@@ -50,7 +50,9 @@ typedef struct rs_model_config {
   int32_t pred_hidden, joint_hidden, max_symbols;
 } rs_model_config;
 
-/* One packed weight tensor, resident on the device (packing: reazonspeech_b200/engine.py). */
+/* One packed weight tensor, resident on the device (packing: reazonspeech_b200/engine.py::pack_weights is the definition of
+ * the names, shapes and value transforms -- e.g. "pred.gate_tab" f32 [V+1, 4*pred_hidden] = W_ih . embed[k] + b_ih + b_hh,
+ * the per-token input half of the LSTM gates; rs_engine_create names the first tensor it misses in rs_last_error). */
 typedef enum rs_dtype { RS_F32 = 0, RS_BF16 = 1, RS_I32 = 2 } rs_dtype;
 typedef struct rs_tensor {
   const char* name;
@@ -67,7 +69,9 @@ typedef enum rs_epilogue {
   RS_EPI_BIAS_RELU_BF16 = 1,  /* out_bf16[M,N]   = relu(acc + bias)                            */
   RS_EPI_BIAS_SWISH_BF16 = 2, /* out_bf16[M,N]   = swish(acc + bias)                           */
   RS_EPI_BIAS_GLU_BF16 = 3,   /* out_bf16[M,N/2] = a * sigmoid(g); W rows interleaved 16/16    */
-  RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias)   */
+  RS_EPI_RESID_F32 = 4,       /* out_f32[M,N]    = resid + alpha * (acc + bias)  (may alias: with out == resid and
+                                 N % 256 == 0 the add is a TMA reduce-add performed by the memory system -- the residual is never
+                                 read into the SM; same fp32 sum, bit-identical to the two-buffer form)   */
   RS_EPI_BIAS_F32 = 5,        /* out_f32[M,N]    = alpha * (acc + bias)                        */
   RS_EPI_BIAS_F16 = 6,        /* out_f16[M,N]    = acc + bias  (IEEE half)                          */
   RS_EPI_QKV_VT = 7           /* fused QKV projection: columns [0, split) -> out_bf16[M, ldo] as RS_EPI_BIAS_BF16,

@@ -471,7 +471,9 @@ class Engine:
         return {n: int(x - v[0]) for n, x in zip(names, v) if n != "_"}
 
     def gemm_cycles(self):
-        """Timeline (SM clocks relative to kernel entry) of the last 2-CTA GEMM launch, for its first and its last cluster."""
+        """Timeline (SM clocks relative to kernel entry) of the last 2-CTA GEMM launch, for its first and its last cluster.
+        Only a library built with RS_BUILD_FLAGS=-DRS_PROF writes the stamps (scripts/diag_gemm_timeline.py); the shipped one
+        returns whatever the buffer held (zeros)."""
         out = (C.c_int64 * 64)()
         self._check(self.lib.rs_debug_gemm_cycles(self.h, out), "rs_debug_gemm_cycles")
         res = {}

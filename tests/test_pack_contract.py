@@ -62,3 +62,29 @@ def test_rel_shift_read_index_contract():
                     pair = e >> 1                                   # funnelshift(w[pair], w[pair + 1], sh) holds elements e, e + 1 of the chunk
                     first_half = 2 * (word + pair) + (1 if sh else 0)
                     assert first_half == cs + 2 * pair and pair + 1 <= 16
+
+
+def test_gate_table_is_the_input_half_of_the_lstm_step():
+    """decode_spec.cu adds pred.gate_tab[token] (built once by pack_weights) to W_hh . h instead of multiplying W_ih with the
+    embedding at every step: one LSTM step through the table equals the oracle's lstm_step, for ordinary tokens and for the
+    start-of-sequence step (blank row = the zero padding embedding -> the bias alone)."""
+    from oracle import nemo_restated as O
+    cfg = ModelConfig.tiny()
+    sd = random_state_dict(cfg, seed=3)
+    pk = pack_weights(sd, cfg)
+    hp = cfg.pred_hidden
+    tab = pk["pred.gate_tab"]
+    assert tab.shape == (cfg.vocab_size + 1, 4 * hp) and tab.dtype == torch.float32
+    l = "decoder.prediction.dec_rnn.lstm."
+    w_hh = sd[l + "weight_hh_l0"]
+    emb = sd["decoder.prediction.embed.weight"]
+    g = torch.Generator().manual_seed(0)
+    for k in (0, 5, cfg.vocab_size - 1, cfg.blank):
+        h, c = torch.randn(hp, generator=g) * 0.5, torch.randn(hp, generator=g) * 0.5
+        gates = tab[k] + w_hh @ h
+        i, f, gg, o = gates.split(hp)
+        c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h2 = torch.sigmoid(o) * torch.tanh(c2)
+        x = torch.zeros(hp) if k == cfg.blank else emb[k]          # the oracle's SOS step feeds zeros (blank as padding)
+        h_ref, c_ref = O.lstm_step(x, h, c, sd)
+        assert (h2 - h_ref).abs().max() < 1e-5 and (c2 - c_ref).abs().max() < 1e-5
