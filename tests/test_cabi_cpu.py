@@ -116,3 +116,26 @@ def test_stage_rows_host_helper():
         assert np.array_equal(dst[3, pad:pad + 4000], waves[3])
     assert call(np.zeros((B, L), np.float32), waves, 0, 1, L_=4000) != 0          # a row does not fit
     assert call(np.zeros((B, L), np.int16), waves, 1, 1, [0] * B) != 0            # int16 rows from float sources
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/rs_engine.h is the drop-in boundary for a cgo / JNI / ctypes binding: it must compile as C99 on its own, and a C
+    program that references every declared entry point must link against the library (no C++ or torch types in the signatures)."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from reazonspeech_b200.engine import _LIB_PATH, load_library
+    load_library()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "rs_engine.h")).read()
+    names = sorted(set(re.findall(r"\b(rs_[a-z0-9_]+)\s*\(", header)))
+    assert "rs_transcribe_batch" in names and "rs_stage_rows" in names
+    src = tmp_path / "use_all.c"
+    src.write_text('#include "rs_engine.h"\n#include <stdio.h>\nint main(void) {\n  const void* fns[] = {' +
+                   ", ".join(f"(const void*){n}" for n in names) + "};\n  printf(\"%d\\n\", (int)(sizeof fns / sizeof fns[0]));\n  return 0;\n}\n")
+    exe = tmp_path / "use_all"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                        _LIB_PATH, "-Wl,-rpath," + os.path.dirname(_LIB_PATH)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
